@@ -1,0 +1,49 @@
+// tmap.h — host-side construction of TMA tensor maps (cuTensorMapEncodeTiled).
+//
+// The driver entry point is resolved at run time through the CUDA runtime
+// (cudaGetDriverEntryPoint), so the library links against libcudart only.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace carel {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
+            cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Row-major bf16 matrix [rows, cols] with row pitch `ld_elems` elements; TMA box =
+// 64 columns (128 B, matches SWIZZLE_128B) x `box_rows` rows.  Out-of-bounds
+// elements are zero-filled.
+inline int make_tmap_bf16_sw128(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols,
+                                uint64_t ld_elems, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_tiled();
+  if (!fn) return -1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : int(r);
+}
+
+}  // namespace carel
