@@ -1,0 +1,83 @@
+"""ctypes binding of libcarel_head.so (the C ABI declared in include/carel_head.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, the
+caller gets an exception.  Build with ``python -m carel_vae_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("CAREL_HEAD_LIB", _PKG / "libcarel_head.so"))
+
+_lib = None
+
+c_f32p = C.c_void_p
+c_ptr = C.c_void_p
+i64 = C.c_int64
+
+_SIGNATURES = {
+    "carel_version": (C.c_int, []),
+    "carel_last_error": (C.c_char_p, []),
+    "carel_launch_count": (i64, []),
+    "carel_gemm_bf16": (C.c_int, [c_ptr, i64, C.c_int, c_ptr, i64, C.c_int, i64, i64, i64, c_ptr, i64,
+                                  c_ptr, C.c_int, c_ptr]),
+    "carel_mmd_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
+    "carel_mmd_fwd": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.POINTER(C.c_float), C.c_int,
+                                C.c_float, C.c_int, i64, i64, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "carel_mmd_finalize": (C.c_int, [c_ptr, i64, i64, c_ptr, c_ptr]),
+    "carel_mmd_bwd": (C.c_int, [c_ptr, i64, i64, i64, C.POINTER(C.c_float), C.c_int, C.c_float, i64, i64,
+                                c_ptr, i64, c_ptr, i64, c_ptr, C.c_size_t, c_ptr]),
+    "carel_pairwise_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
+    "carel_pairwise": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.c_int, C.POINTER(C.c_float),
+                                 C.c_int, C.c_float, c_ptr, i64, c_ptr, C.c_size_t, c_ptr]),
+}
+
+
+class CarelError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise loudly if it is not there."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise CarelError(
+                f"{LIB_PATH} not found: the CUDA extension is required (no CPU / PyTorch fallback). "
+                "Build it with `python -m carel_vae_b200.build`.")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            if not hasattr(handle, name):
+                continue  # declared in a later build step; callers fail loudly when they need it
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def declare(name: str, restype, argtypes) -> None:
+    """Register the signature of an entry point (used by the op modules)."""
+    _SIGNATURES[name] = (restype, argtypes)
+    if _lib is not None and hasattr(_lib, name):
+        fn = getattr(_lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().carel_last_error()
+        raise CarelError(f"{what} failed: {msg.decode() if msg else 'unknown error'}")
+
+
+def float_array(values):
+    arr = (C.c_float * len(values))(*[float(v) for v in values])
+    return arr
+
+
+def launch_count() -> int:
+    return int(lib().carel_launch_count())

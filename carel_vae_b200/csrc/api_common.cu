@@ -1,0 +1,111 @@
+// api_common.cu — error string, version, launch counter, debug GEMM and dense pairwise entry points.
+#include "api_common.cuh"
+#include "epilogues.cuh"
+#include "gemm_launch.cuh"
+#include "pack.cuh"
+
+namespace carel {
+
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> c{0};
+  return c;
+}
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+}  // namespace carel
+
+using namespace carel;
+
+extern "C" int carel_version(void) { return CAREL_VERSION; }
+extern "C" const char* carel_last_error(void) { return error_buffer(); }
+extern "C" int64_t carel_launch_count(void) { return launch_counter().load(); }
+
+extern "C" int carel_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb,
+                               int b_mn, int64_t M, int64_t N, int64_t K, float* c, int64_t ldc,
+                               const float* bias, int ksplit, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(M > 0 && N > 0 && K > 0, "carel_gemm_bf16: empty problem");
+  CAREL_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, "carel_gemm_bf16: lda/ldb must be multiples of 8");
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = make_tmap_bf16_sw128(&ta, a, M, K, lda, 128);
+  else rc = make_tmap_bf16_sw128(&ta, a, K, M, lda, 64);
+  CAREL_REQUIRE(rc == 0, "carel_gemm_bf16: tensor map A failed (%d)", rc);
+  if (!b_mn) rc = make_tmap_bf16_sw128(&tb, b, N, K, ldb, 128);
+  else rc = make_tmap_bf16_sw128(&tb, b, K, N, ldb, 64);
+  CAREL_REQUIRE(rc == 0, "carel_gemm_bf16: tensor map B failed (%d)", rc);
+  GemmSched s;
+  s.m_tiles = int((M + 127) / 128);
+  s.n_tiles = int((N + 255) / 256);
+  s.num_kb = int((K + 63) / 64);
+  s.ksplit = ksplit < 1 ? 1 : (ksplit > s.num_kb ? s.num_kb : ksplit);
+  s.mode = TILE_FULL;
+  s.num_items = s.m_tiles * s.n_tiles * s.ksplit;
+  s.m_tile0 = 0;
+  EpiStore<256>::Params ep;
+  ep.out = c; ep.bias = bias; ep.out_bf16 = nullptr; ep.M = int(M); ep.N = int(N);
+  ep.ld = int(ldc); ep.ld_bf16 = 0; ep.atomic = s.ksplit > 1; ep.scale = 1.f;
+  if (!a_mn && !b_mn) return launch_gemm<EpiStore<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st);
+  if (!a_mn && b_mn) return launch_gemm<EpiStore<256>, 256, 1, false, true>(ta, tb, ta, tb, s, ep, st);
+  if (a_mn && !b_mn) return launch_gemm<EpiStore<256>, 256, 1, true, false>(ta, tb, ta, tb, s, ep, st);
+  return launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// dense pairwise matrices (API completeness; materialises [n1, n2])
+// ------------------------------------------------------------------------------------------
+extern "C" size_t carel_pairwise_workspace_bytes(int64_t n1, int64_t n2, int64_t dim) {
+  const int64_t Kp = round_up64(dim, 64);
+  WsCarver w(nullptr);
+  w.take<__nv_bfloat16>(size_t(n1) * Kp);
+  w.take<__nv_bfloat16>(size_t(n2) * Kp);
+  w.take<float>(size_t(round_up64(n1, 256)));
+  w.take<float>(size_t(round_up64(n2, 256)));
+  return w.bytes();
+}
+
+extern "C" int carel_pairwise(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t n1,
+                              int64_t n2, int64_t dim, int mode, const float* alphas_host,
+                              int n_alpha, float eps, float* out, int64_t ldo, void* ws,
+                              size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(n1 > 0 && n2 > 0 && dim > 0, "carel_pairwise: empty input");
+  CAREL_REQUIRE(n_alpha >= 0 && n_alpha <= kMaxAlphas, "carel_pairwise: at most %d alphas", kMaxAlphas);
+  CAREL_REQUIRE(ws_bytes >= carel_pairwise_workspace_bytes(n1, n2, dim), "carel_pairwise: workspace too small");
+  const int64_t Kp = round_up64(dim, 64);
+  WsCarver w(ws);
+  __nv_bfloat16* pa = w.take<__nv_bfloat16>(size_t(n1) * Kp);
+  __nv_bfloat16* pb = w.take<__nv_bfloat16>(size_t(n2) * Kp);
+  float* na = w.take<float>(size_t(round_up64(n1, 256)));
+  float* nb = w.take<float>(size_t(round_up64(n2, 256)));
+  pack_rows_kernel<<<int((n1 + 7) / 8), 256, 0, st>>>(a, int(n1), int(dim), int(lda), pa, int(Kp), 0, na);
+  CAREL_LAUNCHED();
+  pack_rows_kernel<<<int((n2 + 7) / 8), 256, 0, st>>>(b, int(n2), int(dim), int(ldb), pb, int(Kp), 0, nb);
+  CAREL_LAUNCHED();
+  CUtensorMap ta, tb;
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, pa, n1, Kp, Kp, 128) == 0, "carel_pairwise: tensor map A failed");
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, pb, n2, Kp, Kp, 128) == 0, "carel_pairwise: tensor map B failed");
+  GemmSched s;
+  s.m_tiles = int((n1 + 127) / 128);
+  s.n_tiles = int((n2 + 255) / 256);
+  s.num_kb = int(Kp / 64);
+  s.ksplit = 1; s.mode = TILE_FULL; s.num_items = s.m_tiles * s.n_tiles; s.m_tile0 = 0;
+  EpiPairwise<256>::Params ep;
+  ep.out = out; ep.norms_a = na; ep.norms_b = nb; ep.M = int(n1); ep.N = int(n2); ep.ld = int(ldo);
+  ep.mode = mode; ep.n_alpha = n_alpha; ep.eps = eps;
+  for (int i = 0; i < kMaxAlphas; ++i) ep.alpha[i] = (i < n_alpha) ? alphas_host[i] : 0.f;
+  return launch_gemm<EpiPairwise<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st);
+}

@@ -1,0 +1,54 @@
+// chain_launch.cuh — host-side launcher and work decomposition of chain_tc_kernel.
+#pragma once
+#include "api_common.cuh"
+#include "chain_tc.cuh"
+
+namespace carel {
+
+// Split the inner range so that the number of work items fills whole waves of the persistent
+// grid: pick nsplit in [1, max_split] maximising items / (ceil(items / SMs) * SMs); ties go to
+// the smaller split (less atomic traffic).
+inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int num_kb, int max_split) {
+  ChainSched s;
+  s.owner0 = owner0;
+  s.n_owner = n_owner;
+  s.n_inner = n_inner;
+  s.num_kb = num_kb;
+  const int sms = sm_count();
+  int best = 1;
+  double best_eff = -1.0;
+  for (int sp = 1; sp <= max_split && sp <= (n_inner > 0 ? n_inner : 1); ++sp) {
+    const int per = (n_inner + sp - 1) / sp;
+    if (per * (sp - 1) >= n_inner && sp > 1) continue;  // would create an empty split
+    const long long items = 1LL * n_owner * sp;
+    const long long waves = (items + sms - 1) / sms;
+    // every wave costs `per` inner tiles plus a fixed per-item overhead (~2 tiles)
+    const double cost = double(waves) * (per + 2.0);
+    const double eff = 1.0 / cost;
+    if (eff > best_eff * 1.0001) { best_eff = eff; best = sp; }
+  }
+  s.nsplit = best;
+  s.num_items = n_owner * best;
+  return s;
+}
+
+template <class Pol, int NG, int BN1, int KP>
+int launch_chain(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
+                 const CUtensorMap& b1, const ChainSched& s, const typename Pol::Params& pp,
+                 cudaStream_t st) {
+  using Cfg = ChainCfg<NG, BN1, KP>;
+  auto kern = chain_tc_kernel<Pol, NG, BN1, KP>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int grid = s.num_items < sm_count() ? s.num_items : sm_count();
+  if (grid <= 0) return 0;
+  kern<<<grid, 384, Cfg::kSmemBytes, st>>>(a0, b0, a1, b1, s, pp);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
+}  // namespace carel

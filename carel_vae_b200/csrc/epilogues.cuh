@@ -1,0 +1,227 @@
+// epilogues.cuh — register-level epilogues plugged into gemm_tc_kernel.
+//
+// Each epilogue thread owns ONE accumulator row (TMEM lane) and walks its warp's column half
+// in chunks of 32 fp32 columns (tcgen05.ld 32x32b.x32).  Nothing N x N ever goes to HBM:
+// the epilogues reduce the tile to scalars / row vectors in registers.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace carel {
+
+constexpr int kMaxAlphas = 8;
+
+// ---------------------------------------------------------------------------------------------
+// Plain store: C[row, col] (+)= acc (+ bias[col]);  fp32 output, optional atomic accumulate
+// (split-K / partial products), optional bf16 copy.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct EpiStore {
+  struct Params {
+    float* out;            // [M, ld]
+    const float* bias;     // [N] or nullptr
+    __nv_bfloat16* out_bf16;  // optional [M, ld_bf16]
+    int M, N, ld, ld_bf16;
+    int atomic;            // 1: atomicAdd into out (bias added only by the kb0 == 0 split)
+    float scale;
+  };
+  const Params& p;
+  CAREL_DEVINL EpiStore(const Params& p_, const TileCtx&) : p(p_) {}
+  CAREL_DEVINL void tile(const TileCtx& ctx) {
+    constexpr int HALF = BN / 2;
+    const int cbase = ctx.col0 + ctx.half * HALF;
+    const bool row_ok = ctx.row < p.M;
+#pragma unroll 1
+    for (int c = 0; c < HALF / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(ctx.taddr + ctx.half * HALF + c * 32, r);
+      tmem_ld_wait();
+      const int col = cbase + c * 32;
+      if (!row_ok || col >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = __uint_as_float(r[i]) * p.scale;
+        if (p.bias != nullptr && ctx.kb0 == 0 && col + i < p.N) v[i] += __ldg(p.bias + col + i);
+      }
+      float* o = p.out + size_t(ctx.row) * p.ld + col;
+      if (p.atomic) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col + i < p.N) atomicAdd(o + i, v[i]);
+      } else if (col + 32 <= p.N && (p.ld & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col + i < p.N) o[i] = v[i];
+      }
+      if (p.out_bf16 != nullptr) {
+        __nv_bfloat16* ob = p.out_bf16 + size_t(ctx.row) * p.ld_bf16 + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col + i < p.N) ob[i] = __float2bfloat16_rn(v[i]);
+      }
+    }
+  }
+  CAREL_DEVINL void finish() {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// Pairwise-distance store: out[i, j] = f(|n_i + n_j - 2 a_i.b_j|)
+//   mode 0: sum_alpha exp(-alpha (|d2| + eps))       (the MMD kernel matrix, ret_matrix=True)
+//   mode 1: sqrt(eps + |d2|)                         (reference pdist, norm = 2)
+//   mode 2: -2 a.b + n_i + n_j                       (reference pairwise_distances)
+//   mode 3: exp(-d2 / sigma)  with alpha[0] = 1/sigma (reference GaussianKernelMatrix)
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct EpiPairwise {
+  struct Params {
+    float* out;
+    const float* norms_a;
+    const float* norms_b;
+    int M, N, ld, mode, n_alpha;
+    float eps;
+    float alpha[kMaxAlphas];
+  };
+  const Params& p;
+  CAREL_DEVINL EpiPairwise(const Params& p_, const TileCtx&) : p(p_) {}
+  CAREL_DEVINL void tile(const TileCtx& ctx) {
+    constexpr int HALF = BN / 2;
+    const int cbase = ctx.col0 + ctx.half * HALF;
+    const bool row_ok = ctx.row < p.M;
+    const float ni = row_ok ? __ldg(p.norms_a + ctx.row) : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < HALF / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(ctx.taddr + ctx.half * HALF + c * 32, r);
+      tmem_ld_wait();
+      const int col = cbase + c * 32;
+      if (!row_ok || col >= p.N) continue;
+      float* o = p.out + size_t(ctx.row) * p.ld + col;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (col + i >= p.N) continue;
+        const float d2 = fmaf(-2.f, __uint_as_float(r[i]), ni + __ldg(p.norms_b + col + i));
+        float v;
+        if (p.mode == 0) {
+          v = 0.f;
+          for (int a = 0; a < p.n_alpha; ++a) v += __expf(-p.alpha[a] * (fabsf(d2) + p.eps));
+        } else if (p.mode == 1) {
+          v = sqrtf(p.eps + fabsf(d2));
+        } else if (p.mode == 2) {
+          v = d2;
+        } else {
+          v = __expf(-d2 * p.alpha[0]);
+        }
+        o[i] = v;
+      }
+    }
+  }
+  CAREL_DEVINL void finish() {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// MMD forward (reference MMDStatistic.__call__, drl_classifier_ec_mmd_final_mul.py:547-569).
+// S = cat(x, y) is the row AND the column operand.  For every element of the Gram tile:
+//     d2 = n_i + n_j - 2 s_i.s_j ;  k = sum_alpha exp(-alpha (|d2| + eps))
+// and three block sums are accumulated:  acc[0] = sum_{xx, i!=j} k, acc[1] = sum_{yy, i!=j} k,
+// acc[2] = sum_{xy} k + sum_{yx} k.   tri != 0: only tiles on/above the diagonal are scheduled and
+// every counted pair (j > i) is weighted 2 (K is symmetric).
+// ---------------------------------------------------------------------------------------------
+struct EpiMMDParams {
+  const float* norms;  // [>= roundup(M, 256)], zero padded
+  double* accum;       // [3]
+  int M, n1, tri, n_alpha;
+  float a_scale[kMaxAlphas];  // -alpha * log2(e)
+  float a_shift[kMaxAlphas];  // -alpha * eps * log2(e)
+};
+
+template <int BN>
+struct EpiMMD {
+  using Params = EpiMMDParams;
+  const Params& p;
+  double acc[3];
+  CAREL_DEVINL EpiMMD(const Params& p_, const TileCtx&) : p(p_) { acc[0] = acc[1] = acc[2] = 0.0; }
+
+  template <bool SINGLE>
+  CAREL_DEVINL float kval(float d2) const {
+    const float a = fabsf(d2);
+    if (SINGLE) return ex2_approx(fmaf(a, p.a_scale[0], p.a_shift[0]));
+    float k = 0.f;
+    for (int t = 0; t < p.n_alpha; ++t) k += ex2_approx(fmaf(a, p.a_scale[t], p.a_shift[t]));
+    return k;
+  }
+
+  template <bool SINGLE>
+  CAREL_DEVINL void tile_impl(const TileCtx& ctx) {
+    constexpr int HALF = BN / 2;
+    const int r0 = ctx.tm * 128, r1 = r0 + 127;
+    const int c0 = ctx.col0 + ctx.half * HALF, c1 = c0 + HALF - 1;
+    const bool skip = (r0 >= p.M) || (c0 >= p.M) || (p.tri && c1 <= r0);
+    const bool rows_one_block = (r1 < p.n1) || (r0 >= p.n1);
+    const bool cols_one_block = (c1 < p.n1) || (c0 >= p.n1);
+    const bool off_diag = p.tri ? (c0 > r1) : (c0 > r1 || c1 < r0);
+    const bool fast = !skip && r1 < p.M && c1 < p.M && rows_one_block && cols_one_block && off_diag;
+    const int row = ctx.row;
+    const float ni = __ldg(p.norms + min(row, p.M - 1));
+    const float w = p.tri ? 2.f : 1.f;
+    if (skip) return;  // warp-uniform: nothing to read, the MMA result is discarded
+    if (fast) {
+      float s = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < HALF / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(ctx.taddr + ctx.half * HALF + c * 32, r);
+        const float4* nj4 = reinterpret_cast<const float4*>(p.norms + c0 + c * 32);
+        float nj[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = __ldg(nj4 + i);
+          nj[4 * i] = t.x; nj[4 * i + 1] = t.y; nj[4 * i + 2] = t.z; nj[4 * i + 3] = t.w;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          s += kval<SINGLE>(fmaf(-2.f, __uint_as_float(r[i]), ni + nj[i]));
+      }
+      const int type = (r0 < p.n1) ? ((c0 < p.n1) ? 0 : 2) : ((c0 < p.n1) ? 2 : 1);
+      acc[type] += double(s * w);
+    } else {
+      float s3[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 0; c < HALF / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(ctx.taddr + ctx.half * HALF + c * 32, r);
+        tmem_ld_wait();
+        if (row >= p.M) continue;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = c0 + c * 32 + i;
+          const bool ok = (col < p.M) && (p.tri ? (col > row) : (col != row));
+          if (ok) {
+            const float k = kval<SINGLE>(fmaf(-2.f, __uint_as_float(r[i]), ni + __ldg(p.norms + col)));
+            const int type = (row < p.n1) ? ((col < p.n1) ? 0 : 2) : ((col < p.n1) ? 2 : 1);
+            s3[type] += k;
+          }
+        }
+      }
+      acc[0] += double(s3[0] * w);
+      acc[1] += double(s3[1] * w);
+      acc[2] += double(s3[2] * w);
+    }
+  }
+  CAREL_DEVINL void tile(const TileCtx& ctx) {
+    if (p.n_alpha == 1) tile_impl<true>(ctx); else tile_impl<false>(ctx);
+  }
+  CAREL_DEVINL void finish() {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const double v = warp_sum(acc[t]);
+      if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(p.accum + t, v);
+    }
+  }
+};
+
+}  // namespace carel

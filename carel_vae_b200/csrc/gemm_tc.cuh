@@ -1,0 +1,240 @@
+// gemm_tc.cuh — persistent, warp-specialised tcgen05 GEMM core with pluggable epilogues.
+//
+//   D[128 x BN] (fp32, TMEM) = A_tile[128 x K] * B_tile[BN x K]^T       (bf16 operands)
+//
+// One CTA per SM, 384 threads:
+//   warp 0      TMA producer  (one elected lane)
+//   warp 1      tcgen05.mma issuer (one elected lane)
+//   warp 2      TMEM allocator
+//   warp 3      idle
+//   warps 4-11  epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. and column half (w-4)/4
+//
+// Three pipelines: smem ring (full/empty mbarriers, TMA <-> MMA), TMEM accumulator double
+// buffer (tmem_full/tmem_empty, MMA <-> epilogue), and the static persistent tile schedule.
+//
+// Operand layouts (all 128-byte swizzled, loaded by TMA):
+//   K-major  : global row-major [rows, K]; smem tile = [rows][64 bf16] per 64-wide k-block.
+//   MN-major : global row-major [K, rows]; smem tile = per 64-row chunk [64 k][64 bf16].
+// NG = 1 or 2 independent products per tile (HSIC needs the x- and the y-Gram of the same
+// tile); product g accumulates into TMEM columns [g*BN, (g+1)*BN).
+#pragma once
+#include "common.cuh"
+
+namespace carel {
+
+enum TileMode : int { TILE_FULL = 0, TILE_TRI = 1 };
+
+struct GemmSched {
+  int m_tiles;   // tiles of 128 rows
+  int n_tiles;   // tiles of BN cols
+  int num_kb;    // 64-wide k blocks (per product)
+  int ksplit;    // split-K factor (>=1); item = tile * ksplit + ks
+  int mode;      // TileMode; TILE_TRI requires BN == 256 and a square problem
+  int num_items; // total work items
+  int m_tile0;   // first row tile owned by this launch (row-block sharding across GPUs)
+};
+
+// Sequential decoder of the persistent schedule; every role of a CTA walks the same items.
+struct TileIter {
+  const GemmSched& s;
+  int item;
+  // TRI state
+  int tri_tm, tri_base;
+  int tm, tn, kb0, kb1;
+  CAREL_DEVINL explicit TileIter(const GemmSched& s_) : s(s_), item(blockIdx.x), tri_tm(0), tri_base(0) {}
+  CAREL_DEVINL int tri_count(int t) const { return s.n_tiles - ((s.m_tile0 + t) >> 1); }
+  CAREL_DEVINL bool next() {
+    if (item >= s.num_items) return false;
+    const int tile = item / s.ksplit;
+    const int ks = item - tile * s.ksplit;
+    if (s.mode == TILE_FULL) {
+      tm = tile / s.n_tiles;
+      tn = tile - tm * s.n_tiles;
+    } else {
+      while (tile >= tri_base + tri_count(tri_tm)) {
+        tri_base += tri_count(tri_tm);
+        ++tri_tm;
+      }
+      tm = tri_tm;
+      tn = ((s.m_tile0 + tri_tm) >> 1) + (tile - tri_base);
+    }
+    tm += s.m_tile0;
+    const int per = (s.num_kb + s.ksplit - 1) / s.ksplit;
+    kb0 = ks * per;
+    kb1 = min(kb0 + per, s.num_kb);
+    item += gridDim.x;
+    return true;
+  }
+};
+
+// Context handed to an epilogue for one accumulator tile.
+struct TileCtx {
+  uint32_t taddr;  // TMEM address of (this warp's lane quarter, column 0 of the buffer)
+  int tm, tn;      // tile coordinates
+  int row;         // global row index of this thread (tm*128 + lane quarter*32 + lane)
+  int col0;        // global column of tile column 0 (tn*BN)
+  int half;        // column half handled by this warp: columns [half*BN/2, (half+1)*BN/2)
+  int kb0, kb1;    // k-block range that was accumulated (split-K)
+  int epi_tid;     // 0..255 within the epilogue warps
+};
+
+template <int BN, int NG, bool A_MN, bool B_MN>
+struct GemmCfg {
+  static constexpr int kStageA = 128 * 128;       // 16 KB
+  static constexpr int kStageB = BN * 128;        // 16/32 KB
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kBufCols = NG * BN;        // columns per accumulator buffer
+  static_assert(2 * kBufCols <= 512, "TMEM budget");
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <class Epi, int BN, int NG, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(384, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+               const GemmSched sched, const typename Epi::Params ep) {
+  using Cfg = GemmCfg<BN, NG, A_MN, B_MN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (NG == 2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    TileIter it(sched);
+    int stage = 0;
+    uint32_t phase = 0;
+    while (it.next()) {
+#pragma unroll 1
+      for (int g = 0; g < NG; ++g) {
+        const CUtensorMap* mA = g ? &tmA1 : &tmA0;
+        const CUtensorMap* mB = g ? &tmB1 : &tmB0;
+#pragma unroll 1
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          uint8_t* sB = sA + Cfg::kStageA;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (!A_MN) {
+            tma_load_2d(sA, mA, &full_bar[stage], kb * 64, it.tm * 128);
+          } else {
+            tma_load_2d(sA, mA, &full_bar[stage], it.tm * 128, kb * 64);
+            tma_load_2d(sA + 8192, mA, &full_bar[stage], it.tm * 128 + 64, kb * 64);
+          }
+          if (!B_MN) {
+#pragma unroll
+            for (int nb = 0; nb < BN / 128; ++nb)
+              tma_load_2d(sB + nb * 16384, mB, &full_bar[stage], kb * 64, it.tn * BN + nb * 128);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sB + c * 8192, mB, &full_bar[stage], it.tn * BN + c * 64, kb * 64);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    TileIter it(sched);
+    int stage = 0;
+    uint32_t phase = 0;
+    int buf = 0;
+    uint32_t bphase = 0;
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    while (it.next()) {
+      mbar_wait(&tempty_bar[buf], bphase ^ 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < NG; ++g) {
+        const uint32_t d_addr = tmem_base + buf * Cfg::kBufCols + g * BN;
+#pragma unroll 1
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_base = a_base + Cfg::kStageA;
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint64_t da = A_MN ? make_sdesc_sw128(a_base + k16 * 2048, 8192, 1024)
+                                     : make_sdesc_sw128(a_base + k16 * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_sdesc_sw128(b_base + k16 * 2048, 8192, 1024)
+                                     : make_sdesc_sw128(b_base + k16 * 32, 16, 1024);
+            umma_ss(d_addr, da, db, idesc, (kb > it.kb0 || k16 > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      umma_commit(&tfull_bar[buf]);
+      if (++buf == 2) { buf = 0; bphase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = warp - 4;
+    const int q = warp & 3;
+    TileCtx ctx;
+    ctx.half = e >> 2;
+    ctx.epi_tid = threadIdx.x - 128;
+    Epi epi(ep, ctx);
+    TileIter it(sched);
+    int buf = 0;
+    uint32_t bphase = 0;
+    while (it.next()) {
+      mbar_wait(&tfull_bar[buf], bphase);
+      tc_fence_after();
+      ctx.taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * Cfg::kBufCols;
+      ctx.tm = it.tm;
+      ctx.tn = it.tn;
+      ctx.row = it.tm * 128 + q * 32 + lane;
+      ctx.col0 = it.tn * BN;
+      ctx.kb0 = it.kb0;
+      ctx.kb1 = it.kb1;
+      epi.tile(ctx);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (++buf == 2) { buf = 0; bphase ^= 1; }
+    }
+    epi.finish();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+}  // namespace carel

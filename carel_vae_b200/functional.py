@@ -1,0 +1,126 @@
+"""torch.autograd wrappers over the C ABI (include/carel_head.h).
+
+Every function here launches the hand-written sm_100a kernels through ctypes; PyTorch only owns
+the memory and the stream.  Tensors must live on a CUDA device — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, float_array, lib
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if not t.is_cuda:
+            raise _lib.CarelError(
+                "carel_vae_b200 runs on CUDA tensors only (sm_100a kernels, no CPU fallback); "
+                f"got a tensor on {t.device}")
+
+
+def _rowmajor_f32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 view/copy with unit stride in the last dim (row pitch may be anything)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got shape {tuple(t.shape)}")
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------
+# MMD
+# --------------------------------------------------------------------------------------------
+class _MMDFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, alphas, eps, flags, tile_range):
+        _require_cuda(x, y)
+        xf, yf = _rowmajor_f32(x), _rowmajor_f32(y)
+        n1, d = xf.shape
+        n2, d2 = yf.shape
+        if d != d2:
+            raise ValueError("sample_1 and sample_2 must have the same feature width")
+        L = lib()
+        ws = _workspace(L.carel_mmd_workspace_bytes(n1, n2, d), xf.device)
+        out = torch.empty((), dtype=torch.float32, device=xf.device)
+        al = float_array(alphas)
+        t0, t1 = tile_range
+        partial = None
+        if t0 != 0 or t1 != -1:
+            partial = torch.empty(3, dtype=torch.float64, device=xf.device)
+        check(L.carel_mmd_fwd(_p(xf), xf.stride(0), _p(yf), yf.stride(0), n1, n2, d, al, len(alphas),
+                              float(eps), int(flags), t0, t1, _p(partial),
+                              _p(None if partial is not None else out), _p(ws), ws.numel(), _stream()),
+              "carel_mmd_fwd")
+        ctx.ws = ws
+        ctx.meta = (n1, n2, d, tuple(float(a) for a in alphas), float(eps), t0, t1, x.dtype, y.dtype)
+        if partial is not None:
+            ctx.mark_non_differentiable(partial)
+            return partial
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n1, n2, d, alphas, eps, t0, t1, dtx, dty = ctx.meta
+        ws = ctx.ws
+        g = g.reshape(()).float().contiguous()
+        gx = torch.empty((n1, d), dtype=torch.float32, device=ws.device)
+        gy = torch.empty((n2, d), dtype=torch.float32, device=ws.device)
+        al = float_array(alphas)
+        check(lib().carel_mmd_bwd(_p(g), n1, n2, d, al, len(alphas), eps, t0, t1, _p(gx), d, _p(gy), d,
+                                  _p(ws), ws.numel(), _stream()), "carel_mmd_bwd")
+        return gx.to(dtx), gy.to(dty), None, None, None, None
+
+
+def mmd(sample_1: torch.Tensor, sample_2: torch.Tensor, alphas: Sequence[float], eps: float = 1e-5,
+        full_gram: bool = False) -> torch.Tensor:
+    """Unbiased multi-bandwidth RBF MMD^2 (reference MMDStatistic.__call__,
+    drl_classifier_ec_mmd_final_mul.py:547-569).  0-dim fp32 tensor, differentiable w.r.t. both samples."""
+    flags = 1 if full_gram else 0
+    return _MMDFn.apply(sample_1, sample_2, tuple(alphas), eps, flags, (0, -1))
+
+
+def pairwise(a: torch.Tensor, b: torch.Tensor, mode: int, alphas: Sequence[float] = (), eps: float = 1e-5):
+    """Dense [n1, n2] matrix: mode 0 kernel sum, 1 pdist, 2 squared distances, 3 exp(-d2 * alphas[0])."""
+    _require_cuda(a, b)
+    af, bf = _rowmajor_f32(a), _rowmajor_f32(b)
+    n1, d = af.shape
+    n2 = bf.shape[0]
+    L = lib()
+    ws = _workspace(L.carel_pairwise_workspace_bytes(n1, n2, d), af.device)
+    out = torch.empty((n1, n2), dtype=torch.float32, device=af.device)
+    al = float_array(list(alphas) if len(alphas) else [0.0])
+    check(L.carel_pairwise(_p(af), af.stride(0), _p(bf), bf.stride(0), n1, n2, d, mode, al, len(alphas),
+                           float(eps), _p(out), n2, _p(ws), ws.numel(), _stream()), "carel_pairwise")
+    return out
+
+
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias=None,
+              ksplit: int = 1) -> torch.Tensor:
+    """Debug entry: C = op(A) op(B)^T on the tcgen05 core.  a: [M,K] (or [K,M] if a_mn), bf16."""
+    _require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    a, b = a.contiguous(), b.contiguous()
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N = b.shape[1] if b_mn else b.shape[0]
+    c = torch.zeros((M, N), dtype=torch.float32, device=a.device)
+    check(lib().carel_gemm_bf16(_p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
+                                _p(c), N, _p(bias), ksplit, _stream()), "carel_gemm_bf16")
+    return c

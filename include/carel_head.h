@@ -1,0 +1,86 @@
+/* carel_head.h — C ABI of libcarel_head.so: the B200-native (sm_100a) CAREL-VAE disentanglement head.
+ *
+ * The reference (tk1363704/CAREL-VAE) has no FFI layer: its boundary for this path is the set
+ * of Python callables the drl_classifier_ec_{mmd,hsic,vi,gan}*.py trainers define and call by
+ * name.  Each entry point below is what the drop-in Python module (carel_vae_b200/) binds with
+ * ctypes in place of the ATen call sequence of the cited reference function.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; fp32 row-major unless noted;
+ *     `ld*` are row pitches in elements;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises;
+ *   - the library allocates nothing: scratch comes from the caller (`*_workspace_bytes`);
+ *     a workspace filled by a *_fwd call is the context its *_bwd call consumes;
+ *   - return 0 on success; otherwise carel_last_error() (thread-local) describes the failure;
+ *   - scalar results (losses) are written to device memory, so no call forces a host sync.
+ */
+#ifndef CAREL_HEAD_H_
+#define CAREL_HEAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAREL_VERSION 100 /* 0.1.0 */
+
+/* flags */
+#define CAREL_MMD_FULL_GRAM 1 /* compute all (2N)^2 entries like the reference instead of j > i */
+
+int carel_version(void);
+const char* carel_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t carel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Debug / building block: C[M,N] (+)= A * B^T on the tcgen05 core (bf16 operands, fp32 accum).
+ *   a_mn = 0: A is [M, K] row-major (K-major);  a_mn = 1: A is [K, M] row-major (MN-major)
+ *   b_mn = 0: B is [N, K] row-major;            b_mn = 1: B is [K, N] row-major
+ *   a, b are bf16; ld in elements (multiples of 8).  ksplit > 1 accumulates atomically (C must
+ *   be zeroed by the caller).
+ * ------------------------------------------------------------------------------------------ */
+int carel_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn,
+                    int64_t M, int64_t N, int64_t K, float* c, int64_t ldc, const float* bias,
+                    int ksplit, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MMD  — replaces MMDStatistic.__call__ + pdist
+ *        (drl_classifier_ec_mmd_final_mul.py:537-569, :580-596; call site :231-233).
+ *   mmd = 2 a01 sum K_xy + a00 (sum K_xx - tr K_xx) + a11 (sum K_yy - tr K_yy),
+ *   K = sum_alpha exp(-alpha (|d2| + eps)),  d2 = |x_i|^2 + |y_j|^2 - 2 x_i.y_j.
+ *   The (n1+n2)^2 Gram matrix never leaves the SM.
+ * ------------------------------------------------------------------------------------------ */
+size_t carel_mmd_workspace_bytes(int64_t n1, int64_t n2, int64_t dim);
+/* Forward.  Packs cat(x, y) to bf16 in `ws`, accumulates the three block sums of Gram row tiles
+ * [row_tile_begin, row_tile_end) (128-row tiles; pass 0, -1 for all) into partial_sums[3]
+ * (double: xx off-diagonal, yy off-diagonal, xy + yx) and, if out_mmd != NULL, finalises
+ * out_mmd[0].  Multi-GPU callers all-reduce partial_sums and call carel_mmd_finalize. */
+int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t n1,
+                  int64_t n2, int64_t dim, const float* alphas_host, int n_alpha, float eps,
+                  int flags, int64_t row_tile_begin, int64_t row_tile_end, double* partial_sums,
+                  float* out_mmd, void* ws, size_t ws_bytes, void* stream);
+int carel_mmd_finalize(const double* partial_sums, int64_t n1, int64_t n2, float* out_mmd,
+                       void* stream);
+/* Backward: grad_x[n1,dim], grad_y[n2,dim] (+)= d mmd / d(x,y) * grad_out[0]; rows of the Gram
+ * [row_tile_begin, row_tile_end) only (a rank's rows see every column, so its gradient rows are
+ * complete without a reduction).  `ws` must be the workspace of the matching carel_mmd_fwd. */
+int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int64_t dim,
+                  const float* alphas_host, int n_alpha, float eps, int64_t row_tile_begin,
+                  int64_t row_tile_end, float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* Dense pairwise matrices for API completeness (reference pdist :580-596 with norm=2, the
+ * ret_matrix=True kernel matrix :566-567, hsic.py pairwise_distances :529-532 and
+ * GaussianKernelMatrix :535-537).  mode: 0 kernel sum, 1 pdist, 2 squared distances, 3 exp(-d2/sigma)
+ * with alphas_host[0] = 1/sigma.  out is [n1, n2] fp32. */
+size_t carel_pairwise_workspace_bytes(int64_t n1, int64_t n2, int64_t dim);
+int carel_pairwise(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t n1,
+                   int64_t n2, int64_t dim, int mode, const float* alphas_host, int n_alpha,
+                   float eps, float* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAREL_HEAD_H_ */
