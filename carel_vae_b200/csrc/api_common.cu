@@ -47,14 +47,7 @@ extern "C" int carel_gemm_bf16(const void* a, int64_t lda, int a_mn, const void*
   if (!b_mn) rc = make_tmap_bf16_sw128(&tb, b, N, K, ldb, 128);
   else rc = make_tmap_bf16_sw128(&tb, b, K, N, ldb, 64);
   CAREL_REQUIRE(rc == 0, "carel_gemm_bf16: tensor map B failed (%d)", rc);
-  GemmSched s;
-  s.m_tiles = int((M + 127) / 128);
-  s.n_tiles = int((N + 255) / 256);
-  s.num_kb = int((K + 63) / 64);
-  s.ksplit = ksplit < 1 ? 1 : (ksplit > s.num_kb ? s.num_kb : ksplit);
-  s.mode = TILE_FULL;
-  s.num_items = s.m_tiles * s.n_tiles * s.ksplit;
-  s.m_tile0 = 0;
+  GemmSched s = make_sched(M, N, K, 256, ksplit, TILE_FULL);
   EpiStore<256>::Params ep;
   ep.out = c; ep.bias = bias; ep.out_bf16 = nullptr; ep.M = int(M); ep.N = int(N);
   ep.ld = int(ldc); ep.ld_bf16 = 0; ep.atomic = s.ksplit > 1; ep.scale = 1.f;
@@ -68,12 +61,12 @@ extern "C" int carel_gemm_bf16(const void* a, int64_t lda, int a_mn, const void*
 // dense pairwise matrices (API completeness; materialises [n1, n2])
 // ------------------------------------------------------------------------------------------
 extern "C" size_t carel_pairwise_workspace_bytes(int64_t n1, int64_t n2, int64_t dim) {
-  const int64_t Kp = round_up64(dim, 64);
+  const int ldp = aug_width(int(dim));
   WsCarver w(nullptr);
-  w.take<__nv_bfloat16>(size_t(n1) * Kp);
-  w.take<__nv_bfloat16>(size_t(n2) * Kp);
-  w.take<float>(size_t(round_up64(n1, 256)));
-  w.take<float>(size_t(round_up64(n2, 256)));
+  w.take<__nv_bfloat16>(size_t(n1) * ldp);
+  w.take<__nv_bfloat16>(size_t(n1) * ldp);
+  w.take<__nv_bfloat16>(size_t(n2) * ldp);
+  w.take<__nv_bfloat16>(size_t(n2) * ldp);
   return w.bytes();
 }
 
@@ -84,27 +77,23 @@ extern "C" int carel_pairwise(const float* a, int64_t lda, const float* b, int64
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CAREL_REQUIRE(n1 > 0 && n2 > 0 && dim > 0, "carel_pairwise: empty input");
   CAREL_REQUIRE(n_alpha >= 0 && n_alpha <= kMaxAlphas, "carel_pairwise: at most %d alphas", kMaxAlphas);
-  CAREL_REQUIRE(ws_bytes >= carel_pairwise_workspace_bytes(n1, n2, dim), "carel_pairwise: workspace too small");
-  const int64_t Kp = round_up64(dim, 64);
+  CAREL_REQUIRE(ws != nullptr && ws_bytes >= carel_pairwise_workspace_bytes(n1, n2, dim), "carel_pairwise: workspace too small");
+  const int ldp = aug_width(int(dim));
   WsCarver w(ws);
-  __nv_bfloat16* pa = w.take<__nv_bfloat16>(size_t(n1) * Kp);
-  __nv_bfloat16* pb = w.take<__nv_bfloat16>(size_t(n2) * Kp);
-  float* na = w.take<float>(size_t(round_up64(n1, 256)));
-  float* nb = w.take<float>(size_t(round_up64(n2, 256)));
-  pack_rows_kernel<<<int((n1 + 7) / 8), 256, 0, st>>>(a, int(n1), int(dim), int(lda), pa, int(Kp), 0, na);
+  __nv_bfloat16* aA = w.take<__nv_bfloat16>(size_t(n1) * ldp);
+  __nv_bfloat16* aB = w.take<__nv_bfloat16>(size_t(n1) * ldp);
+  __nv_bfloat16* bA = w.take<__nv_bfloat16>(size_t(n2) * ldp);
+  __nv_bfloat16* bB = w.take<__nv_bfloat16>(size_t(n2) * ldp);
+  pack_rows_kernel<<<int((n1 + 7) / 8), 256, 0, st>>>(a, int(n1), int(dim), int(lda), aA, aB, ldp, 0, 1, nullptr);
   CAREL_LAUNCHED();
-  pack_rows_kernel<<<int((n2 + 7) / 8), 256, 0, st>>>(b, int(n2), int(dim), int(ldb), pb, int(Kp), 0, nb);
+  pack_rows_kernel<<<int((n2 + 7) / 8), 256, 0, st>>>(b, int(n2), int(dim), int(ldb), bA, bB, ldp, 0, 1, nullptr);
   CAREL_LAUNCHED();
   CUtensorMap ta, tb;
-  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, pa, n1, Kp, Kp, 128) == 0, "carel_pairwise: tensor map A failed");
-  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, pb, n2, Kp, Kp, 128) == 0, "carel_pairwise: tensor map B failed");
-  GemmSched s;
-  s.m_tiles = int((n1 + 127) / 128);
-  s.n_tiles = int((n2 + 255) / 256);
-  s.num_kb = int(Kp / 64);
-  s.ksplit = 1; s.mode = TILE_FULL; s.num_items = s.m_tiles * s.n_tiles; s.m_tile0 = 0;
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, aA, n1, ldp, ldp, 128) == 0, "carel_pairwise: tensor map A failed");
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, bB, n2, ldp, ldp, 128) == 0, "carel_pairwise: tensor map B failed");
+  GemmSched s = make_sched(n1, n2, ldp, 256, 1, TILE_FULL);
   EpiPairwise<256>::Params ep;
-  ep.out = out; ep.norms_a = na; ep.norms_b = nb; ep.M = int(n1); ep.N = int(n2); ep.ld = int(ldo);
+  ep.out = out; ep.M = int(n1); ep.N = int(n2); ep.ld = int(ldo);
   ep.mode = mode; ep.n_alpha = n_alpha; ep.eps = eps;
   for (int i = 0; i < kMaxAlphas; ++i) ep.alpha[i] = (i < n_alpha) ? alphas_host[i] : 0.f;
   return launch_gemm<EpiPairwise<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st);

@@ -8,12 +8,13 @@ namespace carel {
 // Split the inner range so that the number of work items fills whole waves of the persistent
 // grid: pick nsplit in [1, max_split] maximising items / (ceil(items / SMs) * SMs); ties go to
 // the smaller split (less atomic traffic).
-inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int num_kb, int max_split) {
+inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int k16, int stages, int max_split) {
   ChainSched s;
   s.owner0 = owner0;
   s.n_owner = n_owner;
   s.n_inner = n_inner;
-  s.num_kb = num_kb;
+  s.k16 = k16;
+  s.stages = stages;
   const int sms = sm_count();
   int best = 1;
   double best_eff = -1.0;
@@ -32,21 +33,24 @@ inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int num
   return s;
 }
 
-template <class Pol, int NG, int BN1, int KP>
+template <class Pol, int NG, int BN1>
 int launch_chain(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
                  const CUtensorMap& b1, const ChainSched& s, const typename Pol::Params& pp,
                  cudaStream_t st) {
-  using Cfg = ChainCfg<NG, BN1, KP>;
-  auto kern = chain_tc_kernel<Pol, NG, BN1, KP>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  using Cfg = ChainCfg<NG, BN1>;
+  auto kern = chain_tc_kernel<Pol, NG, BN1>;
+  CAREL_REQUIRE(16 * s.k16 <= Cfg::kMaxN2, "chain kernel: operand width %d exceeds the TMEM budget (%d)", 16 * s.k16, Cfg::kMaxN2);
+  CAREL_REQUIRE(s.stages >= 2, "chain kernel: operand too wide for the shared-memory ring");
+  const int smem_bytes = Cfg::smem_bytes(s.k16, s.stages);
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
     CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Cfg::kSmemBytes));
-    attr_done = true;
+                                          227 * 1024));
+    attr_bytes = 227 * 1024;
   }
   const int grid = s.num_items < sm_count() ? s.num_items : sm_count();
   if (grid <= 0) return 0;
-  kern<<<grid, 384, Cfg::kSmemBytes, st>>>(a0, b0, a1, b1, s, pp);
+  kern<<<grid, kGemmThreads, smem_bytes, st>>>(a0, b0, a1, b1, s, pp);
   CAREL_LAUNCHED();
   return 0;
 }

@@ -12,116 +12,135 @@ namespace carel {
 // the gradient of the reference MMD (drl_classifier_ec_mmd_final_mul.py:547-569 through
 // pdist :580-589) w.r.t. the stacked sample is
 //   grad s_i = 4 [ (sum_j W_ij) s_i - sum_j W_ij s_j ].
-// P = bf16(W) tile; acc2 = sum_j W_ij s_j; the row sum uses the same rounded W so the two terms
-// stay consistent.
+// Operands are augmented (pack_rows_kernel aug=1): acc1 = -d2/2, so sign(d2) = -sign(acc1) and
+//   W_ij = C_ij * (sum_alpha alpha e_alpha) * sign(acc1)           (one FMUL + one LOP3).
+// P = bf16(W); acc2 = P * [S_j | 1 ...]: columns < dim give sum_j W_ij s_j and column `dim`
+// (the ones column of the B operand) gives sum_j W_ij from the SAME rounded W.
 // ---------------------------------------------------------------------------------------------
 struct MmdBwdParams {
-  const float* norms;
-  const __nv_bfloat16* S;   // [M, Kp]
+  const __nv_bfloat16* SA;  // [M, ldp] augmented row operand (features in columns < dim)
   const float* grad_out;    // device scalar
   float* grad_x;
   float* grad_y;
-  int ldgx, ldgy, dim, Kp;
+  int ldgx, ldgy, dim, ldp;
   int M, n1;
   float c00, c11, c01;
   int n_alpha;
-  float a_scale[kMaxAlphas];  // -alpha log2 e
+  float a_scale[kMaxAlphas];  // -2 alpha log2 e
   float a_shift[kMaxAlphas];  // -alpha eps log2 e
-  float a_neg[kMaxAlphas];    // -alpha
+  float a_pos[kMaxAlphas];    // alpha
 };
 
-template <int KP>
 struct PolMmdBwd {
   using Params = MmdBwdParams;
   const Params& p;
-  float rsum, rtot, ni;
-  CAREL_DEVINL PolMmdBwd(const Params& p_, const ChainCtx&) : p(p_), rsum(0.f), rtot(0.f), ni(0.f) {}
-  CAREL_DEVINL void begin_item(const ChainCtx& ctx) {
-    rsum = 0.f;
-    ni = __ldg(p.norms + min(ctx.row, p.M - 1));
-  }
-  CAREL_DEVINL float kprime(float d2) const {
-    const float a = fabsf(d2);
+  CAREL_DEVINL PolMmdBwd(const Params& p_, const ChainCtx&) : p(p_) {}
+  CAREL_DEVINL void begin_item(const ChainCtx&) {}
+  CAREL_DEVINL float ksum(float a) const {   // sum_alpha alpha * exp(-alpha (|d2| + eps))
     float k = 0.f;
-    if (p.n_alpha == 1) {
-      k = p.a_neg[0] * ex2_approx(fmaf(a, p.a_scale[0], p.a_shift[0]));
-    } else {
-      for (int t = 0; t < p.n_alpha; ++t)
-        k = fmaf(p.a_neg[t], ex2_approx(fmaf(a, p.a_scale[t], p.a_shift[t])), k);
-    }
-    return d2 > 0.f ? k : (d2 < 0.f ? -k : 0.f);
+    for (int t = 0; t < p.n_alpha; ++t)
+      k = fmaf(p.a_pos[t], ex2_approx(fmaf(a, p.a_scale[t], p.a_shift[t])), k);
+    return k;
   }
   CAREL_DEVINL float coef(int row, int col) const {
     const bool rx = row < p.n1, cx = col < p.n1;
     return rx ? (cx ? p.c00 : p.c01) : (cx ? p.c01 : p.c11);
   }
-  template <int NG, int BN1>
-  CAREL_DEVINL void weights(const ChainCtx& ctx, int t, int tcol, uint32_t taddr,
-                            uint32_t (&packed)[16]) {
-    uint32_t r[32];
-    tmem_ld32(taddr, r);
+  static CAREL_DEVINL float with_sign_of(float mag, uint32_t acc_bits) {
+    return __uint_as_float(__float_as_uint(mag) ^ (acc_bits & 0x80000000u));
+  }
+  template <int BN1, class WaitP>
+  CAREL_DEVINL void weights(const ChainCtx& ctx, int t, uint32_t acc1_addr, uint32_t p_addr,
+                            WaitP&& wait_p) {
+    constexpr int N16 = BN1 / 32;   // 16-column chunks per warp per inner tile
     const int r0 = ctx.owner * 128, r1 = r0 + 127;
-    const int j0 = t * BN1 + tcol, j1 = j0 + 31;
+    const int j0 = t * BN1 + ctx.half * (BN1 / 2), j1 = j0 + BN1 / 2 - 1;
     const bool fast = r1 < p.M && j1 < p.M && ((r1 < p.n1) || (r0 >= p.n1)) &&
                       ((j1 < p.n1) || (j0 >= p.n1)) && (j0 > r1 || j1 < r0);
-    float w[32];
     if (fast) {
       const float cf = coef(r0, j0);
-      const float4* nj4 = reinterpret_cast<const float4*>(p.norms + j0);
-      float nj[32];
+      if (p.n_alpha == 1) {
+        const float sc = p.a_scale[0], sh = p.a_shift[0], ca = cf * p.a_pos[0];
+        for_each_chunk16(acc1_addr, N16, [&](int c, const uint32_t (&r)[16]) {
+          uint32_t packed[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 v = __ldg(nj4 + i);
-        nj[4 * i] = v.x; nj[4 * i + 1] = v.y; nj[4 * i + 2] = v.z; nj[4 * i + 3] = v.w;
+          for (int i = 0; i < 8; ++i) {
+            const float w0 = with_sign_of(ca * ex2_approx(fmaf(fabsf(__uint_as_float(r[2 * i])), sc, sh)), r[2 * i]);
+            const float w1 = with_sign_of(ca * ex2_approx(fmaf(fabsf(__uint_as_float(r[2 * i + 1])), sc, sh)), r[2 * i + 1]);
+            packed[i] = pack_bf16x2(w0, w1);
+          }
+          if (c == 0) wait_p();
+          tmem_st8(p_addr + c * 8, packed);
+        });
+      } else {
+        for_each_chunk16(acc1_addr, N16, [&](int c, const uint32_t (&r)[16]) {
+          uint32_t packed[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float w0 = with_sign_of(cf * ksum(fabsf(__uint_as_float(r[2 * i]))), r[2 * i]);
+            const float w1 = with_sign_of(cf * ksum(fabsf(__uint_as_float(r[2 * i + 1]))), r[2 * i + 1]);
+            packed[i] = pack_bf16x2(w0, w1);
+          }
+          if (c == 0) wait_p();
+          tmem_st8(p_addr + c * 8, packed);
+        });
       }
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        w[i] = cf * kprime(fmaf(-2.f, __uint_as_float(r[i]), ni + nj[i]));
     } else {
-      tmem_ld_wait();
+      // boundary / diagonal tiles: same arithmetic, branch-free per-element coefficient
+      const int row = ctx.row;
+      const bool row_ok = row < p.M, rx = row < p.n1;
+      const bool single = p.n_alpha == 1;
+      const float sc = p.a_scale[0], sh = p.a_shift[0], a0 = p.a_pos[0];
+      const float c_same = rx ? p.c00 : p.c01, c_other = rx ? p.c01 : p.c11;
+      for_each_chunk16(acc1_addr, N16, [&](int c, const uint32_t (&r)[16]) {
+        uint32_t packed[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = j0 + i;
-        const bool ok = ctx.row < p.M && col < p.M && col != ctx.row;
-        w[i] = ok ? coef(ctx.row, col) *
-                        kprime(fmaf(-2.f, __uint_as_float(r[i]), ni + __ldg(p.norms + col)))
-                  : 0.f;
-      }
-    }
+        for (int i = 0; i < 8; ++i) {
+          float w[2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const __nv_bfloat162 b = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
-      const float2 f = __bfloat1622float2(b);
-      rsum += f.x + f.y;
-      packed[i] = *reinterpret_cast<const uint32_t*>(&b);
+          for (int h = 0; h < 2; ++h) {
+            const int col = j0 + c * 16 + 2 * i + h;
+            const float a = fabsf(__uint_as_float(r[2 * i + h]));
+            const float k = single ? a0 * ex2_approx(fmaf(a, sc, sh)) : ksum(a);
+            const bool ok = row_ok && col < p.M && col != row;
+            const float cf = ok ? ((col < p.n1) ? c_same : c_other) : 0.f;
+            w[h] = with_sign_of(cf * k, r[2 * i + h]);
+          }
+          packed[i] = pack_bf16x2(w[0], w[1]);
+        }
+        if (c == 0) wait_p();
+        tmem_st8(p_addr + c * 8, packed);
+      });
     }
   }
-  CAREL_DEVINL void pre_final(const ChainCtx& ctx) {
-    __shared__ float rs[2][128];
-    const int rl = ctx.lane_q * 32 + (threadIdx.x & 31);
-    rs[ctx.half][rl] = rsum;
-    named_bar_sync(1, 256);
-    rtot = rs[0][rl] + rs[1][rl];
-    named_bar_sync(1, 256);
-  }
-  CAREL_DEVINL void final(const ChainCtx& ctx, int fcol, const uint32_t (&r)[32], bool valid) {
-    if (!valid || ctx.row >= p.M || fcol >= p.dim) return;
+  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
+    // row sum of the rounded W: the ones column (index dim) of the B operand
+    const uint32_t rtot_bits = tmem_ld1(ctx.acc2_taddr + p.dim);
+    tmem_ld_wait();
+    const float rtot = __uint_as_float(rtot_bits);
+    const int q_split = (ctx.k16 + 1) >> 1;
+    const int q0 = ctx.half ? q_split : 0, q1 = ctx.half ? ctx.k16 : q_split;
     const float g4 = 4.f * __ldg(p.grad_out);
-    const uint4* s4 = reinterpret_cast<const uint4*>(p.S + size_t(ctx.row) * p.Kp + fcol);
-    float* dst = (ctx.row < p.n1) ? p.grad_x + size_t(ctx.row) * p.ldgx
-                                  : p.grad_y + size_t(ctx.row - p.n1) * p.ldgy;
+    const bool row_ok = valid && ctx.row < p.M;
+    const int rowc = min(ctx.row, p.M - 1);
+    const __nv_bfloat16* srow = p.SA + size_t(rowc) * p.ldp;
+    float* dst = (rowc < p.n1) ? p.grad_x + size_t(rowc) * p.ldgx
+                               : p.grad_y + size_t(rowc - p.n1) * p.ldgy;
+#pragma unroll 1
+    for (int q = q0; q < q1; ++q) {
+      uint32_t r[16];
+      tmem_ld16(ctx.acc2_taddr + q * 16, r);
+      const uint4 sv0 = __ldg(reinterpret_cast<const uint4*>(srow + q * 16));
+      const uint4 sv1 = __ldg(reinterpret_cast<const uint4*>(srow + q * 16) + 1);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      const uint32_t u[8] = {sv0.x, sv0.y, sv0.z, sv0.w, sv1.x, sv1.y, sv1.z, sv1.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint4 sv = __ldg(s4 + q);
-      const uint32_t u[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
+      for (int h = 0; h < 8; ++h) {
         const float2 s2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
-        const int f = fcol + q * 8 + h * 2;
-        if (f < p.dim) atomicAdd(dst + f, g4 * (rtot * s2.x - __uint_as_float(r[q * 8 + h * 2])));
-        if (f + 1 < p.dim)
-          atomicAdd(dst + f + 1, g4 * (rtot * s2.y - __uint_as_float(r[q * 8 + h * 2 + 1])));
+        const int f = q * 16 + 2 * h;
+        if (f < p.dim) atomicAdd(dst + f, g4 * (rtot * s2.x - __uint_as_float(r[2 * h])));
+        if (f + 1 < p.dim) atomicAdd(dst + f + 1, g4 * (rtot * s2.y - __uint_as_float(r[2 * h + 1])));
       }
     }
   }

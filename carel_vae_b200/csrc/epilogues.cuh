@@ -69,18 +69,16 @@ struct EpiStore {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Pairwise-distance store: out[i, j] = f(|n_i + n_j - 2 a_i.b_j|)
+// Pairwise-distance store on AUGMENTED operands (pack_rows_kernel, aug = 1): acc = -d2/2.
 //   mode 0: sum_alpha exp(-alpha (|d2| + eps))       (the MMD kernel matrix, ret_matrix=True)
 //   mode 1: sqrt(eps + |d2|)                         (reference pdist, norm = 2)
-//   mode 2: -2 a.b + n_i + n_j                       (reference pairwise_distances)
+//   mode 2: d2 = -2 a.b + n_i + n_j                  (reference pairwise_distances)
 //   mode 3: exp(-d2 / sigma)  with alpha[0] = 1/sigma (reference GaussianKernelMatrix)
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct EpiPairwise {
   struct Params {
     float* out;
-    const float* norms_a;
-    const float* norms_b;
     int M, N, ld, mode, n_alpha;
     float eps;
     float alpha[kMaxAlphas];
@@ -91,7 +89,6 @@ struct EpiPairwise {
     constexpr int HALF = BN / 2;
     const int cbase = ctx.col0 + ctx.half * HALF;
     const bool row_ok = ctx.row < p.M;
-    const float ni = row_ok ? __ldg(p.norms_a + ctx.row) : 0.f;
 #pragma unroll 1
     for (int c = 0; c < HALF / 32; ++c) {
       uint32_t r[32];
@@ -103,7 +100,7 @@ struct EpiPairwise {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         if (col + i >= p.N) continue;
-        const float d2 = fmaf(-2.f, __uint_as_float(r[i]), ni + __ldg(p.norms_b + col + i));
+        const float d2 = -2.f * __uint_as_float(r[i]);
         float v;
         if (p.mode == 0) {
           v = 0.f;
@@ -124,102 +121,97 @@ struct EpiPairwise {
 
 // ---------------------------------------------------------------------------------------------
 // MMD forward (reference MMDStatistic.__call__, drl_classifier_ec_mmd_final_mul.py:547-569).
-// S = cat(x, y) is the row AND the column operand.  For every element of the Gram tile:
-//     d2 = n_i + n_j - 2 s_i.s_j ;  k = sum_alpha exp(-alpha (|d2| + eps))
-// and three block sums are accumulated:  acc[0] = sum_{xx, i!=j} k, acc[1] = sum_{yy, i!=j} k,
+// Operands are the augmented rows of S = cat(x, y), so the accumulator already holds -d2/2:
+//     k = sum_alpha exp(-alpha (|d2| + eps)) = sum_alpha 2^(|acc| * a_scale + a_shift)
+// Three block sums are accumulated:  acc[0] = sum_{xx, i!=j} k, acc[1] = sum_{yy, i!=j} k,
 // acc[2] = sum_{xy} k + sum_{yx} k.   tri != 0: only tiles on/above the diagonal are scheduled and
 // every counted pair (j > i) is weighted 2 (K is symmetric).
+// Hot loop per element: FFMA(|acc|) + MUFU.EX2 + FADD.
 // ---------------------------------------------------------------------------------------------
 struct EpiMMDParams {
-  const float* norms;  // [>= roundup(M, 256)], zero padded
   double* accum;       // [3]
   int M, n1, tri, n_alpha;
-  float a_scale[kMaxAlphas];  // -alpha * log2(e)
-  float a_shift[kMaxAlphas];  // -alpha * eps * log2(e)
+  float a_scale[kMaxAlphas];  // -2 alpha log2(e)
+  float a_shift[kMaxAlphas];  // -alpha eps log2(e)
 };
 
 template <int BN>
 struct EpiMMD {
   using Params = EpiMMDParams;
   const Params& p;
-  double acc[3];
-  CAREL_DEVINL EpiMMD(const Params& p_, const TileCtx&) : p(p_) { acc[0] = acc[1] = acc[2] = 0.0; }
+  double acc0, acc1, acc2;
+  CAREL_DEVINL EpiMMD(const Params& p_, const TileCtx&) : p(p_), acc0(0.0), acc1(0.0), acc2(0.0) {}
 
-  template <bool SINGLE>
-  CAREL_DEVINL float kval(float d2) const {
-    const float a = fabsf(d2);
-    if (SINGLE) return ex2_approx(fmaf(a, p.a_scale[0], p.a_shift[0]));
+  CAREL_DEVINL float kmulti(float a) const {
     float k = 0.f;
     for (int t = 0; t < p.n_alpha; ++t) k += ex2_approx(fmaf(a, p.a_scale[t], p.a_shift[t]));
     return k;
   }
+  CAREL_DEVINL void add(int type, float v) {
+    if (type == 0) acc0 += double(v);
+    else if (type == 1) acc1 += double(v);
+    else acc2 += double(v);
+  }
 
-  template <bool SINGLE>
-  CAREL_DEVINL void tile_impl(const TileCtx& ctx) {
+  CAREL_DEVINL void tile(const TileCtx& ctx) {
     constexpr int HALF = BN / 2;
     const int r0 = ctx.tm * 128, r1 = r0 + 127;
     const int c0 = ctx.col0 + ctx.half * HALF, c1 = c0 + HALF - 1;
     const bool skip = (r0 >= p.M) || (c0 >= p.M) || (p.tri && c1 <= r0);
+    if (skip) return;  // warp-uniform: nothing to read, the MMA result is discarded
     const bool rows_one_block = (r1 < p.n1) || (r0 >= p.n1);
     const bool cols_one_block = (c1 < p.n1) || (c0 >= p.n1);
     const bool off_diag = p.tri ? (c0 > r1) : (c0 > r1 || c1 < r0);
-    const bool fast = !skip && r1 < p.M && c1 < p.M && rows_one_block && cols_one_block && off_diag;
-    const int row = ctx.row;
-    const float ni = __ldg(p.norms + min(row, p.M - 1));
+    const bool fast = r1 < p.M && c1 < p.M && rows_one_block && cols_one_block && off_diag;
     const float w = p.tri ? 2.f : 1.f;
-    if (skip) return;  // warp-uniform: nothing to read, the MMA result is discarded
+    const uint32_t taddr = ctx.taddr + ctx.half * HALF;
     if (fast) {
       float s = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < HALF / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(ctx.taddr + ctx.half * HALF + c * 32, r);
-        const float4* nj4 = reinterpret_cast<const float4*>(p.norms + c0 + c * 32);
-        float nj[32];
+      if (p.n_alpha == 1) {
+        const float sc = p.a_scale[0], sh = p.a_shift[0];
+        for_each_chunk16(taddr, HALF / 16, [&](int, const uint32_t (&r)[16]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 t = __ldg(nj4 + i);
-          nj[4 * i] = t.x; nj[4 * i + 1] = t.y; nj[4 * i + 2] = t.z; nj[4 * i + 3] = t.w;
-        }
-        tmem_ld_wait();
+          for (int i = 0; i < 16; ++i) s += ex2_approx(fmaf(fabsf(__uint_as_float(r[i])), sc, sh));
+        });
+      } else {
+        for_each_chunk16(taddr, HALF / 16, [&](int, const uint32_t (&r)[16]) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          s += kval<SINGLE>(fmaf(-2.f, __uint_as_float(r[i]), ni + nj[i]));
+          for (int i = 0; i < 16; ++i) s += kmulti(fabsf(__uint_as_float(r[i])));
+        });
       }
       const int type = (r0 < p.n1) ? ((c0 < p.n1) ? 0 : 2) : ((c0 < p.n1) ? 2 : 1);
-      acc[type] += double(s * w);
+      add(type, s * w);
     } else {
-      float s3[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int c = 0; c < HALF / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(ctx.taddr + ctx.half * HALF + c * 32, r);
-        tmem_ld_wait();
-        if (row >= p.M) continue;
+      // boundary / diagonal tiles: same arithmetic, branch-free per-element masks
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      const int row = ctx.row;
+      const bool row_ok = row < p.M, rx = row < p.n1;
+      const bool single = p.n_alpha == 1;
+      const float sc = p.a_scale[0], sh = p.a_shift[0];
+      for_each_chunk16(taddr, HALF / 16, [&](int c, const uint32_t (&r)[16]) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = c0 + c * 32 + i;
-          const bool ok = (col < p.M) && (p.tri ? (col > row) : (col != row));
-          if (ok) {
-            const float k = kval<SINGLE>(fmaf(-2.f, __uint_as_float(r[i]), ni + __ldg(p.norms + col)));
-            const int type = (row < p.n1) ? ((col < p.n1) ? 0 : 2) : ((col < p.n1) ? 2 : 1);
-            s3[type] += k;
-          }
+        for (int i = 0; i < 16; ++i) {
+          const int col = c0 + c * 16 + i;
+          const float a = fabsf(__uint_as_float(r[i]));
+          const float k = single ? ex2_approx(fmaf(a, sc, sh)) : kmulti(a);
+          const bool ok = row_ok && (col < p.M) && (p.tri ? (col > row) : (col != row));
+          const bool cx = col < p.n1;
+          s0 += (ok && rx && cx) ? k : 0.f;
+          s1 += (ok && !rx && !cx) ? k : 0.f;
+          s2 += (ok && (rx != cx)) ? k : 0.f;
         }
-      }
-      acc[0] += double(s3[0] * w);
-      acc[1] += double(s3[1] * w);
-      acc[2] += double(s3[2] * w);
+      });
+      acc0 += double(s0 * w);
+      acc1 += double(s1 * w);
+      acc2 += double(s2 * w);
     }
   }
-  CAREL_DEVINL void tile(const TileCtx& ctx) {
-    if (p.n_alpha == 1) tile_impl<true>(ctx); else tile_impl<false>(ctx);
-  }
   CAREL_DEVINL void finish() {
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const double v = warp_sum(acc[t]);
-      if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(p.accum + t, v);
+    const double v0 = warp_sum(acc0), v1 = warp_sum(acc1), v2 = warp_sum(acc2);
+    if ((threadIdx.x & 31) == 0) {
+      if (v0 != 0.0) atomicAdd(p.accum + 0, v0);
+      if (v1 != 0.0) atomicAdd(p.accum + 1, v1);
+      if (v2 != 0.0) atomicAdd(p.accum + 2, v2);
     }
   }
 };

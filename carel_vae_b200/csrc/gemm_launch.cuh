@@ -9,7 +9,7 @@ template <class Epi, int BN, int NG, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
                        const CUtensorMap& b1, const GemmSched& s, const typename Epi::Params& ep,
                        cudaStream_t st) {
-  using Cfg = GemmCfg<BN, NG, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, NG>;
   auto kern = gemm_tc_kernel<Epi, BN, NG, A_MN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -19,7 +19,7 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap&
   }
   const int grid = s.num_items < sm_count() ? s.num_items : sm_count();
   if (grid <= 0) return 0;
-  kern<<<grid, 384, Cfg::kSmemBytes, st>>>(a0, b0, a1, b1, s, ep);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a0, b0, a1, b1, s, ep);
   CAREL_LAUNCHED();
   return 0;
 }
@@ -29,8 +29,9 @@ inline GemmSched make_sched(int64_t M, int64_t N, int64_t K, int BN, int ksplit,
   GemmSched s;
   s.m_tiles = int((M + 127) / 128);
   s.n_tiles = int((N + BN - 1) / BN);
-  s.num_kb = int((K + 63) / 64);
-  s.ksplit = ksplit < 1 ? 1 : (ksplit > s.num_kb ? s.num_kb : ksplit);
+  s.num_k16 = int((K + 15) / 16);
+  const int num_kb = (s.num_k16 + 3) / 4;
+  s.ksplit = ksplit < 1 ? 1 : (ksplit > num_kb ? num_kb : ksplit);
   s.mode = mode;
   s.num_items = s.m_tiles * s.n_tiles * s.ksplit;
   s.m_tile0 = 0;

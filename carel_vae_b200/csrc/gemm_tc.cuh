@@ -2,15 +2,17 @@
 //
 //   D[128 x BN] (fp32, TMEM) = A_tile[128 x K] * B_tile[BN x K]^T       (bf16 operands)
 //
-// One CTA per SM, 384 threads:
-//   warp 0      TMA producer  (one elected lane)
-//   warp 1      tcgen05.mma issuer (one elected lane)
-//   warp 2      TMEM allocator
-//   warp 3      idle
-//   warps 4-11  epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. and column half (w-4)/4
+// One CTA per SM, 320 threads:
+//   warp 0      TMEM allocator, then one lane = TMA producer
+//   warp 1      one lane = tcgen05.mma issuer
+//   warps 2-9   epilogue: warp w reads TMEM lanes 32*(w%4).. and column half (w-2)/4
 //
 // Three pipelines: smem ring (full/empty mbarriers, TMA <-> MMA), TMEM accumulator double
 // buffer (tmem_full/tmem_empty, MMA <-> epilogue), and the static persistent tile schedule.
+//
+// K is counted in 16-wide MMA steps (num_k16), so "augmented" operands whose width is not a
+// multiple of 64 (e.g. 128 features + 16 norm/ones columns) cost only the extra steps: TMA
+// zero-fills the rest of the last 64-wide box and no MMA is issued for it.
 //
 // Operand layouts (all 128-byte swizzled, loaded by TMA):
 //   K-major  : global row-major [rows, K]; smem tile = [rows][64 bf16] per 64-wide k-block.
@@ -22,26 +24,29 @@
 
 namespace carel {
 
+constexpr int kGemmThreads = 320;
+constexpr int kEpiThreads = 256;
+
 enum TileMode : int { TILE_FULL = 0, TILE_TRI = 1 };
 
 struct GemmSched {
-  int m_tiles;   // tiles of 128 rows
-  int n_tiles;   // tiles of BN cols
-  int num_kb;    // 64-wide k blocks (per product)
-  int ksplit;    // split-K factor (>=1); item = tile * ksplit + ks
-  int mode;      // TileMode; TILE_TRI requires BN == 256 and a square problem
-  int num_items; // total work items
-  int m_tile0;   // first row tile owned by this launch (row-block sharding across GPUs)
+  int m_tiles;    // tiles of 128 rows
+  int n_tiles;    // tiles of BN cols
+  int num_k16;    // 16-wide k steps (per product)
+  int ksplit;     // split-K factor (>=1); item = tile * ksplit + ks
+  int mode;       // TileMode; TILE_TRI requires BN == 256 and a square problem
+  int num_items;  // total work items
+  int m_tile0;    // first row tile owned by this launch (row-block sharding across GPUs)
 };
 
 // Sequential decoder of the persistent schedule; every role of a CTA walks the same items.
 struct TileIter {
   const GemmSched& s;
   int item;
-  // TRI state
   int tri_tm, tri_base;
   int tm, tn, kb0, kb1;
-  CAREL_DEVINL explicit TileIter(const GemmSched& s_) : s(s_), item(blockIdx.x), tri_tm(0), tri_base(0) {}
+  CAREL_DEVINL explicit TileIter(const GemmSched& s_)
+      : s(s_), item(blockIdx.x), tri_tm(0), tri_base(0) {}
   CAREL_DEVINL int tri_count(int t) const { return s.n_tiles - ((s.m_tile0 + t) >> 1); }
   CAREL_DEVINL bool next() {
     if (item >= s.num_items) return false;
@@ -59,9 +64,10 @@ struct TileIter {
       tn = ((s.m_tile0 + tri_tm) >> 1) + (tile - tri_base);
     }
     tm += s.m_tile0;
-    const int per = (s.num_kb + s.ksplit - 1) / s.ksplit;
+    const int num_kb = (s.num_k16 + 3) >> 2;
+    const int per = (num_kb + s.ksplit - 1) / s.ksplit;
     kb0 = ks * per;
-    kb1 = min(kb0 + per, s.num_kb);
+    kb1 = min(kb0 + per, num_kb);
     item += gridDim.x;
     return true;
   }
@@ -78,38 +84,39 @@ struct TileCtx {
   int epi_tid;     // 0..255 within the epilogue warps
 };
 
-template <int BN, int NG, bool A_MN, bool B_MN>
+template <int BN, int NG>
 struct GemmCfg {
-  static constexpr int kStageA = 128 * 128;       // 16 KB
-  static constexpr int kStageB = BN * 128;        // 16/32 KB
+  static constexpr int kStageA = 128 * 128;  // 16 KB
+  static constexpr int kStageB = BN * 128;   // 16/32 KB
   static constexpr int kStageBytes = kStageA + kStageB;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = 512;
-  static constexpr int kBufCols = NG * BN;        // columns per accumulator buffer
+  static constexpr int kBufCols = NG * BN;   // columns per accumulator buffer
   static_assert(2 * kBufCols <= 512, "TMEM budget");
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <class Epi, int BN, int NG, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-               const GemmSched sched, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<BN, NG, A_MN, B_MN>;
+               const __grid_constant__ GemmSched sched,
+               const __grid_constant__ typename Epi::Params ep) {
+  using Cfg = GemmCfg<BN, NG>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                  // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 32) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB0);
     if (NG == 2) {
@@ -126,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 0) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -187,13 +194,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_base = a_base + Cfg::kStageA;
+          const int nk = min(4, sched.num_k16 - kb * 4);
 #pragma unroll
           for (int k16 = 0; k16 < 4; ++k16) {
-            const uint64_t da = A_MN ? make_sdesc_sw128(a_base + k16 * 2048, 8192, 1024)
-                                     : make_sdesc_sw128(a_base + k16 * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_sdesc_sw128(b_base + k16 * 2048, 8192, 1024)
-                                     : make_sdesc_sw128(b_base + k16 * 32, 16, 1024);
-            umma_ss(d_addr, da, db, idesc, (kb > it.kb0 || k16 > 0) ? 1u : 0u);
+            if (k16 < nk) {
+              const uint64_t da = A_MN ? make_sdesc_sw128(a_base + k16 * 2048, 8192, 1024)
+                                       : make_sdesc_sw128(a_base + k16 * 32, 16, 1024);
+              const uint64_t db = B_MN ? make_sdesc_sw128(b_base + k16 * 2048, 8192, 1024)
+                                       : make_sdesc_sw128(b_base + k16 * 32, 16, 1024);
+              umma_ss(d_addr, da, db, idesc, (kb > it.kb0 || k16 > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -202,13 +212,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       umma_commit(&tfull_bar[buf]);
       if (++buf == 2) { buf = 0; bphase ^= 1; }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 2) {
     // ===================== epilogue =====================
-    const int e = warp - 4;
     const int q = warp & 3;
     TileCtx ctx;
-    ctx.half = e >> 2;
-    ctx.epi_tid = threadIdx.x - 128;
+    ctx.half = (warp - 2) >> 2;
+    ctx.epi_tid = threadIdx.x - 64;
     Epi epi(ep, ctx);
     TileIter it(sched);
     int buf = 0;
@@ -234,7 +243,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// Software-pipelined walk over an accumulator row segment in chunks of 16 fp32 columns: the
+// tcgen05.ld of chunk c+1 is in flight while chunk c is processed.  The loop is kept ROLLED
+// (body = two chunks, ping-pong registers) so that the hot loop stays inside the ~6 KB L0
+// instruction cache.  f(c, regs16) is called once per chunk; n16 must be even.
+template <class F>
+CAREL_DEVINL void for_each_chunk16(uint32_t taddr, int n16, F&& f) {
+  uint32_t ra[16], rb[16];
+  tmem_ld16(taddr, ra);
+#pragma unroll 1
+  for (int c = 0; c < n16; c += 2) {
+    tmem_ld_wait();
+    tmem_ld16(taddr + (c + 1) * 16, rb);
+    f(c, ra);
+    tmem_ld_wait();
+    if (c + 2 < n16) tmem_ld16(taddr + (c + 2) * 16, ra);
+    f(c + 1, rb);
+  }
 }
 
 }  // namespace carel

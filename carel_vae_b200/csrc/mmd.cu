@@ -11,24 +11,24 @@
 namespace carel {
 
 struct MmdWs {
-  __nv_bfloat16* S;   // [M, Kp] packed cat(x, y)
-  float* norms;       // [roundup(M, 256)]
+  __nv_bfloat16* SA;  // [M, ldp] augmented row operand of cat(x, y)
+  __nv_bfloat16* SB;  // [M, ldp] augmented column operand
   double* accum;      // [4] block sums
   size_t bytes;
 };
 
-static MmdWs carve_mmd(void* ws, int64_t M, int64_t Kp) {
+static MmdWs carve_mmd(void* ws, int64_t M, int64_t ldp) {
   WsCarver w(ws);
   MmdWs r;
-  r.S = w.take<__nv_bfloat16>(size_t(M) * Kp);
-  r.norms = w.take<float>(size_t(round_up64(M, 256)));
+  r.SA = w.take<__nv_bfloat16>(size_t(M) * ldp);
+  r.SB = w.take<__nv_bfloat16>(size_t(M) * ldp);
   r.accum = w.take<double>(4);
   r.bytes = w.bytes();
   return r;
 }
 
 static __global__ void mmd_finalize_kernel(const double* __restrict__ acc, double a00, double a11,
-                                    double a01, float* __restrict__ out) {
+                                           double a01, float* __restrict__ out) {
   if (threadIdx.x == 0 && blockIdx.x == 0)
     out[0] = float(a00 * acc[0] + a11 * acc[1] + a01 * acc[2]);
 }
@@ -38,7 +38,7 @@ static __global__ void mmd_finalize_kernel(const double* __restrict__ acc, doubl
 using namespace carel;
 
 extern "C" size_t carel_mmd_workspace_bytes(int64_t n1, int64_t n2, int64_t dim) {
-  return carve_mmd(nullptr, n1 + n2, round_up64(dim, 64)).bytes;
+  return carve_mmd(nullptr, n1 + n2, aug_width(int(dim))).bytes;
 }
 
 extern "C" int carel_mmd_finalize(const double* partial_sums, int64_t n1, int64_t n2,
@@ -61,24 +61,23 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
   CAREL_REQUIRE(n1 >= 2 && n2 >= 2, "carel_mmd: n_1 and n_2 must be >= 2 (a00 = 1/(n(n-1)))");
   CAREL_REQUIRE(dim > 0, "carel_mmd: dim must be positive");
   CAREL_REQUIRE(n_alpha >= 1 && n_alpha <= kMaxAlphas, "carel_mmd: 1..%d alphas supported", kMaxAlphas);
-  const int64_t M = n1 + n2, Kp = round_up64(dim, 64);
-  MmdWs w = carve_mmd(ws, M, Kp);
+  const int64_t M = n1 + n2;
+  const int ldp = aug_width(int(dim));
+  MmdWs w = carve_mmd(ws, M, ldp);
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_mmd_fwd: workspace too small");
   double* acc = partial_sums ? partial_sums : w.accum;
 
-  pack_rows_kernel<<<int((n1 + 7) / 8), 256, 0, st>>>(x, int(n1), int(dim), int(ldx), w.S, int(Kp), 0, w.norms);
+  pack_rows_kernel<<<int((n1 + 7) / 8), 256, 0, st>>>(x, int(n1), int(dim), int(ldx), w.SA, w.SB, ldp, 0, 1, nullptr);
   CAREL_LAUNCHED();
-  pack_rows_kernel<<<int((n2 + 7) / 8), 256, 0, st>>>(y, int(n2), int(dim), int(ldy), w.S, int(Kp), int(n1), w.norms);
+  pack_rows_kernel<<<int((n2 + 7) / 8), 256, 0, st>>>(y, int(n2), int(dim), int(ldy), w.SA, w.SB, ldp, int(n1), 1, nullptr);
   CAREL_LAUNCHED();
-  // zero the norm padding (read by the vectorised column loads) and the accumulators
-  const int64_t Mpad = round_up64(M, 256);
-  if (Mpad > M) CAREL_CHECK_CUDA(cudaMemsetAsync(w.norms + M, 0, size_t(Mpad - M) * 4, st));
   CAREL_CHECK_CUDA(cudaMemsetAsync(acc, 0, 3 * sizeof(double), st));
 
-  CUtensorMap tm;
-  CAREL_REQUIRE(make_tmap_bf16_sw128(&tm, w.S, M, Kp, Kp, 128) == 0, "carel_mmd_fwd: tensor map failed");
+  CUtensorMap ta, tb;
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.SA, M, ldp, ldp, 128) == 0, "carel_mmd_fwd: tensor map failed");
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.SB, M, ldp, ldp, 128) == 0, "carel_mmd_fwd: tensor map failed");
   const int tri = (flags & CAREL_MMD_FULL_GRAM) ? 0 : 1;
-  GemmSched s = make_sched(M, M, Kp, 256, 1, tri ? TILE_TRI : TILE_FULL);
+  GemmSched s = make_sched(M, M, ldp, 256, 1, tri ? TILE_TRI : TILE_FULL);
   const int t0 = int(row_tile_begin < 0 ? 0 : row_tile_begin);
   const int t1 = int((row_tile_end < 0 || row_tile_end > s.m_tiles) ? s.m_tiles : row_tile_end);
   CAREL_REQUIRE(t0 <= t1, "carel_mmd_fwd: bad row tile range");
@@ -91,26 +90,27 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
     s.num_items = (t1 - t0) * s.n_tiles;
   }
   EpiMMDParams ep;
-  ep.norms = w.norms; ep.accum = acc; ep.M = int(M); ep.n1 = int(n1); ep.tri = tri; ep.n_alpha = n_alpha;
+  ep.accum = acc; ep.M = int(M); ep.n1 = int(n1); ep.tri = tri; ep.n_alpha = n_alpha;
   for (int i = 0; i < kMaxAlphas; ++i) {
     const float a = (i < n_alpha) ? alphas_host[i] : 0.f;
-    ep.a_scale[i] = -a * kLog2e;
+    ep.a_scale[i] = -2.f * a * kLog2e;
     ep.a_shift[i] = -a * eps * kLog2e;
   }
-  if (int rc = launch_gemm<EpiMMD<256>, 256, 1, false, false>(tm, tm, tm, tm, s, ep, st)) return rc;
+  if (int rc = launch_gemm<EpiMMD<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st)) return rc;
   if (out_mmd != nullptr) return carel_mmd_finalize(acc, n1, n2, out_mmd, stream);
   return 0;
 }
 
-template <int KP>
-static int mmd_bwd_launch(const MmdWs& w, const MmdBwdParams& pp, int64_t M, int t0, int t1,
+template <int BN1>
+static int mmd_bwd_launch(const MmdWs& w, const MmdBwdParams& pp, int64_t M, int ldp, int t0, int t1,
                           cudaStream_t st) {
-  constexpr int BN1 = (KP <= 128) ? 128 : 64;
+  using Cfg = ChainCfg<1, BN1>;
   CUtensorMap ta, tb;
-  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.S, M, KP, KP, 128) == 0, "carel_mmd_bwd: tensor map A failed");
-  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.S, M, KP, KP, BN1) == 0, "carel_mmd_bwd: tensor map B failed");
-  ChainSched s = make_chain_sched(t0, t1 - t0, int((M + BN1 - 1) / BN1), KP / 64, 32);
-  return launch_chain<PolMmdBwd<KP>, 1, BN1, KP>(ta, tb, ta, tb, s, pp, st);
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.SA, M, ldp, ldp, 128) == 0, "carel_mmd_bwd: tensor map A failed");
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.SB, M, ldp, ldp, BN1) == 0, "carel_mmd_bwd: tensor map B failed");
+  const int k16 = ldp / 16;
+  ChainSched s = make_chain_sched(t0, t1 - t0, int((M + BN1 - 1) / BN1), k16, Cfg::stages_for(k16), 32);
+  return launch_chain<PolMmdBwd, 1, BN1>(ta, tb, ta, tb, s, pp, st);
 }
 
 extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int64_t dim,
@@ -121,9 +121,10 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CAREL_REQUIRE(n1 >= 2 && n2 >= 2, "carel_mmd: n_1 and n_2 must be >= 2 (a00 = 1/(n(n-1)))");
   CAREL_REQUIRE(n_alpha >= 1 && n_alpha <= kMaxAlphas, "carel_mmd: 1..%d alphas supported", kMaxAlphas);
-  const int64_t M = n1 + n2, Kp = round_up64(dim, 64);
-  CAREL_REQUIRE(Kp <= 256, "carel_mmd_bwd: feature width %lld > 256 is not supported by the fused backward", (long long)dim);
-  MmdWs w = carve_mmd(ws, M, Kp);
+  const int64_t M = n1 + n2;
+  const int ldp = aug_width(int(dim));
+  CAREL_REQUIRE(ldp <= 256, "carel_mmd_bwd: feature width %lld > 250 is not supported by the fused backward", (long long)dim);
+  MmdWs w = carve_mmd(ws, M, ldp);
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_mmd_bwd: workspace too small");
   const int m_tiles = int((M + 127) / 128);
   const int t0 = int(row_tile_begin < 0 ? 0 : row_tile_begin);
@@ -132,8 +133,8 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_x, size_t(ldgx) * 4, 0, size_t(dim) * 4, size_t(n1), st));
   CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_y, size_t(ldgy) * 4, 0, size_t(dim) * 4, size_t(n2), st));
   MmdBwdParams pp;
-  pp.norms = w.norms; pp.S = w.S; pp.grad_out = grad_out; pp.grad_x = grad_x; pp.grad_y = grad_y;
-  pp.ldgx = int(ldgx); pp.ldgy = int(ldgy); pp.dim = int(dim); pp.Kp = int(Kp);
+  pp.SA = w.SA; pp.grad_out = grad_out; pp.grad_x = grad_x; pp.grad_y = grad_y;
+  pp.ldgx = int(ldgx); pp.ldgy = int(ldgy); pp.dim = int(dim); pp.ldp = ldp;
   pp.M = int(M); pp.n1 = int(n1);
   pp.c00 = float(1.0 / (double(n1) * double(n1 - 1)));
   pp.c11 = float(1.0 / (double(n2) * double(n2 - 1)));
@@ -141,14 +142,10 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   pp.n_alpha = n_alpha;
   for (int i = 0; i < kMaxAlphas; ++i) {
     const float a = (i < n_alpha) ? alphas_host[i] : 0.f;
-    pp.a_scale[i] = -a * kLog2e;
+    pp.a_scale[i] = -2.f * a * kLog2e;
     pp.a_shift[i] = -a * eps * kLog2e;
-    pp.a_neg[i] = -a;
+    pp.a_pos[i] = a;
   }
-  switch (Kp) {
-    case 64: return mmd_bwd_launch<64>(w, pp, M, t0, t1, st);
-    case 128: return mmd_bwd_launch<128>(w, pp, M, t0, t1, st);
-    case 192: return mmd_bwd_launch<192>(w, pp, M, t0, t1, st);
-    default: return mmd_bwd_launch<256>(w, pp, M, t0, t1, st);
-  }
+  if (ldp <= ChainCfg<1, 128>::kMaxN2) return mmd_bwd_launch<128>(w, pp, M, ldp, t0, t1, st);
+  return mmd_bwd_launch<64>(w, pp, M, ldp, t0, t1, st);
 }
