@@ -1,0 +1,579 @@
+// bow.cu — carel_bow_{fwd,bwd}: bag-of-words reconstruction decoder + loss
+// (drl_classifier_ec_mmd_final_mul.py:253-254 decoder + Softmax, :381-387 get_reconstruct_loss):
+//
+//   p = softmax(Z W_d^T + b_d),  t = bow (1 - ls) + ls / V,
+//   loss = -mean_{i,j} [ t max(log p, -100) + (1 - t) max(log(1 - p), -100) ]          (BCELoss)
+//
+// The [N, V] logits / probabilities never go to HBM.  With c = ls / V the loss splits into a
+// DENSE part that depends on p only and a SPARSE correction on the non-zeros of bow:
+//   t A + (1-t) B = c A + (1-c) B + (1-ls) bow (A - B),      A = max(log p,-100), B = max(log1p(-p),-100)
+// so the GEMM epilogues never read the 1 GB dense target; it is packed once into an ELL list
+// (HBM-bound pass) and the corrections are O(nnz) warp-per-row work.  Same split in backward:
+//   g = (p - t) / max(p (1-p), 1e-12) / (N V)   (torch's BCELoss backward),  s_i = sum_j g_ij p_ij,
+//   dlogit = p (g - s_i)  =  [u - p S_i] / (N V)  +  sparse,    u = p (p - c) / max(p (1-p), 1e-12).
+//
+// Operands are augmented: ZA = [z, -lse split(3), 1 1 1], WB = [w, 1 1 1, b split(3)], so the
+// accumulator is  log p_ij = z_i.w_j + b_j - lse_i  directly (lse columns are 0 during pass 1).
+//   pass 1  gemm_tc + EpiBowLse   per-row online (max, sum-exp) partials  -> lse
+//   pass 2  gemm_tc + EpiBowLoss  dense loss + row sums S_i
+//   sparse  bow_sparse_kernel     corrections of loss, S_i (fwd) and of dZ, dW, db (bwd)
+//   pass 3  chain_tc + PolBowBwd  dlogit tile -> bf16 (TMEM + HBM copy), dZ += dlogit W_d
+//   pass 4  gemm_tc (MN-major)    [dW | . | db] = dlogit^T [Z | . | 1]
+#include <algorithm>
+
+#include "api_common.cuh"
+#include "chain_launch.cuh"
+#include "chain_policies.cuh"
+#include "epilogues.cuh"
+#include "gemm_launch.cuh"
+#include "pack.cuh"
+
+namespace carel {
+
+constexpr float kTinyLogP = -6.9314718f;   // log(2^-10): below this the 3-term series are exact to 2^-30
+
+struct BowWs {
+  __nv_bfloat16* ZA;    // [N, ldk]
+  __nv_bfloat16* WB;    // [V, ldk]
+  __nv_bfloat16* dl;    // [N, Vp]  dense dlogits (backward)
+  float* part;          // [NTp, Npad] float2 (max, sumexp) partials
+  float* lse;           // [Npad]  holds -lse
+  float* srow;          // [Npad]  S_i = N V s_i
+  float* dWacc;         // [V, ldk] fp32 accumulation of dlogit^T [Z | 1]
+  double* lossacc;      // [2] dense, sparse
+  int* ell_cols;        // [N, cap]
+  float* ell_vals;      // [N, cap]
+  int* ell_nnz;         // [N]  (> cap: row must be scanned densely)
+  size_t bytes;
+  int ldk, Vp, Npad, ntp;
+};
+
+static BowWs carve_bow(void* ws, int64_t N, int64_t K, int64_t V, int64_t cap) {
+  WsCarver w(ws);
+  BowWs r;
+  r.ldk = aug_width(int(K));
+  r.Vp = int(round_up64(V, 64));
+  r.Npad = int(round_up64(N, 128));
+  r.ntp = int((V + 255) / 256) * 2;
+  r.ZA = w.take<__nv_bfloat16>(size_t(N) * r.ldk);
+  r.WB = w.take<__nv_bfloat16>(size_t(V) * r.ldk);
+  r.dl = w.take<__nv_bfloat16>(size_t(N) * r.Vp);
+  r.part = w.take<float>(size_t(r.ntp) * r.Npad * 2);
+  r.lse = w.take<float>(size_t(r.Npad));
+  r.srow = w.take<float>(size_t(r.Npad));
+  r.dWacc = w.take<float>(size_t(V) * r.ldk);
+  r.lossacc = w.take<double>(2);
+  r.ell_cols = w.take<int>(size_t(N) * cap);
+  r.ell_vals = w.take<float>(size_t(N) * cap);
+  r.ell_nnz = w.take<int>(size_t(N));
+  r.bytes = w.bytes();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense BoW target -> ELL (one warp per row, 128-bit loads; HBM-bound)
+// ---------------------------------------------------------------------------------------------
+static __global__ void bow_pack_ell_kernel(const float* __restrict__ bow, int64_t ld, int N, int V,
+                                           int cap, int* __restrict__ cols, float* __restrict__ vals,
+                                           int* __restrict__ nnz) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < N; r += gridDim.x * wpb) {
+    const float* row = bow + size_t(r) * ld;
+    int count = 0;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(bow) & 15) == 0);
+    const int V4 = vec ? (V & ~3) : 0;
+    for (int base = 0; base < V4; base += 128) {
+      const int j = base + lane * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < V4) v = __ldg(reinterpret_cast<const float4*>(row + j));
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool nz = e[q] != 0.f;
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (nz) {
+          const int pos = count + __popc(m & ((1u << lane) - 1u));
+          if (pos < cap) { cols[size_t(r) * cap + pos] = j + q; vals[size_t(r) * cap + pos] = e[q]; }
+        }
+        count += __popc(m);
+      }
+    }
+    for (int base = V4; base < V; base += 32) {
+      const int j = base + lane;
+      const float v = (j < V) ? __ldg(row + j) : 0.f;
+      const bool nz = v != 0.f;
+      const unsigned m = __ballot_sync(0xffffffffu, nz);
+      if (nz) {
+        const int pos = count + __popc(m & ((1u << lane) - 1u));
+        if (pos < cap) { cols[size_t(r) * cap + pos] = j; vals[size_t(r) * cap + pos] = v; }
+      }
+      count += __popc(m);
+    }
+    if (lane == 0) nnz[r] = count;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1 epilogue: per-row online (max, sum exp) over this warp's 128 columns of the tile
+// ---------------------------------------------------------------------------------------------
+struct EpiBowLseParams {
+  float2* part;   // [ntp][Npad]
+  int N, V, Npad;
+};
+template <int BN>
+struct EpiBowLse {
+  using Params = EpiBowLseParams;
+  const Params& p;
+  CAREL_DEVINL EpiBowLse(const Params& p_, const TileCtx&) : p(p_) {}
+  CAREL_DEVINL void tile(const TileCtx& ctx) {
+    constexpr int HALF = BN / 2;
+    const int c0 = ctx.col0 + ctx.half * HALF;
+    float m = -INFINITY, s = 0.f;
+    if (c0 < p.V) {
+      const bool full = c0 + HALF <= p.V;
+      for_each_chunk16(ctx.taddr + ctx.half * HALF, HALF / 16, [&](int c, const uint32_t (&r)[16]) {
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          x[i] = __uint_as_float(r[i]);
+          if (!full && c0 + c * 16 + i >= p.V) x[i] = -INFINITY;
+        }
+        float cm = fmaxf(x[0], x[1]);
+#pragma unroll
+        for (int i = 2; i < 16; ++i) cm = fmaxf(cm, x[i]);
+        if (cm > m) {
+          s *= ex2_approx((m - cm) * kLog2e);
+          m = cm;
+        }
+        if (m > -INFINITY) {
+          const float mm = m * kLog2e;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s += ex2_approx(fmaf(x[i], kLog2e, -mm));
+        }
+      });
+    }
+    if (ctx.row < p.Npad) p.part[size_t(ctx.tn * 2 + ctx.half) * p.Npad + ctx.row] = make_float2(m, s);
+  }
+  CAREL_DEVINL void finish() {}
+};
+
+static CAREL_DEVINL void split3(float h, __nv_bfloat16& h1, __nv_bfloat16& h2, __nv_bfloat16& h3) {
+  h1 = __float2bfloat16_rn(h);
+  const float r1 = h - __bfloat162float(h1);
+  h2 = __float2bfloat16_rn(r1);
+  h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
+}
+
+// lse_i from the partials; writes -lse (3-way bf16 split) into the h columns of ZA and zeroes S_i.
+static __global__ void bow_lse_combine_kernel(const float2* __restrict__ part, int ntp, int Npad, int N,
+                                              int K, __nv_bfloat16* __restrict__ ZA, int ldk,
+                                              float* __restrict__ neg_lse, float* __restrict__ srow) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  float M = -INFINITY;
+  for (int t = 0; t < ntp; ++t) M = fmaxf(M, part[size_t(t) * Npad + r].x);
+  float S = 0.f;
+  for (int t = 0; t < ntp; ++t) {
+    const float2 v = part[size_t(t) * Npad + r];
+    if (v.y > 0.f) S += v.y * __expf(v.x - M);
+  }
+  const float nl = -(M + logf(S));
+  neg_lse[r] = nl;
+  srow[r] = 0.f;
+  __nv_bfloat16 h1, h2, h3;
+  split3(nl, h1, h2, h3);
+  ZA[size_t(r) * ldk + K] = h1;
+  ZA[size_t(r) * ldk + K + 1] = h2;
+  ZA[size_t(r) * ldk + K + 2] = h3;
+}
+
+// exact per-element terms (used for the rare chunks that leave the series' range)
+static CAREL_DEVINL void bow_exact_terms(float x, float c, float& f, float& u) {
+  const float p = __expf(x);
+  const float A = fmaxf(x, -100.f);
+  const float B = fmaxf(log1pf(-p), -100.f);
+  f = c * A + (1.f - c) * B;
+  u = p * (p - c) / fmaxf(p * (1.f - p), 1e-12f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2 epilogue: dense loss  sum_ij [c A + (1-c) B]  and row sums  S_i = sum_j u_ij
+// Fast path (every p in the 16-chunk < 2^-10): power sums S1..S3 of p:
+//   sum log1p(-p) = -(S1 + S2/2 + S3/3) ,  sum u = sum (p-c)/(1-p) = (S1+S2+S3) - c (n + S1 + S2)
+// ---------------------------------------------------------------------------------------------
+struct EpiBowLossParams {
+  double* lossacc;
+  float* srow;
+  int N, V;
+  float c;
+};
+template <int BN>
+struct EpiBowLoss {
+  using Params = EpiBowLossParams;
+  const Params& p;
+  double loss;
+  CAREL_DEVINL EpiBowLoss(const Params& p_, const TileCtx&) : p(p_), loss(0.0) {}
+  CAREL_DEVINL void tile(const TileCtx& ctx) {
+    constexpr int HALF = BN / 2;
+    const int c0 = ctx.col0 + ctx.half * HALF;
+    if (c0 >= p.V || ctx.tm * 128 >= p.N) return;
+    const bool full = c0 + HALF <= p.V;
+    float sx = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, cnt = 0.f, fex = 0.f, uex = 0.f;
+    const float c = p.c;
+    for_each_chunk16(ctx.taddr + ctx.half * HALF, HALF / 16, [&](int ch, const uint32_t (&r)[16]) {
+      float x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
+      float mx = fmaxf(x[0], x[1]), mn = fminf(x[0], x[1]);
+#pragma unroll
+      for (int i = 2; i < 16; ++i) { mx = fmaxf(mx, x[i]); mn = fminf(mn, x[i]); }
+      const bool chunk_full = full || (c0 + ch * 16 + 16 <= p.V);
+      if (chunk_full && mx < kTinyLogP && mn > -27.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float pv = ex2_approx(x[i] * kLog2e);
+          const float p2 = pv * pv;
+          sx += x[i];
+          s1 += pv;
+          s2 += p2;
+          s3 = fmaf(p2, pv, s3);
+        }
+        cnt += 16.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (c0 + ch * 16 + i < p.V) {
+            float f, u;
+            bow_exact_terms(x[i], c, f, u);
+            fex += f;
+            uex += u;
+          }
+        }
+      }
+    });
+    if (ctx.row < p.N) {
+      const float f = c * sx - (1.f - c) * (s1 + 0.5f * s2 + (1.f / 3.f) * s3) + fex;
+      const float u = (s1 + s2 + s3) - c * (cnt + s1 + s2) + uex;
+      loss += double(f);
+      atomicAdd(p.srow + ctx.row, u);
+    }
+  }
+  CAREL_DEVINL void finish() {
+    const double v = warp_sum(loss);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(p.lossacc, v);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// sparse corrections: one warp per row over its ELL entries (or a dense scan if it overflowed)
+//   x = ZA[i] . WB[j]  (same rounded operands as the tensor-core passes)
+//   fwd (mode 0):  lossacc[1] += sum (1-ls) t (A - B) ;  S_i += sum -(1-ls) t p / max(p(1-p),1e-12)
+//   bwd (mode 1):  e = -(1-ls) t p / max(p(1-p),1e-12) * g/(N V);
+//                  dZ[i,:] += e w_j ; dWacc[j,:K] += e z_i ; dWacc[j, K+3] += e   (db column)
+// ---------------------------------------------------------------------------------------------
+struct BowSparseArgs {
+  const __nv_bfloat16* ZA;
+  const __nv_bfloat16* WB;
+  const int* ell_cols;
+  const float* ell_vals;
+  const int* ell_nnz;
+  const float* bow_dense;
+  int64_t ld_bow;
+  int N, V, K, ldk, cap, mode;
+  float one_minus_ls;
+  double* lossacc;
+  float* srow;
+  const float* grad_out;
+  float* grad_z;
+  int64_t ldgz;
+  float* dWacc;
+};
+
+static CAREL_DEVINL float bf16_dot_warp(const __nv_bfloat16* a, const __nv_bfloat16* b, int n, int lane) {
+  float acc = 0.f;
+  for (int k = lane * 8; k < n; k += 256) {
+    const uint4 va = __ldg(reinterpret_cast<const uint4*>(a + k));
+    const uint4 vb = __ldg(reinterpret_cast<const uint4*>(b + k));
+    const uint32_t ua[4] = {va.x, va.y, va.z, va.w}, ub[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ua[q]));
+      const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ub[q]));
+      acc = fmaf(fa.x, fb.x, acc);
+      acc = fmaf(fa.y, fb.y, acc);
+    }
+  }
+  return warp_sum(acc);
+}
+
+static __global__ void bow_sparse_kernel(const BowSparseArgs a) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float scale = (a.mode == 1) ? __ldg(a.grad_out) / (float(a.N) * float(a.V)) : 0.f;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < a.N; r += gridDim.x * wpb) {
+    const __nv_bfloat16* zrow = a.ZA + size_t(r) * a.ldk;
+    const int nnz = a.ell_nnz[r];
+    const bool dense_scan = nnz > a.cap;
+    float dloss = 0.f, du = 0.f;
+    auto handle = [&](int j, float t) {
+      const __nv_bfloat16* wrow = a.WB + size_t(j) * a.ldk;
+      const float x = bf16_dot_warp(zrow, wrow, a.ldk, lane);
+      const float p = __expf(x);
+      const float den = fmaxf(p * (1.f - p), 1e-12f);
+      const float ev = -a.one_minus_ls * t * p / den;
+      if (a.mode == 0) {
+        const float A = fmaxf(x, -100.f), B = fmaxf(log1pf(-p), -100.f);
+        dloss += a.one_minus_ls * t * (A - B);
+        du += ev;
+      } else {
+        const float e = ev * scale;
+        for (int k = lane; k < a.K; k += 32) {
+          atomicAdd(a.grad_z + size_t(r) * a.ldgz + k, e * __bfloat162float(wrow[k]));
+          atomicAdd(a.dWacc + size_t(j) * a.ldk + k, e * __bfloat162float(zrow[k]));
+        }
+        if (lane == 0) atomicAdd(a.dWacc + size_t(j) * a.ldk + a.K + 3, e);
+      }
+    };
+    if (!dense_scan) {
+      for (int q = 0; q < nnz; ++q) handle(a.ell_cols[size_t(r) * a.cap + q], a.ell_vals[size_t(r) * a.cap + q]);
+    } else {
+      const float* brow = a.bow_dense + size_t(r) * a.ld_bow;
+      for (int base = 0; base < a.V; base += 32) {
+        const int j = base + lane;
+        const float v = (j < a.V) ? __ldg(brow + j) : 0.f;
+        unsigned m = __ballot_sync(0xffffffffu, v != 0.f);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          handle(base + src, __shfl_sync(0xffffffffu, v, src));
+        }
+      }
+    }
+    if (a.mode == 0 && lane == 0) {
+      if (dloss != 0.f) atomicAdd(a.lossacc + 1, double(dloss));
+      if (du != 0.f) atomicAdd(a.srow + r, du);
+    }
+  }
+}
+
+static __global__ void bow_loss_finalize_kernel(const double* __restrict__ lossacc, double inv_nv,
+                                                float* __restrict__ out) {
+  if (threadIdx.x == 0) out[0] = float(-(lossacc[0] + lossacc[1]) * inv_nv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 3 policy: P = dense dlogits of the tile (rows = owner clause tile, cols = 64 vocab entries)
+//   dl = (u - p S_i) * g / (N V);   acc2 = sum_v dl w_v  -> atomically added to grad_z
+// ---------------------------------------------------------------------------------------------
+struct BowBwdParams {
+  const float* srow;
+  const float* grad_out;
+  __nv_bfloat16* dl;     // [N, Vp]
+  float* grad_z;
+  int64_t ldgz;
+  int N, V, Vp, K;
+  float c, inv_nv;
+};
+struct PolBowBwd {
+  using Params = BowBwdParams;
+  const Params& p;
+  float Si, scale;
+  CAREL_DEVINL PolBowBwd(const Params& p_, const ChainCtx&) : p(p_), Si(0.f), scale(0.f) {}
+  CAREL_DEVINL void begin_item(const ChainCtx& ctx) {
+    Si = (ctx.row < p.N) ? __ldg(p.srow + ctx.row) : 0.f;
+    scale = __ldg(p.grad_out) * p.inv_nv;
+  }
+  template <int BN1, class WaitP>
+  CAREL_DEVINL void weights(const ChainCtx& ctx, int t, uint32_t acc1_addr, uint32_t p_addr, WaitP&& wait_p) {
+    constexpr int N16 = BN1 / 32;
+    const int j0 = t * BN1 + ctx.half * (BN1 / 2);
+    const bool row_ok = ctx.row < p.N;
+    const float c = p.c;
+    for_each_chunk16(acc1_addr, N16, [&](int ch, const uint32_t (&r)[16]) {
+      float x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
+      float mx = fmaxf(x[0], x[1]), mn = fminf(x[0], x[1]);
+#pragma unroll
+      for (int i = 2; i < 16; ++i) { mx = fmaxf(mx, x[i]); mn = fminf(mn, x[i]); }
+      const int v0 = j0 + ch * 16;
+      float d[16];
+      if (v0 + 16 <= p.V && mx < kTinyLogP && mn > -27.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float pv = ex2_approx(x[i] * kLog2e);
+          const float q = fmaf(pv, fmaf(pv, 1.f, 1.f), 1.f);        // 1 + p + p^2
+          d[i] = fmaf(pv - c, q, -pv * Si) * scale;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float f, u;
+          bow_exact_terms(x[i], c, f, u);
+          d[i] = (v0 + i < p.V) ? (u - __expf(x[i]) * Si) * scale : 0.f;
+        }
+      }
+      uint32_t packed[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) packed[i] = row_ok ? pack_bf16x2(d[2 * i], d[2 * i + 1]) : 0u;
+      if (ch == 0) wait_p();
+      tmem_st8(p_addr + ch * 8, packed);
+      if (row_ok && v0 < p.Vp) {
+        uint4* dst = reinterpret_cast<uint4*>(p.dl + size_t(ctx.row) * p.Vp + v0);
+        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+    });
+  }
+  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
+    const int n16 = p.K / 16;                       // feature columns only
+    const int q_split = (n16 + 1) >> 1;
+    const int q0 = ctx.half ? q_split : 0, q1 = ctx.half ? n16 : q_split;
+    const bool row_ok = valid && ctx.row < p.N;
+    float* dst = p.grad_z + size_t(min(ctx.row, p.N - 1)) * p.ldgz;
+#pragma unroll 1
+    for (int q = q0; q < q1; ++q) {
+      uint32_t r[16];
+      tmem_ld16(ctx.acc2_taddr + q * 16, r);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) atomicAdd(dst + q * 16 + i, __uint_as_float(r[i]));
+    }
+  }
+  CAREL_DEVINL void finish() {}
+};
+
+// scatter [V, ldk] accumulation buffer into grad_w [V, K] and grad_b [V] (column K+3 = ones column of ZA)
+static __global__ void bow_scatter_grads_kernel(const float* __restrict__ acc, int ldk, int V, int K,
+                                                float* __restrict__ gw, float* __restrict__ gb) {
+  const long long total = 1LL * V * (K + 1);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = int(t % (K + 1));
+    const int r = int(t / (K + 1));
+    if (c < K) {
+      if (gw) gw[size_t(r) * K + c] = acc[size_t(r) * ldk + c];
+    } else if (gb) {
+      gb[r] = acc[size_t(r) * ldk + K + 3];
+    }
+  }
+}
+
+}  // namespace carel
+
+using namespace carel;
+
+extern "C" size_t carel_bow_workspace_bytes(int64_t N, int64_t K, int64_t V, int64_t ell_cap) {
+  return carve_bow(nullptr, N, K, V, ell_cap).bytes;
+}
+
+// Pack a dense [N, V] target into the ELL arrays of a workspace (also done implicitly by
+// carel_bow_fwd when bow_dense != NULL).
+extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, const float* dec_b,
+                             const float* bow_dense, int64_t ld_bow, const int32_t* ell_cols_in,
+                             const float* ell_vals_in, const int32_t* ell_nnz_in, int64_t N,
+                             int64_t K, int64_t V, int64_t ell_cap, float label_smoothing,
+                             float* loss_out, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(N > 0 && K > 0 && V > 0 && ell_cap > 0, "carel_bow_fwd: empty problem");
+  CAREL_REQUIRE(K % 16 == 0 && K <= 256, "carel_bow_fwd: decoder input width (2 * ec_dim) must be a multiple of 16 and <= 256, got %lld", (long long)K);
+  CAREL_REQUIRE(bow_dense != nullptr || (ell_cols_in && ell_vals_in && ell_nnz_in), "carel_bow_fwd: need a dense or an ELL target");
+  BowWs w = carve_bow(ws, N, K, V, ell_cap);
+  CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_bow_fwd: workspace too small");
+  const int cap = int(ell_cap);
+  // ---- operands ----
+  pack_rows_kernel<<<int((N + 7) / 8), 256, 0, st>>>(z, int(N), int(K), int(ldz), w.ZA, nullptr, w.ldk, 0, 2, nullptr);
+  CAREL_LAUNCHED();
+  pack_rows_kernel<<<int(std::min<int64_t>((V + 7) / 8, 148 * 32)), 256, 0, st>>>(dec_w, int(V), int(K), int(K), nullptr, w.WB, w.ldk, 0, 1, nullptr, dec_b);
+  CAREL_LAUNCHED();
+  // ---- sparse target ----
+  if (ell_cols_in != nullptr) {
+    CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_cols, ell_cols_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, st));
+    CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_vals, ell_vals_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, st));
+    CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_nnz, ell_nnz_in, size_t(N) * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    bow_pack_ell_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 32)), 256, 0, st>>>(bow_dense, ld_bow, int(N), int(V), cap, w.ell_cols, w.ell_vals, w.ell_nnz);
+    CAREL_LAUNCHED();
+  }
+  CAREL_CHECK_CUDA(cudaMemsetAsync(w.lossacc, 0, 2 * sizeof(double), st));
+  CUtensorMap ta, tb;
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.ZA, N, w.ldk, w.ldk, 128) == 0, "carel_bow_fwd: tensor map Z failed");
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, w.ldk, w.ldk, 128) == 0, "carel_bow_fwd: tensor map W failed");
+  GemmSched s = make_sched(N, V, w.ldk, 256, 1, TILE_FULL);
+  // ---- pass 1: logsumexp ----
+  EpiBowLseParams e1;
+  e1.part = reinterpret_cast<float2*>(w.part); e1.N = int(N); e1.V = int(V); e1.Npad = w.Npad;
+  if (int rc = launch_gemm<EpiBowLse<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e1, st)) return rc;
+  bow_lse_combine_kernel<<<int((N + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(w.part), w.ntp, w.Npad, int(N), int(K), w.ZA, w.ldk, w.lse, w.srow);
+  CAREL_LAUNCHED();
+  // ---- pass 2: dense loss + row sums ----
+  EpiBowLossParams e2;
+  e2.lossacc = w.lossacc; e2.srow = w.srow; e2.N = int(N); e2.V = int(V); e2.c = label_smoothing / float(V);
+  if (int rc = launch_gemm<EpiBowLoss<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e2, st)) return rc;
+  // ---- sparse corrections ----
+  BowSparseArgs sa;
+  sa.ZA = w.ZA; sa.WB = w.WB; sa.ell_cols = w.ell_cols; sa.ell_vals = w.ell_vals; sa.ell_nnz = w.ell_nnz;
+  sa.bow_dense = bow_dense; sa.ld_bow = ld_bow; sa.N = int(N); sa.V = int(V); sa.K = int(K); sa.ldk = w.ldk;
+  sa.cap = cap; sa.mode = 0; sa.one_minus_ls = 1.f - label_smoothing; sa.lossacc = w.lossacc; sa.srow = w.srow;
+  sa.grad_out = nullptr; sa.grad_z = nullptr; sa.ldgz = 0; sa.dWacc = nullptr;
+  bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
+  CAREL_LAUNCHED();
+  bow_loss_finalize_kernel<<<1, 32, 0, st>>>(w.lossacc, 1.0 / (double(N) * double(V)), loss_out);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int64_t ld_bow, int64_t N,
+                             int64_t K, int64_t V, int64_t ell_cap, float label_smoothing,
+                             float* grad_z, int64_t ldgz, float* grad_w, float* grad_b, void* ws,
+                             size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BowWs w = carve_bow(ws, N, K, V, ell_cap);
+  CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_bow_bwd: workspace too small");
+  CAREL_REQUIRE(grad_z != nullptr, "carel_bow_bwd: grad_z is required");
+  const bool need_w = grad_w != nullptr || grad_b != nullptr;
+  CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_z, size_t(ldgz) * 4, 0, size_t(K) * 4, size_t(N), st));
+  if (need_w) CAREL_CHECK_CUDA(cudaMemsetAsync(w.dWacc, 0, size_t(V) * w.ldk * 4, st));
+  // ---- sparse part ----
+  BowSparseArgs sa;
+  sa.ZA = w.ZA; sa.WB = w.WB; sa.ell_cols = w.ell_cols; sa.ell_vals = w.ell_vals; sa.ell_nnz = w.ell_nnz;
+  sa.bow_dense = bow_dense; sa.ld_bow = ld_bow; sa.N = int(N); sa.V = int(V); sa.K = int(K); sa.ldk = w.ldk;
+  sa.cap = int(ell_cap); sa.mode = 1; sa.one_minus_ls = 1.f - label_smoothing; sa.lossacc = nullptr; sa.srow = nullptr;
+  sa.grad_out = grad_out; sa.grad_z = grad_z; sa.ldgz = ldgz; sa.dWacc = w.dWacc;
+  bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
+  CAREL_LAUNCHED();
+  // ---- pass 3: dense dlogits -> dZ (and bf16 copy for pass 4) ----
+  {
+    using Cfg = ChainCfg<1, 64>;
+    CUtensorMap ta, tb;
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.ZA, N, w.ldk, w.ldk, 128) == 0, "carel_bow_bwd: tensor map Z failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
+    const int k16 = w.ldk / 16;
+    ChainSched cs = make_chain_sched(0, int((N + 127) / 128), int((V + 63) / 64), k16, Cfg::stages_for(k16), 16);
+    cs.n2_16 = int(K / 16);
+    BowBwdParams bp;
+    bp.srow = w.srow; bp.grad_out = grad_out; bp.dl = w.dl; bp.grad_z = grad_z; bp.ldgz = ldgz;
+    bp.N = int(N); bp.V = int(V); bp.Vp = w.Vp; bp.K = int(K);
+    bp.c = label_smoothing / float(V); bp.inv_nv = float(1.0 / (double(N) * double(V)));
+    if (int rc = launch_chain<PolBowBwd, 1, 64>(ta, tb, ta, tb, cs, bp, st)) return rc;
+  }
+  // ---- pass 4: [dW | . | db] = dlogit^T [Z | . | 1] ----
+  if (need_w) {
+    CUtensorMap ta, tb;
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.dl, N, V, w.Vp, 64) == 0, "carel_bow_bwd: tensor map dl failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.ZA, N, K + 4, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z^T failed");
+    GemmSched s = make_sched(V, K + 4, N, 256, 1, TILE_FULL);
+    const int tiles = s.m_tiles * s.n_tiles;
+    const int num_kb = (s.num_k16 + 3) / 4;
+    int ks = std::max(1, std::min(num_kb, (4 * sm_count() + tiles - 1) / tiles));
+    s.ksplit = ks;
+    s.num_items = tiles * ks;
+    EpiStore<256>::Params ep;
+    ep.out = w.dWacc; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(V); ep.N = int(K + 4);
+    ep.ld = w.ldk; ep.ld_bf16 = 0; ep.atomic = 1; ep.scale = 1.f;
+    if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st)) return rc;
+    bow_scatter_grads_kernel<<<148 * 4, 256, 0, st>>>(w.dWacc, w.ldk, int(V), int(K), grad_w, grad_b);
+    CAREL_LAUNCHED();
+  }
+  return 0;
+}

@@ -14,6 +14,7 @@ inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int k16
   s.n_owner = n_owner;
   s.n_inner = n_inner;
   s.k16 = k16;
+  s.n2_16 = k16;
   s.stages = stages;
   const int sms = sm_count();
   int best = 1;
@@ -39,7 +40,7 @@ int launch_chain(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap
                  cudaStream_t st) {
   using Cfg = ChainCfg<NG, BN1>;
   auto kern = chain_tc_kernel<Pol, NG, BN1>;
-  CAREL_REQUIRE(16 * s.k16 <= Cfg::kMaxN2, "chain kernel: operand width %d exceeds the TMEM budget (%d)", 16 * s.k16, Cfg::kMaxN2);
+  CAREL_REQUIRE(16 * s.n2_16 <= Cfg::kMaxN2, "chain kernel: operand width %d exceeds the TMEM budget (%d)", 16 * s.n2_16, Cfg::kMaxN2);
   CAREL_REQUIRE(s.stages >= 2, "chain kernel: operand too wide for the shared-memory ring");
   const int smem_bytes = Cfg::smem_bytes(s.k16, s.stages);
   static int attr_bytes = 0;

@@ -26,7 +26,8 @@ struct ChainSched {
   int n_inner;     // inner tiles (BN1 rows each) in total
   int nsplit;      // inner range split factor; item = owner * nsplit + split
   int num_items;
-  int k16;         // operand width in 16-wide steps
+  int k16;         // operand width in 16-wide steps (GEMM-1 K)
+  int n2_16;       // GEMM-2 N in 16-column groups (<= k16; acc2 columns = 16 * n2_16)
   int stages;      // B ring depth (2..4), chosen by the host from the smem budget
 };
 
@@ -58,7 +59,7 @@ struct ChainCtx {
   int lane_q;     // lane quarter (0..3)
   int epi_tid;    // 0..255
   int t0, t1;     // inner tile range of the item
-  int k16;
+  int k16, n2_16;
   uint32_t acc2_taddr;  // TMEM address (lane quarter applied) of acc2 column 0
 };
 
@@ -185,7 +186,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint32_t aphase = 0, acc2_phase = 0, pphase = 0;
     int buf = 0; uint32_t bphase = 0;      // acc1 buffer of the next GEMM-1
     constexpr uint32_t idesc1 = make_idesc_bf16(128, BN1, 0, 0);
-    const uint32_t idesc2 = make_idesc_bf16(128, 16 * K16, 0, 1);
+    const uint32_t idesc2 = make_idesc_bf16(128, 16 * sched.n2_16, 0, 1);
     const uint32_t a_base = smem_u32(sA);
     const uint32_t b_base0 = smem_u32(sB);
     const uint32_t acc2_addr = tmem_base + Cfg::kAcc2Base;
@@ -244,6 +245,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     ctx.lane_q = warp & 3;
     ctx.epi_tid = threadIdx.x - 64;
     ctx.k16 = K16;
+    ctx.n2_16 = sched.n2_16;
     Pol pol(pp, ctx);
     ChainIter iter(sched);
     ChainItem it;

@@ -35,6 +35,7 @@ inline GemmSched make_sched(int64_t M, int64_t N, int64_t K, int BN, int ksplit,
   s.mode = mode;
   s.num_items = s.m_tiles * s.n_tiles * s.ksplit;
   s.m_tile0 = 0;
+  s.n_cols = int(N);
   return s;
 }
 

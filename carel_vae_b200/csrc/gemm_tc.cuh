@@ -37,6 +37,7 @@ struct GemmSched {
   int mode;       // TileMode; TILE_TRI requires BN == 256 and a square problem
   int num_items;  // total work items
   int m_tile0;    // first row tile owned by this launch (row-block sharding across GPUs)
+  int n_cols;     // if > 0: logical N; the last column tile issues a narrower MMA (multiple of 16)
 };
 
 // Sequential decoder of the persistent schedule; every role of a CTA walks the same items.
@@ -181,8 +182,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t phase = 0;
     int buf = 0;
     uint32_t bphase = 0;
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     while (it.next()) {
+      int n_eff = BN;
+      if (sched.n_cols > 0) n_eff = min(BN, ((sched.n_cols - it.tn * BN + 15) >> 4) << 4);
+      const uint32_t idesc = make_idesc_bf16(128, n_eff, A_MN ? 1 : 0, B_MN ? 1 : 0);
       mbar_wait(&tempty_bar[buf], bphase ^ 1);
       tc_fence_after();
 #pragma unroll 1

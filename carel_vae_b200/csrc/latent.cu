@@ -1,0 +1,288 @@
+// latent.cu — carel_latent_{fwd,bwd}: the VAE latent layer of DrlClassifier
+// (drl_classifier_ec_mmd_final_mul.py: get_emotion_emb / get_cause_emb :312-336, sample_prior
+// :345-351, get_kl_loss :525-534).
+//
+//   pre = X [N,D] * W4^T + b4,   W4 = [emotion_mu; emotion_log_var; cause_mu; cause_log_var]  ([4L, D])
+//   z_s = mu_s + eps_s (shared by all rows) * exp(log_var_s)                 s in {emotion, cause}
+//   kl_s = mean_i( -1/2 sum_d (1 + lv - exp(lv) - mu^2) )
+//
+// The projection is ONE tcgen05 GEMM (four nn.Linear fused); reparameterisation + KL are one
+// HBM-bound pass with 128-bit accesses and warp-shuffle reductions.  Backward: one elementwise
+// pass builds d(pre), then dX = dpre * W4 and [dW4 | db4] = dpre^T * [X | 1] on the tensor cores.
+#include <algorithm>
+
+#include "api_common.cuh"
+#include "epilogues.cuh"
+#include "gemm_launch.cuh"
+#include "pack.cuh"
+
+namespace carel {
+
+struct LatentWs {
+  __nv_bfloat16* Xp;    // [N, ldx]   X | 1 (ones column at D) | 0
+  __nv_bfloat16* Wp;    // [2 ldd, ldw]  W4 stacked twice (rows [0,4L) and [ldd, ldd+4L)); forward uses the first copy
+  __nv_bfloat16* dpre;  // [N, 2 ldd]    bf16 d(pre) as hi | lo (two-term split keeps the backward GEMMs ~fp32-accurate)
+  float* dW;            // [2 ldd, ldx]  fp32 accumulation target of [hi | lo]^T [X | 1]
+  double* klacc;        // [2]
+  size_t bytes;
+  int ldx, ldw, ldd;
+};
+
+static LatentWs carve_latent(void* ws, int64_t N, int64_t D, int64_t L) {
+  WsCarver w(ws);
+  LatentWs r;
+  r.ldx = int(round_up64(D + 1, 16));
+  r.ldw = int(round_up64(D, 16));
+  r.ldd = int(round_up64(4 * L, 16));
+  r.Xp = w.take<__nv_bfloat16>(size_t(N) * r.ldx);
+  r.Wp = w.take<__nv_bfloat16>(size_t(2 * r.ldd) * r.ldw);
+  r.dpre = w.take<__nv_bfloat16>(size_t(N) * 2 * r.ldd);
+  r.dW = w.take<float>(size_t(2 * r.ldd) * r.ldx);
+  r.klacc = w.take<double>(2);
+  r.bytes = w.bytes();
+  return r;
+}
+
+// X -> bf16 with a ones column at index D (bias gradients come out of the dW GEMM for free).
+static __global__ void pack_x_ones_kernel(const float* __restrict__ x, int N, int D, int ld,
+                                          __nv_bfloat16* __restrict__ out, int ldo) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < N; r += gridDim.x * wpb) {
+    const float* s = x + size_t(r) * ld;
+    __nv_bfloat16* o = out + size_t(r) * ldo;
+    if (((D & 3) == 0) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+      for (int k = lane * 4; k < D; k += 128) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(s + k));
+        uint2 pk;
+        pk.x = pack_bf16x2(v.x, v.y);
+        pk.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(o + k) = pk;
+      }
+    } else {
+      for (int k = lane; k < D; k += 32) o[k] = __float2bfloat16_rn(__ldg(s + k));
+    }
+    for (int k = D + lane; k < ldo; k += 32) o[k] = __float2bfloat16_rn(k == D ? 1.f : 0.f);
+  }
+}
+
+// One thread per 4 latent dims of one row and one space.  pre layout: [mu_e | lv_e | mu_c | lv_c].
+// Writes z = [z_e | z_c] and accumulates the two KL sums (double) with one atomic per warp.
+static __global__ void reparam_kl_fwd_kernel(const float* __restrict__ pre, int ldp,
+                                             const float* __restrict__ eps_e,
+                                             const float* __restrict__ eps_c, float* __restrict__ z,
+                                             int ldz, int N, int L, double* __restrict__ klacc) {
+  const int L4 = (L + 3) / 4;
+  const long long total = 1LL * N * 2 * L4;
+  float kl_local[2] = {0.f, 0.f};
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = int(t % L4);
+    const int sp = int((t / L4) % 2);
+    const int row = int(t / (2LL * L4));
+    const float* mu = pre + size_t(row) * ldp + sp * 2 * L + c4 * 4;
+    const float* lv = mu + L;
+    const float* eps = (sp ? eps_c : eps_e) + c4 * 4;
+    float* zo = z + size_t(row) * ldz + sp * L + c4 * 4;
+    float s = 0.f;
+    if ((L & 3) == 0 && (ldp & 3) == 0 && (ldz & 3) == 0) {
+      const float4 m4 = *reinterpret_cast<const float4*>(mu);
+      const float4 l4 = *reinterpret_cast<const float4*>(lv);
+      const float4 e4 = __ldg(reinterpret_cast<const float4*>(eps));
+      const float ex = __expf(l4.x), ey = __expf(l4.y), ez = __expf(l4.z), ew = __expf(l4.w);
+      *reinterpret_cast<float4*>(zo) =
+          make_float4(fmaf(e4.x, ex, m4.x), fmaf(e4.y, ey, m4.y), fmaf(e4.z, ez, m4.z), fmaf(e4.w, ew, m4.w));
+      s = (1.f + l4.x - ex - m4.x * m4.x) + (1.f + l4.y - ey - m4.y * m4.y) +
+          (1.f + l4.z - ez - m4.z * m4.z) + (1.f + l4.w - ew - m4.w * m4.w);
+    } else {
+      for (int i = 0; i < 4 && c4 * 4 + i < L; ++i) {
+        const float e = __expf(lv[i]);
+        zo[i] = fmaf(__ldg(eps + i), e, mu[i]);
+        s += 1.f + lv[i] - e - mu[i] * mu[i];
+      }
+    }
+    kl_local[sp] += s;
+  }
+  const float k0 = warp_sum(kl_local[0]), k1 = warp_sum(kl_local[1]);
+  if ((threadIdx.x & 31) == 0) {
+    if (k0 != 0.f) atomicAdd(klacc + 0, double(k0));
+    if (k1 != 0.f) atomicAdd(klacc + 1, double(k1));
+  }
+}
+
+static __global__ void kl_finalize_kernel(const double* __restrict__ klacc, int N, float* __restrict__ kl) {
+  if (threadIdx.x < 2) kl[threadIdx.x] = float(-0.5 * klacc[threadIdx.x] / double(N));
+}
+
+// d(pre) from d(z) and the upstream gradients of the two KL scalars:
+//   dmu = dz + g_kl * mu / N ;  dlv = dz * eps * exp(lv) - g_kl * (1 - exp(lv)) / (2N)
+static __global__ void reparam_kl_bwd_kernel(const float* __restrict__ pre, int ldp,
+                                             const float* __restrict__ eps_e,
+                                             const float* __restrict__ eps_c,
+                                             const float* __restrict__ gz, int ldgz,
+                                             const float* __restrict__ gkl, int N, int L,
+                                             __nv_bfloat16* __restrict__ dpre, int ldd) {
+  const long long total = 1LL * N * 2 * L;
+  const float invN = 1.f / float(N);
+  const float g0 = gkl ? __ldg(gkl) : 0.f, g1 = gkl ? __ldg(gkl + 1) : 0.f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = int(t % L);
+    const int sp = int((t / L) % 2);
+    const int row = int(t / (2LL * L));
+    const float mu = pre[size_t(row) * ldp + sp * 2 * L + c];
+    const float lv = pre[size_t(row) * ldp + sp * 2 * L + L + c];
+    const float eps = __ldg((sp ? eps_c : eps_e) + c);
+    const float dz = gz ? gz[size_t(row) * ldgz + sp * L + c] : 0.f;
+    const float g = sp ? g1 : g0;
+    const float e = __expf(lv);
+    const float dmu = dz + g * mu * invN;
+    const float dlv = dz * eps * e - 0.5f * g * (1.f - e) * invN;
+    __nv_bfloat16* o = dpre + size_t(row) * 2 * ldd + sp * 2 * L;
+    const __nv_bfloat16 mh = __float2bfloat16_rn(dmu), lh = __float2bfloat16_rn(dlv);
+    o[c] = mh;
+    o[L + c] = lh;
+    o[ldd + c] = __float2bfloat16_rn(dmu - __bfloat162float(mh));
+    o[ldd + L + c] = __float2bfloat16_rn(dlv - __bfloat162float(lh));
+  }
+}
+
+// zero the padding columns of dpre (ldd > 4L only when 4L is not a multiple of 16)
+static __global__ void zero_pad_cols_kernel(__nv_bfloat16* p, int rows, int c0, int ldd) {
+  const int w = ldd - c0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < 2LL * rows * w;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / (2 * w);
+    const int q = int(t % (2 * w));
+    p[size_t(r) * 2 * ldd + (q / w) * ldd + c0 + (q % w)] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// scatter the fp32 [4L, ldx] accumulation buffer into the eight nn.Linear gradients
+static __global__ void latent_scatter_grads_kernel(const float* __restrict__ dW, int ldx, int ldd, int L, int D,
+                                                   float* gw0, float* gw1, float* gw2, float* gw3,
+                                                   float* gb0, float* gb1, float* gb2, float* gb3) {
+  float* gw[4] = {gw0, gw1, gw2, gw3};
+  float* gb[4] = {gb0, gb1, gb2, gb3};
+  const long long total = 4LL * L * (D + 1);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = int(t % (D + 1));
+    const int r = int(t / (D + 1));
+    const int blk = r / L, rr = r - blk * L;
+    const float v = dW[size_t(r) * ldx + c] + dW[size_t(ldd + r) * ldx + c];
+    if (c < D) {
+      if (gw[blk]) gw[blk][size_t(rr) * D + c] = v;
+    } else if (gb[blk]) {
+      gb[blk][rr] = v;
+    }
+  }
+}
+
+}  // namespace carel
+
+using namespace carel;
+
+extern "C" size_t carel_latent_workspace_bytes(int64_t N, int64_t D, int64_t L) {
+  return carve_latent(nullptr, N, D, L).bytes;
+}
+
+extern "C" int carel_latent_fwd(const float* x, int64_t ldx, int64_t N, int64_t D, int64_t L,
+                                const float* const* w4, const float* const* b4, const float* eps_e,
+                                const float* eps_c, float* pre, float* z, float* kl, void* ws,
+                                size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(N > 0 && D > 0 && L > 0, "carel_latent_fwd: empty problem");
+  LatentWs w = carve_latent(ws, N, D, L);
+  CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_latent_fwd: workspace too small");
+  pack_x_ones_kernel<<<int((N + 7) / 8), 256, 0, st>>>(x, int(N), int(D), int(ldx), w.Xp, w.ldx);
+  CAREL_LAUNCHED();
+  for (int i = 0; i < 4; ++i) {
+    pack_rows_kernel<<<int((L + 7) / 8), 256, 0, st>>>(w4[i], int(L), int(D), int(D), w.Wp, nullptr,
+                                                       w.ldw, int(i * L), 0, nullptr);
+    CAREL_LAUNCHED();
+    pack_rows_kernel<<<int((L + 7) / 8), 256, 0, st>>>(w4[i], int(L), int(D), int(D), w.Wp, nullptr,
+                                                       w.ldw, int(w.ldd + i * L), 0, nullptr);
+    CAREL_LAUNCHED();
+  }
+  // bias: the four [L] vectors are gathered into pre's first row region by the epilogue via a
+  // contiguous [4L] staging vector living at the head of the dW buffer (free during forward).
+  if (w.ldd > 4 * L) {   // zero the unused rows between / after the two stacked copies of W4
+    CAREL_CHECK_CUDA(cudaMemsetAsync(w.Wp + size_t(4 * L) * w.ldw, 0, size_t(w.ldd - 4 * L) * w.ldw * 2, st));
+    CAREL_CHECK_CUDA(cudaMemsetAsync(w.Wp + size_t(w.ldd + 4 * L) * w.ldw, 0, size_t(w.ldd - 4 * L) * w.ldw * 2, st));
+  }
+  float* bias4 = w.dW;
+  for (int i = 0; i < 4; ++i)
+    CAREL_CHECK_CUDA(cudaMemcpyAsync(bias4 + i * L, b4[i], size_t(L) * 4, cudaMemcpyDeviceToDevice, st));
+  CUtensorMap ta, tb;
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.Xp, N, D, w.ldx, 128) == 0, "carel_latent_fwd: tensor map X failed");
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.Wp, 4 * L, D, w.ldw, 128) == 0, "carel_latent_fwd: tensor map W failed");
+  GemmSched s = make_sched(N, 4 * L, D, 256, 1, TILE_FULL);
+  EpiStore<256>::Params ep;
+  ep.out = pre; ep.bias = bias4; ep.out_bf16 = nullptr; ep.M = int(N); ep.N = int(4 * L);
+  ep.ld = int(4 * L); ep.ld_bf16 = 0; ep.atomic = 0; ep.scale = 1.f;
+  if (int rc = launch_gemm<EpiStore<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st)) return rc;
+  CAREL_CHECK_CUDA(cudaMemsetAsync(w.klacc, 0, 2 * sizeof(double), st));
+  const long long work = N * 2 * ((L + 3) / 4);
+  const int blocks = int(std::min<long long>((work + 255) / 256, 148LL * 16));
+  reparam_kl_fwd_kernel<<<blocks, 256, 0, st>>>(pre, int(4 * L), eps_e, eps_c, z, int(2 * L), int(N), int(L), w.klacc);
+  CAREL_LAUNCHED();
+  kl_finalize_kernel<<<1, 32, 0, st>>>(w.klacc, int(N), kl);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* grad_kl,
+                                const float* pre, const float* eps_e, const float* eps_c, int64_t N,
+                                int64_t D, int64_t L, float* grad_x, int64_t ldgx,
+                                float* const* grad_w4, float* const* grad_b4, void* ws,
+                                size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LatentWs w = carve_latent(ws, N, D, L);
+  CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_latent_bwd: workspace too small");
+  const long long work = N * 2 * L;
+  const int blocks = int(std::min<long long>((work + 255) / 256, 148LL * 16));
+  reparam_kl_bwd_kernel<<<blocks, 256, 0, st>>>(pre, int(4 * L), eps_e, eps_c, grad_z, int(ldgz), grad_kl,
+                                               int(N), int(L), w.dpre, w.ldd);
+  CAREL_LAUNCHED();
+  if (w.ldd > 4 * L) {
+    zero_pad_cols_kernel<<<64, 256, 0, st>>>(w.dpre, int(N), int(4 * L), w.ldd);
+    CAREL_LAUNCHED();
+  }
+  const int64_t K2 = 2 * w.ldd;   // hi | lo
+  CUtensorMap ta, tb;
+  if (grad_x != nullptr) {
+    // dX[N, D] = dpre[N, 4L] * W4[4L, D]     (A K-major, B MN-major)
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.dpre, N, K2, K2, 128) == 0, "carel_latent_bwd: tensor map dpre failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.Wp, K2, D, w.ldw, 64) == 0, "carel_latent_bwd: tensor map W failed");
+    GemmSched s = make_sched(N, D, K2, 256, 1, TILE_FULL);
+    EpiStore<256>::Params ep;
+    ep.out = grad_x; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(N); ep.N = int(D);
+    ep.ld = int(ldgx); ep.ld_bf16 = 0; ep.atomic = 0; ep.scale = 1.f;
+    if (int rc = launch_gemm<EpiStore<256>, 256, 1, false, true>(ta, tb, ta, tb, s, ep, st)) return rc;
+  }
+  bool any_w = false;
+  for (int i = 0; i < 4; ++i) any_w |= (grad_w4[i] != nullptr) || (grad_b4[i] != nullptr);
+  if (any_w) {
+    // [dW4 | db4][4L, D+1] = dpre^T[4L, N] * [X | 1][N, D+1]    (A MN-major, B MN-major, split-K)
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.dpre, N, K2, K2, 64) == 0, "carel_latent_bwd: tensor map dpre^T failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.Xp, N, D + 1, w.ldx, 64) == 0, "carel_latent_bwd: tensor map X failed");
+    GemmSched s = make_sched(K2, D + 1, N, 256, 1, TILE_FULL);
+    const int tiles = s.m_tiles * s.n_tiles;
+    int ks = (2 * sm_count() + tiles - 1) / tiles;
+    const int num_kb = (s.num_k16 + 3) / 4;
+    if (ks > num_kb) ks = num_kb;
+    if (ks < 1) ks = 1;
+    s.ksplit = ks;
+    s.num_items = tiles * ks;
+    CAREL_CHECK_CUDA(cudaMemsetAsync(w.dW, 0, size_t(K2) * w.ldx * 4, st));
+    EpiStore<256>::Params ep;
+    ep.out = w.dW; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(K2); ep.N = int(D + 1);
+    ep.ld = w.ldx; ep.ld_bf16 = 0; ep.atomic = 1; ep.scale = 1.f;
+    if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st)) return rc;
+    latent_scatter_grads_kernel<<<148, 256, 0, st>>>(w.dW, w.ldx, w.ldd, int(L), int(D), grad_w4[0], grad_w4[1],
+                                                    grad_w4[2], grad_w4[3], grad_b4[0], grad_b4[1],
+                                                    grad_b4[2], grad_b4[3]);
+    CAREL_LAUNCHED();
+  }
+  return 0;
+}

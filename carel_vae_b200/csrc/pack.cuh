@@ -17,15 +17,18 @@ inline __host__ __device__ int aug_width(int K) { return (K + 6 + 15) / 16 * 16;
 //              so that  A[i] . B[j] = s_i.s_j - |s_i|^2/2 - |s_j|^2/2 = -d2_ij / 2  accumulates
 //              in the tensor core and column K of B is the constant 1 (row sums for free).
 //   norms (optional) receives |s|^2.
+//   aug == 2:  like aug == 1 with h = 0.
+//   hvec (optional, aug == 1): h = hvec[r] instead of -|s|^2/2 (decoder: bias / -logsumexp).
 static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows, int K, int ld,
                                         __nv_bfloat16* __restrict__ A, __nv_bfloat16* __restrict__ B,
-                                        int ldp, int dst_row0, int aug, float* __restrict__ norms) {
+                                        int ldp, int dst_row0, int aug, float* __restrict__ norms,
+                                        const float* __restrict__ hvec = nullptr) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows;
        r += gridDim.x * warps_per_block) {
     const float* s = src + size_t(r) * ld;
-    __nv_bfloat16* a = A + size_t(dst_row0 + r) * ldp;
+    __nv_bfloat16* a = (A != nullptr) ? A + size_t(dst_row0 + r) * ldp : nullptr;
     __nv_bfloat16* b = (B != nullptr) ? B + size_t(dst_row0 + r) * ldp : nullptr;
     float nrm = 0.f;
     const bool vec = ((K & 3) == 0) && ((ld & 3) == 0) && ((ldp & 3) == 0) &&
@@ -40,7 +43,7 @@ static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows,
         uint2 o;
         o.x = *reinterpret_cast<const uint32_t*>(&lo);
         o.y = *reinterpret_cast<const uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(a + k) = o;
+        if (a != nullptr) *reinterpret_cast<uint2*>(a + k) = o;
         if (b != nullptr) *reinterpret_cast<uint2*>(b + k) = o;
       }
     } else {
@@ -48,14 +51,14 @@ static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows,
         const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(s + k));
         const float f = __bfloat162float(v);
         nrm += f * f;
-        a[k] = v;
+        if (a != nullptr) a[k] = v;
         if (b != nullptr) b[k] = v;
       }
     }
     nrm = warp_sum(nrm);
     if (norms != nullptr && lane == 0) norms[dst_row0 + r] = nrm;
     // tail: augmentation columns and zero padding
-    const float h = -0.5f * nrm;
+    const float h = (aug == 2) ? 0.f : ((hvec != nullptr) ? __ldg(hvec + r) : -0.5f * nrm);
     const __nv_bfloat16 h1 = __float2bfloat16_rn(h);
     const float r1 = h - __bfloat162float(h1);
     const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
@@ -72,7 +75,7 @@ static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows,
         else if (t == 4) { va = one; vb = h2; }
         else if (t == 5) { va = one; vb = h3; }
       }
-      a[k] = va;
+      if (a != nullptr) a[k] = va;
       if (b != nullptr) b[k] = vb;
     }
   }

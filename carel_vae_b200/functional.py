@@ -124,3 +124,127 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool =
     check(lib().carel_gemm_bf16(_p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
                                 _p(c), N, _p(bias), ksplit, _stream()), "carel_gemm_bf16")
     return c
+
+
+# --------------------------------------------------------------------------------------------
+# latent layer: fused 4x Linear + reparameterisation + KL
+# --------------------------------------------------------------------------------------------
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = 0 if t is None else t.data_ptr()
+    return arr
+
+
+class _LatentFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps_e, eps_c, *wb):
+        # wb = (W_emu, b_emu, W_elv, b_elv, W_cmu, b_cmu, W_clv, b_clv)
+        _require_cuda(x, eps_e, eps_c, *wb)
+        xf = _rowmajor_f32(x)
+        N, D = xf.shape
+        ws_ = [w.detach().float().contiguous() for w in wb[0::2]]
+        bs_ = [b.detach().float().contiguous() for b in wb[1::2]]
+        L = ws_[0].shape[0]
+        ee, ec = eps_e.detach().float().contiguous(), eps_c.detach().float().contiguous()
+        lb = lib()
+        ws = _workspace(lb.carel_latent_workspace_bytes(N, D, L), xf.device)
+        pre = torch.empty((N, 4 * L), dtype=torch.float32, device=xf.device)
+        z = torch.empty((N, 2 * L), dtype=torch.float32, device=xf.device)
+        kl = torch.empty(2, dtype=torch.float32, device=xf.device)
+        check(lb.carel_latent_fwd(_p(xf), xf.stride(0), N, D, L, _ptr_array(ws_), _ptr_array(bs_), _p(ee), _p(ec),
+                                  _p(pre), _p(z), _p(kl), _p(ws), ws.numel(), _stream()), "carel_latent_fwd")
+        ctx.ws, ctx.pre, ctx.eps = ws, pre, (ee, ec)
+        ctx.dims = (N, D, L)
+        ctx.x_dtype = x.dtype
+        ctx.wb_meta = [(t.dtype, tuple(t.shape)) for t in wb]
+        ctx.mark_non_differentiable(pre)
+        return z, kl, pre
+
+    @staticmethod
+    def backward(ctx, gz, gkl, _gpre):
+        N, D, L = ctx.dims
+        ws, pre = ctx.ws, ctx.pre
+        ee, ec = ctx.eps
+        dev = ws.device
+        gz = None if gz is None else _rowmajor_f32(gz)
+        gkl = None if gkl is None else gkl.float().contiguous()
+        need = ctx.needs_input_grad
+        gx = torch.empty((N, D), dtype=torch.float32, device=dev) if need[0] else None
+        gws, gbs = [], []
+        for i in range(4):
+            gws.append(torch.empty((L, D), dtype=torch.float32, device=dev) if need[3 + 2 * i] else None)
+            gbs.append(torch.empty((L,), dtype=torch.float32, device=dev) if need[4 + 2 * i] else None)
+        check(lib().carel_latent_bwd(_p(gz), 0 if gz is None else gz.stride(0), _p(gkl), _p(pre), _p(ee), _p(ec),
+                                     N, D, L, _p(gx), D, _ptr_array(gws), _ptr_array(gbs), _p(ws), ws.numel(),
+                                     _stream()), "carel_latent_bwd")
+        out = [None if gx is None else gx.to(ctx.x_dtype), None, None]
+        for i in range(4):
+            out.append(gws[i])
+            out.append(gbs[i])
+        return tuple(out)
+
+
+def latent(x, eps_e, eps_c, w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_clv):
+    """Fused latent layer.  Returns (z [N, 2L] = [z_e | z_c], kl [2] = (kl_e, kl_c), pre [N, 4L] =
+    [mu_e | lv_e | mu_c | lv_c] (detached))."""
+    return _LatentFn.apply(x, eps_e, eps_c, w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_clv)
+
+
+# --------------------------------------------------------------------------------------------
+# BoW reconstruction: decoder GEMM fused with softmax + BCE
+# --------------------------------------------------------------------------------------------
+DEFAULT_ELL_CAP = 64
+
+
+class _BowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, dec_w, dec_b, bow_dense, ell, label_smoothing, ell_cap):
+        _require_cuda(z, dec_w, dec_b)
+        zf = _rowmajor_f32(z)
+        wf = dec_w.detach().float().contiguous()
+        bf_ = dec_b.detach().float().contiguous()
+        N, K = zf.shape
+        V = wf.shape[0]
+        bd = None
+        if bow_dense is not None:
+            bd = _rowmajor_f32(bow_dense)
+            if bd.shape != (N, V):
+                raise ValueError(f"content_bow must be [{N}, {V}], got {tuple(bd.shape)}")
+        cols = vals = nnz = None
+        if ell is not None:
+            cols, vals, nnz = ell
+            cols, vals, nnz = cols.int().contiguous(), vals.float().contiguous(), nnz.int().contiguous()
+            ell_cap = cols.shape[1]
+        lb = lib()
+        ws = _workspace(lb.carel_bow_workspace_bytes(N, K, V, ell_cap), zf.device)
+        loss = torch.empty((), dtype=torch.float32, device=zf.device)
+        check(lb.carel_bow_fwd(_p(zf), zf.stride(0), _p(wf), _p(bf_), _p(bd), 0 if bd is None else bd.stride(0),
+                               _p(cols), _p(vals), _p(nnz), N, K, V, ell_cap, float(label_smoothing), _p(loss),
+                               _p(ws), ws.numel(), _stream()), "carel_bow_fwd")
+        ctx.ws, ctx.bd = ws, bd
+        ctx.meta = (N, K, V, int(ell_cap), float(label_smoothing), z.dtype, dec_w.dtype, dec_b.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        N, K, V, cap, ls, dtz, dtw, dtb = ctx.meta
+        ws, bd = ctx.ws, ctx.bd
+        dev = ws.device
+        g = g.reshape(()).float().contiguous()
+        need = ctx.needs_input_grad
+        gz = torch.empty((N, K), dtype=torch.float32, device=dev)
+        gw = torch.empty((V, K), dtype=torch.float32, device=dev) if need[1] else None
+        gb = torch.empty((V,), dtype=torch.float32, device=dev) if need[2] else None
+        check(lib().carel_bow_bwd(_p(g), _p(bd), 0 if bd is None else bd.stride(0), N, K, V, cap, ls, _p(gz), K,
+                                  _p(gw), _p(gb), _p(ws), ws.numel(), _stream()), "carel_bow_bwd")
+        return (gz.to(dtz) if need[0] else None, None if gw is None else gw.to(dtw),
+                None if gb is None else gb.to(dtb), None, None, None, None)
+
+
+def bow_reconstruction_loss(z, dec_w, dec_b, content_bow=None, label_smoothing: float = 0.1, ell=None,
+                            ell_cap: int = DEFAULT_ELL_CAP):
+    """BCELoss(softmax(z dec_w^T + dec_b), content_bow (1 - ls) + ls / V) without materialising [N, V]
+    (reference :253-254 + get_reconstruct_loss :381-387).  `content_bow` is the reference's dense
+    [N, V] target; `ell=(cols[N,C] int32, vals[N,C] fp32, nnz[N] int32)` is the compact alternative."""
+    return _BowFn.apply(z, dec_w, dec_b, content_bow, ell, label_smoothing, ell_cap)

@@ -80,6 +80,43 @@ int carel_pairwise(const float* a, int64_t lda, const float* b, int64_t ldb, int
                    int64_t n2, int64_t dim, int mode, const float* alphas_host, int n_alpha,
                    float eps, float* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Latent layer — replaces get_emotion_emb / get_cause_emb (drl_classifier_ec_mmd_final_mul.py
+ * :312-336), sample_prior (:345-351) and get_kl_loss (:525-534).
+ *   w4[4], b4[4]: emotion_mu, emotion_log_var, cause_mu, cause_log_var ([L, D] / [L], nn.Linear layout)
+ *   eps_e, eps_c: the [L] noise vectors the caller drew with torch.randn (shared by all rows)
+ *   pre [N, 4L] = [mu_e | lv_e | mu_c | lv_c];  z [N, 2L] = [z_e | z_c];  kl[2] = (kl_e, kl_c)
+ * ------------------------------------------------------------------------------------------ */
+size_t carel_latent_workspace_bytes(int64_t N, int64_t D, int64_t L);
+int carel_latent_fwd(const float* x, int64_t ldx, int64_t N, int64_t D, int64_t L,
+                     const float* const* w4, const float* const* b4, const float* eps_e,
+                     const float* eps_c, float* pre, float* z, float* kl, void* ws, size_t ws_bytes,
+                     void* stream);
+/* grad_z [N, 2L] (may be NULL), grad_kl[2] device (may be NULL); grad_x [N, D] (may be NULL);
+ * grad_w4[i] / grad_b4[i] may be NULL individually. */
+int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* grad_kl, const float* pre,
+                     const float* eps_e, const float* eps_c, int64_t N, int64_t D, int64_t L,
+                     float* grad_x, int64_t ldgx, float* const* grad_w4, float* const* grad_b4,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BoW reconstruction — replaces nn.Softmax(dim=1)(self.decoder(generative_emb)) + get_reconstruct_loss
+ * (drl_classifier_ec_mmd_final_mul.py:253-254, :381-387): BCELoss(softmax(Z W^T + b), bow (1-ls) + ls/V).
+ *   z [N, K] (K = 2 ec_dim, multiple of 16, <= 256), dec_w [V, K], dec_b [V]
+ *   target: dense bow [N, V] (reference layout) and/or an ELL list (cols/vals [N, cap], nnz [N]);
+ *   rows whose nnz exceeds ell_cap are re-scanned from the dense pointer, which must then stay valid
+ *   for the backward call.  loss_out: device scalar.
+ * ------------------------------------------------------------------------------------------ */
+size_t carel_bow_workspace_bytes(int64_t N, int64_t K, int64_t V, int64_t ell_cap);
+int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, const float* dec_b,
+                  const float* bow_dense, int64_t ld_bow, const int32_t* ell_cols,
+                  const float* ell_vals, const int32_t* ell_nnz, int64_t N, int64_t K, int64_t V,
+                  int64_t ell_cap, float label_smoothing, float* loss_out, void* ws, size_t ws_bytes,
+                  void* stream);
+int carel_bow_bwd(const float* grad_out, const float* bow_dense, int64_t ld_bow, int64_t N, int64_t K,
+                  int64_t V, int64_t ell_cap, float label_smoothing, float* grad_z, int64_t ldgz,
+                  float* grad_w, float* grad_b, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

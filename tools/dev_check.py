@@ -124,13 +124,101 @@ def bench_mmd():
             print(f"mmd fwd+bwd n={n} d={d}: {ms * 1e3:.1f} us")
 
 
+
+
+
+def check_latent():
+    import torch.nn.functional as TF
+    for (N, D, L) in [(64, 768, 24), (300, 768, 64), (8192, 768, 128)]:
+        X = bf(torch.tanh(torch.randn(N, D, device=dev))).requires_grad_(True)
+        Ws = [bf(torch.randn(L, D, device=dev) / D ** 0.5).requires_grad_(True) for _ in range(4)]
+        bs = [bf(torch.randn(L, device=dev) * 0.1).requires_grad_(True) for _ in range(4)]
+        ee, ec = torch.randn(L, device=dev), torch.randn(L, device=dev)
+        args = [X, ee, ec]
+        for w_, b_ in zip(Ws, bs):
+            args += [w_, b_]
+        z, kl, pre = F.latent(*args)
+        # reference
+        Xd = X.detach().double().requires_grad_(True)
+        Wd = [w_.detach().double().requires_grad_(True) for w_ in Ws]
+        bd = [b_.detach().double().requires_grad_(True) for b_ in bs]
+        pr = [TF.linear(Xd, w_, b_) for w_, b_ in zip(Wd, bd)]
+        ze = pr[0] + ee.double() * pr[1].exp()
+        zc = pr[2] + ec.double() * pr[3].exp()
+        zr = torch.cat([ze, zc], 1)
+        klr = torch.stack([(-0.5 * (1 + pr[1] - pr[1].exp() - pr[0] ** 2).sum(1)).mean(),
+                           (-0.5 * (1 + pr[3] - pr[3].exp() - pr[2] ** 2).sum(1)).mean()])
+        gzs = torch.randn_like(z)
+        gk = torch.tensor([0.7, -1.3], device=dev)
+        (z * gzs).sum().add((kl * gk).sum()).backward()
+        ((zr * gzs.double()).sum() + (klr * gk.double()).sum()).backward()
+        print(f"latent N={N} L={L}: z {rel(z, zr):.2e} kl {rel(kl, klr):.2e} pre {rel(pre, torch.cat(pr, 1)):.2e} | "
+              f"gX {rel(X.grad, Xd.grad):.2e} gW {max(rel(a.grad, b.grad) for a, b in zip(Ws, Wd)):.2e} "
+              f"gb {max(rel(a.grad, b.grad) for a, b in zip(bs, bd)):.2e}")
+
+
+def check_bow():
+    import torch.nn.functional as TF
+    for (N, K, V, nnz) in [(64, 48, 300, 5), (100, 128, 1000, 24), (256, 256, 5000, 24), (1024, 256, 30000, 24)]:
+        Z = bf(torch.randn(N, K, device=dev) * 1.1).requires_grad_(True)
+        W = bf((torch.rand(V, K, device=dev) * 2 - 1) / K ** 0.5).requires_grad_(True)
+        b = bf((torch.rand(V, device=dev) * 2 - 1) / K ** 0.5).requires_grad_(True)
+        idx = torch.randint(0, V, (N, nnz), device=dev)
+        bow = torch.zeros(N, V, device=dev)
+        bow.scatter_add_(1, idx, torch.ones(N, nnz, device=dev))
+        bow = bow / bow.sum(1, keepdim=True).clamp_min(1)
+        loss = F.bow_reconstruction_loss(Z, W, b, bow)
+        loss.backward()
+        Zd, Wd, bd = (t.detach().double().requires_grad_(True) for t in (Z, W, b))
+        pr = torch.softmax(TF.linear(Zd, Wd, bd), 1)
+        t = bow.double() * 0.9 + 0.1 / V
+        lr = TF.binary_cross_entropy(pr, t)
+        lr.backward()
+        print(f"bow N={N} K={K} V={V}: loss {loss.item():.6e} ref {lr.item():.6e} rel {abs(loss.item() - lr.item()) / abs(lr.item()):.2e} | "
+              f"gZ {rel(Z.grad, Zd.grad):.2e} gW {rel(W.grad, Wd.grad):.2e} gb {rel(b.grad, bd.grad):.2e}")
+
+
+def bench_head_parts():
+    N, D, L, V = 8192, 768, 128, 30000
+    X = torch.tanh(torch.randn(N, D, device=dev)).requires_grad_(True)
+    Ws = [(torch.randn(L, D, device=dev) / D ** 0.5).requires_grad_(True) for _ in range(4)]
+    bs = [(torch.randn(L, device=dev) * 0.1).requires_grad_(True) for _ in range(4)]
+    ee, ec = torch.randn(L, device=dev), torch.randn(L, device=dev)
+    args = [X, ee, ec]
+    for w_, b_ in zip(Ws, bs):
+        args += [w_, b_]
+
+    def lat():
+        z, kl, _ = F.latent(*args)
+        (z.sum() + kl.sum()).backward()
+    print(f"latent fwd+bwd: {timeit(lat) * 1e3:.1f} us")
+    Z = (torch.randn(N, 2 * L, device=dev) * 1.1).requires_grad_(True)
+    W = ((torch.rand(V, 2 * L, device=dev) * 2 - 1) / 16).requires_grad_(True)
+    b = ((torch.rand(V, device=dev) * 2 - 1) / 16).requires_grad_(True)
+    idx = torch.randint(0, V, (N, 24), device=dev)
+    bow = torch.zeros(N, V, device=dev)
+    bow.scatter_add_(1, idx, torch.ones(N, 24, device=dev))
+    bow = bow / bow.sum(1, keepdim=True).clamp_min(1)
+    print(f"bow fwd: {timeit(lambda: F.bow_reconstruction_loss(Z, W, b, bow)) * 1e3:.1f} us")
+
+    def bw():
+        F.bow_reconstruction_loss(Z, W, b, bow).backward()
+    print(f"bow fwd+bwd: {timeit(bw) * 1e3:.1f} us")
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["gemm", "mmd", "bench"]
+    what = sys.argv[1:] or ["gemm", "mmd", "latent", "bow", "bench"]
     t = time.time()
     if "gemm" in what:
         check_gemm()
     if "mmd" in what:
         check_mmd()
+    if "latent" in what:
+        check_latent()
+    if "bow" in what:
+        check_bow()
     if "bench" in what:
         bench_mmd()
+    if "bench2" in what:
+        bench_head_parts()
     print(f"done in {time.time() - t:.1f}s")
