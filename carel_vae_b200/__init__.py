@@ -1,0 +1,18 @@
+"""carel_vae_b200 — B200-native (sm_100a) implementation of the CAREL-VAE disentanglement head.
+
+Drop-in symbols (same names / signatures / state_dict keys as the reference trainers):
+
+    from carel_vae_b200 import DrlClassifier, MMDStatistic, pdist, HSIC, GaussianKernelMatrix, pairwise_distances
+
+Host code is PyTorch (memory, streams, autograd plumbing); the arithmetic runs in the hand-written
+CUDA kernels of libcarel_head.so, reached through the C ABI in include/carel_head.h.  There is no
+CPU / PyTorch fallback: without the built extension every op raises.
+"""
+from ._lib import CarelError, launch_count, lib  # noqa: F401
+from . import functional  # noqa: F401
+from .losses import (GaussianKernelMatrix, HSIC, MMDStatistic, pairwise_distances, pdist,  # noqa: F401
+                     permutation_test_mat)
+from .head import (DrlClassifier, DrlClassifierGAN, DrlClassifierHSIC, DrlClassifierMMD, DrlClassifierVI,  # noqa: F401
+                   IdentityEncoder, VARIANTS, default_opt)
+
+__version__ = "0.1.0"

@@ -29,6 +29,7 @@ struct MmdBwdParams {
   float a_scale[kMaxAlphas];  // -2 alpha log2 e
   float a_shift[kMaxAlphas];  // -alpha eps log2 e
   float a_pos[kMaxAlphas];    // alpha
+  float w_scale, inv_w_scale; // power-of-two scaling that puts W into fp16's range
 };
 
 struct PolMmdBwd {
@@ -58,9 +59,9 @@ struct PolMmdBwd {
     const bool fast = r1 < p.M && j1 < p.M && ((r1 < p.n1) || (r0 >= p.n1)) &&
                       ((j1 < p.n1) || (j0 >= p.n1)) && (j0 > r1 || j1 < r0);
     if (fast) {
-      const float cf = coef(r0, j0);
+      const float cf = coef(r0, j0) * p.w_scale;
       if (p.n_alpha == 1) {
-        const float sc = p.a_scale[0], sh = p.a_shift[0], ca = cf * p.a_pos[0];
+        const float sc = p.a_scale[0], sh = p.a_shift[0], ca = cf * p.a_pos[0];  // cf carries w_scale
         for_each_chunk16(acc1_addr, N16, [&](int c, const uint32_t (&r)[16]) {
           uint32_t packed[8];
 #pragma unroll
@@ -91,7 +92,7 @@ struct PolMmdBwd {
       const bool row_ok = row < p.M, rx = row < p.n1;
       const bool single = p.n_alpha == 1;
       const float sc = p.a_scale[0], sh = p.a_shift[0], a0 = p.a_pos[0];
-      const float c_same = rx ? p.c00 : p.c01, c_other = rx ? p.c01 : p.c11;
+      const float c_same = (rx ? p.c00 : p.c01) * p.w_scale, c_other = (rx ? p.c01 : p.c11) * p.w_scale;
       for_each_chunk16(acc1_addr, N16, [&](int c, const uint32_t (&r)[16]) {
         uint32_t packed[8];
 #pragma unroll
@@ -120,7 +121,7 @@ struct PolMmdBwd {
     const float rtot = __uint_as_float(rtot_bits);
     const int q_split = (ctx.n2_16 + 1) >> 1;
     const int q0 = ctx.half ? q_split : 0, q1 = ctx.half ? ctx.n2_16 : q_split;
-    const float g4 = 4.f * __ldg(p.grad_out);
+    const float g4 = 4.f * __ldg(p.grad_out) * p.inv_w_scale;
     const bool row_ok = valid && ctx.row < p.M;
     const int rowc = min(ctx.row, p.M - 1);
     const __nv_bfloat16* srow = p.SA + size_t(rowc) * p.ldp;

@@ -29,6 +29,7 @@ struct ChainSched {
   int k16;         // operand width in 16-wide steps (GEMM-1 K)
   int n2_16;       // GEMM-2 N in 16-column groups (<= k16; acc2 columns = 16 * n2_16)
   int stages;      // B ring depth (2..4), chosen by the host from the smem budget
+  int p_fp16;      // 1: the policy writes P as fp16 pairs (GEMM-2 A operand is FP16, B stays BF16)
 };
 
 struct ChainItem {
@@ -186,7 +187,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint32_t aphase = 0, acc2_phase = 0, pphase = 0;
     int buf = 0; uint32_t bphase = 0;      // acc1 buffer of the next GEMM-1
     constexpr uint32_t idesc1 = make_idesc_bf16(128, BN1, 0, 0);
-    const uint32_t idesc2 = make_idesc_bf16(128, 16 * sched.n2_16, 0, 1);
+    const uint32_t idesc2 = sched.p_fp16 ? make_idesc_f16a_bf16b(128, 16 * sched.n2_16, 0, 1)
+                                         : make_idesc_bf16(128, 16 * sched.n2_16, 0, 1);
     const uint32_t a_base = smem_u32(sA);
     const uint32_t b_base0 = smem_u32(sB);
     const uint32_t acc2_addr = tmem_base + Cfg::kAcc2Base;

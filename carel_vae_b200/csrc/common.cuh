@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -245,6 +246,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) |
          (uint32_t(b_mn_major) << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
+// Same, with A in FP16 (a_format = 0) and B in BF16: used when the A operand (a weight tile
+// written by an epilogue) needs 11 mantissa bits rather than 8.
+__host__ __device__ constexpr uint32_t make_idesc_f16a_bf16b(int M, int N, int a_mn_major,
+                                                             int b_mn_major) {
+  return (1u << 4) | (0u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) |
+         (uint32_t(b_mn_major) << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
 
 // Shared-memory matrix descriptor, 128-byte swizzle, sm_100 "version 1".
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
@@ -278,6 +286,10 @@ CAREL_DEVINL float lg2_approx(float x) {
 }
 CAREL_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+CAREL_DEVINL uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 CAREL_DEVINL float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }

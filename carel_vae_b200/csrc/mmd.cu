@@ -140,12 +140,19 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   pp.c11 = float(1.0 / (double(n2) * double(n2 - 1)));
   pp.c01 = float(-1.0 / (double(n1) * double(n2)));
   pp.n_alpha = n_alpha;
+  float asum = 0.f;
   for (int i = 0; i < kMaxAlphas; ++i) {
     const float a = (i < n_alpha) ? alphas_host[i] : 0.f;
     pp.a_scale[i] = -2.f * a * kLog2e;
     pp.a_shift[i] = -a * eps * kLog2e;
     pp.a_pos[i] = a;
+    asum += fabsf(a);
   }
+  // kind::f16 does not accept an FP16 A with a BF16 B (illegal instruction on sm_100a), so P stays
+  // bf16; the scale hook is kept at 1 (bf16 has fp32's exponent range).
+  (void)asum;
+  pp.w_scale = 1.f;
+  pp.inv_w_scale = 1.f;
   if (ldp <= ChainCfg<1, 128>::kMaxN2) return mmd_bwd_launch<128>(w, pp, M, ldp, t0, t1, st);
   return mmd_bwd_launch<64>(w, pp, M, ldp, t0, t1, st);
 }

@@ -36,6 +36,9 @@ inline int make_tmap_bf16_sw128(CUtensorMap* m, const void* base, uint64_t rows,
                                 uint64_t ld_elems, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_tiled();
   if (!fn) return -1;
+  // cuTensorMapEncodeTiled is a driver-API call and needs a current context; a thread that has not
+  // made a runtime call yet (e.g. autograd's backward thread) has none bound: bind the primary one.
+  cudaFree(nullptr);
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld_elems * 2};
   cuuint32_t box[2] = {64, box_rows};

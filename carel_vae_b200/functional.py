@@ -248,3 +248,42 @@ def bow_reconstruction_loss(z, dec_w, dec_b, content_bow=None, label_smoothing: 
     (reference :253-254 + get_reconstruct_loss :381-387).  `content_bow` is the reference's dense
     [N, V] target; `ell=(cols[N,C] int32, vals[N,C] fp32, nnz[N] int32)` is the compact alternative."""
     return _BowFn.apply(z, dec_w, dec_b, content_bow, ell, label_smoothing, ell_cap)
+
+
+# --------------------------------------------------------------------------------------------
+# HSIC
+# --------------------------------------------------------------------------------------------
+class _HSICFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, s_x, s_y):
+        _require_cuda(x, y)
+        xf, yf = _rowmajor_f32(x), _rowmajor_f32(y)
+        m, dx = xf.shape
+        m2, dy = yf.shape
+        if m != m2:
+            raise ValueError("HSIC needs paired samples (same number of rows)")
+        lb = lib()
+        ws = _workspace(lb.carel_hsic_workspace_bytes(m, dx, dy), xf.device)
+        out = torch.empty((), dtype=torch.float32, device=xf.device)
+        check(lb.carel_hsic_fwd(_p(xf), xf.stride(0), _p(yf), yf.stride(0), m, dx, dy, float(s_x), float(s_y),
+                                _p(out), _p(ws), ws.numel(), _stream()), "carel_hsic_fwd")
+        ctx.ws = ws
+        ctx.meta = (m, dx, dy, float(s_x), float(s_y), x.dtype, y.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        m, dx, dy, s_x, s_y, dtx, dty = ctx.meta
+        ws = ctx.ws
+        g = g.reshape(()).float().contiguous()
+        need = ctx.needs_input_grad
+        gx = torch.empty((m, dx), dtype=torch.float32, device=ws.device) if need[0] else None
+        gy = torch.empty((m, dy), dtype=torch.float32, device=ws.device) if need[1] else None
+        check(lib().carel_hsic_bwd(_p(g), m, dx, dy, s_x, s_y, _p(gx), dx, _p(gy), dy, _p(ws), ws.numel(),
+                                   _stream()), "carel_hsic_bwd")
+        return (None if gx is None else gx.to(dtx), None if gy is None else gy.to(dty), None, None)
+
+
+def hsic(x: torch.Tensor, y: torch.Tensor, s_x: float = 1.0, s_y: float = 1.0) -> torch.Tensor:
+    """HSIC(x, y) of the reference (hsic.py:540-547) as a 0-dim fp32 tensor, differentiable."""
+    return _HSICFn.apply(x, y, s_x, s_y)

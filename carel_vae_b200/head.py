@@ -1,0 +1,358 @@
+"""Drop-in `DrlClassifier` for the four disentanglement trainers.
+
+Same constructor, method names, return types and state_dict keys as the reference classes
+(drl_classifier_ec_mmd_final_mul.py:149-534, drl_classifier_ec_hsic.py, drl_classifier_ec_vi_final.py,
+drl_classifier_ec_gan.py), so train() / get_pair_preds() / checkpoints are unchanged; everything
+after `.pooler_output` runs on the sm_100a kernels of libcarel_head.so:
+
+    latent projections + reparameterisation + KL   -> functional.latent   (carel_latent_fwd/bwd)
+    MMD / HSIC independence losses                 -> losses.MMDStatistic / losses.HSIC
+    BoW decoder + softmax + BCE                    -> functional.bow_reconstruction_loss
+
+The tiny classifier heads (<= 6 outputs) stay in PyTorch.  Hyper-parameters
+are read from the `opt` passed to __init__ (the reference reads a module-global `opt`).
+
+RNG order per forward matches the reference: randn(L) for emotion, randn(L) for
+cause, then the dropout masks in call order.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as TF
+
+from . import functional as F
+from .losses import HSIC, MMDStatistic
+
+
+class IdentityEncoder(nn.Module):
+    """Stand-in encoder for pre-computed clause embeddings: pooler_output = input_ids.
+    (ECPE_dataset.py:137-154 produces exactly such [N, 768] fp32 embeddings.)"""
+
+    def forward(self, input_ids, attention_mask=None, token_type_ids=None):
+        return SimpleNamespace(pooler_output=input_ids)
+
+
+def _build_encoder(opt):
+    """The reference downloads hfl/chinese-roberta-wwm-ext or roberta-base (:158-163)."""
+    from transformers import BertModel, RobertaModel  # imported lazily: only needed for real text
+    if opt.language == "zh":
+        return BertModel.from_pretrained("hfl/chinese-roberta-wwm-ext",
+                                         cache_dir="model/hfl_chinese-roberta-wwm-ext", return_dict=True)
+    return RobertaModel.from_pretrained("roberta-base", cache_dir="model/roberta-base", return_dict=True)
+
+
+class _DrlClassifierBase(nn.Module):
+    variant = "base"
+
+    def __init__(self, opt, encoder: nn.Module | None = None):
+        super().__init__()
+        self.opt = opt
+        self.encoder = encoder if encoder is not None else _build_encoder(opt)
+        # emotion / cause latent embeddings (same member names => same state_dict keys)
+        self.emotion_mu = nn.Linear(opt.bert_dim, opt.ec_dim)
+        self.emotion_log_var = nn.Linear(opt.bert_dim, opt.ec_dim)
+        self.cause_mu = nn.Linear(opt.bert_dim, opt.ec_dim)
+        self.cause_log_var = nn.Linear(opt.bert_dim, opt.ec_dim)
+        self._build_variant_modules(opt)
+        self.emotion_classifier = nn.Linear(opt.ec_dim, self._emotion_classes(opt))
+        self.cause_classifier = nn.Linear(opt.ec_dim, self._cause_classes(opt))
+        self.pair_classifier = nn.Linear(opt.ec_dim * 2, opt.pair_num_class)
+        self.decoder = nn.Linear(opt.ec_dim * 2, opt.pair_bow_dim)
+        self.dropout = nn.Dropout(opt.dropout)
+        #: capacity of the per-row non-zero list the dense BoW target is packed into on the GPU
+        self.bow_ell_cap = getattr(opt, "bow_ell_cap", F.DEFAULT_ELL_CAP)
+
+    # ---- variant hooks -------------------------------------------------------------------
+    def _build_variant_modules(self, opt):
+        pass
+
+    def _emotion_classes(self, opt):
+        return opt.ec_num_class
+
+    def _cause_classes(self, opt):
+        return opt.ec_num_class
+
+    def _label_classes(self):
+        return self.opt.ec_num_class
+
+    # ---- latent layer --------------------------------------------------------------------
+    def _sentence_emb(self, input_ids, att_masks, token_type_ids):
+        return self.encoder(input_ids, attention_mask=att_masks, token_type_ids=token_type_ids).pooler_output
+
+    def _latents(self, sentence_emb):
+        """Fused path.  Returns (z [N, 2L], kl [2], pre [N, 4L])."""
+        L = self.opt.ec_dim
+        eps_e = torch.randn(L, device=sentence_emb.device)      # same two draws, same order as
+        eps_c = torch.randn(L, device=sentence_emb.device)      # sample_prior(emotion), sample_prior(cause)
+        return F.latent(sentence_emb, eps_e, eps_c,
+                        self.emotion_mu.weight, self.emotion_mu.bias,
+                        self.emotion_log_var.weight, self.emotion_log_var.bias,
+                        self.cause_mu.weight, self.cause_mu.bias,
+                        self.cause_log_var.weight, self.cause_log_var.bias)
+
+    def get_emotion_emb(self, sentence_emb):
+        return self.emotion_mu(sentence_emb), self.emotion_log_var(sentence_emb)
+
+    def get_cause_emb(self, sentence_emb):
+        return self.cause_mu(sentence_emb), self.cause_log_var(sentence_emb)
+
+    def sample_prior(self, mu, log_var):
+        """One epsilon vector of shape [L] shared by every row, scaled by exp(log_var) (:345-351)."""
+        epsilon = torch.randn(mu.size(1), device=mu.device)
+        return mu + epsilon * torch.exp(log_var)
+
+    def get_kl_loss(self, mu, log_var):
+        return torch.mean(-0.5 * torch.sum(1 + log_var - log_var.exp() - mu.pow(2), dim=1))
+
+    def get_annealed_weight(self, iteration, lambda_weight):
+        T = self.opt.kl_ann_iterations
+        return (math.tanh((iteration - T * 1.5) / (T / 3)) + 1) * lambda_weight
+
+    def get_reconstruct_loss(self, reconstruct_pred, content_bow):
+        """Reference signature (probabilities in): BCELoss against the smoothed target (:381-387).
+        forward() does not come through here — it uses the fused decoder+loss kernel."""
+        o = self.opt
+        target = content_bow * (1 - o.label_smoothing) + o.label_smoothing / o.pair_bow_dim
+        return TF.binary_cross_entropy(reconstruct_pred, target)
+
+    def _kl_terms(self, kl, iteration):
+        kl_e, kl_c = kl[0], kl[1]
+        if iteration < self.opt.kl_ann_iterations:
+            w = self.get_annealed_weight(iteration, self.opt.ec_kl_lambda)
+            kl_e, kl_c = w * kl_e, w * kl_c
+        return kl_e, kl_c
+
+    def _reconstruction(self, z, content_bow):
+        return F.bow_reconstruction_loss(z, self.decoder.weight, self.decoder.bias, content_bow,
+                                         self.opt.label_smoothing, ell_cap=self.bow_ell_cap)
+
+    # ---- small classifier heads (PyTorch) -------------------------------------------------
+    def get_emotion_mul_loss(self, emotion_emb, emotion_labels):
+        preds = torch.sigmoid(self.emotion_classifier(self.dropout(emotion_emb)))
+        o = self.opt
+        t = emotion_labels * (1 - o.label_smoothing) + o.label_smoothing / self._label_classes()
+        return TF.binary_cross_entropy(preds, t)
+
+    def get_cause_mul_loss(self, cause_emb, cause_labels):
+        preds = torch.sigmoid(self.cause_classifier(self.dropout(cause_emb)))
+        o = self.opt
+        t = cause_labels * (1 - o.label_smoothing) + o.label_smoothing / self._cause_label_classes()
+        return TF.binary_cross_entropy(preds, t)
+
+    def _cause_label_classes(self):
+        return self.opt.ec_num_class
+
+    def _pair_label_classes(self):
+        return self.opt.ec_num_class
+
+    def get_pair_mul_loss(self, pair_emb, pair_labels):
+        preds = self.pair_classifier(self.dropout(pair_emb))
+        o = self.opt
+        t = pair_labels * (1 - o.label_smoothing) + o.label_smoothing / self._pair_label_classes()
+        pos_weight = (len(pair_labels) - torch.sum(pair_labels)) / torch.sum(pair_labels)
+        return TF.binary_cross_entropy_with_logits(preds, t, pos_weight=pos_weight)
+
+    # ---- inference -----------------------------------------------------------------------
+    def get_pair_preds_tensor(self, input_ids, att_masks, token_type_ids):
+        """Device-side result of get_pair_preds (no host round trip): sigmoid(pair logits) [N, 1]."""
+        z, _, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
+        return torch.sigmoid(self.pair_classifier(z))
+
+    def get_pair_preds(self, input_ids, att_masks, token_type_ids):
+        """Reference return type: rounded python list (:265-282).  Still stochastic at eval."""
+        return self.get_pair_preds_tensor(input_ids, att_masks, token_type_ids).cpu().detach().numpy().round().tolist()
+
+    def _core_params(self):
+        return (list(self.encoder.parameters()) + list(self.decoder.parameters()) +
+                list(self.emotion_classifier.parameters()) + list(self.cause_classifier.parameters()) +
+                list(self.pair_classifier.parameters()))
+
+
+class DrlClassifierMMD(_DrlClassifierBase):
+    """drl_classifier_ec_mmd_final_mul.py (and its newsplit / emnlp siblings with --adapter false)."""
+    variant = "mmd"
+
+    def _emotion_classes(self, opt):
+        return opt.e_num_class
+
+    def _cause_classes(self, opt):
+        return opt.c_num_class
+
+    def _cause_label_classes(self):
+        return self.opt.c_num_class
+
+    def _pair_label_classes(self):
+        return self.opt.pair_num_class
+
+    def get_emotion_mul_loss(self, emotion_emb, emotion_labels):
+        preds = self.emotion_classifier(self.dropout(emotion_emb))          # 6-class CE (:461-476)
+        return TF.cross_entropy(preds, emotion_labels.flatten())
+
+    def get_pair_mul_loss(self, pair_emb, pair_labels):
+        loss = super().get_pair_mul_loss(pair_emb, pair_labels)
+        # reference :510-511 replaces an infinite loss by 0 after a host sync; same value, no sync
+        return torch.where(torch.isinf(loss), torch.zeros_like(loss), loss)
+
+    def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,
+                iteration):
+        o, L = self.opt, self.opt.ec_dim
+        z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
+        z_e, z_c = z[:, :L], z[:, L:]
+        emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
+        cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
+        mmd_loss = -MMDStatistic(input_ids.shape[0], input_ids.shape[0])(z_e, z_c, [0.1])
+        pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
+        kl_e, kl_c = self._kl_terms(kl, iteration)
+        reconstruction_loss = self._reconstruction(z, content_bow)
+        return (o.mmd_loss_weight * mmd_loss + o.emo_mul_loss_weight * emo_mul_loss +
+                o.cau_mul_loss_weight * cau_mul_loss + o.pair_mul_loss_weight * pair_mul_loss +
+                kl_e + kl_c + reconstruction_loss)
+
+    def get_params(self):
+        """The four latent projections are NOT handed to the optimiser, as in the reference (:284-297)."""
+        return self._core_params()
+
+
+class DrlClassifierHSIC(_DrlClassifierBase):
+    """drl_classifier_ec_hsic.py."""
+    variant = "hsic"
+
+    def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,
+                iteration):
+        o, L = self.opt, self.opt.ec_dim
+        z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
+        z_e, z_c = z[:, :L], z[:, L:]
+        emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
+        cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
+        hsic_loss = HSIC(z_e, z_c)
+        pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
+        kl_e, kl_c = self._kl_terms(kl, iteration)
+        reconstruction_loss = self._reconstruction(z, content_bow)
+        return (hsic_loss + o.ec_mul_loss_weight * (emo_mul_loss + cau_mul_loss) +
+                o.pair_mul_loss_weight * pair_mul_loss + kl_e + kl_c + reconstruction_loss)
+
+    def get_params(self):
+        return self._core_params()
+
+
+class DrlClassifierVI(_DrlClassifierBase):
+    """drl_classifier_ec_vi_final.py / drl_classifier_ec_vi.py: KL + CLUB upper bound."""
+    variant = "vi"
+
+    def _build_variant_modules(self, opt):
+        L = opt.ec_dim
+        self.ec_mu = nn.Sequential(nn.Linear(L, L), nn.ReLU(), nn.Linear(L, L))
+        self.ec_log_var = nn.Sequential(nn.Linear(L, L), nn.ReLU(), nn.Linear(L, L), nn.Tanh())
+
+    def _emotion_classes(self, opt):
+        return 6
+
+    def get_emotion_mul_loss(self, emotion_emb, emotion_labels):
+        preds = self.emotion_classifier(self.dropout(emotion_emb))
+        return TF.cross_entropy(preds, emotion_labels.flatten())
+
+    def get_ec_emb(self, cause_emb):
+        return self.ec_mu(cause_emb), self.ec_log_var(cause_emb)
+
+    def get_ec_aprx_loss(self, e_embedding, c_embedding):
+        ec_mu, ec_log_var = self.get_ec_emb(c_embedding.detach())
+        return -((-(ec_mu - e_embedding) ** 2 / ec_log_var.exp() - ec_log_var).sum(dim=1).mean(dim=0))
+
+    def get_ec_upper_loss(self, e_embedding, c_embedding):
+        ec_mu, ec_log_var = self.get_ec_emb(c_embedding)
+        random_index = torch.randperm(e_embedding.shape[0]).long()          # CPU generator, as the reference
+        positive = -(ec_mu - e_embedding) ** 2 / ec_log_var.exp()
+        negative = -(ec_mu - e_embedding[random_index.to(e_embedding.device)]) ** 2 / ec_log_var.exp()
+        return (positive.sum(dim=-1) - negative.sum(dim=-1)).mean() / 2.0
+
+    def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,
+                iteration):
+        o, L = self.opt, self.opt.ec_dim
+        z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
+        z_e, z_c = z[:, :L], z[:, L:]
+        emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
+        cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
+        ec_aprx_loss = self.get_ec_aprx_loss(z_e, z_c)
+        pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
+        kl_e, kl_c = self._kl_terms(kl, iteration)
+        reconstruction_loss = self._reconstruction(z, content_bow)
+        loss = (o.ec_mul_loss_weight * (emo_mul_loss + cau_mul_loss) + o.pair_mul_loss_weight * pair_mul_loss +
+                kl_e + kl_c + reconstruction_loss)
+        return z_e, z_c, ec_aprx_loss, loss
+
+    def get_params(self):
+        ec_aprx_params = list(self.ec_mu.parameters()) + list(self.ec_log_var.parameters())
+        return ec_aprx_params, self._core_params()
+
+
+class DrlClassifierGAN(_DrlClassifierBase):
+    """drl_classifier_ec_gan.py: adversarial discriminators on the detached latents + entropy terms."""
+    variant = "gan"
+
+    def _build_variant_modules(self, opt):
+        self.ec_disc = nn.Linear(opt.ec_dim, opt.ec_num_class)
+        self.ce_disc = nn.Linear(opt.ec_dim, opt.ec_num_class)
+
+    def get_ec_disc_preds(self, cause_emb):
+        return torch.sigmoid(self.ec_disc(self.dropout(cause_emb.detach())))
+
+    def get_ce_disc_preds(self, emotion_emb):
+        return torch.sigmoid(self.ce_disc(self.dropout(emotion_emb.detach())))
+
+    def get_ec_disc_loss(self, ec_disc_preds, ec_labels):
+        o = self.opt
+        t = ec_labels * (1 - o.label_smoothing) + o.label_smoothing / o.ec_num_class
+        return TF.binary_cross_entropy(ec_disc_preds, t)
+
+    def get_entropy_loss(self, preds):
+        return torch.mean(torch.sum(preds * torch.log(preds + self.opt.epsilon), dim=1))
+
+    def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,
+                iteration):
+        o, L = self.opt, self.opt.ec_dim
+        z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
+        z_e, z_c = z[:, :L], z[:, L:]
+        ec_disc_preds = self.get_ec_disc_preds(z_c)
+        ec_disc_loss = self.get_ec_disc_loss(ec_disc_preds, emotion_labels)
+        ec_entropy_loss = self.get_entropy_loss(ec_disc_preds)
+        emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
+        ce_disc_preds = self.get_ce_disc_preds(z_e)
+        ce_disc_loss = self.get_ec_disc_loss(ce_disc_preds, cause_labels)
+        ce_entropy_loss = self.get_entropy_loss(ce_disc_preds)
+        cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
+        pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
+        kl_e, kl_c = self._kl_terms(kl, iteration)
+        reconstruction_loss = self._reconstruction(z, content_bow)
+        loss = (o.ecce_adv_loss_weight * (ec_entropy_loss + ce_entropy_loss) +
+                o.ec_mul_loss_weight * (emo_mul_loss + cau_mul_loss) + o.pair_mul_loss_weight * pair_mul_loss +
+                kl_e + kl_c + reconstruction_loss)
+        return ec_disc_loss, ce_disc_loss, loss
+
+    def get_params(self):
+        return self.ec_disc.parameters(), self.ce_disc.parameters(), self._core_params()
+
+
+VARIANTS = {"mmd": DrlClassifierMMD, "hsic": DrlClassifierHSIC, "vi": DrlClassifierVI, "gan": DrlClassifierGAN}
+
+#: the canonical trainer's class under the reference's own name
+DrlClassifier = DrlClassifierMMD
+
+
+def default_opt(variant: str = "mmd", **kw) -> SimpleNamespace:
+    """argparse defaults of the reference trainers (mmd:30-58, hsic:30-57, vi_final:30-56, gan:30-57)."""
+    o = SimpleNamespace(bert_dim=768, ec_dim=24, pair_bow_dim=23771, kl_ann_iterations=20000, ec_kl_lambda=0.03,
+                        label_smoothing=0.1, dropout=0.5, epsilon=1e-8, pair_num_class=1, language="en")
+    if variant == "mmd":
+        o.e_num_class, o.c_num_class = 6, 1
+        o.mmd_loss_weight, o.emo_mul_loss_weight, o.cau_mul_loss_weight, o.pair_mul_loss_weight = 30, 10, 10, 30
+    else:
+        o.ec_num_class, o.ec_mul_loss_weight = 1, 10
+        o.pair_mul_loss_weight = 30 if variant == "vi" else 25
+        o.ecce_adv_loss_weight = 1 if variant == "gan" else 3
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o

@@ -117,6 +117,20 @@ int carel_bow_bwd(const float* grad_out, const float* bow_dense, int64_t ld_bow,
                   int64_t V, int64_t ell_cap, float label_smoothing, float* grad_z, int64_t ldgz,
                   float* grad_w, float* grad_b, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * HSIC — replaces HSIC / GaussianKernelMatrix / pairwise_distances (drl_classifier_ec_hsic.py:529-547):
+ *   trace(L H K H) / (m-1)^2 with K = exp(-d2_x / s_x), L = exp(-d2_y / s_y), evaluated in O(m^2)
+ *   (no centring matmuls).  out: device scalar.  The workspace of the forward call carries the row
+ *   sums the backward call needs.
+ * ------------------------------------------------------------------------------------------ */
+size_t carel_hsic_workspace_bytes(int64_t m, int64_t dx, int64_t dy);
+int carel_hsic_fwd(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t m, int64_t dx,
+                   int64_t dy, float s_x, float s_y, float* out, void* ws, size_t ws_bytes,
+                   void* stream);
+int carel_hsic_bwd(const float* grad_out, int64_t m, int64_t dx, int64_t dy, float s_x, float s_y,
+                   float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy, void* ws,
+                   size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

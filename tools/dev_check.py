@@ -178,6 +178,25 @@ def check_bow():
               f"gZ {rel(Z.grad, Zd.grad):.2e} gW {rel(W.grad, Wd.grad):.2e} gb {rel(b.grad, bd.grad):.2e}")
 
 
+def check_hsic():
+    for (m, d, sx, sy) in [(64, 24, 30.0, 30.0), (200, 64, 100.0, 150.0), (1024, 128, 300.0, 300.0), (500, 128, 1.0, 1.0),
+                           (4096, 128, 300.0, 300.0)]:
+        x = bf(torch.randn(m, d, device=dev) * 1.1).requires_grad_(True)
+        y = bf(0.5 * x.detach() + torch.randn(m, d, device=dev)).requires_grad_(True)
+        out = F.hsic(x, y, sx, sy)
+        gx, gy = torch.autograd.grad(out, (x, y))
+        xd, yd = x.detach().double().requires_grad_(True), y.detach().double().requires_grad_(True)
+
+        def gram(t, s):
+            n = (t * t).sum(1, keepdim=True)
+            return torch.exp(-(n + n.T - 2 * t @ t.T) / s)
+        K, L = gram(xd, sx), gram(yd, sy)
+        ref = ((K * L).sum() - 2.0 / m * (K.sum(1) * L.sum(1)).sum() + K.sum() * L.sum() / m ** 2) / (m - 1) ** 2
+        rgx, rgy = torch.autograd.grad(ref, (xd, yd))
+        print(f"hsic m={m} d={d} s=({sx},{sy}): val {out.item():.6e} ref {ref.item():.6e} rel {abs(out.item() - ref.item()) / abs(ref.item()):.2e} | "
+              f"gx {rel(gx, rgx):.2e} gy {rel(gy, rgy):.2e} (|g| {rgx.norm().item():.2e})")
+
+
 def bench_head_parts():
     N, D, L, V = 8192, 768, 128, 30000
     X = torch.tanh(torch.randn(N, D, device=dev)).requires_grad_(True)
@@ -217,6 +236,8 @@ if __name__ == "__main__":
         check_latent()
     if "bow" in what:
         check_bow()
+    if "hsic" in what:
+        check_hsic()
     if "bench" in what:
         bench_mmd()
     if "bench2" in what:
