@@ -131,14 +131,21 @@ class _DrlClassifierBase(nn.Module):
                                          self.opt.label_smoothing, ell_cap=self.bow_ell_cap)
 
     # ---- small classifier heads (PyTorch) -------------------------------------------------
+    def _drop(self, x):
+        """nn.Dropout on a CONTIGUOUS tensor: the mask torch draws depends on the memory layout, and the
+        reference's dropout inputs are contiguous (z_e / z_c are column views of one buffer here)."""
+        if self.training and self.dropout.p > 0:
+            return self.dropout(x.contiguous())
+        return x
+
     def get_emotion_mul_loss(self, emotion_emb, emotion_labels):
-        preds = torch.sigmoid(self.emotion_classifier(self.dropout(emotion_emb)))
+        preds = torch.sigmoid(self.emotion_classifier(self._drop(emotion_emb)))
         o = self.opt
         t = emotion_labels * (1 - o.label_smoothing) + o.label_smoothing / self._label_classes()
         return TF.binary_cross_entropy(preds, t)
 
     def get_cause_mul_loss(self, cause_emb, cause_labels):
-        preds = torch.sigmoid(self.cause_classifier(self.dropout(cause_emb)))
+        preds = torch.sigmoid(self.cause_classifier(self._drop(cause_emb)))
         o = self.opt
         t = cause_labels * (1 - o.label_smoothing) + o.label_smoothing / self._cause_label_classes()
         return TF.binary_cross_entropy(preds, t)
@@ -150,7 +157,7 @@ class _DrlClassifierBase(nn.Module):
         return self.opt.ec_num_class
 
     def get_pair_mul_loss(self, pair_emb, pair_labels):
-        preds = self.pair_classifier(self.dropout(pair_emb))
+        preds = self.pair_classifier(self._drop(pair_emb))
         o = self.opt
         t = pair_labels * (1 - o.label_smoothing) + o.label_smoothing / self._pair_label_classes()
         pos_weight = (len(pair_labels) - torch.sum(pair_labels)) / torch.sum(pair_labels)
@@ -189,7 +196,7 @@ class DrlClassifierMMD(_DrlClassifierBase):
         return self.opt.pair_num_class
 
     def get_emotion_mul_loss(self, emotion_emb, emotion_labels):
-        preds = self.emotion_classifier(self.dropout(emotion_emb))          # 6-class CE (:461-476)
+        preds = self.emotion_classifier(self._drop(emotion_emb))          # 6-class CE (:461-476)
         return TF.cross_entropy(preds, emotion_labels.flatten())
 
     def get_pair_mul_loss(self, pair_emb, pair_labels):
@@ -252,7 +259,7 @@ class DrlClassifierVI(_DrlClassifierBase):
         return 6
 
     def get_emotion_mul_loss(self, emotion_emb, emotion_labels):
-        preds = self.emotion_classifier(self.dropout(emotion_emb))
+        preds = self.emotion_classifier(self._drop(emotion_emb))
         return TF.cross_entropy(preds, emotion_labels.flatten())
 
     def get_ec_emb(self, cause_emb):
@@ -298,10 +305,10 @@ class DrlClassifierGAN(_DrlClassifierBase):
         self.ce_disc = nn.Linear(opt.ec_dim, opt.ec_num_class)
 
     def get_ec_disc_preds(self, cause_emb):
-        return torch.sigmoid(self.ec_disc(self.dropout(cause_emb.detach())))
+        return torch.sigmoid(self.ec_disc(self._drop(cause_emb.detach())))
 
     def get_ce_disc_preds(self, emotion_emb):
-        return torch.sigmoid(self.ce_disc(self.dropout(emotion_emb.detach())))
+        return torch.sigmoid(self.ce_disc(self._drop(emotion_emb.detach())))
 
     def get_ec_disc_loss(self, ec_disc_preds, ec_labels):
         o = self.opt

@@ -1,0 +1,165 @@
+"""GPU (-m gpu): the drop-in DrlClassifier variants against the oracle restatement of the reference
+forward (oracle/head_oracle.py, itself pinned to the reference by tests/test_oracle_golden.py).
+
+Protocol ("bf16 mode"): parameters and clause embeddings are rounded to bf16 once and handed to both
+sides; the oracle then runs in fp64.  Same device RNG stream on both sides, so eps_e, eps_c and the
+dropout masks are identical (RNG consumption order is part of the drop-in contract).
+"""
+import pytest
+import torch
+
+from oracle import head_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import carel_vae_b200 as cv
+DEV = "cuda"
+
+
+def bf(x):
+    return x.bfloat16().float()
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+
+def _setup(variant, N, L, V, D, dropout, seed):
+    opt = cv.default_opt(variant, ec_dim=L, pair_bow_dim=V, bert_dim=D, dropout=dropout)
+    torch.manual_seed(1234 + seed)
+    model = cv.VARIANTS[variant](opt, encoder=cv.IdentityEncoder()).to(DEV)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(bf(p))
+    b = ho.synthetic_batch(N, V, D=D, seed=seed, device=DEV, emotion_float=variant in ("hsic", "gan"))
+    b["X"] = bf(b["X"])
+    return opt, model, b
+
+
+def _total(variant, out):
+    outs = out if isinstance(out, tuple) else (out,)
+    if variant == "vi":
+        return outs, outs[2] + outs[3]
+    if variant == "gan":
+        return outs, outs[0] + outs[1] + outs[2]
+    return outs, outs[0]
+
+
+@pytest.mark.parametrize("variant", ["mmd", "hsic", "vi", "gan"])
+@pytest.mark.parametrize("N,L,V,D,dropout", [(64, 64, 3000, 768, 0.0), (96, 24, 1001, 768, 0.5), (512, 128, 5000, 768, 0.0)])
+def test_forward_backward_matches_oracle(variant, N, L, V, D, dropout):
+    opt, model, b = _setup(variant, N, L, V, D, dropout, seed=N)
+    model.train()
+    X = b["X"].clone().requires_grad_(True)
+    emo = b["emo"] if variant in ("mmd", "vi") else b["emo"].float()
+    torch.manual_seed(99)
+    out = model(X, None, None, emo, b["cau"], b["pair"], b["bow"], 3)
+    outs, total = _total(variant, out)
+    params = dict(model.named_parameters())
+    grads = torch.autograd.grad(total, [X] + list(params.values()), allow_unused=True)
+
+    # oracle on the same RNG stream.  fp64 when dropout is off; with dropout the masks only coincide if
+    # the dropout inputs have the product's dtype (fp32), so the oracle then runs in fp32 like the reference.
+    dt = torch.float64 if dropout == 0.0 else torch.float32
+    p64 = {k: v.detach().to(dt).requires_grad_(True) for k, v in params.items()}
+    X64 = b["X"].to(dt).requires_grad_(True)
+    torch.manual_seed(99)
+    emo64 = emo if emo.dtype == torch.int64 else emo.to(dt)
+    oref = ho.HeadOracle(opt, variant).forward(p64, X64, emo64, b["cau"].to(dt), b["pair"].to(dt), b["bow"].to(dt), 3)
+    orefs, rtotal = _total(variant, oref)
+    rgrads = torch.autograd.grad(rtotal, [X64] + list(p64.values()), allow_unused=True)
+
+    for o, r in zip(outs, orefs):
+        assert rel(o.detach(), r.detach()) < 1e-3, (variant, "output")
+    # the fp32 oracle (dropout case) carries its own ~1e-3 noise on the Gram-loss gradient
+    gtol = 2e-3 if dropout == 0.0 else 4e-3
+    assert rel(grads[0], rgrads[0]) < gtol, (variant, "grad X", rel(grads[0], rgrads[0]))
+    for (k, g), r in zip(zip(params.keys(), grads[1:]), rgrads[1:]):
+        if r is None:
+            assert g is None or float(g.abs().max()) == 0.0
+            continue
+        assert rel(g, r) < gtol, (variant, k, rel(g, r))
+
+
+@pytest.mark.parametrize("variant", ["mmd", "hsic", "vi", "gan"])
+def test_golden_reference_head(golden_dir, variant):
+    """The reference's own outputs (fp32, parameters not bf16-representable): bf16 operand rounding is
+    the whole error budget here."""
+    for c in [c for c in torch.load(golden_dir / "head.pt") if c["variant"] == variant]:
+        opt = cv.default_opt(variant, ec_dim=c["L"], pair_bow_dim=c["V"], bert_dim=c["D"], dropout=c["dropout"])
+        model = cv.VARIANTS[variant](opt, encoder=cv.IdentityEncoder())
+        model.load_state_dict(c["state"])          # reference checkpoint loads unchanged
+        model = model.to(DEV).train()
+        if c["dropout"] > 0:
+            continue                               # CPU and CUDA generators differ: masks not comparable
+        b = ho.synthetic_batch(c["N"], c["V"], D=c["D"], seed=c["seed"], device=DEV,
+                               emotion_float=variant in ("hsic", "gan"))
+        emo = b["emo"] if variant in ("mmd", "vi") else b["emo"].float()
+        # inject the reference's CPU-generated noise: seed 77+seed, two randn(L) draws
+        torch.manual_seed(77 + c["seed"])
+        eps = [torch.randn(c["L"]), torch.randn(c["L"])]
+        it = iter(eps)
+        orig = torch.randn
+        try:
+            torch.randn = lambda *a, **k: next(it).to(DEV)
+            out = model(b["X"], None, None, emo, b["cau"], b["pair"], b["bow"], c["iteration"])
+        finally:
+            torch.randn = orig
+        outs = out if isinstance(out, tuple) else (out,)
+        for o, r in zip(outs, c["outputs"]):
+            assert rel(o.detach().cpu(), r) < 1e-2, (variant, float(o.flatten()[0]), float(r.flatten()[0]))
+
+
+def test_vi_upper_loss_and_two_optimisers():
+    """vi_final train loop (:766-781): aprx step, then get_ec_upper_loss with the updated net."""
+    opt, model, b = _setup("vi", 128, 24, 1000, 768, 0.0, seed=3)
+    aprx_params, core_params = model.get_params()
+    o1 = torch.optim.Adam(aprx_params, lr=3e-3)
+    o2 = torch.optim.Adam(core_params, lr=1e-5)
+    z_e, z_c, aprx, loss = model(b["X"], None, None, b["emo"], b["cau"], b["pair"], b["bow"], 0)
+    o1.zero_grad()
+    aprx.backward(retain_graph=True)
+    o1.step()
+    torch.manual_seed(0)
+    rj = model.get_ec_upper_loss(z_e, z_c)
+    loss = loss + 0.5 * rj
+    o2.zero_grad()
+    loss.backward()
+    o2.step()
+    assert torch.isfinite(loss) and torch.isfinite(rj)
+
+
+def test_get_pair_preds_and_inference_tensor():
+    opt, model, b = _setup("mmd", 200, 24, 1000, 768, 0.5, seed=4)
+    model.eval()
+    torch.manual_seed(11)
+    preds = model.get_pair_preds(b["X"], None, None)
+    torch.manual_seed(11)
+    t = model.get_pair_preds_tensor(b["X"], None, None)
+    assert isinstance(preds, list) and len(preds) == 200 and len(preds[0]) == 1
+    assert preds == t.detach().cpu().numpy().round().tolist()
+    p = {k: v.detach() for k, v in model.named_parameters()}
+    torch.manual_seed(11)
+    ref = ho.HeadOracle(opt, "mmd").pair_preds(p, b["X"])
+    assert (t.detach() - ref).abs().max().item() < 2e-3
+
+
+def test_train_steps_reduce_loss():
+    """A few Adam steps over get_params() (the reference's optimiser set) run under anomaly detection
+    (mmd:837) and move the loss."""
+    opt, model, b = _setup("mmd", 256, 64, 2000, 768, 0.0, seed=5)
+    optim = torch.optim.Adam(model.get_params(), lr=1e-3)
+    losses = []
+    for it in range(5):
+        torch.manual_seed(1)
+        with torch.autograd.set_detect_anomaly(True):
+            loss = model(b["X"], None, None, b["emo"], b["cau"], b["pair"], b["bow"], it)
+            optim.zero_grad()
+            loss.backward()
+            optim.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    assert all(p.grad is not None for p in model.emotion_mu.parameters())   # projections receive gradients ...
+    assert not any(p is q for p in model.get_params() for q in model.emotion_mu.parameters())  # ... but are not stepped
