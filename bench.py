@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline workload on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): MMD-VAE head train step — latent projections + reparam + KL,
+-MMD, classifier heads, BoW decoder + softmax-BCE over V = 30000 — on N = 8192 synthetic 768-d clause
+embeddings, latent 128, bf16 tensor-core operands / fp32 accumulation, Adam over model.get_params().
+One "step" = forward + backward + optimiser step on one such batch.  At --gpus N every rank runs its
+own 8192-clause batch (weak scaling) with ONE flat NCCL all-reduce of the optimiser's gradients.
+
+Printed JSON (rank 0, one line): value = aggregate 8192-clause steps/s with inputs resident in HBM;
+e2e = the same through the drop-in call with HOST buffers (pinned H2D of X, labels and the dense
+[N, V] fp32 BoW target the reference layout prescribes, D2H of the loss) inside the timed region;
+roofline = the MMD Gram kernel at N = 8192, d = 768 (the kernel BASELINE.json's metric names) against
+the measured bf16 peak; cpu_baseline = the oracle port of the reference step on the host cores.
+`--impl reference` times that CPU implementation alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_ROWS, D_EMB, LATENT, VOCAB, NNZ = 8192, 768, 128, 30000, 24
+STEP_FLOPS = 3 * (2 * N_ROWS * D_EMB * 4 * LATENT + 2 * (2 * N_ROWS) ** 2 * LATENT + 2 * N_ROWS * 2 * LATENT * VOCAB)
+GRAM_FLOPS = 2 * (2 * N_ROWS) ** 2 * D_EMB          # full Gram, no symmetry credit
+METRIC = "vae_head_train_steps_per_s"
+UNIT = "8192-clause steps/s"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], hbm_gbs=d["hbm_gbs"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def synthetic_batch(device, seed=0):
+    """SURVEY.md §8(d) canonical inputs (host tensors)."""
+    g = torch.Generator().manual_seed(seed)
+    X = torch.tanh(torch.randn(N_ROWS, D_EMB, generator=g))
+    emo = torch.randint(0, 6, (N_ROWS, 1), generator=g)
+    pair = (torch.rand(N_ROWS, 1, generator=g) < 0.5).float()
+    idx = torch.randint(0, VOCAB, (N_ROWS, NNZ), generator=g)
+    bow = torch.zeros(N_ROWS, VOCAB)
+    bow.scatter_add_(1, idx, torch.ones(N_ROWS, NNZ))
+    bow = bow / bow.sum(1, keepdim=True).clamp_min(1.0)
+    return dict(X=X, emo=emo, cau=pair.clone(), pair=pair, bow=bow)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import carel_vae_b200 as cv
+    from carel_vae_b200 import _lib, functional as F
+    from carel_vae_b200.parallel import FlatGradBucket
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    opt = cv.default_opt("mmd", ec_dim=LATENT, pair_bow_dim=VOCAB, bert_dim=D_EMB, dropout=0.5)
+    torch.manual_seed(1234)
+    model = cv.DrlClassifierMMD(opt, encoder=cv.IdentityEncoder()).to(dev).train()
+    host = synthetic_batch(dev, seed=rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    static = {k: v.to(dev) for k, v in host.items()}            # device-resident inputs (value) / H2D targets (e2e)
+    params = model.get_params()
+    bucket = FlatGradBucket(params)
+    # the four latent projections receive gradients but are not stepped (reference get_params, mmd:292-297)
+    optim = torch.optim.Adam(params, lr=1e-5, capturable=True)
+    loss_buf = torch.zeros((), device=dev)
+    it_counter = [0]
+
+    def step():
+        bucket.zero_()
+        for p in model.parameters():
+            if p.grad is not None and not any(p is q for q in params):
+                p.grad = None
+        loss = model(static["X"], None, None, static["emo"], static["cau"], static["pair"], static["bow"], it_counter[0])
+        loss.backward()
+        bucket.allreduce_mean()
+        optim.step()
+        loss_buf.copy_(loss.detach())
+
+    torch.manual_seed(7 + rank)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- CUDA graph of the whole step (streams + graphs instead of a tracing compiler) ----
+    graph, use_graph = None, not args.no_graph
+    if use_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture failed, running eagerly: {repr(e)[:300]}", file=sys.stderr)
+            graph, use_graph = None, False
+            torch.cuda.synchronize()
+    run_step = graph.replay if graph is not None else step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(max(args.warmup, 3)):
+        run_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    total_ms = timed(run_step, args.steps)
+    launches_eager = None
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * 1e3 / ms_per_step
+
+    # ---- e2e: host buffers -> H2D -> step -> D2H loss ----
+    loss_host = torch.zeros((), pin_memory=True)
+
+    def e2e_step():
+        for k in ("X", "emo", "cau", "pair", "bow"):
+            static[k].copy_(pinned[k], non_blocking=True)
+        run_step()
+        loss_host.copy_(loss_buf, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in pinned)
+
+    # ---- launches per step + per-kernel breakdown (eager pass, events inside the library) ----
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    step()
+    torch.cuda.synchronize()
+    launches_eager = _lib.launch_count() - l0
+    kernels = {}
+    if rank == 0:
+        _lib.timing_enable(True)
+        for _ in range(3):
+            step()
+        rep = _lib.timing_report()
+        _lib.timing_enable(False)
+        kernels = {k: round(v[0] / v[1] * 1e3, 1) for k, v in rep.items()}       # us per launch
+
+    # ---- roofline: the MMD Gram kernel at N = 8192, d = 768 (BASELINE metric point) ----
+    roof, gram = None, None
+    if rank == 0:
+        pk = peaks()
+        g = torch.Generator().manual_seed(0)
+        xs = torch.tanh(torch.randn(N_ROWS, D_EMB, generator=g)).to(dev)
+        ys = torch.tanh(torch.randn(N_ROWS, D_EMB, generator=g)).to(dev)
+        xs, ys = xs / xs.norm(dim=1, keepdim=True), ys / ys.norm(dim=1, keepdim=True)
+        res = {}
+        for name, full in (("triangular", False), ("full_gram", True)):
+            for _ in range(5):
+                F.mmd(xs, ys, [0.1], full_gram=full)
+            _lib.timing_enable(True)
+            for _ in range(20):
+                F.mmd(xs, ys, [0.1], full_gram=full)
+            rep = _lib.timing_report()
+            _lib.timing_enable(False)
+            ms = rep["mmd_gram_fwd"][0] / rep["mmd_gram_fwd"][1]
+            res[name] = ms
+        achieved = GRAM_FLOPS / (res["triangular"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiMMD> (MMD Gram forward, N=8192, d=768, j>i schedule)",
+                "achieved": round(achieved, 1), "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                "frac": round(achieved / pk["bf16_burst"], 3), "traffic": None, "peak_source": pk["source"],
+                "note": "algorithmic FLOPs = 2*(2N)^2*d (full Gram, SURVEY §8d); the kernel executes the j>i half, "
+                        "so executed-FLOP tensor utilisation is ~half of frac; full_gram variant below executes all of it",
+                "full_gram_tflops": round(GRAM_FLOPS / (res["full_gram"] * 1e-3) / 1e12, 1),
+                "full_gram_frac": round(GRAM_FLOPS / (res["full_gram"] * 1e-3) / 1e12 / pk["bf16_burst"], 3),
+                "us_per_launch": {k: round(v * 1e3, 1) for k, v in res.items()}}
+        gram = {"metric": "mmd_gram_tflops_n8192_d768", "value": round(achieved, 1), "unit": "TFLOP/s (algorithmic)"}
+        step_tflops = STEP_FLOPS / (ms_per_step * 1e-3) / 1e12
+        roof_step = {"bound": "tensor", "achieved": round(step_tflops, 1), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": round(step_tflops / pk["bf16_sustained"], 3),
+                     "note": "whole step, algorithmic 6.03e11 FLOP / step time vs sustained bf16 peak"}
+
+    # ---- cpu baseline (rank 0, N = 1 only): the oracle port of the reference step on the host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference(max_steps=2, budget_s=40.0)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": "drl_classifier_ec_mmd_final_mul MMD-VAE head + BoW reconstruction, "
+                                      "N=8192 clauses/GPU, d=768, latent=128, vocab=30000, Adam(get_params)",
+                          "global_batch": N_ROWS * world, "parallelism": f"dp{world}", "cuda_graph": use_graph,
+                          "l2": "inputs larger than L2 (dense BoW target 983 MB/step is re-read every step)"},
+               "clocks": clocks,
+               "e2e": {"value": round(world * 1e3 / e2e_ms, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3),
+                       "note": "dense fp32 [N,V] BoW target copied from pinned host memory every step (reference layout)"},
+               "gpu_launches": int(launches_eager) * args.steps, "gpu_launches_per_step": int(launches_eager),
+               "roofline": roof, "roofline_step": roof_step, "gram": gram, "kernels_us": kernels,
+               "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference head on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(max_steps: int, budget_s: float, warmup: int = 1):
+    from oracle import head_oracle as ho
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    opt = ho.default_opt("mmd", ec_dim=LATENT, pair_bow_dim=VOCAB, bert_dim=D_EMB, dropout=0.5)
+    params = {k: v.requires_grad_(True) for k, v in ho.init_state(opt, "mmd", seed=1234).items()}
+    stepped = [v for k, v in params.items() if not any(k.startswith(p) for p in
+               ("emotion_mu", "emotion_log_var", "cause_mu", "cause_log_var"))]
+    optim = torch.optim.Adam(stepped, lr=1e-5)
+    b = synthetic_batch("cpu", seed=0)
+    oracle = ho.HeadOracle(opt, "mmd")
+
+    def step(it):
+        loss = oracle.forward(params, b["X"], b["emo"], b["cau"], b["pair"], b["bow"], it)
+        optim.zero_grad()
+        for v in params.values():
+            v.grad = None
+        loss.backward()
+        optim.step()
+        return float(loss)
+
+    torch.manual_seed(7)
+    t_all = time.perf_counter()
+    times = []
+    for i in range(warmup + max_steps):
+        t0 = time.perf_counter()
+        step(i)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_all > budget_s and times:
+            break
+    best = min(times)
+    return {"value": round(1.0 / best, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} full 8192-clause train steps (best of) after {warmup} warm-up; fp32, Adam(get_params), "
+                      f"oracle/head_oracle.py restatement of drl_classifier_ec_mmd_final_mul.py",
+            "s_per_step": round(best, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    cpu = cpu_reference(max_steps=max(1, min(args.steps, 8)), budget_s=150.0, warmup=min(max(args.warmup, 1), 2))
+    out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / cpu["value"], 2),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "drl_classifier_ec_mmd_final_mul MMD-VAE head + BoW reconstruction, N=8192 clauses, "
+                                  "d=768, latent=128, vocab=30000, Adam(get_params) — CPU, host cores"},
+           "cpu_baseline": cpu,
+           "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,8 @@ _SIGNATURES = {
     "carel_version": (C.c_int, []),
     "carel_last_error": (C.c_char_p, []),
     "carel_launch_count": (i64, []),
+    "carel_timing_enable": (None, [C.c_int]),
+    "carel_timing_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "carel_gemm_bf16": (C.c_int, [c_ptr, i64, C.c_int, c_ptr, i64, C.c_int, i64, i64, i64, c_ptr, i64,
                                   c_ptr, C.c_int, c_ptr]),
     "carel_mmd_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
@@ -96,3 +98,18 @@ def float_array(values):
 
 def launch_count() -> int:
     return int(lib().carel_launch_count())
+
+
+def timing_enable(on: bool) -> None:
+    lib().carel_timing_enable(1 if on else 0)
+
+
+def timing_report() -> dict:
+    """{tag: (total_ms, launches)} of the tensor-core kernels launched since timing was enabled."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().carel_timing_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        tag, ms, cnt = line.split()
+        out[tag] = (float(ms), int(cnt))
+    return out

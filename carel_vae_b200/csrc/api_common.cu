@@ -1,4 +1,8 @@
 // api_common.cu — error string, version, launch counter, debug GEMM and dense pairwise entry points.
+#include <map>
+#include <string>
+#include <vector>
+
 #include "api_common.cuh"
 #include "epilogues.cuh"
 #include "gemm_launch.cuh"
@@ -25,9 +29,64 @@ int sm_count() {
   return n;
 }
 
+namespace {
+struct TimingEntry {
+  const char* tag;
+  cudaEvent_t e0, e1;
+};
+bool g_timing = false;
+std::vector<TimingEntry> g_entries;
+}  // namespace
+bool timing_enabled() { return g_timing; }
+void timing_begin(const char* tag, cudaStream_t st) {
+  if (!g_timing) return;
+  TimingEntry e;
+  e.tag = tag;
+  cudaEventCreate(&e.e0);
+  cudaEventCreate(&e.e1);
+  cudaEventRecord(e.e0, st);
+  g_entries.push_back(e);
+}
+void timing_end(cudaStream_t st) {
+  if (!g_timing || g_entries.empty()) return;
+  cudaEventRecord(g_entries.back().e1, st);
+}
+
 }  // namespace carel
 
 using namespace carel;
+
+extern "C" void carel_timing_enable(int on) {
+  g_timing = on != 0;
+  if (!g_timing) {
+    for (auto& e : g_entries) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+    g_entries.clear();
+  }
+}
+// Writes "tag total_ms count\n" lines (one per kernel tag, in first-launch order) and clears the log.
+extern "C" int carel_timing_report(char* buf, size_t n) {
+  cudaDeviceSynchronize();
+  std::vector<const char*> order;
+  std::map<std::string, std::pair<double, int>> agg;
+  for (auto& e : g_entries) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.e0, e.e1) != cudaSuccess) ms = 0.f;
+    auto it = agg.find(e.tag);
+    if (it == agg.end()) { agg[e.tag] = {ms, 1}; order.push_back(e.tag); }
+    else { it->second.first += ms; it->second.second += 1; }
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+  g_entries.clear();
+  size_t off = 0;
+  if (n > 0) buf[0] = 0;
+  for (const char* t : order) {
+    const int w = snprintf(buf + off, off < n ? n - off : 0, "%s %.6f %d\n", t, agg[t].first, agg[t].second);
+    if (w < 0 || off + size_t(w) >= n) break;
+    off += size_t(w);
+  }
+  return int(off);
+}
 
 extern "C" int carel_version(void) { return CAREL_VERSION; }
 extern "C" const char* carel_last_error(void) { return error_buffer(); }

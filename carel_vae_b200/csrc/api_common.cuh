@@ -37,6 +37,13 @@ inline int set_error(const char* fmt, ...) {
     if (!(cond)) return set_error(__VA_ARGS__);   \
   } while (0)
 
+// Optional per-kernel timing (eager profiling passes only — never enable under graph capture):
+// when enabled, the launch helpers bracket each tensor-core kernel with CUDA events on the launch
+// stream; carel_timing_report() synchronises and sums them per tag.
+bool timing_enabled();
+void timing_begin(const char* tag, cudaStream_t st);
+void timing_end(cudaStream_t st);
+
 // count + check a kernel launch
 #define CAREL_LAUNCHED()                               \
   do {                                                 \

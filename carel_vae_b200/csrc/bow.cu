@@ -503,13 +503,13 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   // ---- pass 1: logsumexp ----
   EpiBowLseParams e1;
   e1.part = reinterpret_cast<float2*>(w.part); e1.N = int(N); e1.V = int(V); e1.Npad = w.Npad;
-  if (int rc = launch_gemm<EpiBowLse<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e1, st)) return rc;
+  if (int rc = launch_gemm<EpiBowLse<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e1, st, "bow_pass1_lse")) return rc;
   bow_lse_combine_kernel<<<int((N + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(w.part), w.ntp, w.Npad, int(N), int(K), w.ZA, w.ldk, w.lse, w.srow);
   CAREL_LAUNCHED();
   // ---- pass 2: dense loss + row sums ----
   EpiBowLossParams e2;
   e2.lossacc = w.lossacc; e2.srow = w.srow; e2.N = int(N); e2.V = int(V); e2.c = label_smoothing / float(V);
-  if (int rc = launch_gemm<EpiBowLoss<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e2, st)) return rc;
+  if (int rc = launch_gemm<EpiBowLoss<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e2, st, "bow_pass2_loss")) return rc;
   // ---- sparse corrections ----
   BowSparseArgs sa;
   sa.ZA = w.ZA; sa.WB = w.WB; sa.ell_cols = w.ell_cols; sa.ell_vals = w.ell_vals; sa.ell_nnz = w.ell_nnz;
@@ -555,7 +555,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
     bp.srow = w.srow; bp.grad_out = grad_out; bp.dl = w.dl; bp.grad_z = grad_z; bp.ldgz = ldgz;
     bp.N = int(N); bp.V = int(V); bp.Vp = w.Vp; bp.K = int(K);
     bp.c = label_smoothing / float(V); bp.inv_nv = float(1.0 / (double(N) * double(V)));
-    if (int rc = launch_chain<PolBowBwd, 1, 64>(ta, tb, ta, tb, cs, bp, st)) return rc;
+    if (int rc = launch_chain<PolBowBwd, 1, 64>(ta, tb, ta, tb, cs, bp, st, "bow_pass3_dlogits_dz")) return rc;
   }
   // ---- pass 4: [dW | . | db] = dlogit^T [Z | . | 1] ----
   if (need_w) {
@@ -571,7 +571,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
     EpiStore<256>::Params ep;
     ep.out = w.dWacc; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(V); ep.N = int(K + 4);
     ep.ld = w.ldk; ep.ld_bf16 = 0; ep.atomic = 1; ep.scale = 1.f;
-    if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st)) return rc;
+    if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st, "bow_pass4_dw")) return rc;
     bow_scatter_grads_kernel<<<148 * 4, 256, 0, st>>>(w.dWacc, w.ldk, int(V), int(K), grad_w, grad_b);
     CAREL_LAUNCHED();
   }

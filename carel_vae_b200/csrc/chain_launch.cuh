@@ -38,7 +38,7 @@ inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int k16
 template <class Pol, int NG, int BN1>
 int launch_chain(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
                  const CUtensorMap& b1, const ChainSched& s, const typename Pol::Params& pp,
-                 cudaStream_t st) {
+                 cudaStream_t st, const char* tag = "chain_tc") {
   using Cfg = ChainCfg<NG, BN1>;
   auto kern = chain_tc_kernel<Pol, NG, BN1>;
   CAREL_REQUIRE(16 * s.n2_16 <= Cfg::kMaxN2, "chain kernel: operand width %d exceeds the TMEM budget (%d)", 16 * s.n2_16, Cfg::kMaxN2);
@@ -52,7 +52,9 @@ int launch_chain(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap
   }
   const int grid = s.num_items < sm_count() ? s.num_items : sm_count();
   if (grid <= 0) return 0;
+  timing_begin(tag, st);
   kern<<<grid, kGemmThreads, smem_bytes, st>>>(a0, b0, a1, b1, s, pp);
+  timing_end(st);
   CAREL_LAUNCHED();
   return 0;
 }

@@ -8,7 +8,7 @@ namespace carel {
 template <class Epi, int BN, int NG, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
                        const CUtensorMap& b1, const GemmSched& s, const typename Epi::Params& ep,
-                       cudaStream_t st) {
+                       cudaStream_t st, const char* tag = "gemm_tc") {
   using Cfg = GemmCfg<BN, NG>;
   auto kern = gemm_tc_kernel<Epi, BN, NG, A_MN, B_MN>;
   static bool attr_done = false;
@@ -19,7 +19,9 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap&
   }
   const int grid = s.num_items < sm_count() ? s.num_items : sm_count();
   if (grid <= 0) return 0;
+  timing_begin(tag, st);
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a0, b0, a1, b1, s, ep);
+  timing_end(st);
   CAREL_LAUNCHED();
   return 0;
 }

@@ -268,7 +268,7 @@ extern "C" int carel_hsic_fwd(const float* x, int64_t ldx, const float* y, int64
   EpiHsicParams ep;
   ep.rK = w.rK; ep.rL = w.rL; ep.acc = w.acc; ep.m = int(m);
   ep.cx = 2.f * kLog2e / s_x; ep.cy = 2.f * kLog2e / s_y;
-  if (int rc = launch_gemm<EpiHsic<128>, 128, 2, false, false>(xa, xb, ya, yb, s, ep, st)) return rc;
+  if (int rc = launch_gemm<EpiHsic<128>, 128, 2, false, false>(xa, xb, ya, yb, s, ep, st, "hsic_gram_fwd")) return rc;
   hsic_finalize_kernel<<<1, 1024, 0, st>>>(w.rK, w.rL, w.acc, int(m), w.cK, w.cL, w.mean, out);
   CAREL_LAUNCHED();
   return 0;
@@ -308,8 +308,8 @@ extern "C" int carel_hsic_bwd(const float* grad_out, int64_t m, int64_t dx, int6
     pp.c_oth = 2.f * kLog2e / (side ? s_x : s_y);
     pp.neg_inv_s = -1.f / (side ? s_y : s_x);
     pp.norm = norm;
-    int rc = side ? launch_chain<PolHsicBwd, 2, 64>(ya, yb, xa, xb, cs, pp, st)
-                  : launch_chain<PolHsicBwd, 2, 64>(xa, xb, ya, yb, cs, pp, st);
+    int rc = side ? launch_chain<PolHsicBwd, 2, 64>(ya, yb, xa, xb, cs, pp, st, "hsic_gram_bwd")
+                  : launch_chain<PolHsicBwd, 2, 64>(xa, xb, ya, yb, cs, pp, st, "hsic_gram_bwd");
     if (rc) return rc;
   }
   return 0;

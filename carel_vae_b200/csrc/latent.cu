@@ -220,7 +220,7 @@ extern "C" int carel_latent_fwd(const float* x, int64_t ldx, int64_t N, int64_t 
   EpiStore<256>::Params ep;
   ep.out = pre; ep.bias = bias4; ep.out_bf16 = nullptr; ep.M = int(N); ep.N = int(4 * L);
   ep.ld = int(4 * L); ep.ld_bf16 = 0; ep.atomic = 0; ep.scale = 1.f;
-  if (int rc = launch_gemm<EpiStore<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st)) return rc;
+  if (int rc = launch_gemm<EpiStore<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st, "latent_proj_fwd")) return rc;
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.klacc, 0, 2 * sizeof(double), st));
   const long long work = N * 2 * ((L + 3) / 4);
   const int blocks = int(std::min<long long>((work + 255) / 256, 148LL * 16));
@@ -258,7 +258,7 @@ extern "C" int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* 
     EpiStore<256>::Params ep;
     ep.out = grad_x; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(N); ep.N = int(D);
     ep.ld = int(ldgx); ep.ld_bf16 = 0; ep.atomic = 0; ep.scale = 1.f;
-    if (int rc = launch_gemm<EpiStore<256>, 256, 1, false, true>(ta, tb, ta, tb, s, ep, st)) return rc;
+    if (int rc = launch_gemm<EpiStore<256>, 256, 1, false, true>(ta, tb, ta, tb, s, ep, st, "latent_dx")) return rc;
   }
   bool any_w = false;
   for (int i = 0; i < 4; ++i) any_w |= (grad_w4[i] != nullptr) || (grad_b4[i] != nullptr);
@@ -278,7 +278,7 @@ extern "C" int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* 
     EpiStore<256>::Params ep;
     ep.out = w.dW; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(K2); ep.N = int(D + 1);
     ep.ld = w.ldx; ep.ld_bf16 = 0; ep.atomic = 1; ep.scale = 1.f;
-    if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st)) return rc;
+    if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st, "latent_dw")) return rc;
     latent_scatter_grads_kernel<<<148, 256, 0, st>>>(w.dW, w.ldx, w.ldd, int(L), int(D), grad_w4[0], grad_w4[1],
                                                     grad_w4[2], grad_w4[3], grad_b4[0], grad_b4[1],
                                                     grad_b4[2], grad_b4[3]);

@@ -96,7 +96,7 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
     ep.a_scale[i] = -2.f * a * kLog2e;
     ep.a_shift[i] = -a * eps * kLog2e;
   }
-  if (int rc = launch_gemm<EpiMMD<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st)) return rc;
+  if (int rc = launch_gemm<EpiMMD<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st, "mmd_gram_fwd")) return rc;
   if (out_mmd != nullptr) return carel_mmd_finalize(acc, n1, n2, out_mmd, stream);
   return 0;
 }
@@ -110,7 +110,7 @@ static int mmd_bwd_launch(const MmdWs& w, const MmdBwdParams& pp, int64_t M, int
   CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.SB, M, ldp, ldp, BN1) == 0, "carel_mmd_bwd: tensor map B failed");
   const int k16 = ldp / 16;
   ChainSched s = make_chain_sched(t0, t1 - t0, int((M + BN1 - 1) / BN1), k16, Cfg::stages_for(k16), 32);
-  return launch_chain<PolMmdBwd, 1, BN1>(ta, tb, ta, tb, s, pp, st);
+  return launch_chain<PolMmdBwd, 1, BN1>(ta, tb, ta, tb, s, pp, st, "mmd_gram_bwd");
 }
 
 extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int64_t dim,

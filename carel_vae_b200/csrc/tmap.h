@@ -29,6 +29,20 @@ inline EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+inline void ensure_context() {
+  typedef CUresult (*GetCurFn)(CUcontext*);
+  static GetCurFn get_cur = nullptr;
+  if (!get_cur) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      get_cur = reinterpret_cast<GetCurFn>(p);
+  }
+  CUcontext ctx = nullptr;
+  if (get_cur == nullptr || get_cur(&ctx) != CUDA_SUCCESS || ctx == nullptr) cudaFree(nullptr);
+}
+
 // Row-major bf16 matrix [rows, cols] with row pitch `ld_elems` elements; TMA box =
 // 64 columns (128 B, matches SWIZZLE_128B) x `box_rows` rows.  Out-of-bounds
 // elements are zero-filled.
@@ -38,7 +52,8 @@ inline int make_tmap_bf16_sw128(CUtensorMap* m, const void* base, uint64_t rows,
   if (!fn) return -1;
   // cuTensorMapEncodeTiled is a driver-API call and needs a current context; a thread that has not
   // made a runtime call yet (e.g. autograd's backward thread) has none bound: bind the primary one.
-  cudaFree(nullptr);
+  // (Checked first so that nothing but the encode itself happens while a stream is being captured.)
+  ensure_context();
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld_elems * 2};
   cuuint32_t box[2] = {64, box_rows};

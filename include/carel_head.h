@@ -33,6 +33,11 @@ int carel_version(void);
 const char* carel_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t carel_launch_count(void);
+/* Per-kernel timing for eager profiling passes (never under CUDA-graph capture): when enabled every
+ * tensor-core kernel launch is bracketed by CUDA events on its stream; carel_timing_report writes
+ * "tag total_ms count" lines into buf (device-synchronising) and clears the log. */
+void carel_timing_enable(int on);
+int carel_timing_report(char* buf, size_t n);
 
 /* ------------------------------------------------------------------------------------------
  * Debug / building block: C[M,N] (+)= A * B^T on the tcgen05 core (bf16 operands, fp32 accum).
