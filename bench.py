@@ -129,24 +129,31 @@ def run_ours(args):
     loss_buf = torch.zeros((), device=dev)
     it_counter = [0]
 
-    def step():
+    def compute():
         bucket.zero_()
         for p in model.parameters():
             if p.grad is not None and not any(p is q for q in params):
                 p.grad = None
         loss = model(static["X"], None, None, static["emo"], static["cau"], static["pair"], static["bow"], it_counter[0])
         loss.backward()
-        bucket.allreduce_mean()
-        optim.step()
         loss_buf.copy_(loss.detach())
+
+    def update():
+        optim.step()
+
+    def step():
+        compute()
+        bucket.allreduce_mean()          # one flat NCCL all-reduce (no-op at N = 1)
+        update()
 
     torch.manual_seed(7 + rank)
     for _ in range(3):
         step()
     torch.cuda.synchronize()
 
-    # ---- CUDA graph of the whole step (streams + graphs instead of a tracing compiler) ----
-    graph, use_graph = None, not args.no_graph
+    # ---- CUDA graphs of the step (streams + graphs instead of a tracing compiler).  At N > 1 the NCCL
+    # all-reduce stays OUTSIDE the graphs: graph(fwd+bwd) -> all_reduce(flat bucket) -> graph(Adam). ----
+    graphs, use_graph = None, not args.no_graph
     if use_graph:
         try:
             s = torch.cuda.Stream()
@@ -155,20 +162,39 @@ def run_ours(args):
                 step()
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step()
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            if world == 1:
+                with torch.cuda.graph(g1):
+                    compute()
+                    update()
+                graphs = (g1, None)
+            else:
+                with torch.cuda.graph(g1):
+                    compute()
+                with torch.cuda.graph(g2, pool=g1.pool()):
+                    update()
+                graphs = (g1, g2)
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] CUDA-graph capture failed, running eagerly: {repr(e)[:300]}", file=sys.stderr)
-            graph, use_graph = None, False
+            graphs, use_graph = None, False
             torch.cuda.synchronize()
-    run_step = graph.replay if graph is not None else step
+
+    def run_step():
+        if graphs is None:
+            step()
+        elif graphs[1] is None:
+            graphs[0].replay()
+        else:
+            graphs[0].replay()
+            bucket.allreduce_mean()
+            graphs[1].replay()
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
     def timed(fn, k):
@@ -219,13 +245,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_eager = _lib.launch_count() - l0
     kernels = {}
-    if rank == 0:
-        _lib.timing_enable(True)
-        for _ in range(3):
-            step()
-        rep = _lib.timing_report()
-        _lib.timing_enable(False)
-        kernels = {k: round(v[0] / v[1] * 1e3, 1) for k, v in rep.items()}       # us per launch
+    _lib.timing_enable(True)                 # every rank runs the same (collective) steps
+    for _ in range(3):
+        step()
+    rep = _lib.timing_report()
+    _lib.timing_enable(False)
+    kernels = {k: round(v[0] / v[1] * 1e3, 1) for k, v in rep.items()}       # us per launch
 
     # ---- roofline: the MMD Gram kernel at N = 8192, d = 768 (BASELINE metric point) ----
     roof, gram = None, None

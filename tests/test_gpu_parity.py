@@ -257,3 +257,40 @@ def test_bow_extreme_logits_take_the_exact_path():
     assert relv(loss, ref) < 2e-3
     assert torch.isfinite(Z.grad).all() and torch.isfinite(W.grad).all() and torch.isfinite(b.grad).all()
     assert rel(Z.grad, Zd.grad) < 5e-3
+
+
+def test_mmd_row_block_sharding_emulated_ranks():
+    """each 'rank' owns a range of 128-row Gram tiles and sees every column.  Emulated on
+    one GPU (ranks as consecutive launches): partial block sums add up to the full statistic and each
+    rank's gradient rows are complete without any reduction."""
+    import ctypes as C
+    from carel_vae_b200 import parallel as par
+    from carel_vae_b200._lib import lib, check, float_array
+    torch.manual_seed(3)
+    n1, n2, d, alphas, world = 1500, 1100, 64, [0.1, 0.02], 4
+    x = bf(torch.randn(n1, d, device=DEV) * 1.1).requires_grad_(True)
+    y = bf(torch.randn(n2, d, device=DEV) * 1.1 + 0.3).requires_grad_(True)
+    full = F.mmd(x, y, alphas)
+    gx, gy = torch.autograd.grad(full, (x, y))
+    L = lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    total = torch.zeros(3, dtype=torch.float64, device=DEV)
+    gxs, gys = torch.zeros_like(gx), torch.zeros_like(gy)
+    one = torch.ones((), device=DEV)
+    al = float_array(alphas)
+    for (t0, t1) in par.balanced_tri_ranges(n1 + n2, world):
+        ws = torch.empty(L.carel_mmd_workspace_bytes(n1, n2, d), dtype=torch.uint8, device=DEV)
+        part = torch.zeros(3, dtype=torch.float64, device=DEV)
+        xd, yd = x.detach(), y.detach()
+        check(L.carel_mmd_fwd(C.c_void_p(xd.data_ptr()), d, C.c_void_p(yd.data_ptr()), d, n1, n2, d, al, len(alphas),
+                              1e-5, 0, t0, t1, C.c_void_p(part.data_ptr()), None, C.c_void_p(ws.data_ptr()), ws.numel(), st), "fwd")
+        total += part
+        px, py = torch.empty_like(gx), torch.empty_like(gy)
+        check(L.carel_mmd_bwd(C.c_void_p(one.data_ptr()), n1, n2, d, al, len(alphas), 1e-5, t0, t1,
+                              C.c_void_p(px.data_ptr()), d, C.c_void_p(py.data_ptr()), d, C.c_void_p(ws.data_ptr()), ws.numel(), st), "bwd")
+        # rows outside the rank's block are untouched zeros; inside they are the complete gradient
+        gxs += px
+        gys += py
+    val = par.finalize_mmd(total, n1, n2)
+    assert relv(val, full) < 1e-6
+    assert rel(gxs, gx) < 1e-5 and rel(gys, gy) < 1e-5

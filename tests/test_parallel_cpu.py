@@ -1,0 +1,95 @@
+"""CPU, world_size 2 over gloo: the host logic of the multi-GPU path (row-tile partition, partial-sum
+all-reduce + finalize, flat gradient bucket).  The per-rank partial sums come from a torch stand-in of
+the kernel's contract (block sums of a row-tile range) so no GPU is needed."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from carel_vae_b200 import parallel as par
+from oracle import head_oracle as ho
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _partial_cpu(x, y, alphas, eps, t0, t1):
+    """Contract of carel_mmd_fwd(row_tile_begin=t0, row_tile_end=t1) in its triangular mode: block sums over
+    pairs (i, j) with i in the row tiles and j > i, each weighted 2."""
+    s = torch.cat([x, y]).double()
+    n1, M = x.shape[0], s.shape[0]
+    n = (s * s).sum(1)
+    r0, r1 = t0 * 128, min(t1 * 128, M)
+    out = torch.zeros(3, dtype=torch.float64)
+    if r1 <= r0:
+        return out
+    d2 = n[r0:r1, None] + n[None, :] - 2 * s[r0:r1] @ s.T
+    K = sum(torch.exp(-a * (d2.abs() + eps)) for a in alphas)
+    i = torch.arange(r0, r1)[:, None]
+    j = torch.arange(M)[None, :]
+    upper = (j > i).double() * 2.0
+    rx, cx = i < n1, j < n1
+    out[0] = (K * upper * (rx & cx)).sum()
+    out[1] = (K * upper * (~rx & ~cx)).sum()
+    out[2] = (K * upper * (rx != cx)).sum()
+    return out
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.randn(300, 16, generator=g), torch.randn(420, 16, generator=g) + 0.3
+    val = par.sharded_mmd(x, y, [0.1, 1.0], partial_fn=_partial_cpu)
+    ref = ho.mmd_statistic(x.double(), y.double(), [0.1, 1.0])
+    # data-parallel gradient bucket
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(8, 4)
+    bucket = par.FlatGradBucket(lin.parameters())
+    bucket.zero_()
+    (lin(torch.ones(2, 8) * (rank + 1)).sum()).backward()
+    local = bucket.flat.clone()
+    bucket.allreduce_mean()
+    q.put((rank, float(val), float(ref), local, bucket.flat.clone(), lin.weight.grad.data_ptr() == bucket.flat.data_ptr()))
+    dist.destroy_process_group()
+
+
+def test_row_tile_partition_covers_everything():
+    for n_rows in (1, 128, 129, 16384, 262144, 1000):
+        for world in (1, 2, 3, 8):
+            tiles = (n_rows + 127) // 128
+            cover = []
+            for r in range(world):
+                t0, t1 = par.row_tile_range(n_rows, r, world)
+                cover += list(range(t0, t1))
+            assert cover == list(range(tiles))
+            rs = par.balanced_tri_ranges(n_rows, world)
+            assert rs[0][0] == 0 and rs[-1][1] == tiles and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+    # triangular balance: the work per rank is within one row of tiles of the mean
+    rs = par.balanced_tri_ranges(262144, 8)
+    ncol = 262144 // 256
+    work = [sum(ncol - t // 2 for t in range(a, b)) for a, b in rs]
+    assert max(work) - min(work) <= 2 * ncol
+
+
+def test_sharded_mmd_and_flat_bucket_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, val, ref, local, reduced, is_view in res:
+        assert abs(val - ref) <= 1e-6 * abs(ref)
+        assert is_view
+    assert torch.allclose(res[0][4], (res[0][3] + res[1][3]) / 2)
+    assert torch.equal(res[0][4], res[1][4])
