@@ -99,7 +99,19 @@ def synthetic_batch(device, seed=0):
     bow = torch.zeros(N_ROWS, VOCAB)
     bow.scatter_add_(1, idx, torch.ones(N_ROWS, NNZ))
     bow = bow / bow.sum(1, keepdim=True).clamp_min(1.0)
-    return dict(X=X, emo=emo, cau=pair.clone(), pair=pair, bow=bow)
+    # compact form of the same target: per-row non-zero list, capacity 32
+    cap = 32
+    cols = torch.zeros(N_ROWS, cap, dtype=torch.int32)
+    vals = torch.zeros(N_ROWS, cap)
+    srt, _ = torch.sort(idx, dim=1)
+    first = torch.ones_like(srt, dtype=torch.bool)
+    first[:, 1:] = srt[:, 1:] != srt[:, :-1]
+    pos = torch.cumsum(first.int(), 1) - 1
+    nnz = first.sum(1).int()
+    rows = torch.arange(N_ROWS)[:, None].expand_as(srt)
+    cols[rows[first], pos[first]] = srt[first].int()
+    vals[rows[first], pos[first]] = bow[rows[first], srt[first]]
+    return dict(X=X, emo=emo, cau=pair.clone(), pair=pair, bow=bow, ell_cols=cols, ell_vals=vals, ell_nnz=nnz)
 
 
 def run_ours(args):
@@ -129,67 +141,73 @@ def run_ours(args):
     loss_buf = torch.zeros((), device=dev)
     it_counter = [0]
 
-    def compute():
-        bucket.zero_()
-        for p in model.parameters():
-            if p.grad is not None and not any(p is q for q in params):
-                p.grad = None
-        loss = model(static["X"], None, None, static["emo"], static["cau"], static["pair"], static["bow"], it_counter[0])
-        loss.backward()
-        loss_buf.copy_(loss.detach())
+    def make_stepper(target):
+        """(eager step, graph-replaying step) for a BoW target given as static device tensor(s)."""
+        def compute():
+            bucket.zero_()
+            for p in model.parameters():
+                if p.grad is not None and not any(p is q for q in params):
+                    p.grad = None
+            loss = model(static["X"], None, None, static["emo"], static["cau"], static["pair"], target, it_counter[0])
+            loss.backward()
+            loss_buf.copy_(loss.detach())
 
-    def update():
-        optim.step()
+        def update():
+            optim.step()
 
-    def step():
-        compute()
-        bucket.allreduce_mean()          # one flat NCCL all-reduce (no-op at N = 1)
-        update()
+        def step():
+            compute()
+            bucket.allreduce_mean()          # one flat NCCL all-reduce (no-op at N = 1)
+            update()
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        # CUDA graphs of the step (streams + graphs instead of a tracing compiler).  At N > 1 the NCCL
+        # all-reduce stays OUTSIDE the graphs: graph(fwd+bwd) -> all_reduce(flat bucket) -> graph(Adam).
+        graphs = None
+        if not args.no_graph:
+            try:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    step()
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                if world == 1:
+                    with torch.cuda.graph(g1):
+                        compute()
+                        update()
+                    graphs = (g1, None)
+                else:
+                    with torch.cuda.graph(g1):
+                        compute()
+                    with torch.cuda.graph(g2, pool=g1.pool()):
+                        update()
+                    graphs = (g1, g2)
+                torch.cuda.synchronize()
+            except Exception as e:  # noqa: BLE001
+                if rank == 0:
+                    print(f"[bench] CUDA-graph capture failed, running eagerly: {repr(e)[:300]}", file=sys.stderr)
+                graphs = None
+                torch.cuda.synchronize()
+
+        def run_step():
+            if graphs is None:
+                step()
+            elif graphs[1] is None:
+                graphs[0].replay()
+            else:
+                graphs[0].replay()
+                bucket.allreduce_mean()
+                graphs[1].replay()
+        return step, run_step, graphs is not None
 
     torch.manual_seed(7 + rank)
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-
-    # ---- CUDA graphs of the step (streams + graphs instead of a tracing compiler).  At N > 1 the NCCL
-    # all-reduce stays OUTSIDE the graphs: graph(fwd+bwd) -> all_reduce(flat bucket) -> graph(Adam). ----
-    graphs, use_graph = None, not args.no_graph
-    if use_graph:
-        try:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                step()
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            if world == 1:
-                with torch.cuda.graph(g1):
-                    compute()
-                    update()
-                graphs = (g1, None)
-            else:
-                with torch.cuda.graph(g1):
-                    compute()
-                with torch.cuda.graph(g2, pool=g1.pool()):
-                    update()
-                graphs = (g1, g2)
-            torch.cuda.synchronize()
-        except Exception as e:  # noqa: BLE001
-            if rank == 0:
-                print(f"[bench] CUDA-graph capture failed, running eagerly: {repr(e)[:300]}", file=sys.stderr)
-            graphs, use_graph = None, False
-            torch.cuda.synchronize()
-
-    def run_step():
-        if graphs is None:
-            step()
-        elif graphs[1] is None:
-            graphs[0].replay()
-        else:
-            graphs[0].replay()
-            bucket.allreduce_mean()
-            graphs[1].replay()
+    step, run_step, use_graph = make_stepper(static["bow"])
+    ell_target = (static["ell_cols"], static["ell_vals"], static["ell_nnz"])
+    _, run_step_ell, _ = make_stepper(ell_target)
 
     def barrier():
         torch.cuda.synchronize()
@@ -236,7 +254,23 @@ def run_ours(args):
         e2e_step()
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
-    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in pinned)
+    dense_keys = ("X", "emo", "cau", "pair", "bow")
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in dense_keys)
+
+    # same, with the BoW target handed over as its non-zero list instead of dense rows
+    ell_keys = ("X", "emo", "cau", "pair", "ell_cols", "ell_vals", "ell_nnz")
+
+    def e2e_ell_step():
+        for k in ell_keys:
+            static[k].copy_(pinned[k], non_blocking=True)
+        run_step_ell()
+        loss_host.copy_(loss_buf, non_blocking=True)
+
+    for _ in range(2):
+        e2e_ell_step()
+    e2e_ell_ms = timed(e2e_ell_step, args.steps) / args.steps
+    h2d_ell = sum(pinned[k].numel() * pinned[k].element_size() for k in ell_keys)
+    ell_resident_ms = timed(run_step_ell, args.steps) / args.steps
 
     # ---- launches per step + per-kernel breakdown (eager pass, events inside the library) ----
     torch.cuda.synchronize()
@@ -303,6 +337,10 @@ def run_ours(args):
                "e2e": {"value": round(world * 1e3 / e2e_ms, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3),
                        "note": "dense fp32 [N,V] BoW target copied from pinned host memory every step (reference layout)"},
+               "e2e_ell": {"value": round(world * 1e3 / e2e_ell_ms, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_ell,
+                           "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ell_ms, 3),
+                           "resident_ms_per_step": round(ell_resident_ms, 4),
+                           "note": "BoW target passed as an ELL non-zero list (cols/vals [N,32], nnz [N]) instead of dense rows"},
                "gpu_launches": int(launches_eager) * args.steps, "gpu_launches_per_step": int(launches_eager),
                "roofline": roof, "roofline_step": roof_step, "gram": gram, "kernels_us": kernels,
                "cpu_baseline": cpu}

@@ -54,7 +54,7 @@ static BowWs carve_bow(void* ws, int64_t N, int64_t K, int64_t V, int64_t cap) {
   r.ldk = aug_width(int(K));
   r.Vp = int(round_up64(V, 64));
   r.Npad = int(round_up64(N, 128));
-  r.ntp = int((V + 255) / 256) * 2;
+  r.ntp = int((V + 255) / 256) * kColSplit;
   r.ZA = w.take<__nv_bfloat16>(size_t(N) * r.ldk);
   r.WB = w.take<__nv_bfloat16>(size_t(V) * r.ldk);
   r.dl = w.take<__nv_bfloat16>(size_t(N) * r.Vp);
@@ -126,7 +126,7 @@ struct EpiBowLse {
   const Params& p;
   CAREL_DEVINL EpiBowLse(const Params& p_, const TileCtx&) : p(p_) {}
   CAREL_DEVINL void tile(const TileCtx& ctx) {
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / kColSplit;
     const int c0 = ctx.col0 + ctx.half * HALF;
     float m = -INFINITY, s = 0.f;
     if (c0 < p.V) {
@@ -152,7 +152,7 @@ struct EpiBowLse {
         }
       });
     }
-    if (ctx.row < p.Npad) p.part[size_t(ctx.tn * 2 + ctx.half) * p.Npad + ctx.row] = make_float2(m, s);
+    if (ctx.row < p.Npad) p.part[size_t(ctx.tn * kColSplit + ctx.half) * p.Npad + ctx.row] = make_float2(m, s);
   }
   CAREL_DEVINL void finish() {}
 };
@@ -214,7 +214,7 @@ struct EpiBowLoss {
   double loss;
   CAREL_DEVINL EpiBowLoss(const Params& p_, const TileCtx&) : p(p_), loss(0.0) {}
   CAREL_DEVINL void tile(const TileCtx& ctx) {
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / kColSplit;
     const int c0 = ctx.col0 + ctx.half * HALF;
     if (c0 >= p.V || ctx.tm * 128 >= p.N) return;
     const bool full = c0 + HALF <= p.V;

@@ -53,7 +53,7 @@ int launch_chain(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap
   const int grid = s.num_items < sm_count() ? s.num_items : sm_count();
   if (grid <= 0) return 0;
   timing_begin(tag, st);
-  kern<<<grid, kGemmThreads, smem_bytes, st>>>(a0, b0, a1, b1, s, pp);
+  kern<<<grid, kChainThreads, smem_bytes, st>>>(a0, b0, a1, b1, s, pp);
   timing_end(st);
   CAREL_LAUNCHED();
   return 0;

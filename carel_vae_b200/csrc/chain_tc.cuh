@@ -87,7 +87,7 @@ struct ChainCfg {
 };
 
 template <class Pol, int NG, int BN1>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kChainThreads, 1)
 chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                 const __grid_constant__ ChainSched sched,

@@ -27,7 +27,7 @@ struct EpiStore {
   const Params& p;
   CAREL_DEVINL EpiStore(const Params& p_, const TileCtx&) : p(p_) {}
   CAREL_DEVINL void tile(const TileCtx& ctx) {
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / kColSplit;
     const int cbase = ctx.col0 + ctx.half * HALF;
     const bool row_ok = ctx.row < p.M;
 #pragma unroll 1
@@ -86,7 +86,7 @@ struct EpiPairwise {
   const Params& p;
   CAREL_DEVINL EpiPairwise(const Params& p_, const TileCtx&) : p(p_) {}
   CAREL_DEVINL void tile(const TileCtx& ctx) {
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / kColSplit;
     const int cbase = ctx.col0 + ctx.half * HALF;
     const bool row_ok = ctx.row < p.M;
 #pragma unroll 1
@@ -154,7 +154,7 @@ struct EpiMMD {
   }
 
   CAREL_DEVINL void tile(const TileCtx& ctx) {
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / kColSplit;
     const int r0 = ctx.tm * 128, r1 = r0 + 127;
     const int c0 = ctx.col0 + ctx.half * HALF, c1 = c0 + HALF - 1;
     const bool skip = (r0 >= p.M) || (c0 >= p.M) || (p.tri && c1 <= r0);

@@ -5,7 +5,7 @@
 // One CTA per SM, 320 threads:
 //   warp 0      TMEM allocator, then one lane = TMA producer
 //   warp 1      one lane = tcgen05.mma issuer
-//   warps 2-9   epilogue: warp w reads TMEM lanes 32*(w%4).. and column half (w-2)/4
+//   warps 2..   epilogue: 4*kColSplit warps; warp w reads TMEM lanes 32*(w%4).. and column part (w-2)/4
 //
 // Three pipelines: smem ring (full/empty mbarriers, TMA <-> MMA), TMEM accumulator double
 // buffer (tmem_full/tmem_empty, MMA <-> epilogue), and the static persistent tile schedule.
@@ -24,8 +24,15 @@
 
 namespace carel {
 
-constexpr int kGemmThreads = 320;
-constexpr int kEpiThreads = 256;
+// Epilogue column split: kColSplit groups of 4 warps, each group owning BN / kColSplit columns of the
+// accumulator tile (4 = 16 epilogue warps, 4 per SM sub-partition, to hide MUFU / TMEM-load latency).
+#ifndef CAREL_GEMM_COLSPLIT
+#define CAREL_GEMM_COLSPLIT 4
+#endif
+constexpr int kColSplit = CAREL_GEMM_COLSPLIT;
+constexpr int kEpiThreads = 128 * kColSplit;
+constexpr int kGemmThreads = 64 + kEpiThreads;
+constexpr int kChainThreads = 320;
 
 enum TileMode : int { TILE_FULL = 0, TILE_TRI = 1 };
 
@@ -80,7 +87,7 @@ struct TileCtx {
   int tm, tn;      // tile coordinates
   int row;         // global row index of this thread (tm*128 + lane quarter*32 + lane)
   int col0;        // global column of tile column 0 (tn*BN)
-  int half;        // column half handled by this warp: columns [half*BN/2, (half+1)*BN/2)
+  int half;        // column part handled by this warp: columns [half*BN/kColSplit, (half+1)*BN/kColSplit)
   int kb0, kb1;    // k-block range that was accumulated (split-K)
   int epi_tid;     // 0..255 within the epilogue warps
 };
@@ -130,7 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], 4 * kColSplit);
     }
     fence_mbar_init();
   }

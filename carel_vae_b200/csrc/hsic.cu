@@ -68,7 +68,7 @@ struct EpiHsic {
   double sKL, sK, sL;
   CAREL_DEVINL EpiHsic(const Params& p_, const TileCtx&) : p(p_), sKL(0.0), sK(0.0), sL(0.0) {}
   CAREL_DEVINL void tile(const TileCtx& ctx) {
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / kColSplit;
     const int c0 = ctx.col0 + ctx.half * HALF;
     if (c0 >= p.m || ctx.tm * 128 >= p.m) return;
     const bool full = (c0 + HALF <= p.m) && (ctx.tm * 128 + 128 <= p.m);

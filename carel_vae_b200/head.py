@@ -127,6 +127,11 @@ class _DrlClassifierBase(nn.Module):
         return kl_e, kl_c
 
     def _reconstruction(self, z, content_bow):
+        """`content_bow` is the reference's dense [N, V] fp32 target, or — SURVEY §8f.1 — the compact
+        ELL triple (cols int32 [N, C], vals fp32 [N, C], nnz int32 [N]) of its non-zeros."""
+        if isinstance(content_bow, (tuple, list)):
+            return F.bow_reconstruction_loss(z, self.decoder.weight, self.decoder.bias, None,
+                                             self.opt.label_smoothing, ell=tuple(content_bow))
         return F.bow_reconstruction_loss(z, self.decoder.weight, self.decoder.bias, content_bow,
                                          self.opt.label_smoothing, ell_cap=self.bow_ell_cap)
 
