@@ -15,7 +15,6 @@ inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int k16
   s.n_inner = n_inner;
   s.k16 = k16;
   s.n2_16 = k16;
-  s.p_fp16 = 0;
   s.stages = stages;
   const int sms = sm_count();
   int best = 1;

@@ -34,8 +34,12 @@ struct MmdBwdParams {
 
 struct PolMmdBwd {
   using Params = MmdBwdParams;
+  static constexpr bool kHiLo = true;     // P = W as bf16 hi + lo: the 2^-9 rounding of a single bf16 would
+                                          // otherwise dominate the gradient error of small samples
   const Params& p;
-  CAREL_DEVINL PolMmdBwd(const Params& p_, const ChainCtx&) : p(p_) {}
+  bool fast;
+  float cf;
+  CAREL_DEVINL PolMmdBwd(const Params& p_, const ChainCtx&) : p(p_), fast(false), cf(0.f) {}
   CAREL_DEVINL void begin_item(const ChainCtx&) {}
   CAREL_DEVINL float ksum(float a) const {   // sum_alpha alpha * exp(-alpha (|d2| + eps))
     float k = 0.f;
@@ -50,70 +54,42 @@ struct PolMmdBwd {
   static CAREL_DEVINL float with_sign_of(float mag, uint32_t acc_bits) {
     return __uint_as_float(__float_as_uint(mag) ^ (acc_bits & 0x80000000u));
   }
-  template <int BN1, class WaitP>
-  CAREL_DEVINL void weights(const ChainCtx& ctx, int t, uint32_t acc1_addr, uint32_t p_addr,
-                            WaitP&& wait_p) {
-    constexpr int N16 = BN1 / 32;   // 16-column chunks per warp per inner tile
-    const int r0 = ctx.owner * 128, r1 = r0 + 127;
-    const int j0 = t * BN1 + ctx.half * (BN1 / 2), j1 = j0 + BN1 / 2 - 1;
-    const bool fast = r1 < p.M && j1 < p.M && ((r1 < p.n1) || (r0 >= p.n1)) &&
-                      ((j1 < p.n1) || (j0 >= p.n1)) && (j0 > r1 || j1 < r0);
+  // columns [j0, j0 + R) of this thread: uniform coefficient, no diagonal, fully in range?
+  CAREL_DEVINL void begin_tile(const ChainCtx& ctx, int j0, int R) {
+    const int r0 = ctx.owner * 128, r1 = r0 + 127, j1 = j0 + R - 1;
+    fast = r1 < p.M && j1 < p.M && ((r1 < p.n1) || (r0 >= p.n1)) && ((j1 < p.n1) || (j0 >= p.n1)) &&
+           (j0 > r1 || j1 < r0);
+    cf = coef(r0, j0) * p.w_scale;
+  }
+  CAREL_DEVINL void weights16(const ChainCtx& ctx, int jc, const uint32_t (&r)[16], const uint32_t (&)[16],
+                              float (&w)[16]) {
+    const bool single = p.n_alpha == 1;
+    const float sc = p.a_scale[0], sh = p.a_shift[0], a0 = p.a_pos[0];
     if (fast) {
-      const float cf = coef(r0, j0) * p.w_scale;
-      if (p.n_alpha == 1) {
-        const float sc = p.a_scale[0], sh = p.a_shift[0], ca = cf * p.a_pos[0];  // cf carries w_scale
-        for_each_chunk16(acc1_addr, N16, [&](int c, const uint32_t (&r)[16]) {
-          uint32_t packed[8];
+      const float ca = cf * a0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float w0 = with_sign_of(ca * ex2_approx(fmaf(fabsf(__uint_as_float(r[2 * i])), sc, sh)), r[2 * i]);
-            const float w1 = with_sign_of(ca * ex2_approx(fmaf(fabsf(__uint_as_float(r[2 * i + 1])), sc, sh)), r[2 * i + 1]);
-            packed[i] = pack_bf16x2(w0, w1);
-          }
-          if (c == 0) wait_p();
-          tmem_st8(p_addr + c * 8, packed);
-        });
-      } else {
-        for_each_chunk16(acc1_addr, N16, [&](int c, const uint32_t (&r)[16]) {
-          uint32_t packed[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float w0 = with_sign_of(cf * ksum(fabsf(__uint_as_float(r[2 * i]))), r[2 * i]);
-            const float w1 = with_sign_of(cf * ksum(fabsf(__uint_as_float(r[2 * i + 1]))), r[2 * i + 1]);
-            packed[i] = pack_bf16x2(w0, w1);
-          }
-          if (c == 0) wait_p();
-          tmem_st8(p_addr + c * 8, packed);
-        });
+      for (int i = 0; i < 16; ++i) {
+        const float a = fabsf(__uint_as_float(r[i]));
+        const float k = single ? ca * ex2_approx(fmaf(a, sc, sh)) : cf * ksum(a);
+        w[i] = with_sign_of(k, r[i]);
       }
     } else {
       // boundary / diagonal tiles: same arithmetic, branch-free per-element coefficient
       const int row = ctx.row;
       const bool row_ok = row < p.M, rx = row < p.n1;
-      const bool single = p.n_alpha == 1;
-      const float sc = p.a_scale[0], sh = p.a_shift[0], a0 = p.a_pos[0];
       const float c_same = (rx ? p.c00 : p.c01) * p.w_scale, c_other = (rx ? p.c01 : p.c11) * p.w_scale;
-      for_each_chunk16(acc1_addr, N16, [&](int c, const uint32_t (&r)[16]) {
-        uint32_t packed[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float w[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int col = j0 + c * 16 + 2 * i + h;
-            const float a = fabsf(__uint_as_float(r[2 * i + h]));
-            const float k = single ? a0 * ex2_approx(fmaf(a, sc, sh)) : ksum(a);
-            const bool ok = row_ok && col < p.M && col != row;
-            const float cf = ok ? ((col < p.n1) ? c_same : c_other) : 0.f;
-            w[h] = with_sign_of(cf * k, r[2 * i + h]);
-          }
-          packed[i] = pack_bf16x2(w[0], w[1]);
-        }
-        if (c == 0) wait_p();
-        tmem_st8(p_addr + c * 8, packed);
-      });
+      for (int i = 0; i < 16; ++i) {
+        const int col = jc + i;
+        const float a = fabsf(__uint_as_float(r[i]));
+        const float k = single ? a0 * ex2_approx(fmaf(a, sc, sh)) : ksum(a);
+        const bool ok = row_ok && col < p.M && col != row;
+        const float c = ok ? ((col < p.n1) ? c_same : c_other) : 0.f;
+        w[i] = with_sign_of(c * k, r[i]);
+      }
     }
   }
+  CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
   CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
     // row sum of the rounded W: the ones column (index dim) of the B operand
     const uint32_t rtot_bits = tmem_ld1(ctx.acc2_taddr + p.dim);

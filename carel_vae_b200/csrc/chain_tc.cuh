@@ -2,18 +2,23 @@
 //
 //   for an owner row tile o (128 rows) and every inner tile t of BN1 rows:
 //     acc1[g] = A_o[g] * B_t[g]^T                 (GEMM-1, NG products, fp32 in TMEM)
-//     P       = policy.weights(acc1)  -> bf16     (epilogue warps, written back to TMEM)
-//     acc2   += P * B_t[0]                        (GEMM-2: A = P from TMEM, B = the SAME smem tile
-//                                                  of product 0 read MN-major; fp32 in TMEM)
+//     P       = policy weights(acc1) -> bf16      (epilogue warps; written IN PLACE over the acc1
+//                                                  columns they were computed from, optionally as a
+//                                                  hi + lo pair of bf16 = 16 mantissa bits)
+//     acc2   += P * B_t[0]                        (GEMM-2: A = P from TMEM, B = the SAME smem tile of
+//                                                  product 0 read MN-major; fp32 in TMEM)
 //   policy.final(acc2)                            (once per work item)
 //
 // Used by the backward passes: MMD / HSIC (P = C (.) K', acc2 = sum_j W_ij s_j) and the BoW
 // decoder (P = dlogits tile, acc2 = dZ).  The N x N (or N x V) matrix P never leaves the SM.
 //
 // 320 threads: warp 0 TMEM allocator + TMA producer lane, warp 1 MMA issuer lane, warps 2-9
-// epilogue (warp w: TMEM lanes 32*(w%4).., column half (w-2)/4).
-// The operand width is K16 16-wide steps (runtime, <= 16); GEMM-2 has N = 16*K16.
-// TMEM columns: acc1 2 x NG x BN1 | P BN1/2 | acc2 16*K16   (<= 512).
+// epilogue (warp w: TMEM lanes 32*(w%4).., column half (w-2)/4 of the inner tile).
+// TMEM columns: acc1 2 buffers x NG x BN1 | acc2 16*n2_16   (<= 512).  Within an acc1 buffer the half
+// h of product 0 (columns [h R, (h+1) R), R = BN1/2) is overwritten by its own thread with
+// P_hi (R/2 columns of packed bf16 pairs) followed by P_lo (R/2 columns).
+// Ordering: tcgen05.mma instructions of one thread execute in issue order, so GEMM-1 of tile t+2
+// (which overwrites the buffer holding P of tile t) needs no barrier beyond being issued after GEMM-2(t).
 #pragma once
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -29,7 +34,6 @@ struct ChainSched {
   int k16;         // operand width in 16-wide steps (GEMM-1 K)
   int n2_16;       // GEMM-2 N in 16-column groups (<= k16; acc2 columns = 16 * n2_16)
   int stages;      // B ring depth (2..4), chosen by the host from the smem budget
-  int p_fp16;      // 1: the policy writes P as fp16 pairs (GEMM-2 A operand is FP16, B stays BF16)
 };
 
 struct ChainItem {
@@ -68,9 +72,7 @@ template <int NG, int BN1>
 struct ChainCfg {
   static_assert(BN1 == 64 || BN1 == 128, "BN1");
   static constexpr int kAcc1Cols = NG * BN1;       // per buffer
-  static constexpr int kPCols = BN1 / 2;           // packed bf16 pairs
-  static constexpr int kPBase = 2 * kAcc1Cols;
-  static constexpr int kAcc2Base = kPBase + kPCols;
+  static constexpr int kAcc2Base = 2 * kAcc1Cols;
   static constexpr int kMaxN2 = (512 - kAcc2Base) < 256 ? (512 - kAcc2Base) : 256;
   static constexpr int kMaxStages = 4;
   static __host__ __device__ int kb(int k16) { return (k16 + 3) / 4; }
@@ -94,6 +96,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ typename Pol::Params pp) {
   using Cfg = ChainCfg<NG, BN1>;
   constexpr int MAXST = Cfg::kMaxStages;
+  constexpr int R = BN1 / 2;                 // columns of the inner tile per epilogue thread
+  constexpr bool HILO = Pol::kHiLo;
   const int K16 = sched.k16;
   const int KB = Cfg::kb(K16);
   const int STAGES = sched.stages;
@@ -110,10 +114,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint64_t* a_full = bars + 2 * MAXST;       // [1]
   uint64_t* a_empty = a_full + 1;            // [1]
   uint64_t* acc1_full = a_empty + 1;         // [2]
-  uint64_t* acc1_empty = acc1_full + 2;      // [2]
-  uint64_t* p_full = acc1_empty + 2;         // [1]
-  uint64_t* p_empty = p_full + 1;            // [1]
-  uint64_t* acc2_full = p_empty + 1;         // [1]
+  uint64_t* p_full = acc1_full + 2;          // [2]
+  uint64_t* acc2_full = p_full + 2;          // [1]
   uint64_t* acc2_empty = acc2_full + 1;      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
@@ -134,10 +136,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1);
-      mbar_init(&acc1_empty[i], 8);
+      mbar_init(&p_full[i], 8);
     }
-    mbar_init(p_full, 8);
-    mbar_init(p_empty, 1);
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 8);
     fence_mbar_init();
@@ -181,47 +181,27 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // ===================== MMA issuer =====================
     ChainIter iter(sched);
     ChainItem it;
-    int stage = 0;          // stage of the tile whose GEMM-1 is issued next
-    uint32_t phase = 0;
-    int g2_stage = 0;       // stage of the tile whose GEMM-2 is issued next
-    uint32_t aphase = 0, acc2_phase = 0, pphase = 0;
-    int buf = 0; uint32_t bphase = 0;      // acc1 buffer of the next GEMM-1
+    int g1_stage = 0; uint32_t g1_phase = 0;   // smem stage of the next GEMM-1
+    int g2_stage = 0;                          // smem stage of the next GEMM-2
+    int g1_buf = 0;                            // acc1 buffer of the next GEMM-1
+    int g2_buf = 0; uint32_t p_phase0 = 0, p_phase1 = 0;
+    uint32_t aphase = 0, acc2_phase = 0;
     constexpr uint32_t idesc1 = make_idesc_bf16(128, BN1, 0, 0);
-    const uint32_t idesc2 = sched.p_fp16 ? make_idesc_f16a_bf16b(128, 16 * sched.n2_16, 0, 1)
-                                         : make_idesc_bf16(128, 16 * sched.n2_16, 0, 1);
+    const uint32_t idesc2 = make_idesc_bf16(128, 16 * sched.n2_16, 0, 1);
     const uint32_t a_base = smem_u32(sA);
     const uint32_t b_base0 = smem_u32(sB);
     const uint32_t acc2_addr = tmem_base + Cfg::kAcc2Base;
-    const uint32_t p_addr = tmem_base + Cfg::kPBase;
     while (iter.next(it)) {
       mbar_wait(a_full, aphase);
       aphase ^= 1;
       bool first_g2 = true;
-      auto issue_g2 = [&]() {
-        mbar_wait(p_full, pphase);
-        pphase ^= 1;
-        if (first_g2) mbar_wait(acc2_empty, acc2_phase ^ 1);
+      auto issue_g1 = [&]() {
+        mbar_wait(&b_full[g1_stage], g1_phase);
         tc_fence_after();
-        const uint32_t b_tile = b_base0 + g2_stage * b_bytes;   // product 0, MN-major view
-#pragma unroll
-        for (int k16 = 0; k16 < BN1 / 16; ++k16) {
-          const uint64_t db = make_sdesc_sw128(b_tile + k16 * 2048, BN1 * 128, 1024);
-          umma_ts(acc2_addr, p_addr + k16 * 8, db, idesc2, (first_g2 && k16 == 0) ? 0u : 1u);
-        }
-        first_g2 = false;
-        umma_commit(&b_empty[g2_stage]);
-        umma_commit(p_empty);
-        if (++g2_stage == STAGES) g2_stage = 0;
-      };
-#pragma unroll 1
-      for (int t = it.t0; t < it.t1; ++t) {
-        mbar_wait(&b_full[stage], phase);
-        mbar_wait(&acc1_empty[buf], bphase ^ 1);
-        tc_fence_after();
-        const uint32_t b_tile = b_base0 + stage * b_bytes;
+        const uint32_t b_tile = b_base0 + g1_stage * b_bytes;
 #pragma unroll 1
         for (int g = 0; g < NG; ++g) {
-          const uint32_t d_addr = tmem_base + buf * Cfg::kAcc1Cols + g * BN1;
+          const uint32_t d_addr = tmem_base + g1_buf * Cfg::kAcc1Cols + g * BN1;
 #pragma unroll 1
           for (int k = 0; k < K16; ++k) {
             const int kb = k >> 2, k16 = k & 3;
@@ -230,12 +210,39 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             umma_ss(d_addr, da, db, idesc1, k ? 1u : 0u);
           }
         }
-        umma_commit(&acc1_full[buf]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        if (++buf == 2) { buf = 0; bphase ^= 1; }
-        if (t > it.t0) issue_g2();
+        umma_commit(&acc1_full[g1_buf]);
+        if (++g1_stage == STAGES) { g1_stage = 0; g1_phase ^= 1; }
+        g1_buf ^= 1;
+      };
+      auto issue_g2 = [&]() {
+        if (g2_buf == 0) { mbar_wait(&p_full[0], p_phase0); p_phase0 ^= 1; }
+        else { mbar_wait(&p_full[1], p_phase1); p_phase1 ^= 1; }
+        if (first_g2) mbar_wait(acc2_empty, acc2_phase ^ 1);
+        tc_fence_after();
+        const uint32_t b_tile = b_base0 + g2_stage * b_bytes;   // product 0, MN-major view
+        const uint32_t p_base = tmem_base + g2_buf * Cfg::kAcc1Cols;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int part = 0; part < (HILO ? 2 : 1); ++part) {
+#pragma unroll
+            for (int k16 = 0; k16 < R / 16; ++k16) {
+              const uint64_t db = make_sdesc_sw128(b_tile + (h * R + k16 * 16) * 128, BN1 * 128, 1024);
+              umma_ts(acc2_addr, p_base + h * R + part * (R / 2) + k16 * 8, db, idesc2, first_g2 ? 0u : 1u);
+              first_g2 = false;
+            }
+          }
+        }
+        umma_commit(&b_empty[g2_stage]);
+        if (++g2_stage == STAGES) g2_stage = 0;
+        g2_buf ^= 1;
+      };
+      if (it.t1 > it.t0) issue_g1();
+#pragma unroll 1
+      for (int t = it.t0; t < it.t1; ++t) {
+        if (t + 1 < it.t1) issue_g1();
+        issue_g2();
       }
-      if (it.t1 > it.t0) issue_g2();
       umma_commit(acc2_full);
       umma_commit(a_empty);
       acc2_phase ^= 1;
@@ -251,11 +258,11 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     Pol pol(pp, ctx);
     ChainIter iter(sched);
     ChainItem it;
-    int buf = 0; uint32_t bphase = 0;
-    uint32_t pphase = 0, acc2_phase = 0;
+    int buf = 0;
+    uint32_t full_phase0 = 0, full_phase1 = 0;
+    uint32_t acc2_phase = 0;
     const uint32_t lane_off = uint32_t(ctx.lane_q * 32) << 16;
     ctx.acc2_taddr = tmem_base + lane_off + Cfg::kAcc2Base;
-    const uint32_t p_addr = tmem_base + lane_off + Cfg::kPBase + ctx.half * (Cfg::kPCols / 2);
     while (iter.next(it)) {
       ctx.owner = it.owner;
       ctx.row = it.owner * 128 + ctx.lane_q * 32 + lane;
@@ -264,21 +271,44 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       pol.begin_item(ctx);
 #pragma unroll 1
       for (int t = it.t0; t < it.t1; ++t) {
-        mbar_wait(&acc1_full[buf], bphase);
+        if (buf == 0) { mbar_wait(&acc1_full[0], full_phase0); full_phase0 ^= 1; }
+        else { mbar_wait(&acc1_full[1], full_phase1); full_phase1 ^= 1; }
         tc_fence_after();
-        const uint32_t acc1_addr = tmem_base + lane_off + buf * Cfg::kAcc1Cols + ctx.half * (BN1 / 2);
-        pol.template weights<BN1>(ctx, t, acc1_addr, p_addr, [&]() {
-          mbar_wait(p_empty, pphase ^ 1);
-          pphase ^= 1;
-        });
+        // this thread's region of product 0 (product 1 sits BN1 columns further)
+        const uint32_t reg0 = tmem_base + lane_off + buf * Cfg::kAcc1Cols + ctx.half * R;
+        uint32_t r0[R / 16][16];
+        uint32_t r1[NG == 2 ? R / 16 : 1][16];
+#pragma unroll
+        for (int c = 0; c < R / 16; ++c) {
+          tmem_ld16(reg0 + c * 16, r0[c]);
+          if (NG == 2) tmem_ld16(reg0 + BN1 + c * 16, r1[NG == 2 ? c : 0]);
+        }
+        tmem_ld_wait();
+        const int j0 = t * BN1 + ctx.half * R;
+        pol.begin_tile(ctx, j0, R);
+#pragma unroll
+        for (int c = 0; c < R / 16; ++c) {
+          float w[16];
+          pol.weights16(ctx, j0 + c * 16, r0[c], r1[NG == 2 ? c : 0], w);
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 b = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
+            hi[i] = *reinterpret_cast<const uint32_t*>(&b);
+            if (HILO) {
+              const float2 f = __bfloat1622float2(b);
+              lo[i] = pack_bf16x2(w[2 * i] - f.x, w[2 * i + 1] - f.y);
+            }
+          }
+          tmem_st8(reg0 + c * 8, hi);
+          if (HILO) tmem_st8(reg0 + R / 2 + c * 8, lo);
+          pol.store16(ctx, j0 + c * 16, hi);
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(p_full);
-          mbar_arrive(&acc1_empty[buf]);
-        }
-        if (++buf == 2) { buf = 0; bphase ^= 1; }
+        if (lane == 0) mbar_arrive(&p_full[buf]);
+        buf ^= 1;
       }
       mbar_wait(acc2_full, acc2_phase);
       acc2_phase ^= 1;

@@ -158,48 +158,33 @@ struct HsicBwdParams {
 };
 struct PolHsicBwd {
   using Params = HsicBwdParams;
+  static constexpr bool kHiLo = true;
   const Params& p;
   float ci;
   CAREL_DEVINL PolHsicBwd(const Params& p_, const ChainCtx&) : p(p_), ci(0.f) {}
   CAREL_DEVINL void begin_item(const ChainCtx& ctx) {
     ci = __ldg(p.c_other + min(ctx.row, p.m - 1)) + __ldg(p.mean_other);
   }
-  template <int BN1, class WaitP>
-  CAREL_DEVINL void weights(const ChainCtx& ctx, int t, uint32_t acc1_addr, uint32_t p_addr, WaitP&& wait_p) {
-    constexpr int N16 = BN1 / 32;
-    const int j0 = t * BN1 + ctx.half * (BN1 / 2);
+  CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
+  CAREL_DEVINL void weights16(const ChainCtx& ctx, int jc, const uint32_t (&rs)[16], const uint32_t (&ro)[16],
+                              float (&w)[16]) {
+    const float4* cj4 = reinterpret_cast<const float4*>(p.c_other + jc);
+    float cj[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldg(cj4 + i);
+      cj[4 * i] = v.x; cj[4 * i + 1] = v.y; cj[4 * i + 2] = v.z; cj[4 * i + 3] = v.w;
+    }
     const bool row_ok = ctx.row < p.m;
-#pragma unroll 1
-    for (int c = 0; c < N16; ++c) {
-      uint32_t rs[16], ro[16];
-      tmem_ld16(acc1_addr + c * 16, rs);
-      tmem_ld16(acc1_addr + BN1 + c * 16, ro);
-      const float4* cj4 = reinterpret_cast<const float4*>(p.c_other + j0 + c * 16);
-      float cj[16];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = __ldg(cj4 + i);
-        cj[4 * i] = v.x; cj[4 * i + 1] = v.y; cj[4 * i + 2] = v.z; cj[4 * i + 3] = v.w;
-      }
-      tmem_ld_wait();
-      uint32_t packed[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float w[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int e = 2 * i + h;
-          const float Ks = ex2_approx(__uint_as_float(rs[e]) * p.c_self);
-          const float Ko = ex2_approx(__uint_as_float(ro[e]) * p.c_oth);
-          const bool ok = row_ok && (j0 + c * 16 + e < p.m);
-          w[h] = ok ? p.neg_inv_s * Ks * (Ko + ci + cj[e]) : 0.f;
-        }
-        packed[i] = pack_bf16x2(w[0], w[1]);
-      }
-      if (c == 0) wait_p();
-      tmem_st8(p_addr + c * 8, packed);
+    for (int e = 0; e < 16; ++e) {
+      const float Ks = ex2_approx(__uint_as_float(rs[e]) * p.c_self);
+      const float Ko = ex2_approx(__uint_as_float(ro[e]) * p.c_oth);
+      const bool ok = row_ok && (jc + e < p.m);
+      w[e] = ok ? p.neg_inv_s * Ks * (Ko + ci + cj[e]) : 0.f;
     }
   }
+  CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
   CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
     const uint32_t rtot_bits = tmem_ld1(ctx.acc2_taddr + p.dim);   // ones column: sum_j w_ij
     tmem_ld_wait();
