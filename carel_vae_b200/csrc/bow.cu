@@ -164,19 +164,24 @@ static CAREL_DEVINL void split3(float h, __nv_bfloat16& h1, __nv_bfloat16& h2, _
   h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
 }
 
-// lse_i from the partials; writes -lse (3-way bf16 split) into the h columns of ZA and zeroes S_i.
+// lse_i from the partials (one warp per row, lanes over the partials); writes -lse (3-way bf16 split)
+// into the h columns of ZA and zeroes S_i.
 static __global__ void bow_lse_combine_kernel(const float2* __restrict__ part, int ntp, int Npad, int N,
                                               int K, __nv_bfloat16* __restrict__ ZA, int ldk,
                                               float* __restrict__ neg_lse, float* __restrict__ srow) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= N) return;
   float M = -INFINITY;
-  for (int t = 0; t < ntp; ++t) M = fmaxf(M, part[size_t(t) * Npad + r].x);
+  for (int t = lane; t < ntp; t += 32) M = fmaxf(M, part[size_t(t) * Npad + r].x);
+  M = warp_max(M);
   float S = 0.f;
-  for (int t = 0; t < ntp; ++t) {
+  for (int t = lane; t < ntp; t += 32) {
     const float2 v = part[size_t(t) * Npad + r];
     if (v.y > 0.f) S += v.y * __expf(v.x - M);
   }
+  S = warp_sum(S);
+  if (lane != 0) return;
   const float nl = -(M + logf(S));
   neg_lse[r] = nl;
   srow[r] = 0.f;
@@ -289,68 +294,151 @@ struct BowSparseArgs {
   float* dWacc;
 };
 
-static CAREL_DEVINL float bf16_dot_warp(const __nv_bfloat16* a, const __nv_bfloat16* b, int n, int lane) {
-  float acc = 0.f;
-  for (int k = lane * 8; k < n; k += 256) {
-    const uint4 va = __ldg(reinterpret_cast<const uint4*>(a + k));
-    const uint4 vb = __ldg(reinterpret_cast<const uint4*>(b + k));
-    const uint32_t ua[4] = {va.x, va.y, va.z, va.w}, ub[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ua[q]));
-      const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ub[q]));
-      acc = fmaf(fa.x, fb.x, acc);
-      acc = fmaf(fa.y, fb.y, acc);
-    }
-  }
-  return warp_sum(acc);
-}
+// One warp per row; 4 non-zeros in flight (one per 8-lane group); the row's own operand (ZA[i], 8-element
+// chunks c = (lane & 7) + 8 k) stays in registers for all of its non-zeros.
+constexpr int kSparseChunks = 5;     // 8 lanes x 5 chunks x 8 elements = 320 >= ldk (<= 272)
 
-static __global__ void bow_sparse_kernel(const BowSparseArgs a) {
+static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseArgs a) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int grp = lane >> 3, gl = lane & 7;
+  const int nchunk = a.ldk >> 3;
   const float scale = (a.mode == 1) ? __ldg(a.grad_out) / (float(a.N) * float(a.V)) : 0.f;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < a.N; r += gridDim.x * wpb) {
     const __nv_bfloat16* zrow = a.ZA + size_t(r) * a.ldk;
+    uint4 zreg[kSparseChunks];
+#pragma unroll
+    for (int k = 0; k < kSparseChunks; ++k) {
+      const int c = gl + 8 * k;
+      zreg[k] = (c < nchunk) ? __ldg(reinterpret_cast<const uint4*>(zrow) + c) : make_uint4(0, 0, 0, 0);
+    }
     const int nnz = a.ell_nnz[r];
     const bool dense_scan = nnz > a.cap;
     float dloss = 0.f, du = 0.f;
-    auto handle = [&](int j, float t) {
-      const __nv_bfloat16* wrow = a.WB + size_t(j) * a.ldk;
-      const float x = bf16_dot_warp(zrow, wrow, a.ldk, lane);
+    float dz[kSparseChunks][8];
+    if (a.mode == 1) {
+#pragma unroll
+      for (int k = 0; k < kSparseChunks; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dz[k][i] = 0.f;
+    }
+    // handle up to 4 (j, t) pairs at once: group g takes pair g (valid = pair exists)
+    auto handle4 = [&](int j, float t, bool valid) {
+      const __nv_bfloat16* wrow = a.WB + size_t(valid ? j : 0) * a.ldk;
+      uint4 wreg[kSparseChunks];
+#pragma unroll
+      for (int k = 0; k < kSparseChunks; ++k) {
+        const int c = gl + 8 * k;
+        wreg[k] = (valid && c < nchunk) ? __ldg(reinterpret_cast<const uint4*>(wrow) + c) : make_uint4(0, 0, 0, 0);
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kSparseChunks; ++k) {
+        const uint32_t uz[4] = {zreg[k].x, zreg[k].y, zreg[k].z, zreg[k].w};
+        const uint32_t uw[4] = {wreg[k].x, wreg[k].y, wreg[k].z, wreg[k].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uz[q]));
+          const float2 fw = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[q]));
+          acc = fmaf(fz.x, fw.x, acc);
+          acc = fmaf(fz.y, fw.y, acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (!valid) return;
+      const float x = acc;
       const float p = __expf(x);
       const float den = fmaxf(p * (1.f - p), 1e-12f);
       const float ev = -a.one_minus_ls * t * p / den;
       if (a.mode == 0) {
-        const float A = fmaxf(x, -100.f), B = fmaxf(log1pf(-p), -100.f);
-        dloss += a.one_minus_ls * t * (A - B);
-        du += ev;
+        if (gl == 0) {
+          const float A = fmaxf(x, -100.f), B = fmaxf(log1pf(-p), -100.f);
+          dloss += a.one_minus_ls * t * (A - B);
+          du += ev;
+        }
       } else {
         const float e = ev * scale;
-        for (int k = lane; k < a.K; k += 32) {
-          atomicAdd(a.grad_z + size_t(r) * a.ldgz + k, e * __bfloat162float(wrow[k]));
-          atomicAdd(a.dWacc + size_t(j) * a.ldk + k, e * __bfloat162float(zrow[k]));
+        float* dwrow = a.dWacc + size_t(j) * a.ldk;
+#pragma unroll
+        for (int k = 0; k < kSparseChunks; ++k) {
+          const int c = gl + 8 * k;
+          if (c * 8 < a.K) {
+            const uint32_t uz[4] = {zreg[k].x, zreg[k].y, zreg[k].z, zreg[k].w};
+            const uint32_t uw[4] = {wreg[k].x, wreg[k].y, wreg[k].z, wreg[k].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 fz = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uz[q]));
+              const float2 fw = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[q]));
+              dz[k][2 * q] = fmaf(e, fw.x, dz[k][2 * q]);
+              dz[k][2 * q + 1] = fmaf(e, fw.y, dz[k][2 * q + 1]);
+              atomicAdd(dwrow + c * 8 + 2 * q, e * fz.x);
+              atomicAdd(dwrow + c * 8 + 2 * q + 1, e * fz.y);
+            }
+          }
         }
-        if (lane == 0) atomicAdd(a.dWacc + size_t(j) * a.ldk + a.K + 3, e);
+        if (gl == 0) atomicAdd(dwrow + a.K + 3, e);
       }
     };
     if (!dense_scan) {
-      for (int q = 0; q < nnz; ++q) handle(a.ell_cols[size_t(r) * a.cap + q], a.ell_vals[size_t(r) * a.cap + q]);
+      for (int base = 0; base < nnz; base += 32) {
+        const int q = base + lane;
+        const int myj = (q < nnz) ? a.ell_cols[size_t(r) * a.cap + q] : 0;
+        const float myt = (q < nnz) ? a.ell_vals[size_t(r) * a.cap + q] : 0.f;
+        const int cnt = min(32, nnz - base);
+        for (int s4 = 0; s4 < cnt; s4 += 4) {
+          const int src = s4 + grp;
+          const int j = __shfl_sync(0xffffffffu, myj, src & 31);
+          const float t = __shfl_sync(0xffffffffu, myt, src & 31);
+          handle4(j, t, src < cnt);
+        }
+      }
     } else {
       const float* brow = a.bow_dense + size_t(r) * a.ld_bow;
       for (int base = 0; base < a.V; base += 32) {
-        const int j = base + lane;
-        const float v = (j < a.V) ? __ldg(brow + j) : 0.f;
+        const int jj = base + lane;
+        const float v = (jj < a.V) ? __ldg(brow + jj) : 0.f;
         unsigned m = __ballot_sync(0xffffffffu, v != 0.f);
         while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          handle(base + src, __shfl_sync(0xffffffffu, v, src));
+          // pop up to four set bits; group g takes the g-th
+          int srcs[4];
+          int n = 0;
+          unsigned mm = m;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            srcs[g] = mm ? (__ffs(mm) - 1) : 0;
+            if (mm) { ++n; mm &= mm - 1; }
+          }
+          m = mm;
+          const int src = srcs[grp];
+          handle4(base + src, __shfl_sync(0xffffffffu, v, src), grp < n);
         }
       }
     }
-    if (a.mode == 0 && lane == 0) {
-      if (dloss != 0.f) atomicAdd(a.lossacc + 1, double(dloss));
-      if (du != 0.f) atomicAdd(a.srow + r, du);
+    if (a.mode == 0) {
+      // combine the four group leaders
+      dloss += __shfl_xor_sync(0xffffffffu, dloss, 8);
+      dloss += __shfl_xor_sync(0xffffffffu, dloss, 16);
+      du += __shfl_xor_sync(0xffffffffu, du, 8);
+      du += __shfl_xor_sync(0xffffffffu, du, 16);
+      if (lane == 0) {
+        if (dloss != 0.f) atomicAdd(a.lossacc + 1, double(dloss));
+        if (du != 0.f) atomicAdd(a.srow + r, du);
+      }
+    } else {
+      // sum the per-group dz partials and write the row (this kernel owns grad_z[r, :] at this point)
+      float* gz = a.grad_z + size_t(r) * a.ldgz;
+#pragma unroll
+      for (int k = 0; k < kSparseChunks; ++k) {
+        const int c = gl + 8 * k;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = dz[k][i];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (grp == 0 && c * 8 + i < a.K) gz[c * 8 + i] = v;
+        }
+      }
     }
   }
 }
@@ -499,7 +587,7 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   EpiBowLseParams e1;
   e1.part = reinterpret_cast<float2*>(w.part); e1.N = int(N); e1.V = int(V); e1.Npad = w.Npad;
   if (int rc = launch_gemm<EpiBowLse<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e1, st, "bow_pass1_lse")) return rc;
-  bow_lse_combine_kernel<<<int((N + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(w.part), w.ntp, w.Npad, int(N), int(K), w.ZA, w.ldk, w.lse, w.srow);
+  bow_lse_combine_kernel<<<int((N + 7) / 8), 256, 0, st>>>(reinterpret_cast<const float2*>(w.part), w.ntp, w.Npad, int(N), int(K), w.ZA, w.ldk, w.lse, w.srow);
   CAREL_LAUNCHED();
   // ---- pass 2: dense loss + row sums ----
   EpiBowLossParams e2;
@@ -527,7 +615,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_bow_bwd: workspace too small");
   CAREL_REQUIRE(grad_z != nullptr, "carel_bow_bwd: grad_z is required");
   const bool need_w = grad_w != nullptr || grad_b != nullptr;
-  CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_z, size_t(ldgz) * 4, 0, size_t(K) * 4, size_t(N), st));
+  // grad_z[r, 0:K] is fully written (not accumulated) by the sparse kernel, pass 3 then adds to it
   if (need_w) CAREL_CHECK_CUDA(cudaMemsetAsync(w.dWacc, 0, size_t(V) * w.ldk * 4, st));
   // ---- sparse part ----
   BowSparseArgs sa;

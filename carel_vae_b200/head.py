@@ -17,6 +17,7 @@ cause, then the dropout masks in call order.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from types import SimpleNamespace
 
@@ -69,6 +70,22 @@ class _DrlClassifierBase(nn.Module):
     # ---- variant hooks -------------------------------------------------------------------
     def _build_variant_modules(self, opt):
         pass
+
+    # ---- stream fork/join for the tiny classifier heads --------------------------------------
+    def _side(self, device):
+        """The classifier heads are ~100 launch-latency-bound PyTorch kernels; they run on a side stream
+        (forked after the latent layer, joined before the loss is assembled) so that they overlap the
+        tensor-core kernels instead of serialising with them.  Host program order — and therefore the
+        RNG consumption order of the dropout masks — is unchanged.  Autograd replays each backward op on
+        the stream of its forward op, so the backward pass overlaps the same way; the fork/join is
+        captured by CUDA graphs as parallel branches."""
+        if not getattr(self.opt, "overlap_heads", True):
+            return None
+        streams = self.__dict__.setdefault("_side_streams", {})
+        key = torch.device(device).index
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
 
     def _emotion_classes(self, opt):
         return opt.ec_num_class
@@ -214,15 +231,21 @@ class DrlClassifierMMD(_DrlClassifierBase):
         o, L = self.opt, self.opt.ec_dim
         z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
         z_e, z_c = z[:, :L], z[:, L:]
-        emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
-        cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
+        side, main = self._side(z.device), torch.cuda.current_stream()
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
+            cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
+            pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
+            heads = (o.emo_mul_loss_weight * emo_mul_loss + o.cau_mul_loss_weight * cau_mul_loss +
+                     o.pair_mul_loss_weight * pair_mul_loss)
         mmd_loss = -MMDStatistic(input_ids.shape[0], input_ids.shape[0])(z_e, z_c, [0.1])
-        pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
         kl_e, kl_c = self._kl_terms(kl, iteration)
         reconstruction_loss = self._reconstruction(z, content_bow)
-        return (o.mmd_loss_weight * mmd_loss + o.emo_mul_loss_weight * emo_mul_loss +
-                o.cau_mul_loss_weight * cau_mul_loss + o.pair_mul_loss_weight * pair_mul_loss +
-                kl_e + kl_c + reconstruction_loss)
+        if side is not None:
+            main.wait_stream(side)
+        return o.mmd_loss_weight * mmd_loss + heads + kl_e + kl_c + reconstruction_loss
 
     def get_params(self):
         """The four latent projections are NOT handed to the optimiser, as in the reference (:284-297)."""
