@@ -44,6 +44,11 @@ struct BowWs {
   int* ell_cols;        // [N, cap]
   float* ell_vals;      // [N, cap]
   int* ell_nnz;         // [N]  (> cap: row must be scanned densely)
+  float* ell_ev;        // [N, cap]  per non-zero: -(1-ls) t p / max(p(1-p),1e-12)  (forward -> backward)
+  int* colptr;          // [V+1]  CSC view of the ELL list (built on the device every forward)
+  int* fillpos;         // [V+1]
+  int* csc_row;         // [N*cap]
+  int* csc_slot;        // [N*cap]
   size_t bytes;
   int ldk, Vp, Npad, ntp;
 };
@@ -66,6 +71,11 @@ static BowWs carve_bow(void* ws, int64_t N, int64_t K, int64_t V, int64_t cap) {
   r.ell_cols = w.take<int>(size_t(N) * cap);
   r.ell_vals = w.take<float>(size_t(N) * cap);
   r.ell_nnz = w.take<int>(size_t(N));
+  r.ell_ev = w.take<float>(size_t(N) * cap);
+  r.colptr = w.take<int>(size_t(V) + 1);
+  r.fillpos = w.take<int>(size_t(V) + 1);
+  r.csc_row = w.take<int>(size_t(N) * cap);
+  r.csc_slot = w.take<int>(size_t(N) * cap);
   r.bytes = w.bytes();
   return r;
 }
@@ -282,6 +292,8 @@ struct BowSparseArgs {
   const int* ell_cols;
   const float* ell_vals;
   const int* ell_nnz;
+  float* ell_ev;         // mode 0: written; mode 1: unused
+  int overflow_only;     // mode 1: handle only rows that overflowed the ELL list (the rest goes through CSC)
   const float* bow_dense;
   int64_t ld_bow;
   int N, V, K, ldk, cap, mode;
@@ -313,6 +325,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
     }
     const int nnz = a.ell_nnz[r];
     const bool dense_scan = nnz > a.cap;
+    if (a.mode == 1 && a.overflow_only && !dense_scan) continue;
     float dloss = 0.f, du = 0.f;
     float dz[kSparseChunks][8];
     if (a.mode == 1) {
@@ -322,7 +335,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
         for (int i = 0; i < 8; ++i) dz[k][i] = 0.f;
     }
     // handle up to 4 (j, t) pairs at once: group g takes pair g (valid = pair exists)
-    auto handle4 = [&](int j, float t, bool valid) {
+    auto handle4 = [&](int j, float t, bool valid, int slot) {
       const __nv_bfloat16* wrow = a.WB + size_t(valid ? j : 0) * a.ldk;
       uint4 wreg[kSparseChunks];
 #pragma unroll
@@ -353,6 +366,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
       const float ev = -a.one_minus_ls * t * p / den;
       if (a.mode == 0) {
         if (gl == 0) {
+          if (slot >= 0) a.ell_ev[slot] = ev;
           const float A = fmaxf(x, -100.f), B = fmaxf(log1pf(-p), -100.f);
           dloss += a.one_minus_ls * t * (A - B);
           du += ev;
@@ -390,7 +404,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
           const int src = s4 + grp;
           const int j = __shfl_sync(0xffffffffu, myj, src & 31);
           const float t = __shfl_sync(0xffffffffu, myt, src & 31);
-          handle4(j, t, src < cnt);
+          handle4(j, t, src < cnt, int(size_t(r) * a.cap) + base + src);
         }
       }
     } else {
@@ -411,7 +425,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
           }
           m = mm;
           const int src = srcs[grp];
-          handle4(base + src, __shfl_sync(0xffffffffu, v, src), grp < n);
+          handle4(base + src, __shfl_sync(0xffffffffu, v, src), grp < n, -1);
         }
       }
     }
@@ -440,6 +454,132 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSC view of the ELL list (counting sort by vocabulary index), so that the sparse part of dW is a
+// gather per word instead of 256 fp32 atomics per non-zero.
+// ---------------------------------------------------------------------------------------------
+static __global__ void csc_count_kernel(const int* __restrict__ cols, const int* __restrict__ nnz, int N,
+                                        int cap, int* __restrict__ cnt) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < 1LL * N * cap;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int r = int(t / cap), q = int(t % cap), n = nnz[r];
+    if (n <= cap && q < n) atomicAdd(cnt + cols[t], 1);
+  }
+}
+// cnt may alias fillpos (each thread reads its own range before overwriting it)
+static __global__ void csc_scan_kernel(const int* cnt, int V, int* colptr, int* fillpos) {
+  __shared__ int part[1024];
+  const int per = (V + blockDim.x - 1) / blockDim.x;
+  const int b = threadIdx.x * per, e = min(b + per, V);
+  int s = 0;
+  for (int i = b; i < e; ++i) s += cnt[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < blockDim.x; off <<= 1) {
+    const int v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - s;
+  for (int i = b; i < e; ++i) {
+    const int c = cnt[i];
+    colptr[i] = run;
+    fillpos[i] = run;
+    run += c;
+  }
+  if (threadIdx.x == blockDim.x - 1) colptr[V] = part[threadIdx.x];
+}
+static __global__ void csc_fill_kernel(const int* __restrict__ cols, const int* __restrict__ nnz, int N,
+                                       int cap, int* __restrict__ fillpos, int* __restrict__ csc_row,
+                                       int* __restrict__ csc_slot) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < 1LL * N * cap;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int r = int(t / cap), q = int(t % cap), n = nnz[r];
+    if (n <= cap && q < n) {
+      const int pos = atomicAdd(fillpos + cols[t], 1);
+      csc_row[pos] = r;
+      csc_slot[pos] = int(t);
+    }
+  }
+}
+
+// sparse part of dZ: one warp per row, dz_r = scale * sum_q ev_q * w_{j_q}; writes grad_z[r, 0:K]
+// (zeros for rows without non-zeros; overflow rows are written by bow_sparse_kernel instead).
+static __global__ void bow_sparse_dz_kernel(const __nv_bfloat16* __restrict__ WB, int ldk, int K,
+                                            const int* __restrict__ cols, const int* __restrict__ nnz,
+                                            const float* __restrict__ ev, int N, int cap,
+                                            const float* __restrict__ grad_out, float inv_nv,
+                                            float* __restrict__ grad_z, int64_t ldgz) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float scale = __ldg(grad_out) * inv_nv;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < N; r += gridDim.x * wpb) {
+    const int n = nnz[r];
+    if (n > cap) continue;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool act = lane * 8 < K;
+    for (int q = 0; q < n; ++q) {
+      const int j = __ldg(cols + size_t(r) * cap + q);
+      const float e = __ldg(ev + size_t(r) * cap + q);
+      if (act) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(WB + size_t(j) * ldk) + lane);
+        const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
+          acc[2 * h] = fmaf(e, f.x, acc[2 * h]);
+          acc[2 * h + 1] = fmaf(e, f.y, acc[2 * h + 1]);
+        }
+      }
+    }
+    if (act) {
+      float* gz = grad_z + size_t(r) * ldgz + lane * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (lane * 8 + i < K) gz[i] = acc[i] * scale;
+    }
+  }
+}
+
+// sparse part of [dW | db]: one warp per vocabulary word, gather over the rows that contain it.
+static __global__ void bow_sparse_dw_kernel(const __nv_bfloat16* __restrict__ ZA, int ldk, int K,
+                                            const int* __restrict__ colptr, const int* __restrict__ csc_row,
+                                            const int* __restrict__ csc_slot, const float* __restrict__ ev,
+                                            int V, const float* __restrict__ grad_out, float inv_nv,
+                                            float* __restrict__ dWacc) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float scale = __ldg(grad_out) * inv_nv;
+  for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < V; j += gridDim.x * wpb) {
+    const int p0 = colptr[j], p1 = colptr[j + 1];
+    if (p1 == p0) continue;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float esum = 0.f;
+    const bool act = lane * 8 < K;
+    for (int pz = p0; pz < p1; ++pz) {
+      const int r = __ldg(csc_row + pz);
+      const float e = __ldg(ev + __ldg(csc_slot + pz));
+      esum += e;
+      if (act) {
+        const uint4 z = __ldg(reinterpret_cast<const uint4*>(ZA + size_t(r) * ldk) + lane);
+        const uint32_t u[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
+          acc[2 * h] = fmaf(e, f.x, acc[2 * h]);
+          acc[2 * h + 1] = fmaf(e, f.y, acc[2 * h + 1]);
+        }
+      }
+    }
+    float* dw = dWacc + size_t(j) * ldk;
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (lane * 8 + i < K) atomicAdd(dw + lane * 8 + i, acc[i] * scale);
+    }
+    if (lane == 0) atomicAdd(dw + K + 3, esum * scale);
   }
 }
 
@@ -598,10 +738,19 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   sa.ZA = w.ZA; sa.WB = w.WB; sa.ell_cols = w.ell_cols; sa.ell_vals = w.ell_vals; sa.ell_nnz = w.ell_nnz;
   sa.bow_dense = bow_dense; sa.ld_bow = ld_bow; sa.N = int(N); sa.V = int(V); sa.K = int(K); sa.ldk = w.ldk;
   sa.cap = cap; sa.mode = 0; sa.one_minus_ls = 1.f - label_smoothing; sa.lossacc = w.lossacc; sa.srow = w.srow;
+  sa.ell_ev = w.ell_ev; sa.overflow_only = 0;
   sa.grad_out = nullptr; sa.grad_z = nullptr; sa.ldgz = 0; sa.dWacc = nullptr;
   bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
   CAREL_LAUNCHED();
   bow_loss_finalize_kernel<<<1, 32, 0, st>>>(w.lossacc, 1.0 / (double(N) * double(V)), loss_out);
+  CAREL_LAUNCHED();
+  // CSC view of the non-zero list for the backward gather (cheap: N*cap entries)
+  CAREL_CHECK_CUDA(cudaMemsetAsync(w.fillpos, 0, (size_t(V) + 1) * 4, st));
+  csc_count_kernel<<<148 * 2, 256, 0, st>>>(w.ell_cols, w.ell_nnz, int(N), cap, w.fillpos);
+  CAREL_LAUNCHED();
+  csc_scan_kernel<<<1, 1024, 0, st>>>(w.fillpos, int(V), w.colptr, w.fillpos);
+  CAREL_LAUNCHED();
+  csc_fill_kernel<<<148 * 2, 256, 0, st>>>(w.ell_cols, w.ell_nnz, int(N), cap, w.fillpos, w.csc_row, w.csc_slot);
   CAREL_LAUNCHED();
   return 0;
 }
@@ -617,14 +766,27 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   const bool need_w = grad_w != nullptr || grad_b != nullptr;
   // grad_z[r, 0:K] is fully written (not accumulated) by the sparse kernel, pass 3 then adds to it
   if (need_w) CAREL_CHECK_CUDA(cudaMemsetAsync(w.dWacc, 0, size_t(V) * w.ldk * 4, st));
-  // ---- sparse part ----
-  BowSparseArgs sa;
-  sa.ZA = w.ZA; sa.WB = w.WB; sa.ell_cols = w.ell_cols; sa.ell_vals = w.ell_vals; sa.ell_nnz = w.ell_nnz;
-  sa.bow_dense = bow_dense; sa.ld_bow = ld_bow; sa.N = int(N); sa.V = int(V); sa.K = int(K); sa.ldk = w.ldk;
-  sa.cap = int(ell_cap); sa.mode = 1; sa.one_minus_ls = 1.f - label_smoothing; sa.lossacc = nullptr; sa.srow = nullptr;
-  sa.grad_out = grad_out; sa.grad_z = grad_z; sa.ldgz = ldgz; sa.dWacc = w.dWacc;
-  bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
+  // ---- sparse part: gathers through the ELL (rows) and CSC (words) views; rows that overflowed the ELL
+  // list fall back to the scan + atomics kernel ----
+  const float inv_nv = float(1.0 / (double(N) * double(V)));
+  bow_sparse_dz_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(
+      w.WB, w.ldk, int(K), w.ell_cols, w.ell_nnz, w.ell_ev, int(N), int(ell_cap), grad_out, inv_nv, grad_z, ldgz);
   CAREL_LAUNCHED();
+  if (need_w) {
+    bow_sparse_dw_kernel<<<148 * 16, 256, 0, st>>>(w.ZA, w.ldk, int(K), w.colptr, w.csc_row, w.csc_slot, w.ell_ev,
+                                                  int(V), grad_out, inv_nv, w.dWacc);
+    CAREL_LAUNCHED();
+  }
+  if (bow_dense != nullptr) {
+    BowSparseArgs sa;
+    sa.ZA = w.ZA; sa.WB = w.WB; sa.ell_cols = w.ell_cols; sa.ell_vals = w.ell_vals; sa.ell_nnz = w.ell_nnz;
+    sa.ell_ev = nullptr; sa.overflow_only = 1;
+    sa.bow_dense = bow_dense; sa.ld_bow = ld_bow; sa.N = int(N); sa.V = int(V); sa.K = int(K); sa.ldk = w.ldk;
+    sa.cap = int(ell_cap); sa.mode = 1; sa.one_minus_ls = 1.f - label_smoothing; sa.lossacc = nullptr; sa.srow = nullptr;
+    sa.grad_out = grad_out; sa.grad_z = grad_z; sa.ldgz = ldgz; sa.dWacc = w.dWacc;
+    bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
+    CAREL_LAUNCHED();
+  }
   // ---- pass 3: dense dlogits -> dZ (and bf16 copy for pass 4) ----
   {
     using Cfg = ChainCfg<1, 64>;
@@ -637,7 +799,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
     BowBwdParams bp;
     bp.srow = w.srow; bp.grad_out = grad_out; bp.dl = w.dl; bp.grad_z = grad_z; bp.ldgz = ldgz;
     bp.N = int(N); bp.V = int(V); bp.Vp = w.Vp; bp.K = int(K);
-    bp.c = label_smoothing / float(V); bp.inv_nv = float(1.0 / (double(N) * double(V)));
+    bp.c = label_smoothing / float(V); bp.inv_nv = inv_nv;
     if (int rc = launch_chain<PolBowBwd, 1, 64>(ta, tb, ta, tb, cs, bp, st, "bow_pass3_dlogits_dz")) return rc;
   }
   // ---- pass 4: [dW | . | db] = dlogit^T [Z | . | 1] ----
