@@ -649,8 +649,7 @@ struct PolBowBwd {
   }
   CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
     const int n16 = p.K / 16;                       // feature columns only
-    const int q_split = (n16 + 1) >> 1;
-    const int q0 = ctx.half ? q_split : 0, q1 = ctx.half ? n16 : q_split;
+    const int q0 = (n16 * ctx.half) / kChainSplit, q1 = (n16 * (ctx.half + 1)) / kChainSplit;
     const bool row_ok = valid && ctx.row < p.N;
     float* dst = p.grad_z + size_t(min(ctx.row, p.N - 1)) * p.ldgz;
 #pragma unroll 1

@@ -95,8 +95,7 @@ struct PolMmdBwd {
     const uint32_t rtot_bits = tmem_ld1(ctx.acc2_taddr + p.dim);
     tmem_ld_wait();
     const float rtot = __uint_as_float(rtot_bits);
-    const int q_split = (ctx.n2_16 + 1) >> 1;
-    const int q0 = ctx.half ? q_split : 0, q1 = ctx.half ? ctx.n2_16 : q_split;
+    const int q0 = (ctx.n2_16 * ctx.half) / kChainSplit, q1 = (ctx.n2_16 * (ctx.half + 1)) / kChainSplit;
     const float g4 = 4.f * __ldg(p.grad_out) * p.inv_w_scale;
     const bool row_ok = valid && ctx.row < p.M;
     const int rowc = min(ctx.row, p.M - 1);

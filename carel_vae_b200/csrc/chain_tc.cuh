@@ -12,10 +12,10 @@
 // Used by the backward passes: MMD / HSIC (P = C (.) K', acc2 = sum_j W_ij s_j) and the BoW
 // decoder (P = dlogits tile, acc2 = dZ).  The N x N (or N x V) matrix P never leaves the SM.
 //
-// 320 threads: warp 0 TMEM allocator + TMA producer lane, warp 1 MMA issuer lane, warps 2-9
-// epilogue (warp w: TMEM lanes 32*(w%4).., column half (w-2)/4 of the inner tile).
+// 64 + 128*kChainSplit threads: warp 0 TMEM allocator + TMA producer lane, warp 1 MMA issuer lane, then
+// 4*kChainSplit epilogue warps (warp w: TMEM lanes 32*(w%4).., column part (w-2)/4 of the inner tile).
 // TMEM columns: acc1 2 buffers x NG x BN1 | acc2 16*n2_16   (<= 512).  Within an acc1 buffer the half
-// h of product 0 (columns [h R, (h+1) R), R = BN1/2) is overwritten by its own thread with
+// part h of product 0 (columns [h R, (h+1) R), R = BN1/kChainSplit) is overwritten by its own thread with
 // P_hi (R/2 columns of packed bf16 pairs) followed by P_lo (R/2 columns).
 // Ordering: tcgen05.mma instructions of one thread execute in issue order, so GEMM-1 of tile t+2
 // (which overwrites the buffer holding P of tile t) needs no barrier beyond being issued after GEMM-2(t).
@@ -96,7 +96,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ typename Pol::Params pp) {
   using Cfg = ChainCfg<NG, BN1>;
   constexpr int MAXST = Cfg::kMaxStages;
-  constexpr int R = BN1 / 2;                 // columns of the inner tile per epilogue thread
+  constexpr int R = BN1 / kChainSplit;       // columns of the inner tile per epilogue thread
   constexpr bool HILO = Pol::kHiLo;
   const int K16 = sched.k16;
   const int KB = Cfg::kb(K16);
@@ -136,10 +136,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1);
-      mbar_init(&p_full[i], 8);
+      mbar_init(&p_full[i], 4 * kChainSplit);
     }
     mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, 8);
+    mbar_init(acc2_empty, 4 * kChainSplit);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -222,7 +222,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t b_tile = b_base0 + g2_stage * b_bytes;   // product 0, MN-major view
         const uint32_t p_base = tmem_base + g2_buf * Cfg::kAcc1Cols;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kChainSplit; ++h) {
 #pragma unroll
           for (int part = 0; part < (HILO ? 2 : 1); ++part) {
 #pragma unroll

@@ -32,7 +32,11 @@ namespace carel {
 constexpr int kColSplit = CAREL_GEMM_COLSPLIT;
 constexpr int kEpiThreads = 128 * kColSplit;
 constexpr int kGemmThreads = 64 + kEpiThreads;
-constexpr int kChainThreads = 320;
+#ifndef CAREL_CHAIN_COLSPLIT
+#define CAREL_CHAIN_COLSPLIT 4
+#endif
+constexpr int kChainSplit = CAREL_CHAIN_COLSPLIT;   // column parts of an inner tile (4 epilogue warps each)
+constexpr int kChainThreads = 64 + 128 * kChainSplit;
 
 enum TileMode : int { TILE_FULL = 0, TILE_TRI = 1 };
 

@@ -189,8 +189,7 @@ struct PolHsicBwd {
     const uint32_t rtot_bits = tmem_ld1(ctx.acc2_taddr + p.dim);   // ones column: sum_j w_ij
     tmem_ld_wait();
     const float rtot = __uint_as_float(rtot_bits);
-    const int q_split = (ctx.n2_16 + 1) >> 1;
-    const int q0 = ctx.half ? q_split : 0, q1 = ctx.half ? ctx.n2_16 : q_split;
+    const int q0 = (ctx.n2_16 * ctx.half) / kChainSplit, q1 = (ctx.n2_16 * (ctx.half + 1)) / kChainSplit;
     const float g = p.norm * __ldg(p.grad_out);
     const bool row_ok = valid && ctx.row < p.m;
     const int rowc = min(ctx.row, p.m - 1);
