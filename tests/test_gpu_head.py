@@ -72,8 +72,10 @@ def test_forward_backward_matches_oracle(variant, N, L, V, D, dropout):
     rgrads = torch.autograd.grad(rtotal, [X64] + list(p64.values()), allow_unused=True)
 
     for o, r in zip(outs, orefs):
-        assert rel(o.detach(), r.detach()) < 1e-3, (variant, "output")
+        assert rel(o.detach(), r.detach()) < (1e-4 if dropout == 0.0 else 1e-3), (variant, "output")
     # the fp32 oracle (dropout case) carries its own ~1e-3 noise on the Gram-loss gradient
+    # head level: the latent sample z is an INTERMEDIATE, so its bf16 rounding as a tensor-core operand of the
+    # MMD / decoder kernels is not shared with the oracle (op-level tests, where it is, are at 1e-5..3e-4)
     gtol = 2e-3 if dropout == 0.0 else 4e-3
     assert rel(grads[0], rgrads[0]) < gtol, (variant, "grad X", rel(grads[0], rgrads[0]))
     for (k, g), r in zip(zip(params.keys(), grads[1:]), rgrads[1:]):
