@@ -43,9 +43,11 @@ _SIGNATURES = {
     "carel_bow_bwd": (C.c_int, [c_ptr, c_ptr, i64, i64, i64, i64, i64, C.c_float, c_ptr, i64, c_ptr, c_ptr,
                                 c_ptr, C.c_size_t, c_ptr]),
     "carel_hsic_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
-    "carel_hsic_fwd": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.c_float, C.c_float, c_ptr, c_ptr,
+    "carel_hsic_fwd": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.c_float, C.c_float, i64, i64, c_ptr, c_ptr,
                                  C.c_size_t, c_ptr]),
-    "carel_hsic_bwd": (C.c_int, [c_ptr, i64, i64, i64, C.c_float, C.c_float, c_ptr, i64, c_ptr, i64, c_ptr,
+    "carel_hsic_ws_layout": (C.c_int, [i64, i64, i64, C.POINTER(i64)]),
+    "carel_hsic_finalize": (C.c_int, [i64, i64, i64, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "carel_hsic_bwd": (C.c_int, [c_ptr, i64, i64, i64, C.c_float, C.c_float, i64, i64, c_ptr, i64, c_ptr, i64, c_ptr,
                                  C.c_size_t, c_ptr]),
     "carel_pairwise_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "carel_pairwise": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.c_int, C.POINTER(C.c_float),

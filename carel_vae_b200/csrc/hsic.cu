@@ -224,9 +224,29 @@ extern "C" size_t carel_hsic_workspace_bytes(int64_t m, int64_t dx, int64_t dy) 
   return carve_hsic(nullptr, m, std::max(dx, dy)).bytes;
 }
 
+// Byte offsets inside the workspace of the quantities a multi-GPU caller all-reduces between the
+// partial forward and carel_hsic_finalize: rK [m] double, rL [m] double, acc [4] double.
+extern "C" int carel_hsic_ws_layout(int64_t m, int64_t dx, int64_t dy, int64_t* offsets3) {
+  const uintptr_t base = 1 << 20;   // any non-null, 256-aligned pseudo base: only the differences matter
+  HsicWs w = carve_hsic(reinterpret_cast<void*>(base), m, std::max(dx, dy));
+  offsets3[0] = int64_t(reinterpret_cast<uintptr_t>(w.rK) - base);
+  offsets3[1] = int64_t(reinterpret_cast<uintptr_t>(w.rL) - base);
+  offsets3[2] = int64_t(reinterpret_cast<uintptr_t>(w.acc) - base);
+  return 0;
+}
+
+extern "C" int carel_hsic_finalize(int64_t m, int64_t dx, int64_t dy, float* out, void* ws, size_t ws_bytes,
+                                   void* stream) {
+  HsicWs w = carve_hsic(ws, m, std::max(dx, dy));
+  CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_hsic_finalize: workspace too small");
+  hsic_finalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(w.rK, w.rL, w.acc, int(m), w.cK, w.cL, w.mean, out);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
 extern "C" int carel_hsic_fwd(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t m,
-                              int64_t dx, int64_t dy, float s_x, float s_y, float* out, void* ws,
-                              size_t ws_bytes, void* stream) {
+                              int64_t dx, int64_t dy, float s_x, float s_y, int64_t row_tile_begin,
+                              int64_t row_tile_end, float* out, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CAREL_REQUIRE(m >= 2 && dx > 0 && dy > 0, "carel_hsic_fwd: need m >= 2 and non-empty features");
   CAREL_REQUIRE(s_x != 0.f && s_y != 0.f, "carel_hsic_fwd: zero bandwidth");
@@ -249,18 +269,25 @@ extern "C" int carel_hsic_fwd(const float* x, int64_t ldx, const float* y, int64
                 make_tmap_bf16_sw128(&ya, w.YA, m, w.ldp, w.ldp, 128) == 0 &&
                 make_tmap_bf16_sw128(&yb, w.YB, m, w.ldp, w.ldp, 128) == 0, "carel_hsic_fwd: tensor map failed");
   GemmSched s = make_sched(m, m, w.ldp, 128, 1, TILE_FULL);
+  const int t0 = int(row_tile_begin < 0 ? 0 : row_tile_begin);
+  const int t1 = int((row_tile_end < 0 || row_tile_end > s.m_tiles) ? s.m_tiles : row_tile_end);
+  CAREL_REQUIRE(t0 <= t1, "carel_hsic_fwd: bad row tile range");
+  s.m_tile0 = t0;
+  s.num_items = (t1 - t0) * s.n_tiles;
   EpiHsicParams ep;
   ep.rK = w.rK; ep.rL = w.rL; ep.acc = w.acc; ep.m = int(m);
   ep.cx = 2.f * kLog2e / s_x; ep.cy = 2.f * kLog2e / s_y;
   if (int rc = launch_gemm<EpiHsic<128>, 128, 2, false, false>(xa, xb, ya, yb, s, ep, st, "hsic_gram_fwd")) return rc;
-  hsic_finalize_kernel<<<1, 1024, 0, st>>>(w.rK, w.rL, w.acc, int(m), w.cK, w.cL, w.mean, out);
-  CAREL_LAUNCHED();
+  // out == NULL: partial forward of a row block (multi-GPU); the caller all-reduces rK, rL, acc
+  // (carel_hsic_ws_layout) and calls carel_hsic_finalize.
+  if (out != nullptr) return carel_hsic_finalize(m, dx, dy, out, ws, ws_bytes, stream);
   return 0;
 }
 
 extern "C" int carel_hsic_bwd(const float* grad_out, int64_t m, int64_t dx, int64_t dy, float s_x,
-                              float s_y, float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy,
-                              void* ws, size_t ws_bytes, void* stream) {
+                              float s_y, int64_t row_tile_begin, int64_t row_tile_end, float* grad_x,
+                              int64_t ldgx, float* grad_y, int64_t ldgy, void* ws, size_t ws_bytes,
+                              void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   HsicWs w = carve_hsic(ws, m, std::max(dx, dy));
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_hsic_bwd: workspace too small");
@@ -275,7 +302,11 @@ extern "C" int carel_hsic_bwd(const float* grad_out, int64_t m, int64_t dx, int6
     const int r3 = make_tmap_bf16_sw128(&yb, w.YB, m, w.ldp, w.ldp, 64);
     CAREL_REQUIRE((r0 | r1 | r2 | r3) == 0, "carel_hsic_bwd: tensor map failed (%d %d %d %d; m=%lld ldp=%d)", r0, r1, r2, r3, (long long)m, w.ldp);
   }
-  ChainSched cs = make_chain_sched(0, int((m + 127) / 128), int((m + 63) / 64), k16, Cfg::stages_for(k16), 32);
+  const int m_tiles = int((m + 127) / 128);
+  const int t0 = int(row_tile_begin < 0 ? 0 : row_tile_begin);
+  const int t1 = int((row_tile_end < 0 || row_tile_end > m_tiles) ? m_tiles : row_tile_end);
+  CAREL_REQUIRE(t0 <= t1, "carel_hsic_bwd: bad row tile range");
+  ChainSched cs = make_chain_sched(t0, t1 - t0, int((m + 63) / 64), k16, Cfg::stages_for(k16), 32);
   const float norm = float(4.0 / ((double(m) - 1.0) * (double(m) - 1.0)));
   for (int side = 0; side < 2; ++side) {
     float* g = side ? grad_y : grad_x;

@@ -255,7 +255,7 @@ def bow_reconstruction_loss(z, dec_w, dec_b, content_bow=None, label_smoothing: 
 # --------------------------------------------------------------------------------------------
 class _HSICFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, y, s_x, s_y):
+    def forward(ctx, x, y, s_x, s_y, tile_range, reduce_fn):
         _require_cuda(x, y)
         xf, yf = _rowmajor_f32(x), _rowmajor_f32(y)
         m, dx = xf.shape
@@ -265,25 +265,37 @@ class _HSICFn(torch.autograd.Function):
         lb = lib()
         ws = _workspace(lb.carel_hsic_workspace_bytes(m, dx, dy), xf.device)
         out = torch.empty((), dtype=torch.float32, device=xf.device)
-        check(lb.carel_hsic_fwd(_p(xf), xf.stride(0), _p(yf), yf.stride(0), m, dx, dy, float(s_x), float(s_y),
-                                _p(out), _p(ws), ws.numel(), _stream()), "carel_hsic_fwd")
+        t0, t1 = tile_range
+        sharded = reduce_fn is not None
+        check(lb.carel_hsic_fwd(_p(xf), xf.stride(0), _p(yf), yf.stride(0), m, dx, dy, float(s_x), float(s_y), t0, t1,
+                                _p(None if sharded else out), _p(ws), ws.numel(), _stream()), "carel_hsic_fwd")
+        if sharded:
+            offs = (C.c_int64 * 3)()
+            lb.carel_hsic_ws_layout(m, dx, dy, offs)
+            for off, n in ((offs[0], m), (offs[1], m), (offs[2], 4)):
+                reduce_fn(ws[off:off + 8 * n].view(torch.float64))     # sum over ranks, in place
+            check(lb.carel_hsic_finalize(m, dx, dy, _p(out), _p(ws), ws.numel(), _stream()), "carel_hsic_finalize")
         ctx.ws = ws
-        ctx.meta = (m, dx, dy, float(s_x), float(s_y), x.dtype, y.dtype)
+        ctx.meta = (m, dx, dy, float(s_x), float(s_y), t0, t1, x.dtype, y.dtype)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        m, dx, dy, s_x, s_y, dtx, dty = ctx.meta
+        m, dx, dy, s_x, s_y, t0, t1, dtx, dty = ctx.meta
         ws = ctx.ws
         g = g.reshape(()).float().contiguous()
         need = ctx.needs_input_grad
         gx = torch.empty((m, dx), dtype=torch.float32, device=ws.device) if need[0] else None
         gy = torch.empty((m, dy), dtype=torch.float32, device=ws.device) if need[1] else None
-        check(lib().carel_hsic_bwd(_p(g), m, dx, dy, s_x, s_y, _p(gx), dx, _p(gy), dy, _p(ws), ws.numel(),
+        check(lib().carel_hsic_bwd(_p(g), m, dx, dy, s_x, s_y, t0, t1, _p(gx), dx, _p(gy), dy, _p(ws), ws.numel(),
                                    _stream()), "carel_hsic_bwd")
-        return (None if gx is None else gx.to(dtx), None if gy is None else gy.to(dty), None, None)
+        return (None if gx is None else gx.to(dtx), None if gy is None else gy.to(dty), None, None, None, None)
 
 
-def hsic(x: torch.Tensor, y: torch.Tensor, s_x: float = 1.0, s_y: float = 1.0) -> torch.Tensor:
-    """HSIC(x, y) of the reference (hsic.py:540-547) as a 0-dim fp32 tensor, differentiable."""
-    return _HSICFn.apply(x, y, s_x, s_y)
+def hsic(x: torch.Tensor, y: torch.Tensor, s_x: float = 1.0, s_y: float = 1.0, tile_range=(0, -1),
+         reduce_fn=None) -> torch.Tensor:
+    """HSIC(x, y) of the reference (hsic.py:540-547) as a 0-dim fp32 tensor, differentiable.
+    `tile_range` / `reduce_fn` implement the multi-GPU row-block sharding (see parallel.sharded_hsic):
+    the rank computes Gram row tiles [t0, t1) only, `reduce_fn(t)` sums a float64 tensor over the ranks in
+    place; the gradient rows of the rank's block are complete (other rows are zero)."""
+    return _HSICFn.apply(x, y, s_x, s_y, tuple(tile_range), reduce_fn)

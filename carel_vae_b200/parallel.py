@@ -80,6 +80,22 @@ def sharded_mmd(x: torch.Tensor, y: torch.Tensor, alphas: Sequence[float], group
     return finalize_mmd(partial, x.shape[0], y.shape[0]).to(torch.float32)
 
 
+def sharded_hsic(x: torch.Tensor, y: torch.Tensor, s_x: float = 1.0, s_y: float = 1.0, group=None) -> torch.Tensor:
+    """HSIC of replicated paired samples with the Gram row blocks sharded over the ranks of `group`
+    (SURVEY.md §8(e)): forward partials = three scalars + the row sums of the rank's rows, combined by
+    all-reduces of 2m + 4 doubles; the backward of a row block needs no collective (each rank gets the
+    gradient rows of its block, zeros elsewhere — all-reduce / all-gather them if every rank needs all rows)."""
+    from . import functional as F
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    t0, t1 = row_tile_range(x.shape[0], rank, world)
+
+    def reduce_fn(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return F.hsic(x, y, s_x, s_y, tile_range=(t0, t1), reduce_fn=reduce_fn)
+
+
 class FlatGradBucket:
     """One flat fp32 gradient buffer for a parameter list; param.grad become views into it."""
 

@@ -129,12 +129,19 @@ int carel_bow_bwd(const float* grad_out, const float* bow_dense, int64_t ld_bow,
  *   sums the backward call needs.
  * ------------------------------------------------------------------------------------------ */
 size_t carel_hsic_workspace_bytes(int64_t m, int64_t dx, int64_t dy);
+/* Forward of Gram row tiles [row_tile_begin, row_tile_end) (128-row tiles; 0, -1 = all).  With out != NULL
+ * the value is finalised.  Multi-GPU: every rank passes its row block with out = NULL, all-reduces the
+ * three regions of `ws` that carel_hsic_ws_layout names (row sums rK, rL: m doubles each; acc: 4 doubles;
+ * offsets in bytes) and calls carel_hsic_finalize.  Backward of a row block needs no collective. */
 int carel_hsic_fwd(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t m, int64_t dx,
-                   int64_t dy, float s_x, float s_y, float* out, void* ws, size_t ws_bytes,
-                   void* stream);
+                   int64_t dy, float s_x, float s_y, int64_t row_tile_begin, int64_t row_tile_end,
+                   float* out, void* ws, size_t ws_bytes, void* stream);
+int carel_hsic_ws_layout(int64_t m, int64_t dx, int64_t dy, int64_t* offsets3);
+int carel_hsic_finalize(int64_t m, int64_t dx, int64_t dy, float* out, void* ws, size_t ws_bytes,
+                        void* stream);
 int carel_hsic_bwd(const float* grad_out, int64_t m, int64_t dx, int64_t dy, float s_x, float s_y,
-                   float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy, void* ws,
-                   size_t ws_bytes, void* stream);
+                   int64_t row_tile_begin, int64_t row_tile_end, float* grad_x, int64_t ldgx,
+                   float* grad_y, int64_t ldgy, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }
