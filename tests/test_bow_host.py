@@ -1,0 +1,36 @@
+"""CPU: host-side BoW target production against a literal restatement of the reference loop
+(ECPEDataset._get_bow_representations, drl_classifier_ec_mmd_final_mul.py:107-119)."""
+import numpy as np
+import torch
+
+from carel_vae_b200.bow import BowEncoder, bow_tokenize
+
+
+def _reference_rows(bow_features, words):
+    rep = np.zeros(shape=len(bow_features), dtype=np.float32)
+    for word in words:
+        if word in bow_features:
+            rep[bow_features.index(word)] += 1
+    rep /= np.max([np.sum(rep), 1])
+    return rep
+
+
+def test_dense_and_ell_match_reference_loop():
+    rng = np.random.default_rng(0)
+    vocab = [f"w{i}" for i in range(500)] + ["w3"]          # a duplicate entry: list.index takes the first
+    enc = BowEncoder(vocab)
+    batch = [[f"w{int(j)}" for j in rng.integers(0, 700, size=rng.integers(0, 40))] for _ in range(50)]
+    batch.append([])                                          # empty sample: all-zero target
+    dense = np.stack([enc.dense(w) for w in batch])
+    ref = np.stack([_reference_rows(vocab, w) for w in batch])
+    assert np.array_equal(dense, ref)
+    cols, vals, nnz = enc.ell_batch(batch, cap=48)
+    rebuilt = torch.zeros(len(batch), len(vocab))
+    for b in range(len(batch)):
+        n = int(nnz[b])
+        rebuilt[b, cols[b, :n].long()] = vals[b, :n]
+    assert torch.equal(rebuilt, torch.from_numpy(ref))
+
+
+def test_bow_tokenize_matches_reference_rule():
+    assert bow_tokenize("Hello, World!  it's Ġfine.") == ["hello", "world", "its", "fine"]
