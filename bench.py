@@ -137,7 +137,7 @@ def run_ours(args):
     params = model.get_params()
     bucket = FlatGradBucket(params)
     # the four latent projections receive gradients but are not stepped (reference get_params, mmd:292-297)
-    optim = torch.optim.Adam(params, lr=1e-5, capturable=True)
+    optim = torch.optim.Adam(params, lr=1e-5, capturable=True, fused=True)
     loss_buf = torch.zeros((), device=dev)
     it_counter = [0]
 

@@ -35,7 +35,7 @@ constexpr float kTinyLogP = -6.9314718f;   // log(2^-10): below this the 3-term 
 struct BowWs {
   __nv_bfloat16* ZA;    // [N, ldk]
   __nv_bfloat16* WB;    // [V, ldk]
-  __nv_bfloat16* dl;    // [N, Vp]  dense dlogits (backward)
+  __nv_bfloat16* dlT;   // [V, Np]  dense dlogits, vocabulary-major (backward)
   float* part;          // [NTp, Npad] float2 (max, sumexp) partials
   float* lse;           // [Npad]  holds -lse
   float* srow;          // [Npad]  S_i = N V s_i
@@ -50,19 +50,19 @@ struct BowWs {
   int* csc_row;         // [N*cap]
   int* csc_slot;        // [N*cap]
   size_t bytes;
-  int ldk, Vp, Npad, ntp;
+  int ldk, Np, Npad, ntp;
 };
 
 static BowWs carve_bow(void* ws, int64_t N, int64_t K, int64_t V, int64_t cap) {
   WsCarver w(ws);
   BowWs r;
   r.ldk = aug_width(int(K));
-  r.Vp = int(round_up64(V, 64));
+  r.Np = int(round_up64(N, 64));
   r.Npad = int(round_up64(N, 128));
   r.ntp = int((V + 255) / 256) * kColSplit;
   r.ZA = w.take<__nv_bfloat16>(size_t(N) * r.ldk);
   r.WB = w.take<__nv_bfloat16>(size_t(V) * r.ldk);
-  r.dl = w.take<__nv_bfloat16>(size_t(N) * r.Vp);
+  r.dlT = w.take<__nv_bfloat16>(size_t(V) * r.Np);
   r.part = w.take<float>(size_t(r.ntp) * r.Npad * 2);
   r.lse = w.take<float>(size_t(r.Npad));
   r.srow = w.take<float>(size_t(r.Npad));
@@ -589,60 +589,71 @@ static __global__ void bow_loss_finalize_kernel(const double* __restrict__ lossa
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 3 policy: P = dense dlogits of the tile (rows = owner clause tile, cols = 64 vocab entries)
-//   dl = (u - p S_i) * g / (N V);   acc2 = sum_v dl w_v  -> atomically added to grad_z
+// pass 3 policy (vocabulary-major): owner = 128 vocabulary rows, inner tiles = 64 clause rows.
+//   acc1[v, i] = log p_iv ;  P[v, i] = dlogit_iv = (u - p S_i) g / (N V)  (bf16, also stored as dl^T [V, Npad]);
+//   acc2 = dW_v = sum_i P[v, i] z_i  (GEMM-2 over the SAME ZA tile, read MN-major; atomically added to dWacc);
+//   db_v = sum_i P[v, i] is a thread-local sum (each epilogue thread owns one vocabulary row).
 // ---------------------------------------------------------------------------------------------
 struct BowBwdParams {
-  const float* srow;
+  const float* srow;     // [Npad]  S_i (zero beyond N)
   const float* grad_out;
-  __nv_bfloat16* dl;     // [N, Vp]
-  float* grad_z;
-  int64_t ldgz;
-  int N, V, Vp, K;
+  __nv_bfloat16* dlT;    // [V, Np]
+  float* dWacc;          // [V, ldk]
+  int N, V, Np, K, ldk;
   float c, inv_nv;
 };
 struct PolBowBwd {
   using Params = BowBwdParams;
   static constexpr bool kHiLo = false;    // measured decoder gradients are 6e-5..3e-4 with a single bf16 P
   const Params& p;
-  float Si, scale;
-  CAREL_DEVINL PolBowBwd(const Params& p_, const ChainCtx&) : p(p_), Si(0.f), scale(0.f) {}
-  CAREL_DEVINL void begin_item(const ChainCtx& ctx) {
-    Si = (ctx.row < p.N) ? __ldg(p.srow + ctx.row) : 0.f;
+  float scale, dbsum;
+  CAREL_DEVINL PolBowBwd(const Params& p_, const ChainCtx&) : p(p_), scale(0.f), dbsum(0.f) {}
+  CAREL_DEVINL void begin_item(const ChainCtx&) {
     scale = __ldg(p.grad_out) * p.inv_nv;
+    dbsum = 0.f;
   }
   CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
-  CAREL_DEVINL void weights16(const ChainCtx& ctx, int v0, const uint32_t (&r)[16], const uint32_t (&)[16],
+  CAREL_DEVINL void weights16(const ChainCtx& ctx, int i0, const uint32_t (&r)[16], const uint32_t (&)[16],
                               float (&d)[16]) {
     const float c = p.c;
-    float x[16];
+    float x[16], S[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
+    const float4* s4 = reinterpret_cast<const float4*>(p.srow + i0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldg(s4 + i);
+      S[4 * i] = v.x; S[4 * i + 1] = v.y; S[4 * i + 2] = v.z; S[4 * i + 3] = v.w;
+    }
     float mx = fmaxf(x[0], x[1]), mn = fminf(x[0], x[1]);
 #pragma unroll
     for (int i = 2; i < 16; ++i) { mx = fmaxf(mx, x[i]); mn = fminf(mn, x[i]); }
-    if (ctx.row >= p.N) {
+    if (ctx.row >= p.V) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) d[i] = 0.f;
-    } else if (v0 + 16 <= p.V && mx < kTinyLogP && mn > -27.f) {
+    } else if (i0 + 16 <= p.N && mx < kTinyLogP && mn > -27.f) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float pv = ex2_approx(x[i] * kLog2e);
         const float q = fmaf(pv, fmaf(pv, 1.f, 1.f), 1.f);        // 1 + p + p^2
-        d[i] = fmaf(pv - c, q, -pv * Si) * scale;
+        d[i] = fmaf(pv - c, q, -pv * S[i]) * scale;
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float f, u;
         bow_exact_terms(x[i], c, f, u);
-        d[i] = (v0 + i < p.V) ? (u - __expf(x[i]) * Si) * scale : 0.f;
+        d[i] = (i0 + i < p.N) ? (u - __expf(x[i]) * S[i]) * scale : 0.f;
       }
     }
+    float t = 0.f;                       // db_v: thread-local column sum (fp32, before the bf16 rounding)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += d[i];
+    dbsum += t;
   }
-  CAREL_DEVINL void store16(const ChainCtx& ctx, int v0, const uint32_t (&packed)[8]) {
-    if (ctx.row < p.N && v0 < p.Vp) {
-      uint4* dst = reinterpret_cast<uint4*>(p.dl + size_t(ctx.row) * p.Vp + v0);
+  CAREL_DEVINL void store16(const ChainCtx& ctx, int i0, const uint32_t (&packed)[8]) {
+    if (ctx.row < p.V && i0 < p.Np) {
+      uint4* dst = reinterpret_cast<uint4*>(p.dlT + size_t(ctx.row) * p.Np + i0);
       dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
     }
@@ -650,8 +661,8 @@ struct PolBowBwd {
   CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
     const int n16 = p.K / 16;                       // feature columns only
     const int q0 = (n16 * ctx.half) / kChainSplit, q1 = (n16 * (ctx.half + 1)) / kChainSplit;
-    const bool row_ok = valid && ctx.row < p.N;
-    float* dst = p.grad_z + size_t(min(ctx.row, p.N - 1)) * p.ldgz;
+    const bool row_ok = valid && ctx.row < p.V;
+    float* dst = p.dWacc + size_t(min(ctx.row, p.V - 1)) * p.ldk;
 #pragma unroll 1
     for (int q = q0; q < q1; ++q) {
       uint32_t r[16];
@@ -661,6 +672,7 @@ struct PolBowBwd {
 #pragma unroll
       for (int i = 0; i < 16; ++i) atomicAdd(dst + q * 16 + i, __uint_as_float(r[i]));
     }
+    if (row_ok && dbsum != 0.f) atomicAdd(dst + p.K + 3, dbsum);    // every column part adds its share
   }
   CAREL_DEVINL void finish() {}
 };
@@ -786,36 +798,35 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
     bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
     CAREL_LAUNCHED();
   }
-  // ---- pass 3: dense dlogits -> dZ (and bf16 copy for pass 4) ----
+  // ---- pass 3: dense dlogits (vocabulary-major) -> dW (TMEM) + db, bf16 copy dl^T for pass 4 ----
   {
     using Cfg = ChainCfg<1, 64>;
     CUtensorMap ta, tb;
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.ZA, N, w.ldk, w.ldk, 128) == 0, "carel_bow_bwd: tensor map Z failed");
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.WB, V, w.ldk, w.ldk, 128) == 0, "carel_bow_bwd: tensor map W failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.ZA, N, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z failed");
     const int k16 = w.ldk / 16;
-    ChainSched cs = make_chain_sched(0, int((N + 127) / 128), int((V + 63) / 64), k16, Cfg::stages_for(k16), 16);
+    ChainSched cs = make_chain_sched(0, int((V + 127) / 128), int((N + 63) / 64), k16, Cfg::stages_for(k16), 16);
     cs.n2_16 = int(K / 16);
     BowBwdParams bp;
-    bp.srow = w.srow; bp.grad_out = grad_out; bp.dl = w.dl; bp.grad_z = grad_z; bp.ldgz = ldgz;
-    bp.N = int(N); bp.V = int(V); bp.Vp = w.Vp; bp.K = int(K);
+    bp.srow = w.srow; bp.grad_out = grad_out; bp.dlT = w.dlT; bp.dWacc = w.dWacc;
+    bp.N = int(N); bp.V = int(V); bp.Np = w.Np; bp.K = int(K); bp.ldk = w.ldk;
     bp.c = label_smoothing / float(V); bp.inv_nv = inv_nv;
-    if (int rc = launch_chain<PolBowBwd, 1, 64>(ta, tb, ta, tb, cs, bp, st, "bow_pass3_dlogits_dz")) return rc;
+    if (int rc = launch_chain<PolBowBwd, 1, 64>(ta, tb, ta, tb, cs, bp, st, "bow_pass3_dlogits_dw")) return rc;
   }
-  // ---- pass 4: [dW | . | db] = dlogit^T [Z | . | 1] ----
-  if (need_w) {
+  // ---- pass 4: dZ += dlogit W_d = (dl^T)^T W_d  (both operands MN-major, split-K over the vocabulary) ----
+  {
     CUtensorMap ta, tb;
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.dl, N, V, w.Vp, 64) == 0, "carel_bow_bwd: tensor map dl failed");
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.ZA, N, K + 4, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z^T failed");
-    GemmSched s = make_sched(V, K + 4, N, 256, 1, TILE_FULL);
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.dlT, V, N, w.Np, 64) == 0, "carel_bow_bwd: tensor map dl^T failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, K, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
+    GemmSched s = make_sched(N, K, V, 256, 1, TILE_FULL);
     const int tiles = s.m_tiles * s.n_tiles;
-    const int num_kb = (s.num_k16 + 3) / 4;
-    int ks = std::max(1, std::min(num_kb, (4 * sm_count() + tiles - 1) / tiles));
-    s.ksplit = ks;
-    s.num_items = tiles * ks;
+    set_ksplit(s, (4 * sm_count() + tiles - 1) / tiles);
     EpiStore<256>::Params ep;
-    ep.out = w.dWacc; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(V); ep.N = int(K + 4);
-    ep.ld = w.ldk; ep.ld_bf16 = 0; ep.atomic = 1; ep.scale = 1.f;
-    if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st, "bow_pass4_dw")) return rc;
+    ep.out = grad_z; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(N); ep.N = int(K);
+    ep.ld = int(ldgz); ep.ld_bf16 = 0; ep.atomic = 1; ep.scale = 1.f;
+    if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st, "bow_pass4_dz")) return rc;
+  }
+  if (need_w) {
     bow_scatter_grads_kernel<<<148 * 4, 256, 0, st>>>(w.dWacc, w.ldk, int(V), int(K), grad_w, grad_b);
     CAREL_LAUNCHED();
   }

@@ -29,7 +29,7 @@ struct EpiStore {
   CAREL_DEVINL void tile(const TileCtx& ctx) {
     constexpr int HALF = BN / kColSplit;
     const int cbase = ctx.col0 + ctx.half * HALF;
-    const bool row_ok = ctx.row < p.M;
+    const bool row_ok = ctx.row < p.M && ctx.kb1 > ctx.kb0;   // an empty split-K item holds no valid accumulator
 #pragma unroll 1
     for (int c = 0; c < HALF / 32; ++c) {
       uint32_t r[32];

@@ -27,15 +27,23 @@ int launch_gemm(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap&
 }
 
 
+// Split-K factor without empty splits: `desired` is rounded so that every split owns >= 1 k-block.
+inline void set_ksplit(GemmSched& s, int desired) {
+  const int num_kb = (s.num_k16 + 3) / 4;
+  if (desired < 1) desired = 1;
+  if (desired > num_kb) desired = num_kb;
+  const int per = (num_kb + desired - 1) / desired;
+  s.ksplit = (num_kb + per - 1) / per;
+  s.num_items = s.m_tiles * s.n_tiles * s.ksplit;
+}
+
 inline GemmSched make_sched(int64_t M, int64_t N, int64_t K, int BN, int ksplit, int mode) {
   GemmSched s;
   s.m_tiles = int((M + 127) / 128);
   s.n_tiles = int((N + BN - 1) / BN);
   s.num_k16 = int((K + 15) / 16);
-  const int num_kb = (s.num_k16 + 3) / 4;
-  s.ksplit = ksplit < 1 ? 1 : (ksplit > num_kb ? num_kb : ksplit);
   s.mode = mode;
-  s.num_items = s.m_tiles * s.n_tiles * s.ksplit;
+  set_ksplit(s, ksplit);
   s.m_tile0 = 0;
   s.n_cols = int(N);
   return s;

@@ -268,12 +268,7 @@ extern "C" int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* 
     CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.Xp, N, D + 1, w.ldx, 64) == 0, "carel_latent_bwd: tensor map X failed");
     GemmSched s = make_sched(K2, D + 1, N, 256, 1, TILE_FULL);
     const int tiles = s.m_tiles * s.n_tiles;
-    int ks = (2 * sm_count() + tiles - 1) / tiles;
-    const int num_kb = (s.num_k16 + 3) / 4;
-    if (ks > num_kb) ks = num_kb;
-    if (ks < 1) ks = 1;
-    s.ksplit = ks;
-    s.num_items = tiles * ks;
+    set_ksplit(s, (2 * sm_count() + tiles - 1) / tiles);
     CAREL_CHECK_CUDA(cudaMemsetAsync(w.dW, 0, size_t(K2) * w.ldx * 4, st));
     EpiStore<256>::Params ep;
     ep.out = w.dW; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(K2); ep.N = int(D + 1);
