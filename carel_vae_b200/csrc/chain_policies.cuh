@@ -30,6 +30,7 @@ struct MmdBwdParams {
   float a_shift[kMaxAlphas];  // -alpha eps log2 e
   float a_pos[kMaxAlphas];    // alpha
   float w_scale, inv_w_scale; // power-of-two scaling that puts W into fp16's range
+  int atomic;                 // 0: each gradient row is produced by exactly one work item -> plain stores
 };
 
 struct PolMmdBwd {
@@ -111,12 +112,26 @@ struct PolMmdBwd {
       tmem_ld_wait();
       if (!row_ok) continue;
       const uint32_t u[8] = {sv0.x, sv0.y, sv0.z, sv0.w, sv1.x, sv1.y, sv1.z, sv1.w};
+      float v[16];
 #pragma unroll
       for (int h = 0; h < 8; ++h) {
         const float2 s2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
-        const int f = q * 16 + 2 * h;
-        if (f < p.dim) atomicAdd(dst + f, g4 * (rtot * s2.x - __uint_as_float(r[2 * h])));
-        if (f + 1 < p.dim) atomicAdd(dst + f + 1, g4 * (rtot * s2.y - __uint_as_float(r[2 * h + 1])));
+        v[2 * h] = g4 * (rtot * s2.x - __uint_as_float(r[2 * h]));
+        v[2 * h + 1] = g4 * (rtot * s2.y - __uint_as_float(r[2 * h + 1]));
+      }
+      const int f0 = q * 16;
+      if (!p.atomic && f0 + 16 <= p.dim && ((reinterpret_cast<uintptr_t>(dst + f0) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<float4*>(dst + f0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else if (!p.atomic) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (f0 + i < p.dim) dst[f0 + i] = v[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (f0 + i < p.dim) atomicAdd(dst + f0 + i, v[i]);
       }
     }
   }

@@ -188,7 +188,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint32_t aphase = 0, acc2_phase = 0;
     constexpr uint32_t idesc1 = make_idesc_bf16(128, BN1, 0, 0);
     const uint32_t idesc2 = make_idesc_bf16(128, 16 * sched.n2_16, 0, 1);
-    const uint32_t a_base = smem_u32(sA);
+    const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(sA), 16, 1024);
     const uint32_t b_base0 = smem_u32(sB);
     const uint32_t acc2_addr = tmem_base + Cfg::kAcc2Base;
     while (iter.next(it)) {
@@ -202,12 +202,16 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll 1
         for (int g = 0; g < NG; ++g) {
           const uint32_t d_addr = tmem_base + g1_buf * Cfg::kAcc1Cols + g * BN1;
+          uint64_t da = sdesc_advance(a_desc0, g * KB * 16384);
+          uint64_t db = make_sdesc_sw128(b_tile + g * KB * (BN1 * 128), 16, 1024);
 #pragma unroll 1
-          for (int k = 0; k < K16; ++k) {
-            const int kb = k >> 2, k16 = k & 3;
-            const uint64_t da = make_sdesc_sw128(a_base + (g * KB + kb) * 16384 + k16 * 32, 16, 1024);
-            const uint64_t db = make_sdesc_sw128(b_tile + (g * KB + kb) * (BN1 * 128) + k16 * 32, 16, 1024);
-            umma_ss(d_addr, da, db, idesc1, k ? 1u : 0u);
+          for (int kb = 0; kb < KB; ++kb) {
+            const int nk = min(4, K16 - kb * 4);
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              if (k16 < nk) umma_ss(d_addr, sdesc_advance(da, k16 * 32), sdesc_advance(db, k16 * 32), idesc1, (kb | k16) ? 1u : 0u);
+            da = sdesc_advance(da, 16384);
+            db = sdesc_advance(db, BN1 * 128);
           }
         }
         umma_commit(&acc1_full[g1_buf]);
@@ -219,7 +223,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         else { mbar_wait(&p_full[1], p_phase1); p_phase1 ^= 1; }
         if (first_g2) mbar_wait(acc2_empty, acc2_phase ^ 1);
         tc_fence_after();
-        const uint32_t b_tile = b_base0 + g2_stage * b_bytes;   // product 0, MN-major view
+        const uint64_t db0 = make_sdesc_sw128(b_base0 + g2_stage * b_bytes, BN1 * 128, 1024);   // product 0, MN-major view
         const uint32_t p_base = tmem_base + g2_buf * Cfg::kAcc1Cols;
 #pragma unroll
         for (int h = 0; h < kChainSplit; ++h) {
@@ -227,8 +231,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           for (int part = 0; part < (HILO ? 2 : 1); ++part) {
 #pragma unroll
             for (int k16 = 0; k16 < R / 16; ++k16) {
-              const uint64_t db = make_sdesc_sw128(b_tile + (h * R + k16 * 16) * 128, BN1 * 128, 1024);
-              umma_ts(acc2_addr, p_base + h * R + part * (R / 2) + k16 * 8, db, idesc2, first_g2 ? 0u : 1u);
+              umma_ts(acc2_addr, p_base + h * R + part * (R / 2) + k16 * 8, sdesc_advance(db0, (h * R + k16 * 16) * 128),
+                      idesc2, first_g2 ? 0u : 1u);
               first_g2 = false;
             }
           }

@@ -271,6 +271,10 @@ CAREL_DEVINL uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
   return d;
 }
 
+// Advance the start-address field of a descriptor by `bytes` (multiple of 16; the field is 14 bits of
+// addr >> 4 and all our tiles live inside one CTA's < 256 KB window, so a plain add cannot carry out).
+CAREL_DEVINL uint64_t sdesc_advance(uint64_t desc, uint32_t bytes) { return desc + uint64_t(bytes >> 4); }
+
 // ----------------------------------------------------------------------------
 // math / misc
 // ----------------------------------------------------------------------------

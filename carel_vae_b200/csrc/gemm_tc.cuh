@@ -207,17 +207,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_base = a_base + Cfg::kStageA;
+          const uint64_t da0 = A_MN ? make_sdesc_sw128(a_base, 8192, 1024) : make_sdesc_sw128(a_base, 16, 1024);
+          const uint64_t db0 = B_MN ? make_sdesc_sw128(a_base + Cfg::kStageA, 8192, 1024)
+                                    : make_sdesc_sw128(a_base + Cfg::kStageA, 16, 1024);
           const int nk = min(4, sched.num_k16 - kb * 4);
 #pragma unroll
           for (int k16 = 0; k16 < 4; ++k16) {
-            if (k16 < nk) {
-              const uint64_t da = A_MN ? make_sdesc_sw128(a_base + k16 * 2048, 8192, 1024)
-                                       : make_sdesc_sw128(a_base + k16 * 32, 16, 1024);
-              const uint64_t db = B_MN ? make_sdesc_sw128(b_base + k16 * 2048, 8192, 1024)
-                                       : make_sdesc_sw128(b_base + k16 * 32, 16, 1024);
-              umma_ss(d_addr, da, db, idesc, (kb > it.kb0 || k16 > 0) ? 1u : 0u);
-            }
+            if (k16 < nk)
+              umma_ss(d_addr, sdesc_advance(da0, k16 * (A_MN ? 2048 : 32)),
+                      sdesc_advance(db0, k16 * (B_MN ? 2048 : 32)), idesc, (kb > it.kb0 || k16 > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -102,14 +102,22 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
 }
 
 template <int BN1>
-static int mmd_bwd_launch(const MmdWs& w, const MmdBwdParams& pp, int64_t M, int ldp, int t0, int t1,
-                          cudaStream_t st) {
+static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, int t0, int t1,
+                          float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy, int64_t n1, int64_t n2,
+                          int64_t dim, cudaStream_t st) {
   using Cfg = ChainCfg<1, BN1>;
   CUtensorMap ta, tb;
   CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.SA, M, ldp, ldp, 128) == 0, "carel_mmd_bwd: tensor map A failed");
   CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.SB, M, ldp, ldp, BN1) == 0, "carel_mmd_bwd: tensor map B failed");
   const int k16 = ldp / 16;
   ChainSched s = make_chain_sched(t0, t1 - t0, int((M + BN1 - 1) / BN1), k16, Cfg::stages_for(k16), 32);
+  // rows outside [t0, t1) * 128 must read as zero; with one work item per row tile the rows inside are
+  // written exactly once (plain stores), otherwise partial sums are accumulated atomically
+  pp.atomic = s.nsplit > 1;
+  if (pp.atomic || t0 > 0 || t1 * 128 < M) {
+    CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_x, size_t(ldgx) * 4, 0, size_t(dim) * 4, size_t(n1), st));
+    CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_y, size_t(ldgy) * 4, 0, size_t(dim) * 4, size_t(n2), st));
+  }
   return launch_chain<PolMmdBwd, 1, BN1>(ta, tb, ta, tb, s, pp, st, "mmd_gram_bwd");
 }
 
@@ -130,8 +138,6 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   const int t0 = int(row_tile_begin < 0 ? 0 : row_tile_begin);
   const int t1 = int((row_tile_end < 0 || row_tile_end > m_tiles) ? m_tiles : row_tile_end);
   CAREL_REQUIRE(t0 <= t1, "carel_mmd_bwd: bad row tile range");
-  CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_x, size_t(ldgx) * 4, 0, size_t(dim) * 4, size_t(n1), st));
-  CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_y, size_t(ldgy) * 4, 0, size_t(dim) * 4, size_t(n2), st));
   MmdBwdParams pp;
   pp.SA = w.SA; pp.grad_out = grad_out; pp.grad_x = grad_x; pp.grad_y = grad_y;
   pp.ldgx = int(ldgx); pp.ldgy = int(ldgy); pp.dim = int(dim); pp.ldp = ldp;
@@ -153,6 +159,6 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   (void)asum;
   pp.w_scale = 1.f;
   pp.inv_w_scale = 1.f;
-  if (ldp <= ChainCfg<1, 128>::kMaxN2) return mmd_bwd_launch<128>(w, pp, M, ldp, t0, t1, st);
-  return mmd_bwd_launch<64>(w, pp, M, ldp, t0, t1, st);
+  if (ldp <= ChainCfg<1, 128>::kMaxN2) return mmd_bwd_launch<128>(w, pp, M, ldp, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
+  return mmd_bwd_launch<64>(w, pp, M, ldp, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
 }
