@@ -8,7 +8,7 @@ Host code is PyTorch (memory, streams, autograd plumbing); the arithmetic runs i
 CUDA kernels of libcarel_head.so, reached through the C ABI in include/carel_head.h.  There is no
 CPU / PyTorch fallback: without the built extension every op raises.
 """
-from ._lib import CarelError, launch_count, lib  # noqa: F401
+from ._lib import CarelError, get_precision, launch_count, lib, set_precision  # noqa: F401
 from . import functional  # noqa: F401
 from .losses import (GaussianKernelMatrix, HSIC, MMDStatistic, pairwise_distances, pdist,  # noqa: F401
                      permutation_test_mat)

@@ -26,12 +26,12 @@ _SIGNATURES = {
     "carel_timing_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "carel_gemm_bf16": (C.c_int, [c_ptr, i64, C.c_int, c_ptr, i64, C.c_int, i64, i64, i64, c_ptr, i64,
                                   c_ptr, C.c_int, c_ptr]),
-    "carel_mmd_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
+    "carel_mmd_workspace_bytes": (C.c_size_t, [i64, i64, i64, C.c_int]),
     "carel_mmd_fwd": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.POINTER(C.c_float), C.c_int,
-                                C.c_float, C.c_int, i64, i64, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+                                C.c_float, C.c_int, i64, i64, c_ptr, c_ptr, c_ptr, C.c_size_t, C.c_int, c_ptr]),
     "carel_mmd_finalize": (C.c_int, [c_ptr, i64, i64, c_ptr, c_ptr]),
     "carel_mmd_bwd": (C.c_int, [c_ptr, i64, i64, i64, C.POINTER(C.c_float), C.c_int, C.c_float, i64, i64,
-                                c_ptr, i64, c_ptr, i64, c_ptr, C.c_size_t, c_ptr]),
+                                c_ptr, i64, c_ptr, i64, c_ptr, C.c_size_t, C.c_int, c_ptr]),
     "carel_latent_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "carel_latent_fwd": (C.c_int, [c_ptr, i64, i64, i64, i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_ptr,
                                    c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
@@ -115,3 +115,26 @@ def timing_report() -> dict:
         tag, ms, cnt = line.split()
         out[tag] = (float(ms), int(cnt))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# precision mode of the ops: "bf16" (tensor-core operands rounded to bf16; default) or "fp32"
+# (operands split into two bf16 terms, ~1e-5 accurate, 3x the tensor work)
+# ------------------------------------------------------------------------------------------------
+_PRECISION = {"bf16": 0, "fp32": 1}
+_default_precision = "bf16"
+
+
+def set_precision(mode: str) -> None:
+    global _default_precision
+    if mode not in _PRECISION:
+        raise ValueError(f"precision must be one of {list(_PRECISION)}")
+    _default_precision = mode
+
+
+def get_precision() -> str:
+    return _default_precision
+
+
+def precision_code(mode=None) -> int:
+    return _PRECISION[_default_precision if mode is None else mode]

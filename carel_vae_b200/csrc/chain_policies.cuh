@@ -31,6 +31,10 @@ struct MmdBwdParams {
   float a_pos[kMaxAlphas];    // alpha
   float w_scale, inv_w_scale; // power-of-two scaling that puts W into fp16's range
   int atomic;                 // 0: each gradient row is produced by exactly one work item -> plain stores
+  // fp32 mode (3-term split operands, pack3_rows_kernel): acc2 holds W.s1 in columns [0, kp) and W.s2 in
+  // [kp, 2 kp), the row sum in column 2 kp; s_i itself is read in fp32 from S32.
+  int split, kp, ld32;
+  const float* S32;
 };
 
 struct PolMmdBwd {
@@ -92,11 +96,12 @@ struct PolMmdBwd {
   }
   CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
   CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
-    // row sum of the rounded W: the ones column (index dim) of the B operand
-    const uint32_t rtot_bits = tmem_ld1(ctx.acc2_taddr + p.dim);
+    // row sum of the rounded W: the ones column of the B operand
+    const uint32_t rtot_bits = tmem_ld1(ctx.acc2_taddr + (p.split ? 2 * p.kp : p.dim));
     tmem_ld_wait();
     const float rtot = __uint_as_float(rtot_bits);
-    const int q0 = (ctx.n2_16 * ctx.half) / kChainSplit, q1 = (ctx.n2_16 * (ctx.half + 1)) / kChainSplit;
+    const int nfeat16 = p.split ? (p.kp >> 4) : ctx.n2_16;
+    const int q0 = (nfeat16 * ctx.half) / kChainSplit, q1 = (nfeat16 * (ctx.half + 1)) / kChainSplit;
     const float g4 = 4.f * __ldg(p.grad_out) * p.inv_w_scale;
     const bool row_ok = valid && ctx.row < p.M;
     const int rowc = min(ctx.row, p.M - 1);
@@ -105,19 +110,33 @@ struct PolMmdBwd {
                                : p.grad_y + size_t(rowc - p.n1) * p.ldgy;
 #pragma unroll 1
     for (int q = q0; q < q1; ++q) {
-      uint32_t r[16];
+      uint32_t r[16], r2[16];
+      float sv[16];
       tmem_ld16(ctx.acc2_taddr + q * 16, r);
-      const uint4 sv0 = __ldg(reinterpret_cast<const uint4*>(srow + q * 16));
-      const uint4 sv1 = __ldg(reinterpret_cast<const uint4*>(srow + q * 16) + 1);
+      if (p.split) {
+        tmem_ld16(ctx.acc2_taddr + p.kp + q * 16, r2);
+        const float* s32 = p.S32 + size_t(rowc) * p.ld32 + q * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sv[i] = (q * 16 + i < p.dim) ? __ldg(s32 + i) : 0.f;
+      } else {
+        const uint4 sv0 = __ldg(reinterpret_cast<const uint4*>(srow + q * 16));
+        const uint4 sv1 = __ldg(reinterpret_cast<const uint4*>(srow + q * 16) + 1);
+        const uint32_t u[8] = {sv0.x, sv0.y, sv0.z, sv0.w, sv1.x, sv1.y, sv1.z, sv1.w};
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const float2 s2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
+          sv[2 * h] = s2.x;
+          sv[2 * h + 1] = s2.y;
+        }
+      }
       tmem_ld_wait();
       if (!row_ok) continue;
-      const uint32_t u[8] = {sv0.x, sv0.y, sv0.z, sv0.w, sv1.x, sv1.y, sv1.z, sv1.w};
       float v[16];
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        const float2 s2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
-        v[2 * h] = g4 * (rtot * s2.x - __uint_as_float(r[2 * h]));
-        v[2 * h + 1] = g4 * (rtot * s2.y - __uint_as_float(r[2 * h + 1]));
+      for (int i = 0; i < 16; ++i) {
+        float g = __uint_as_float(r[i]);
+        if (p.split) g += __uint_as_float(r2[i]);
+        v[i] = g4 * (rtot * sv[i] - g);
       }
       const int f0 = q * 16;
       if (!p.atomic && f0 + 16 <= p.dim && ((reinterpret_cast<uintptr_t>(dst + f0) & 15) == 0)) {

@@ -14,15 +14,20 @@ struct MmdWs {
   __nv_bfloat16* SA;  // [M, ldp] augmented row operand of cat(x, y)
   __nv_bfloat16* SB;  // [M, ldp] augmented column operand
   double* accum;      // [4] block sums
+  float* S32;         // [M, dim] fp32 copy of cat(x, y) (fp32 mode only)
   size_t bytes;
+  int ldp;
 };
 
-static MmdWs carve_mmd(void* ws, int64_t M, int64_t ldp) {
+// precision 0: bf16 operands [s | aug] (aug_width);  1: two-term split operands (split_width)
+static MmdWs carve_mmd(void* ws, int64_t M, int64_t dim, int precision) {
   WsCarver w(ws);
   MmdWs r;
-  r.SA = w.take<__nv_bfloat16>(size_t(M) * ldp);
-  r.SB = w.take<__nv_bfloat16>(size_t(M) * ldp);
+  r.ldp = precision ? split_width(int(dim)) : aug_width(int(dim));
+  r.SA = w.take<__nv_bfloat16>(size_t(M) * r.ldp);
+  r.SB = w.take<__nv_bfloat16>(size_t(M) * r.ldp);
   r.accum = w.take<double>(4);
+  r.S32 = precision ? w.take<float>(size_t(M) * dim) : nullptr;
   r.bytes = w.bytes();
   return r;
 }
@@ -37,8 +42,8 @@ static __global__ void mmd_finalize_kernel(const double* __restrict__ acc, doubl
 
 using namespace carel;
 
-extern "C" size_t carel_mmd_workspace_bytes(int64_t n1, int64_t n2, int64_t dim) {
-  return carve_mmd(nullptr, n1 + n2, aug_width(int(dim))).bytes;
+extern "C" size_t carel_mmd_workspace_bytes(int64_t n1, int64_t n2, int64_t dim, int precision) {
+  return carve_mmd(nullptr, n1 + n2, dim, precision).bytes;
 }
 
 extern "C" int carel_mmd_finalize(const double* partial_sums, int64_t n1, int64_t n2,
@@ -56,21 +61,29 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
                              int64_t n2, int64_t dim, const float* alphas_host, int n_alpha,
                              float eps, int flags, int64_t row_tile_begin, int64_t row_tile_end,
                              double* partial_sums, float* out_mmd, void* ws, size_t ws_bytes,
-                             void* stream) {
+                             int precision, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CAREL_REQUIRE(n1 >= 2 && n2 >= 2, "carel_mmd: n_1 and n_2 must be >= 2 (a00 = 1/(n(n-1)))");
   CAREL_REQUIRE(dim > 0, "carel_mmd: dim must be positive");
   CAREL_REQUIRE(n_alpha >= 1 && n_alpha <= kMaxAlphas, "carel_mmd: 1..%d alphas supported", kMaxAlphas);
   const int64_t M = n1 + n2;
-  const int ldp = aug_width(int(dim));
-  MmdWs w = carve_mmd(ws, M, ldp);
+  MmdWs w = carve_mmd(ws, M, dim, precision);
+  const int ldp = w.ldp;
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_mmd_fwd: workspace too small");
   double* acc = partial_sums ? partial_sums : w.accum;
 
-  pack_rows_kernel<<<int((n1 + 7) / 8), 256, 0, st>>>(x, int(n1), int(dim), int(ldx), w.SA, w.SB, ldp, 0, 1, nullptr);
-  CAREL_LAUNCHED();
-  pack_rows_kernel<<<int((n2 + 7) / 8), 256, 0, st>>>(y, int(n2), int(dim), int(ldy), w.SA, w.SB, ldp, int(n1), 1, nullptr);
-  CAREL_LAUNCHED();
+  if (!precision) {
+    pack_rows_kernel<<<int((n1 + 7) / 8), 256, 0, st>>>(x, int(n1), int(dim), int(ldx), w.SA, w.SB, ldp, 0, 1, nullptr);
+    CAREL_LAUNCHED();
+    pack_rows_kernel<<<int((n2 + 7) / 8), 256, 0, st>>>(y, int(n2), int(dim), int(ldy), w.SA, w.SB, ldp, int(n1), 1, nullptr);
+    CAREL_LAUNCHED();
+  } else {
+    const Pack3Out oa{w.SA, 0, 0}, ob{w.SB, 1, 1};
+    pack3_rows_kernel<<<int((n1 + 7) / 8), 256, 0, st>>>(x, int(n1), int(dim), int(ldx), oa, ob, 0, 0, nullptr, w.S32, int(dim));
+    CAREL_LAUNCHED();
+    pack3_rows_kernel<<<int((n2 + 7) / 8), 256, 0, st>>>(y, int(n2), int(dim), int(ldy), oa, ob, int(n1), 0, nullptr, w.S32, int(dim));
+    CAREL_LAUNCHED();
+  }
   CAREL_CHECK_CUDA(cudaMemsetAsync(acc, 0, 3 * sizeof(double), st));
 
   CUtensorMap ta, tb;
@@ -102,7 +115,7 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
 }
 
 template <int BN1>
-static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, int t0, int t1,
+static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, int n2_16, int t0, int t1,
                           float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy, int64_t n1, int64_t n2,
                           int64_t dim, cudaStream_t st) {
   using Cfg = ChainCfg<1, BN1>;
@@ -111,6 +124,7 @@ static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, i
   CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.SB, M, ldp, ldp, BN1) == 0, "carel_mmd_bwd: tensor map B failed");
   const int k16 = ldp / 16;
   ChainSched s = make_chain_sched(t0, t1 - t0, int((M + BN1 - 1) / BN1), k16, Cfg::stages_for(k16), 32);
+  s.n2_16 = n2_16;
   // rows outside [t0, t1) * 128 must read as zero; with one work item per row tile the rows inside are
   // written exactly once (plain stores), otherwise partial sums are accumulated atomically
   pp.atomic = s.nsplit > 1;
@@ -125,20 +139,22 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
                              const float* alphas_host, int n_alpha, float eps,
                              int64_t row_tile_begin, int64_t row_tile_end, float* grad_x,
                              int64_t ldgx, float* grad_y, int64_t ldgy, void* ws, size_t ws_bytes,
-                             void* stream) {
+                             int precision, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CAREL_REQUIRE(n1 >= 2 && n2 >= 2, "carel_mmd: n_1 and n_2 must be >= 2 (a00 = 1/(n(n-1)))");
   CAREL_REQUIRE(n_alpha >= 1 && n_alpha <= kMaxAlphas, "carel_mmd: 1..%d alphas supported", kMaxAlphas);
   const int64_t M = n1 + n2;
-  const int ldp = aug_width(int(dim));
-  CAREL_REQUIRE(ldp <= 256, "carel_mmd_bwd: feature width %lld > 250 is not supported by the fused backward", (long long)dim);
-  MmdWs w = carve_mmd(ws, M, ldp);
+  MmdWs w = carve_mmd(ws, M, dim, precision);
+  const int ldp = w.ldp;
+  const int n2cols = precision ? 2 * split_kp(int(dim)) + 16 : ldp;      // GEMM-2 width
+  CAREL_REQUIRE(n2cols <= 256, "carel_mmd_bwd: feature width %lld is not supported by the fused backward (max 250 in bf16 mode, 120 in fp32 mode)", (long long)dim);
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_mmd_bwd: workspace too small");
   const int m_tiles = int((M + 127) / 128);
   const int t0 = int(row_tile_begin < 0 ? 0 : row_tile_begin);
   const int t1 = int((row_tile_end < 0 || row_tile_end > m_tiles) ? m_tiles : row_tile_end);
   CAREL_REQUIRE(t0 <= t1, "carel_mmd_bwd: bad row tile range");
   MmdBwdParams pp;
+  pp.split = precision ? 1 : 0; pp.kp = split_kp(int(dim)); pp.ld32 = int(dim); pp.S32 = w.S32;
   pp.SA = w.SA; pp.grad_out = grad_out; pp.grad_x = grad_x; pp.grad_y = grad_y;
   pp.ldgx = int(ldgx); pp.ldgy = int(ldgy); pp.dim = int(dim); pp.ldp = ldp;
   pp.M = int(M); pp.n1 = int(n1);
@@ -159,6 +175,5 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   (void)asum;
   pp.w_scale = 1.f;
   pp.inv_w_scale = 1.f;
-  if (ldp <= ChainCfg<1, 128>::kMaxN2) return mmd_bwd_launch<128>(w, pp, M, ldp, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
-  return mmd_bwd_launch<64>(w, pp, M, ldp, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
+  return mmd_bwd_launch<128>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
 }

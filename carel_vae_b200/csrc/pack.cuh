@@ -81,4 +81,75 @@ static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// "fp32 mode" operands: every value is split into two bf16 terms v = v1 + v2 (16 mantissa bits) and the
+// product a.b ~ a1 b1 + a2 b1 + a1 b2 is obtained from ONE bf16 GEMM by concatenating along K:
+//     pattern P (0): [ v1 | v1 | aug | v2 ]      pattern Q (1): [ v1 | v2 | aug | v1 ]
+// (each block Kp = roundup16(K) wide, aug = 16 columns), a P row against a Q row gives all three terms.
+// The aug block is [h1 h2 h3 1 1 1 0..] (type A) or [1 1 1 h1 h2 h3 0..] (type B) as in pack_rows_kernel,
+// with h = -|v|^2/2 (the TRUE fp32 norm: off-diagonal products are unbiased around v.w, so using the
+// truncated self-product would shift every d2 by ~2^-18 |v|^2), hvec[r], or 0.
+// The first 2 Kp columns of a Q row are v1 | v2, which is what GEMM-2 of the chain kernel multiplies with.
+// ---------------------------------------------------------------------------------------------
+inline __host__ __device__ int split_kp(int K) { return (K + 15) / 16 * 16; }
+inline __host__ __device__ int split_width(int K) { return 3 * split_kp(K) + 16; }
+
+struct Pack3Out {
+  __nv_bfloat16* ptr;   // nullptr = not produced
+  int pattern;          // 0 = P, 1 = Q
+  int aug_type;         // 0 = A, 1 = B
+};
+
+static __global__ void pack3_rows_kernel(const float* __restrict__ src, int rows, int K, int ld, Pack3Out o0,
+                                         Pack3Out o1, int dst_row0, int hmode /*0 norm, 1 hvec, 2 zero*/,
+                                         const float* __restrict__ hvec, float* __restrict__ copy32, int ld32) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int Kp = split_kp(K), W = split_width(K);
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f), one = __float2bfloat16_rn(1.f);
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows;
+       r += gridDim.x * warps_per_block) {
+    const float* s = src + size_t(r) * ld;
+    __nv_bfloat16* d0 = o0.ptr ? o0.ptr + size_t(dst_row0 + r) * W : nullptr;
+    __nv_bfloat16* d1 = o1.ptr ? o1.ptr + size_t(dst_row0 + r) * W : nullptr;
+    float nrm = 0.f;
+    for (int k = lane; k < Kp; k += 32) {
+      const float v = (k < K) ? __ldg(s + k) : 0.f;
+      const __nv_bfloat16 v1 = __float2bfloat16_rn(v);
+      const float f1 = __bfloat162float(v1);
+      const __nv_bfloat16 v2 = __float2bfloat16_rn(v - f1);
+      nrm = fmaf(v, v, nrm);
+      if (d0) {
+        d0[k] = v1;
+        d0[Kp + k] = o0.pattern ? v2 : v1;
+        d0[2 * Kp + 16 + k] = o0.pattern ? v1 : v2;
+      }
+      if (d1) {
+        d1[k] = v1;
+        d1[Kp + k] = o1.pattern ? v2 : v1;
+        d1[2 * Kp + 16 + k] = o1.pattern ? v1 : v2;
+      }
+      if (copy32 != nullptr && k < K) copy32[size_t(dst_row0 + r) * ld32 + k] = v;
+    }
+    nrm = warp_sum(nrm);
+    const float h = (hmode == 2) ? 0.f : ((hmode == 1) ? __ldg(hvec + r) : -0.5f * nrm);
+    const __nv_bfloat16 h1 = __float2bfloat16_rn(h);
+    const float r1 = h - __bfloat162float(h1);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
+    if (lane < 16) {
+      const __nv_bfloat16 hv[3] = {h1, h2, h3};
+      for (int o = 0; o < 2; ++o) {
+        __nv_bfloat16* d = o ? d1 : d0;
+        if (!d) continue;
+        const int type = o ? o1.aug_type : o0.aug_type;
+        __nv_bfloat16 v = zero;
+        if (lane < 3) v = type ? one : hv[lane];
+        else if (lane < 6) v = type ? hv[lane - 3] : one;
+        d[2 * Kp + lane] = v;
+      }
+    }
+  }
+}
+
 }  // namespace carel

@@ -50,7 +50,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 class _MMDFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, y, alphas, eps, flags, tile_range):
+    def forward(ctx, x, y, alphas, eps, flags, tile_range, prec=0):
         _require_cuda(x, y)
         xf, yf = _rowmajor_f32(x), _rowmajor_f32(y)
         n1, d = xf.shape
@@ -58,7 +58,7 @@ class _MMDFn(torch.autograd.Function):
         if d != d2:
             raise ValueError("sample_1 and sample_2 must have the same feature width")
         L = lib()
-        ws = _workspace(L.carel_mmd_workspace_bytes(n1, n2, d), xf.device)
+        ws = _workspace(L.carel_mmd_workspace_bytes(n1, n2, d, prec), xf.device)
         out = torch.empty((), dtype=torch.float32, device=xf.device)
         al = float_array(alphas)
         t0, t1 = tile_range
@@ -67,10 +67,10 @@ class _MMDFn(torch.autograd.Function):
             partial = torch.empty(3, dtype=torch.float64, device=xf.device)
         check(L.carel_mmd_fwd(_p(xf), xf.stride(0), _p(yf), yf.stride(0), n1, n2, d, al, len(alphas),
                               float(eps), int(flags), t0, t1, _p(partial),
-                              _p(None if partial is not None else out), _p(ws), ws.numel(), _stream()),
+                              _p(None if partial is not None else out), _p(ws), ws.numel(), prec, _stream()),
               "carel_mmd_fwd")
         ctx.ws = ws
-        ctx.meta = (n1, n2, d, tuple(float(a) for a in alphas), float(eps), t0, t1, x.dtype, y.dtype)
+        ctx.meta = (n1, n2, d, tuple(float(a) for a in alphas), float(eps), t0, t1, x.dtype, y.dtype, prec)
         if partial is not None:
             ctx.mark_non_differentiable(partial)
             return partial
@@ -78,23 +78,23 @@ class _MMDFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        n1, n2, d, alphas, eps, t0, t1, dtx, dty = ctx.meta
+        n1, n2, d, alphas, eps, t0, t1, dtx, dty, prec = ctx.meta
         ws = ctx.ws
         g = g.reshape(()).float().contiguous()
         gx = torch.empty((n1, d), dtype=torch.float32, device=ws.device)
         gy = torch.empty((n2, d), dtype=torch.float32, device=ws.device)
         al = float_array(alphas)
         check(lib().carel_mmd_bwd(_p(g), n1, n2, d, al, len(alphas), eps, t0, t1, _p(gx), d, _p(gy), d,
-                                  _p(ws), ws.numel(), _stream()), "carel_mmd_bwd")
-        return gx.to(dtx), gy.to(dty), None, None, None, None
+                                  _p(ws), ws.numel(), prec, _stream()), "carel_mmd_bwd")
+        return gx.to(dtx), gy.to(dty), None, None, None, None, None
 
 
 def mmd(sample_1: torch.Tensor, sample_2: torch.Tensor, alphas: Sequence[float], eps: float = 1e-5,
-        full_gram: bool = False) -> torch.Tensor:
+        full_gram: bool = False, precision: str | None = None) -> torch.Tensor:
     """Unbiased multi-bandwidth RBF MMD^2 (reference MMDStatistic.__call__,
     drl_classifier_ec_mmd_final_mul.py:547-569).  0-dim fp32 tensor, differentiable w.r.t. both samples."""
     flags = 1 if full_gram else 0
-    return _MMDFn.apply(sample_1, sample_2, tuple(alphas), eps, flags, (0, -1))
+    return _MMDFn.apply(sample_1, sample_2, tuple(alphas), eps, flags, (0, -1), _lib.precision_code(precision))
 
 
 def pairwise(a: torch.Tensor, b: torch.Tensor, mode: int, alphas: Sequence[float] = (), eps: float = 1e-5):

@@ -71,7 +71,7 @@ def sharded_mmd(x: torch.Tensor, y: torch.Tensor, alphas: Sequence[float], group
     t0, t1 = ranges[rank]
     if partial_fn is None:
         from . import functional as F
-        partial = F._MMDFn.apply(x, y, tuple(alphas), eps, 0, (t0, t1 if t1 > t0 else t0))
+        partial = F._MMDFn.apply(x, y, tuple(alphas), eps, 0, (t0, t1 if t1 > t0 else t0), 0)
     else:
         partial = partial_fn(x, y, alphas, eps, t0, t1)
     partial = partial.clone()

@@ -28,6 +28,8 @@ extern "C" {
 
 /* flags */
 #define CAREL_MMD_FULL_GRAM 1 /* compute all (2N)^2 entries like the reference instead of j > i */
+#define CAREL_BF16 0
+#define CAREL_FP32 1
 
 int carel_version(void);
 const char* carel_last_error(void);
@@ -57,7 +59,10 @@ int carel_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t
  *   K = sum_alpha exp(-alpha (|d2| + eps)),  d2 = |x_i|^2 + |y_j|^2 - 2 x_i.y_j.
  *   The (n1+n2)^2 Gram matrix never leaves the SM.
  * ------------------------------------------------------------------------------------------ */
-size_t carel_mmd_workspace_bytes(int64_t n1, int64_t n2, int64_t dim);
+/* precision: CAREL_BF16 (0) = bf16 tensor-core operands; CAREL_FP32 (1) = every operand split into two bf16
+ * terms (x1 x1' + x2 x1' + x1 x2' in one K-concatenated bf16 GEMM, fp32 accumulate): ~fp32-accurate results
+ * (1e-5) at 3x the tensor work.  The fused backward supports dim <= 250 (bf16) / 120 (fp32). */
+size_t carel_mmd_workspace_bytes(int64_t n1, int64_t n2, int64_t dim, int precision);
 /* Forward.  Packs cat(x, y) to bf16 in `ws`, accumulates the three block sums of Gram row tiles
  * [row_tile_begin, row_tile_end) (128-row tiles; pass 0, -1 for all) into partial_sums[3]
  * (double: xx off-diagonal, yy off-diagonal, xy + yx) and, if out_mmd != NULL, finalises
@@ -65,7 +70,7 @@ size_t carel_mmd_workspace_bytes(int64_t n1, int64_t n2, int64_t dim);
 int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t n1,
                   int64_t n2, int64_t dim, const float* alphas_host, int n_alpha, float eps,
                   int flags, int64_t row_tile_begin, int64_t row_tile_end, double* partial_sums,
-                  float* out_mmd, void* ws, size_t ws_bytes, void* stream);
+                  float* out_mmd, void* ws, size_t ws_bytes, int precision, void* stream);
 int carel_mmd_finalize(const double* partial_sums, int64_t n1, int64_t n2, float* out_mmd,
                        void* stream);
 /* Backward: grad_x[n1,dim], grad_y[n2,dim] (+)= d mmd / d(x,y) * grad_out[0]; rows of the Gram
@@ -74,7 +79,7 @@ int carel_mmd_finalize(const double* partial_sums, int64_t n1, int64_t n2, float
 int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int64_t dim,
                   const float* alphas_host, int n_alpha, float eps, int64_t row_tile_begin,
                   int64_t row_tile_end, float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy,
-                  void* ws, size_t ws_bytes, void* stream);
+                  void* ws, size_t ws_bytes, int precision, void* stream);
 
 /* Dense pairwise matrices for API completeness (reference pdist :580-596 with norm=2, the
  * ret_matrix=True kernel matrix :566-567, hsic.py pairwise_distances :529-532 and

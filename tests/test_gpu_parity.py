@@ -277,15 +277,15 @@ def test_mmd_row_block_sharding_emulated_ranks():
     one = torch.ones((), device=DEV)
     al = float_array(alphas)
     for (t0, t1) in par.balanced_tri_ranges(n1 + n2, world):
-        ws = torch.empty(L.carel_mmd_workspace_bytes(n1, n2, d), dtype=torch.uint8, device=DEV)
+        ws = torch.empty(L.carel_mmd_workspace_bytes(n1, n2, d, 0), dtype=torch.uint8, device=DEV)
         part = torch.zeros(3, dtype=torch.float64, device=DEV)
         xd, yd = x.detach(), y.detach()
         check(L.carel_mmd_fwd(C.c_void_p(xd.data_ptr()), d, C.c_void_p(yd.data_ptr()), d, n1, n2, d, al, len(alphas),
-                              1e-5, 0, t0, t1, C.c_void_p(part.data_ptr()), None, C.c_void_p(ws.data_ptr()), ws.numel(), st), "fwd")
+                              1e-5, 0, t0, t1, C.c_void_p(part.data_ptr()), None, C.c_void_p(ws.data_ptr()), ws.numel(), 0, st), "fwd")
         total += part
         px, py = torch.empty_like(gx), torch.empty_like(gy)
         check(L.carel_mmd_bwd(C.c_void_p(one.data_ptr()), n1, n2, d, al, len(alphas), 1e-5, t0, t1,
-                              C.c_void_p(px.data_ptr()), d, C.c_void_p(py.data_ptr()), d, C.c_void_p(ws.data_ptr()), ws.numel(), st), "bwd")
+                              C.c_void_p(px.data_ptr()), d, C.c_void_p(py.data_ptr()), d, C.c_void_p(ws.data_ptr()), ws.numel(), 0, st), "bwd")
         # rows outside the rank's block are untouched zeros; inside they are the complete gradient
         gxs += px
         gys += py
@@ -322,3 +322,22 @@ def test_hsic_row_block_sharding_emulated_ranks():
         gxs += px
         gys += py
     assert rel(gxs, gx) < 1e-5 and rel(gys, gy) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# fp32 mode (north_star: 1e-5 relative): arbitrary fp32 inputs, NOT rounded to bf16 beforehand
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n1,n2,d,alphas", [(2, 3, 8, [0.1]), (64, 64, 64, [0.1]), (50, 70, 24, [0.1]),
+                                            (300, 300, 64, [0.1, 0.01, 1.0]), (2048, 2048, 64, [0.1]),
+                                            (700, 900, 80, [0.05])])
+def test_mmd_fp32_mode(n1, n2, d, alphas):
+    torch.manual_seed(n1 + d + 1)
+    x = (torch.randn(n1, d, device=DEV) * 1.1).requires_grad_(True)
+    y = (torch.randn(n2, d, device=DEV) * 1.1 + 0.3).requires_grad_(True)
+    xd, yd = x.detach().double().requires_grad_(True), y.detach().double().requires_grad_(True)
+    ref = ho.mmd_statistic(xd, yd, alphas)
+    rgx, rgy = torch.autograd.grad(ref, (xd, yd))
+    out = F.mmd(x, y, alphas, precision="fp32")
+    gx, gy = torch.autograd.grad(out, (x, y))
+    assert relv(out, ref) < 1e-5
+    assert rel(gx, rgx) < 1e-5 and rel(gy, rgy) < 1e-5
