@@ -22,8 +22,8 @@ OBJ = PKG / "csrc" / "_obj"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DCAREL_NO_FAST_MATH",
-]
+    "-Xcompiler", "-fPIC", "-DCAREL_NO_FAST_MATH",
+] + os.environ.get("CAREL_EXTRA_FLAGS", "").split()
 
 
 def _newest_header() -> float:

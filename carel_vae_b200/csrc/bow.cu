@@ -13,12 +13,13 @@
 //   dlogit = p (g - s_i)  =  [u - p S_i] / (N V)  +  sparse,    u = p (p - c) / max(p (1-p), 1e-12).
 //
 // Operands are augmented: ZA = [z, -lse split(3), 1 1 1], WB = [w, 1 1 1, b split(3)], so the
-// accumulator is  log p_ij = z_i.w_j + b_j - lse_i  directly (lse columns are 0 during pass 1).
-//   pass 1  gemm_tc + EpiBowLse   per-row online (max, sum-exp) partials  -> lse
-//   pass 2  gemm_tc + EpiBowLoss  dense loss + row sums S_i
+// accumulator is  log p_ij = z_i.w_j + b_j - lse_i  directly (lse columns are 0 during pass F).
+//   pass F  gemm_tc + EpiBowFused  ONE dense pass: per-row online max + power sums -> lse, dense loss, S_i
+//           (bow_combine_kernel); rows outside the series' range are flagged and redone exactly by
+//   pass 2  gemm_tc + EpiBowLoss   (skips every row tile without a flagged row)
 //   sparse  bow_sparse_kernel     corrections of loss, S_i (fwd) and of dZ, dW, db (bwd)
-//   pass 3  chain_tc + PolBowBwd  dlogit tile -> bf16 (TMEM + HBM copy), dZ += dlogit W_d
-//   pass 4  gemm_tc (MN-major)    [dW | . | db] = dlogit^T [Z | . | 1]
+//   pass 3  chain_tc + PolBowBwdW  owner = vocabulary tile: dlogit tile -> bf16 (TMEM only), dW += dlogit^T Z, db
+//   pass 4  chain_tc + PolBowBwdZ  owner = clause tile:     dlogit tile recomputed,          dZ += dlogit W_d
 #include <algorithm>
 
 #include "api_common.cuh"
@@ -35,8 +36,11 @@ constexpr float kTinyLogP = -6.9314718f;   // log(2^-10): below this the 3-term 
 struct BowWs {
   __nv_bfloat16* ZA;    // [N, ldk]
   __nv_bfloat16* WB;    // [V, ldk]
-  __nv_bfloat16* dlT;   // [V, Np]  dense dlogits, vocabulary-major (backward)
-  float* part;          // [NTp, Npad] float2 (max, sumexp) partials
+  float4* part4;        // [ntp, Npad] pass-F partials (m, T1, T2, T3)
+  float2* part2;        // [ntp, Npad] pass-F partials (T4, min)
+  float* wsum;          // [ldk] column sums of WB
+  int* row_flag;        // [Npad] 1: row needs the exact pass
+  int* tile_flag;       // [Npad/128]
   float* lse;           // [Npad]  holds -lse
   float* srow;          // [Npad]  S_i = N V s_i
   float* dWacc;         // [V, ldk] fp32 accumulation of dlogit^T [Z | 1]
@@ -62,8 +66,11 @@ static BowWs carve_bow(void* ws, int64_t N, int64_t K, int64_t V, int64_t cap) {
   r.ntp = int((V + 255) / 256) * kColSplit;
   r.ZA = w.take<__nv_bfloat16>(size_t(N) * r.ldk);
   r.WB = w.take<__nv_bfloat16>(size_t(V) * r.ldk);
-  r.dlT = w.take<__nv_bfloat16>(size_t(V) * r.Np);
-  r.part = w.take<float>(size_t(r.ntp) * r.Npad * 2);
+  r.part4 = w.take<float4>(size_t(r.ntp) * r.Npad);
+  r.part2 = w.take<float2>(size_t(r.ntp) * r.Npad);
+  r.wsum = w.take<float>(size_t(r.ldk));
+  r.row_flag = w.take<int>(size_t(r.Npad));
+  r.tile_flag = w.take<int>(size_t(r.Npad / 128));
   r.lse = w.take<float>(size_t(r.Npad));
   r.srow = w.take<float>(size_t(r.Npad));
   r.dWacc = w.take<float>(size_t(V) * r.ldk);
@@ -124,48 +131,103 @@ static __global__ void bow_pack_ell_kernel(const float* __restrict__ bow, int64_
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 1 epilogue: per-row online (max, sum exp) over this warp's 128 columns of the tile
+// pass F epilogue (the ONE dense forward pass): per row and per 64-column part, with m = running max,
+//   T_k = sum_j exp(k (x_ij - m)), k = 1..4,   and   mn = min_j x_ij.
+// From these the combine kernel gets lse_i, the power sums S_k = sum_j p_ij^k = T_k / T_1^k and with them
+//   sum_j log1p(-p) = -(S1 + S2/2 + S3/3 + S4/4 + ...),   sum_j (p - c)/(1 - p) = (S1+S2+S3+S4+..) - c (V + S1+S2+S3+..)
+// (S1 = 1), valid to 2^-20 whenever max_j p_ij < 2^-5; rows beyond that (or with a clamped log) are flagged
+// and redone exactly by the EpiBowLoss pass.  Hot loop per PAIR of elements: FFMA2, 2 MUFU.EX2, FMUL2,
+// 2 FADD2, 2 FFMA2 and one FMNMX3 each for max and min.
 // ---------------------------------------------------------------------------------------------
-struct EpiBowLseParams {
-  float2* part;   // [ntp][Npad]
+struct EpiBowFusedParams {
+  float4* part4;   // [ntp][Npad]  (m, T1, T2, T3)
+  float2* part2;   // [ntp][Npad]  (T4, mn)
   int N, V, Npad;
 };
 template <int BN>
-struct EpiBowLse {
-  using Params = EpiBowLseParams;
+struct EpiBowFused {
+  using Params = EpiBowFusedParams;
   const Params& p;
-  CAREL_DEVINL EpiBowLse(const Params& p_, const TileCtx&) : p(p_) {}
+  CAREL_DEVINL EpiBowFused(const Params& p_, const TileCtx&) : p(p_) {}
   CAREL_DEVINL void tile(const TileCtx& ctx) {
     constexpr int HALF = BN / kColSplit;
     const int c0 = ctx.col0 + ctx.half * HALF;
-    float m = -INFINITY, s = 0.f;
+    float m = -INFINITY, mn = INFINITY;
+    float2 t1 = make_float2(0.f, 0.f), t2 = t1, t3 = t1, t4 = t1;
     if (c0 < p.V) {
       const bool full = c0 + HALF <= p.V;
+      const float2 l2e = make_float2(kLog2e, kLog2e);
       for_each_chunk16(ctx.taddr + ctx.half * HALF, HALF / 16, [&](int c, const uint32_t (&r)[16]) {
         float x[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          x[i] = __uint_as_float(r[i]);
-          if (!full && c0 + c * 16 + i >= p.V) x[i] = -INFINITY;
-        }
-        float cm = fmaxf(x[0], x[1]);
+        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
+        float cm, cn;
+        if (full) {
+          cm = fmax3(x[0], x[1], x[2]);
+          cn = fmin3(x[0], x[1], x[2]);
 #pragma unroll
-        for (int i = 2; i < 16; ++i) cm = fmaxf(cm, x[i]);
-        if (cm > m) {
-          s *= ex2_approx((m - cm) * kLog2e);
+          for (int i = 3; i < 15; i += 2) { cm = fmax3(cm, x[i], x[i + 1]); cn = fmin3(cn, x[i], x[i + 1]); }
+          cm = fmaxf(cm, x[15]);
+          cn = fminf(cn, x[15]);
+        } else {
+          cm = -INFINITY;
+          cn = INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool ok = c0 + c * 16 + i < p.V;
+            cn = fminf(cn, ok ? x[i] : INFINITY);
+            x[i] = ok ? x[i] : -INFINITY;
+            cm = fmaxf(cm, x[i]);
+          }
+        }
+        mn = fminf(mn, cn);
+        if (cm > m) {          // rescale the running sums to the new reference (rare after the first chunks)
+          const float sc = ex2_approx((m - cm) * kLog2e), sc2 = sc * sc;
+          t1.x *= sc; t1.y *= sc;
+          t2.x *= sc2; t2.y *= sc2;
+          t3.x *= sc2 * sc; t3.y *= sc2 * sc;
+          t4.x *= sc2 * sc2; t4.y *= sc2 * sc2;
           m = cm;
         }
         if (m > -INFINITY) {
-          const float mm = m * kLog2e;
+          const float nm = -m * kLog2e;
+          const float2 nm2 = make_float2(nm, nm);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) s += ex2_approx(fmaf(x[i], kLog2e, -mm));
+          for (int i = 0; i < 16; i += 2) {
+            const float2 t = __ffma2_rn(make_float2(x[i], x[i + 1]), l2e, nm2);
+            const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+            const float2 e2 = __fmul2_rn(e, e);
+            t1 = __fadd2_rn(t1, e);
+            t2 = __fadd2_rn(t2, e2);
+            t3 = __ffma2_rn(e2, e, t3);
+            t4 = __ffma2_rn(e2, e2, t4);
+          }
         }
       });
     }
-    if (ctx.row < p.Npad) p.part[size_t(ctx.tn * kColSplit + ctx.half) * p.Npad + ctx.row] = make_float2(m, s);
+    if (ctx.row < p.Npad) {
+      const size_t o = size_t(ctx.tn * kColSplit + ctx.half) * p.Npad + ctx.row;
+      p.part4[o] = make_float4(m, t1.x + t1.y, t2.x + t2.y, t3.x + t3.y);
+      p.part2[o] = make_float2(t4.x + t4.y, mn);
+    }
   }
   CAREL_DEVINL void finish() {}
 };
+
+// column sums of the packed decoder operand WB [V, ldk] (bf16 -> fp32): sum_j x_ij = ZA_i . wsum
+static __global__ void bow_colsum_kernel(const __nv_bfloat16* __restrict__ WB, int V, int ldk,
+                                         float* __restrict__ wsum) {
+  const int w = threadIdx.x;               // bf16 pair index
+  if (w * 2 >= ldk) return;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int r = blockIdx.x; r < V; r += gridDim.x) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(WB + size_t(r) * ldk + 2 * w));
+    acc.x += f.x;
+    acc.y += f.y;
+  }
+  atomicAdd(wsum + 2 * w, acc.x);
+  atomicAdd(wsum + 2 * w + 1, acc.y);
+}
 
 static CAREL_DEVINL void split3(float h, __nv_bfloat16& h1, __nv_bfloat16& h2, __nv_bfloat16& h3) {
   h1 = __float2bfloat16_rn(h);
@@ -174,32 +236,74 @@ static CAREL_DEVINL void split3(float h, __nv_bfloat16& h1, __nv_bfloat16& h2, _
   h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
 }
 
-// lse_i from the partials (one warp per row, lanes over the partials); writes -lse (3-way bf16 split)
-// into the h columns of ZA and zeroes S_i.
-static __global__ void bow_lse_combine_kernel(const float2* __restrict__ part, int ntp, int Npad, int N,
-                                              int K, __nv_bfloat16* __restrict__ ZA, int ldk,
-                                              float* __restrict__ neg_lse, float* __restrict__ srow) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= N) return;
-  float M = -INFINITY;
-  for (int t = lane; t < ntp; t += 32) M = fmaxf(M, part[size_t(t) * Npad + r].x);
-  M = warp_max(M);
-  float S = 0.f;
-  for (int t = lane; t < ntp; t += 32) {
-    const float2 v = part[size_t(t) * Npad + r];
-    if (v.y > 0.f) S += v.y * __expf(v.x - M);
+// Combine the pass-F partials of a row (one warp per row): lse_i, power sums, dense loss term and
+// S_i = sum_j u_ij; writes -lse (3-way bf16 split) into the h columns of ZA.  Rows outside the series'
+// range are flagged (row_flag / tile_flag) and contribute nothing here.
+constexpr int kCombineWarps = 8;
+static __global__ void __launch_bounds__(kCombineWarps * 32)
+bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ part2, int ntp, int Npad, int N,
+                   int V, int K, int ldk, float c, const float* __restrict__ wsum, __nv_bfloat16* __restrict__ ZA,
+                   float* __restrict__ neg_lse, float* __restrict__ srow, double* __restrict__ lossacc,
+                   int* __restrict__ row_flag, int* __restrict__ tile_flag) {
+  __shared__ double sh_loss[kCombineWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * kCombineWarps + wid;
+  double f = 0.0;
+  if (r < N) {
+    float M = -INFINITY;
+    for (int t = lane; t < ntp; t += 32) M = fmaxf(M, part4[size_t(t) * Npad + r].x);
+    M = warp_max(M);
+    float T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f, mn = INFINITY;
+    for (int t = lane; t < ntp; t += 32) {
+      const float4 a = part4[size_t(t) * Npad + r];
+      const float2 b = part2[size_t(t) * Npad + r];
+      if (a.y > 0.f) {
+        const float w = __expf(a.x - M), w2 = w * w;
+        T1 = fmaf(a.y, w, T1);
+        T2 = fmaf(a.z, w2, T2);
+        T3 = fmaf(a.w, w2 * w, T3);
+        T4 = fmaf(b.x, w2 * w2, T4);
+      }
+      mn = fminf(mn, b.y);
+    }
+    T1 = warp_sum(T1); T2 = warp_sum(T2); T3 = warp_sum(T3); T4 = warp_sum(T4);
+    mn = -warp_max(-mn);
+    // sum_j x_ij from the column sums of the packed operand (the h columns of ZA are still zero here)
+    float sx = 0.f;
+    const __nv_bfloat16* zrow = ZA + size_t(r) * ldk;
+    for (int k = lane; k < ldk; k += 32) sx = fmaf(__bfloat162float(zrow[k]), __ldg(wsum + k), sx);
+    sx = warp_sum(sx);
+    if (lane == 0) {
+      const float lse = M + logf(T1);
+      const float i1 = 1.f / T1, i2 = i1 * i1;
+      const float S2 = T2 * i2, S3 = T3 * i2 * i1, S4 = T4 * i2 * i2;
+      const bool valid = (i1 < 0.03125f) && (mn - lse > -27.f);
+      float u = 0.f;
+      if (valid) {
+        f = double(c) * (double(sx) - double(V) * double(lse)) -
+            double(1.f - c) * (1.0 + double(0.5f * S2 + (1.f / 3.f) * S3 + 0.25f * S4));
+        u = (1.f + S2 + S3 + S4) - c * (float(V) + 1.f + S2 + S3);
+      } else {
+        tile_flag[r >> 7] = 1;
+      }
+      row_flag[r] = valid ? 0 : 1;
+      srow[r] = u;
+      const float nl = -lse;
+      neg_lse[r] = nl;
+      __nv_bfloat16 h1, h2, h3;
+      split3(nl, h1, h2, h3);
+      ZA[size_t(r) * ldk + K] = h1;
+      ZA[size_t(r) * ldk + K + 1] = h2;
+      ZA[size_t(r) * ldk + K + 2] = h3;
+    }
   }
-  S = warp_sum(S);
-  if (lane != 0) return;
-  const float nl = -(M + logf(S));
-  neg_lse[r] = nl;
-  srow[r] = 0.f;
-  __nv_bfloat16 h1, h2, h3;
-  split3(nl, h1, h2, h3);
-  ZA[size_t(r) * ldk + K] = h1;
-  ZA[size_t(r) * ldk + K + 1] = h2;
-  ZA[size_t(r) * ldk + K + 2] = h3;
+  if (lane == 0) sh_loss[wid] = f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kCombineWarps; ++i) t += sh_loss[i];
+    if (t != 0.0) atomicAdd(lossacc, t);
+  }
 }
 
 // exact per-element terms (used for the rare chunks that leave the series' range)
@@ -219,6 +323,7 @@ static CAREL_DEVINL void bow_exact_terms(float x, float c, float& f, float& u) {
 struct EpiBowLossParams {
   double* lossacc;
   float* srow;
+  const int* row_flag;   // optional: only flagged rows contribute (exact redo of the rows pass F could not take)
   int N, V;
   float c;
 };
@@ -266,7 +371,7 @@ struct EpiBowLoss {
         }
       }
     });
-    if (ctx.row < p.N) {
+    if (ctx.row < p.N && (p.row_flag == nullptr || p.row_flag[ctx.row] != 0)) {
       const float f = c * sx - (1.f - c) * (s1 + 0.5f * s2 + (1.f / 3.f) * s3) + fex;
       const float u = (s1 + s2 + s3) - c * (cnt + s1 + s2) + uex;
       loss += double(f);
@@ -589,75 +694,97 @@ static __global__ void bow_loss_finalize_kernel(const double* __restrict__ lossa
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 3 policy (vocabulary-major): owner = 128 vocabulary rows, inner tiles = 64 clause rows.
-//   acc1[v, i] = log p_iv ;  P[v, i] = dlogit_iv = (u - p S_i) g / (N V)  (bf16, also stored as dl^T [V, Npad]);
-//   acc2 = dW_v = sum_i P[v, i] z_i  (GEMM-2 over the SAME ZA tile, read MN-major; atomically added to dWacc);
-//   db_v = sum_i P[v, i] is a thread-local sum (each epilogue thread owns one vocabulary row).
+// Backward chain policies.  Both recompute acc1 = log p (ZA . WB incl. bias and -lse) and turn it into the
+// dense part of dlogit,  d = [u - p S_i] g / (N V),  u = p (p - c) / max(p (1-p), 1e-12):
+//   fast path (all 16 p < 2^-10, none clamped):  u = (p - c)(1 + p + p^2)  (relative truncation 2^-30),
+//   written with packed fp32 pairs:  d = ((p - c) scale) q + p Sn,  q = 1 + p (1 + p),  Sn = -S_i scale.
+//   any other chunk: exact per-element terms.
+//   PolBowBwdW  owner = 128 vocabulary rows, inner = 64 clause rows:  acc2 = dW_v = sum_i d_iv z_i (GEMM-2 over
+//               the SAME ZA tile read MN-major), db_v = thread-local sum;  S_i varies along the columns and is
+//               prefetched before the accumulator barrier.
+//   PolBowBwdZ  owner = 128 clause rows, inner = 64 vocabulary rows:   acc2 = dZ_i = sum_v d_iv w_v;  S_i is a
+//               per-thread constant.
+// Neither writes the [N, V] dlogits anywhere: the recompute costs one more GEMM-1 but no HBM round trip.
 // ---------------------------------------------------------------------------------------------
 struct BowBwdParams {
   const float* srow;     // [Npad]  S_i (zero beyond N)
   const float* grad_out;
-  __nv_bfloat16* dlT;    // [V, Np]
-  float* dWacc;          // [V, ldk]
-  int N, V, Np, K, ldk;
+  float* dWacc;          // [V, ldk]     (W policy)
+  float* grad_z;         // [N, ldgz]    (Z policy)
+  int64_t ldgz;
+  int N, V, K, ldk;
   float c, inv_nv;
 };
-struct PolBowBwd {
+
+// d[16] from 16 log-probabilities; Sn[i] = -S * scale per element
+static CAREL_DEVINL void bow_dlogit16(const uint32_t (&r)[16], const float (&Sn)[16], float c, float scale,
+                                      bool in_range, int n_valid, float (&d)[16]) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
+  float mx = fmax3(x[0], x[1], x[2]), mn = fmin3(x[0], x[1], x[2]);
+#pragma unroll
+  for (int i = 3; i < 15; i += 2) { mx = fmax3(mx, x[i], x[i + 1]); mn = fmin3(mn, x[i], x[i + 1]); }
+  mx = fmaxf(mx, x[15]);
+  mn = fminf(mn, x[15]);
+  if (in_range && mx < kTinyLogP && mn > -27.f) {
+    const float2 l2e = make_float2(kLog2e, kLog2e), one = make_float2(1.f, 1.f);
+    const float2 sc = make_float2(scale, scale), mcs = make_float2(-c * scale, -c * scale);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float2 t = __fmul2_rn(make_float2(x[i], x[i + 1]), l2e);
+      const float2 pv = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+      const float2 q = __ffma2_rn(pv, __fadd2_rn(pv, one), one);              // 1 + p + p^2
+      const float2 a = __ffma2_rn(pv, sc, mcs);                               // (p - c) scale
+      const float2 m = __fmul2_rn(pv, make_float2(Sn[i], Sn[i + 1]));         // -p S scale
+      const float2 o = __ffma2_rn(a, q, m);
+      d[i] = o.x;
+      d[i + 1] = o.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float f, u;
+      bow_exact_terms(x[i], c, f, u);
+      d[i] = (i < n_valid) ? fmaf(u, scale, __expf(x[i]) * Sn[i]) : 0.f;
+    }
+  }
+}
+
+struct PolBowBwdW {
   using Params = BowBwdParams;
   static constexpr bool kHiLo = false;    // measured decoder gradients are 6e-5..3e-4 with a single bf16 P
   const Params& p;
   float scale, dbsum;
-  CAREL_DEVINL PolBowBwd(const Params& p_, const ChainCtx&) : p(p_), scale(0.f), dbsum(0.f) {}
+  float Sn[16];
+  CAREL_DEVINL PolBowBwdW(const Params& p_, const ChainCtx&) : p(p_), scale(0.f), dbsum(0.f) {}
   CAREL_DEVINL void begin_item(const ChainCtx&) {
     scale = __ldg(p.grad_out) * p.inv_nv;
     dbsum = 0.f;
   }
-  CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
-  CAREL_DEVINL void weights16(const ChainCtx& ctx, int i0, const uint32_t (&r)[16], const uint32_t (&)[16],
-                              float (&d)[16]) {
-    const float c = p.c;
-    float x[16], S[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
+  CAREL_DEVINL void prefetch(const ChainCtx&, int i0) {
     const float4* s4 = reinterpret_cast<const float4*>(p.srow + i0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 v = __ldg(s4 + i);
-      S[4 * i] = v.x; S[4 * i + 1] = v.y; S[4 * i + 2] = v.z; S[4 * i + 3] = v.w;
+      Sn[4 * i] = -v.x * scale; Sn[4 * i + 1] = -v.y * scale; Sn[4 * i + 2] = -v.z * scale; Sn[4 * i + 3] = -v.w * scale;
     }
-    float mx = fmaxf(x[0], x[1]), mn = fminf(x[0], x[1]);
-#pragma unroll
-    for (int i = 2; i < 16; ++i) { mx = fmaxf(mx, x[i]); mn = fminf(mn, x[i]); }
+  }
+  CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
+  CAREL_DEVINL void weights16(const ChainCtx& ctx, int i0, const uint32_t (&r)[16], const uint32_t (&)[16],
+                              float (&d)[16]) {
     if (ctx.row >= p.V) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) d[i] = 0.f;
-    } else if (i0 + 16 <= p.N && mx < kTinyLogP && mn > -27.f) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float pv = ex2_approx(x[i] * kLog2e);
-        const float q = fmaf(pv, fmaf(pv, 1.f, 1.f), 1.f);        // 1 + p + p^2
-        d[i] = fmaf(pv - c, q, -pv * S[i]) * scale;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float f, u;
-        bow_exact_terms(x[i], c, f, u);
-        d[i] = (i0 + i < p.N) ? (u - __expf(x[i]) * S[i]) * scale : 0.f;
-      }
+      return;
     }
+    bow_dlogit16(r, Sn, p.c, scale, i0 + 16 <= p.N, p.N - i0, d);
     float t = 0.f;                       // db_v: thread-local column sum (fp32, before the bf16 rounding)
 #pragma unroll
     for (int i = 0; i < 16; ++i) t += d[i];
     dbsum += t;
   }
-  CAREL_DEVINL void store16(const ChainCtx& ctx, int i0, const uint32_t (&packed)[8]) {
-    if (ctx.row < p.V && i0 < p.Np) {
-      uint4* dst = reinterpret_cast<uint4*>(p.dlT + size_t(ctx.row) * p.Np + i0);
-      dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-      dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-    }
-  }
+  CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
   CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
     const int n16 = p.K / 16;                       // feature columns only
     const int q0 = (n16 * ctx.half) / kChainSplit, q1 = (n16 * (ctx.half + 1)) / kChainSplit;
@@ -670,9 +797,57 @@ struct PolBowBwd {
       tmem_ld_wait();
       if (!row_ok) continue;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) atomicAdd(dst + q * 16 + i, __uint_as_float(r[i]));
+      for (int i = 0; i < 16; i += 4)
+        red_add_v4(dst + q * 16 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                   __uint_as_float(r[i + 3]));
     }
     if (row_ok && dbsum != 0.f) atomicAdd(dst + p.K + 3, dbsum);    // every column part adds its share
+  }
+  CAREL_DEVINL void finish() {}
+};
+
+struct PolBowBwdZ {
+  using Params = BowBwdParams;
+  static constexpr bool kHiLo = false;
+  const Params& p;
+  float scale;
+  float Sn[16];
+  CAREL_DEVINL PolBowBwdZ(const Params& p_, const ChainCtx&) : p(p_), scale(0.f) {}
+  CAREL_DEVINL void begin_item(const ChainCtx& ctx) {
+    scale = __ldg(p.grad_out) * p.inv_nv;
+    const float sn = (ctx.row < p.N) ? -__ldg(p.srow + ctx.row) * scale : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Sn[i] = sn;
+  }
+  CAREL_DEVINL void prefetch(const ChainCtx&, int) {}
+  CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
+  CAREL_DEVINL void weights16(const ChainCtx&, int v0, const uint32_t (&r)[16], const uint32_t (&)[16],
+                              float (&d)[16]) {
+    bow_dlogit16(r, Sn, p.c, scale, v0 + 16 <= p.V, p.V - v0, d);
+  }
+  CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
+  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
+    const int n16 = p.K / 16;
+    const int q0 = (n16 * ctx.half) / kChainSplit, q1 = (n16 * (ctx.half + 1)) / kChainSplit;
+    const bool row_ok = valid && ctx.row < p.N;
+    float* dst = p.grad_z + size_t(min(ctx.row, p.N - 1)) * p.ldgz;
+    const bool vec = ((p.ldgz & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.grad_z) & 15) == 0);
+#pragma unroll 1
+    for (int q = q0; q < q1; ++q) {
+      uint32_t r[16];
+      tmem_ld16(ctx.acc2_taddr + q * 16, r);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      if (vec) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          red_add_v4(dst + q * 16 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                     __uint_as_float(r[i + 3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(dst + q * 16 + i, __uint_as_float(r[i]));
+      }
+    }
   }
   CAREL_DEVINL void finish() {}
 };
@@ -734,16 +909,24 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.ZA, N, w.ldk, w.ldk, 128) == 0, "carel_bow_fwd: tensor map Z failed");
   CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, w.ldk, w.ldk, 128) == 0, "carel_bow_fwd: tensor map W failed");
   GemmSched s = make_sched(N, V, w.ldk, 256, 1, TILE_FULL);
-  // ---- pass 1: logsumexp ----
-  EpiBowLseParams e1;
-  e1.part = reinterpret_cast<float2*>(w.part); e1.N = int(N); e1.V = int(V); e1.Npad = w.Npad;
-  if (int rc = launch_gemm<EpiBowLse<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e1, st, "bow_pass1_lse")) return rc;
-  bow_lse_combine_kernel<<<int((N + 7) / 8), 256, 0, st>>>(reinterpret_cast<const float2*>(w.part), w.ntp, w.Npad, int(N), int(K), w.ZA, w.ldk, w.lse, w.srow);
+  // ---- pass F: the one dense pass (online max, power sums) + per-row combine ----
+  CAREL_CHECK_CUDA(cudaMemsetAsync(w.wsum, 0, size_t(w.ldk) * 4, st));
+  CAREL_CHECK_CUDA(cudaMemsetAsync(w.tile_flag, 0, size_t(w.Npad / 128) * 4, st));
+  bow_colsum_kernel<<<148 * 4, (w.ldk / 2 + 31) / 32 * 32, 0, st>>>(w.WB, int(V), w.ldk, w.wsum);
   CAREL_LAUNCHED();
-  // ---- pass 2: dense loss + row sums ----
+  EpiBowFusedParams e1;
+  e1.part4 = w.part4; e1.part2 = w.part2; e1.N = int(N); e1.V = int(V); e1.Npad = w.Npad;
+  if (int rc = launch_gemm<EpiBowFused<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e1, st, "bow_passF")) return rc;
+  bow_combine_kernel<<<int((N + kCombineWarps - 1) / kCombineWarps), kCombineWarps * 32, 0, st>>>(
+      w.part4, w.part2, w.ntp, w.Npad, int(N), int(V), int(K), w.ldk, label_smoothing / float(V), w.wsum, w.ZA,
+      w.lse, w.srow, w.lossacc, w.row_flag, w.tile_flag);
+  CAREL_LAUNCHED();
+  // ---- exact redo of the flagged rows (skips every row tile without a flag: normally all of them) ----
   EpiBowLossParams e2;
-  e2.lossacc = w.lossacc; e2.srow = w.srow; e2.N = int(N); e2.V = int(V); e2.c = label_smoothing / float(V);
-  if (int rc = launch_gemm<EpiBowLoss<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e2, st, "bow_pass2_loss")) return rc;
+  e2.lossacc = w.lossacc; e2.srow = w.srow; e2.row_flag = w.row_flag; e2.N = int(N); e2.V = int(V);
+  e2.c = label_smoothing / float(V);
+  s.row_tile_flags = w.tile_flag;
+  if (int rc = launch_gemm<EpiBowLoss<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e2, st, "bow_pass2_exact")) return rc;
   // ---- sparse corrections ----
   BowSparseArgs sa;
   sa.ZA = w.ZA; sa.WB = w.WB; sa.ell_cols = w.ell_cols; sa.ell_vals = w.ell_vals; sa.ell_nnz = w.ell_nnz;
@@ -798,33 +981,29 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
     bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
     CAREL_LAUNCHED();
   }
-  // ---- pass 3: dense dlogits (vocabulary-major) -> dW (TMEM) + db, bf16 copy dl^T for pass 4 ----
-  {
-    using Cfg = ChainCfg<1, 64>;
+  const int k16 = w.ldk / 16;
+  BowBwdParams bp;
+  bp.srow = w.srow; bp.grad_out = grad_out; bp.dWacc = w.dWacc; bp.grad_z = grad_z; bp.ldgz = ldgz;
+  bp.N = int(N); bp.V = int(V); bp.K = int(K); bp.ldk = w.ldk;
+  bp.c = label_smoothing / float(V); bp.inv_nv = inv_nv;
+  using Cfg = ChainCfg<1, 64>;
+  // ---- pass 3 (vocabulary-major): dense dlogits -> [dW | db] accumulated in TMEM per 128 words ----
+  if (need_w) {
     CUtensorMap ta, tb;
     CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.WB, V, w.ldk, w.ldk, 128) == 0, "carel_bow_bwd: tensor map W failed");
     CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.ZA, N, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z failed");
-    const int k16 = w.ldk / 16;
     ChainSched cs = make_chain_sched(0, int((V + 127) / 128), int((N + 63) / 64), k16, Cfg::stages_for(k16), 16);
     cs.n2_16 = int(K / 16);
-    BowBwdParams bp;
-    bp.srow = w.srow; bp.grad_out = grad_out; bp.dlT = w.dlT; bp.dWacc = w.dWacc;
-    bp.N = int(N); bp.V = int(V); bp.Np = w.Np; bp.K = int(K); bp.ldk = w.ldk;
-    bp.c = label_smoothing / float(V); bp.inv_nv = inv_nv;
-    if (int rc = launch_chain<PolBowBwd, 1, 64>(ta, tb, ta, tb, cs, bp, st, "bow_pass3_dlogits_dw")) return rc;
+    if (int rc = launch_chain<PolBowBwdW, 1, 64>(ta, tb, ta, tb, cs, bp, st, "bow_pass3_dw")) return rc;
   }
-  // ---- pass 4: dZ += dlogit W_d = (dl^T)^T W_d  (both operands MN-major, split-K over the vocabulary) ----
+  // ---- pass 4 (clause-major): dense dlogits -> dZ accumulated in TMEM per 128 clauses ----
   {
     CUtensorMap ta, tb;
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.dlT, V, N, w.Np, 64) == 0, "carel_bow_bwd: tensor map dl^T failed");
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, K, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
-    GemmSched s = make_sched(N, K, V, 256, 1, TILE_FULL);
-    const int tiles = s.m_tiles * s.n_tiles;
-    set_ksplit(s, (4 * sm_count() + tiles - 1) / tiles);
-    EpiStore<256>::Params ep;
-    ep.out = grad_z; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(N); ep.N = int(K);
-    ep.ld = int(ldgz); ep.ld_bf16 = 0; ep.atomic = 1; ep.scale = 1.f;
-    if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st, "bow_pass4_dz")) return rc;
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.ZA, N, w.ldk, w.ldk, 128) == 0, "carel_bow_bwd: tensor map Z failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
+    ChainSched cs = make_chain_sched(0, int((N + 127) / 128), int((V + 63) / 64), k16, Cfg::stages_for(k16), 64);
+    cs.n2_16 = int(K / 16);
+    if (int rc = launch_chain<PolBowBwdZ, 1, 64>(ta, tb, ta, tb, cs, bp, st, "bow_pass4_dz")) return rc;
   }
   if (need_w) {
     bow_scatter_grads_kernel<<<148 * 4, 256, 0, st>>>(w.dWacc, w.ldk, int(V), int(K), grad_w, grad_b);
@@ -832,3 +1011,11 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   }
   return 0;
 }
+
+#ifdef CAREL_CHAIN_TRACE
+// debug: copy the chain-kernel timeline of this translation unit (8 x 256 clock64 values) to the host
+extern "C" int carel_debug_chain_trace(long long* host_dst) {
+  CAREL_CHECK_CUDA(cudaMemcpyFromSymbol(host_dst, carel::g_chain_trace, sizeof(long long) * 8 * 256));
+  return 0;
+}
+#endif

@@ -46,6 +46,7 @@ struct PolMmdBwd {
   float cf;
   CAREL_DEVINL PolMmdBwd(const Params& p_, const ChainCtx&) : p(p_), fast(false), cf(0.f) {}
   CAREL_DEVINL void begin_item(const ChainCtx&) {}
+  CAREL_DEVINL void prefetch(const ChainCtx&, int) {}
   CAREL_DEVINL float ksum(float a) const {   // sum_alpha alpha * exp(-alpha (|d2| + eps))
     float k = 0.f;
     for (int t = 0; t < p.n_alpha; ++t)

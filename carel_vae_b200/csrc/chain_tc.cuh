@@ -12,8 +12,8 @@
 // Used by the backward passes: MMD / HSIC (P = C (.) K', acc2 = sum_j W_ij s_j) and the BoW
 // decoder (P = dlogits tile, acc2 = dZ).  The N x N (or N x V) matrix P never leaves the SM.
 //
-// 64 + 128*kChainSplit threads: warp 0 TMEM allocator + TMA producer lane, warp 1 MMA issuer lane, then
-// 4*kChainSplit epilogue warps (warp w: TMEM lanes 32*(w%4).., column part (w-2)/4 of the inner tile).
+// 128*kChainSplit + 64 threads: 4*kChainSplit epilogue warps (warp w: TMEM lanes 32*(w%4).., column part w/4 of the
+// inner tile), then the TMEM allocator + TMA producer warp and the MMA issuer warp (highest ids: scheduler priority).
 // TMEM columns: acc1 2 buffers x NG x BN1 | acc2 16*n2_16   (<= 512).  Within an acc1 buffer the half
 // part h of product 0 (columns [h R, (h+1) R), R = BN1/kChainSplit) is overwritten by its own thread with
 // P_hi (R/2 columns of packed bf16 pairs) followed by P_lo (R/2 columns).
@@ -24,6 +24,16 @@
 #include "gemm_tc.cuh"
 
 namespace carel {
+
+// Debug timeline (build with CAREL_EXTRA_FLAGS=-DCAREL_CHAIN_TRACE): block 0 records clock64() of the main
+// pipeline events of its first 256 inner tiles; read back with carel_debug_chain_trace().
+#ifdef CAREL_CHAIN_TRACE
+static __device__ long long g_chain_trace[8 * 256];
+#define CAREL_TRACE(slot, idx) \
+  do { if (blockIdx.x == 0 && (idx) < 256) g_chain_trace[(slot) * 256 + (idx)] = clock64(); } while (0)
+#else
+#define CAREL_TRACE(slot, idx) do {} while (0)
+#endif
 
 struct ChainSched {
   int n_owner;     // owner tiles (128 rows) in this launch
@@ -120,8 +130,13 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Roles: warps [0, kEpi) epilogue; warp kEpi = TMEM allocator + TMA producer lane; warp kEpi + 1 = MMA issuer
+  // lane.  The two single-lane roles sit in the HIGHEST warp ids on purpose: the SMSP arbiter prefers higher
+  // warp ids, and an MMA issuer that has to queue behind spinning / MUFU-heavy epilogue warps starves the
+  // tensor pipe (measured: narrow MMAs took 109 clk per issue instead of 55).
+  constexpr int kEpi = 4 * kChainSplit;
 
-  if (threadIdx.x == 32) {
+  if (threadIdx.x == (kEpi + 1) * 32) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB0);
     if (NG == 2) {
@@ -142,18 +157,20 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     mbar_init(acc2_empty, 4 * kChainSplit);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == kEpi) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kEpi && elect_one()) {   // elect.sync: ptxas knows ONE lane runs this region, so the
+    // uniform-register operands of UTMALDG / UTCHMMA need no per-instruction broadcast loop
     // ===================== TMA producer =====================
     ChainIter iter(sched);
     ChainItem it;
     int stage = 0;
     uint32_t phase = 0, aphase = 0;
+    int trace_n = 0; (void)trace_n;
     while (iter.next(it)) {
       mbar_wait(a_empty, aphase ^ 1);
       mbar_expect_tx(a_full, a_bytes);
@@ -166,6 +183,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll 1
       for (int t = it.t0; t < it.t1; ++t) {
         mbar_wait(&b_empty[stage], phase ^ 1);
+        CAREL_TRACE(0, trace_n); ++trace_n;
         mbar_expect_tx(&b_full[stage], b_bytes);
         uint8_t* dst = sB + stage * b_bytes;
 #pragma unroll 1
@@ -177,7 +195,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == kEpi + 1 && elect_one()) {
     // ===================== MMA issuer =====================
     ChainIter iter(sched);
     ChainItem it;
@@ -186,6 +204,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     int g1_buf = 0;                            // acc1 buffer of the next GEMM-1
     int g2_buf = 0; uint32_t p_phase0 = 0, p_phase1 = 0;
     uint32_t aphase = 0, acc2_phase = 0;
+    int trace_g1 = 0, trace_g2 = 0; (void)trace_g1; (void)trace_g2;
     constexpr uint32_t idesc1 = make_idesc_bf16(128, BN1, 0, 0);
     const uint32_t idesc2 = make_idesc_bf16(128, 16 * sched.n2_16, 0, 1);
     const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(sA), 16, 1024);
@@ -197,6 +216,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       bool first_g2 = true;
       auto issue_g1 = [&]() {
         mbar_wait(&b_full[g1_stage], g1_phase);
+        CAREL_TRACE(1, trace_g1); ++trace_g1;
         tc_fence_after();
         const uint32_t b_tile = b_base0 + g1_stage * b_bytes;
 #pragma unroll 1
@@ -214,6 +234,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             db = sdesc_advance(db, BN1 * 128);
           }
         }
+        CAREL_TRACE(6, trace_g1 - 1);
         umma_commit(&acc1_full[g1_buf]);
         if (++g1_stage == STAGES) { g1_stage = 0; g1_phase ^= 1; }
         g1_buf ^= 1;
@@ -222,6 +243,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (g2_buf == 0) { mbar_wait(&p_full[0], p_phase0); p_phase0 ^= 1; }
         else { mbar_wait(&p_full[1], p_phase1); p_phase1 ^= 1; }
         if (first_g2) mbar_wait(acc2_empty, acc2_phase ^ 1);
+        CAREL_TRACE(2, trace_g2); ++trace_g2;
         tc_fence_after();
         const uint64_t db0 = make_sdesc_sw128(b_base0 + g2_stage * b_bytes, BN1 * 128, 1024);   // product 0, MN-major view
         const uint32_t p_base = tmem_base + g2_buf * Cfg::kAcc1Cols;
@@ -237,6 +259,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
           }
         }
+        CAREL_TRACE(7, trace_g2 - 1);
         umma_commit(&b_empty[g2_stage]);
         if (++g2_stage == STAGES) g2_stage = 0;
         g2_buf ^= 1;
@@ -251,12 +274,12 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       umma_commit(a_empty);
       acc2_phase ^= 1;
     }
-  } else if (warp >= 2) {
+  } else if (warp < kEpi) {
     // ===================== epilogue =====================
     ChainCtx ctx;
-    ctx.half = (warp - 2) >> 2;
+    ctx.half = warp >> 2;
     ctx.lane_q = warp & 3;
-    ctx.epi_tid = threadIdx.x - 64;
+    ctx.epi_tid = threadIdx.x;
     ctx.k16 = K16;
     ctx.n2_16 = sched.n2_16;
     Pol pol(pp, ctx);
@@ -265,6 +288,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     int buf = 0;
     uint32_t full_phase0 = 0, full_phase1 = 0;
     uint32_t acc2_phase = 0;
+    int trace_e = 0; (void)trace_e;
+    const bool tracer = (threadIdx.x == 0); (void)tracer;
     const uint32_t lane_off = uint32_t(ctx.lane_q * 32) << 16;
     ctx.acc2_taddr = tmem_base + lane_off + Cfg::kAcc2Base;
     while (iter.next(it)) {
@@ -275,8 +300,10 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       pol.begin_item(ctx);
 #pragma unroll 1
       for (int t = it.t0; t < it.t1; ++t) {
+        pol.prefetch(ctx, t * BN1 + ctx.half * R);       // loads that do not depend on acc1: issued before the wait
         if (buf == 0) { mbar_wait(&acc1_full[0], full_phase0); full_phase0 ^= 1; }
         else { mbar_wait(&acc1_full[1], full_phase1); full_phase1 ^= 1; }
+        if (tracer) CAREL_TRACE(3, trace_e);
         tc_fence_after();
         // this thread's region of product 0 (product 1 sits BN1 columns further)
         const uint32_t reg0 = tmem_base + lane_off + buf * Cfg::kAcc1Cols + ctx.half * R;
@@ -288,6 +315,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if (NG == 2) tmem_ld16(reg0 + BN1 + c * 16, r1[NG == 2 ? c : 0]);
         }
         tmem_ld_wait();
+        if (tracer) CAREL_TRACE(4, trace_e);
         const int j0 = t * BN1 + ctx.half * R;
         pol.begin_tile(ctx, j0, R);
 #pragma unroll
@@ -312,6 +340,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[buf]);
+        if (tracer) { CAREL_TRACE(5, trace_e); ++trace_e; }
         buf ^= 1;
       }
       mbar_wait(acc2_full, acc2_phase);
@@ -327,7 +356,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == kEpi) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace carel

@@ -166,6 +166,7 @@ struct PolHsicBwd {
     ci = __ldg(p.c_other + min(ctx.row, p.m - 1)) + __ldg(p.mean_other);
   }
   CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
+  CAREL_DEVINL void prefetch(const ChainCtx&, int) {}
   CAREL_DEVINL void weights16(const ChainCtx& ctx, int jc, const uint32_t (&rs)[16], const uint32_t (&ro)[16],
                               float (&w)[16]) {
     const float4* cj4 = reinterpret_cast<const float4*>(p.c_other + jc);

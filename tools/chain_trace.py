@@ -1,0 +1,34 @@
+"""Timeline of the decoder chain kernels (debug build: CAREL_EXTRA_FLAGS=-DCAREL_CHAIN_TRACE python -m carel_vae_b200.build --force)
+usage: python tools/chain_trace.py [dw|dz]"""
+import ctypes as C, sys
+import torch
+sys.path.insert(0, ".")
+from carel_vae_b200 import functional as F, _lib
+which = sys.argv[1] if len(sys.argv) > 1 else "dz"
+n, d, V = 8192, 128, 30000
+torch.manual_seed(0)
+Z = (torch.randn(n, 2 * d, device="cuda") * 1.1).requires_grad_(True)
+W = ((torch.rand(V, 2 * d, device="cuda") * 2 - 1) / 16).requires_grad_(which == "dw")
+b = ((torch.rand(V, device="cuda") * 2 - 1) / 16).requires_grad_(which == "dw")
+idx = torch.randint(0, V, (n, 24), device="cuda")
+bow = torch.zeros(n, V, device="cuda")
+bow.scatter_add_(1, idx, torch.ones(n, 24, device="cuda"))
+bow = bow / bow.sum(1, keepdim=True).clamp_min(1)
+for _ in range(2):
+    o = F.bow_reconstruction_loss(Z, W, b, bow)
+    o.backward()
+torch.cuda.synchronize()
+L = _lib.lib()._handle if hasattr(_lib.lib(), "_handle") else None
+h = C.CDLL(str(_lib.LIB_PATH)) if hasattr(_lib, "LIB_PATH") else None
+lib = C.CDLL("carel_vae_b200/libcarel_head.so")
+buf = (C.c_longlong * (8 * 256))()
+assert lib.carel_debug_chain_trace(buf) == 0
+ev = [[buf[s * 256 + i] for i in range(256)] for s in range(8)]
+t0 = min(v for v in ev[0] if v > 0)
+names = ["load_issue", "g1_issue", "g2_issue", "epi_acc1_ready", "epi_ld_done", "epi_p_arrive", "g1_issued", "g2_issued"]
+print("tile " + " ".join(f"{n:>14s}" for n in names))
+for i in list(range(0, 8)) + list(range(100, 112)):
+    print(f"{i:4d} " + " ".join(f"{ev[s][i] - t0:14d}" for s in range(8)))
+for s in range(8):
+    d_ = [ev[s][i + 1] - ev[s][i] for i in range(20, 120)]
+    print(names[s], "mean period", sum(d_) / len(d_))
