@@ -42,6 +42,8 @@ struct BowWs {
   int* row_flag;        // [Npad] 1: row needs the exact pass
   int* tile_flag;       // [Npad/128]
   float* lse;           // [Npad]  holds -lse
+  float* nlse2;         // [Npad]  -lse log2(e) (0 beyond N)
+  float* bl2e;          // [V rounded up to 64]  b log2(e) (0 beyond V)
   float* srow;          // [Npad]  S_i = N V s_i
   float* dWacc;         // [V, ldk] fp32 accumulation of dlogit^T [Z | 1]
   double* lossacc;      // [2] dense, sparse
@@ -70,8 +72,10 @@ static BowWs carve_bow(void* ws, int64_t N, int64_t K, int64_t V, int64_t cap) {
   r.part2 = w.take<float2>(size_t(r.ntp) * r.Npad);
   r.wsum = w.take<float>(size_t(r.ldk));
   r.row_flag = w.take<int>(size_t(r.Npad));
-  r.tile_flag = w.take<int>(size_t(r.Npad / 128));
+  r.tile_flag = w.take<int>(size_t(r.Npad / 128) + 1);   // [0] = any, [1 + tile]
   r.lse = w.take<float>(size_t(r.Npad));
+  r.nlse2 = w.take<float>(size_t(r.Npad));
+  r.bl2e = w.take<float>(size_t(round_up64(V, 64)));
   r.srow = w.take<float>(size_t(r.Npad));
   r.dWacc = w.take<float>(size_t(V) * r.ldk);
   r.lossacc = w.take<double>(2);
@@ -214,19 +218,37 @@ struct EpiBowFused {
   CAREL_DEVINL void finish() {}
 };
 
+// b log2(e) for the backward chains (zero padded to a multiple of 64)
+static __global__ void bow_bias_kernel(const float* __restrict__ b, int V, int Vpad, float* __restrict__ bl2e) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < Vpad) bl2e[j] = (j < V) ? __ldg(b + j) * kLog2e : 0.f;
+}
+
 // column sums of the packed decoder operand WB [V, ldk] (bf16 -> fp32): sum_j x_ij = ZA_i . wsum
+// block = (ldk/2 pair columns rounded to 32) x 4 row lanes; grid-stride over rows, one atomicAdd per column and block
 static __global__ void bow_colsum_kernel(const __nv_bfloat16* __restrict__ WB, int V, int ldk,
                                          float* __restrict__ wsum) {
-  const int w = threadIdx.x;               // bf16 pair index
-  if (w * 2 >= ldk) return;
+  extern __shared__ float2 sh_cs[];          // [blockDim.y][blockDim.x]
+  const int w = threadIdx.x;                 // bf16 pair index
+  const bool act = w * 2 < ldk;
   float2 acc = make_float2(0.f, 0.f);
-  for (int r = blockIdx.x; r < V; r += gridDim.x) {
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(WB + size_t(r) * ldk + 2 * w));
-    acc.x += f.x;
-    acc.y += f.y;
+  if (act) {
+    for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < V; r += gridDim.x * blockDim.y) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(WB + size_t(r) * ldk + 2 * w));
+      acc.x += f.x;
+      acc.y += f.y;
+    }
   }
-  atomicAdd(wsum + 2 * w, acc.x);
-  atomicAdd(wsum + 2 * w + 1, acc.y);
+  sh_cs[threadIdx.y * blockDim.x + w] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && act) {
+    for (int y = 1; y < blockDim.y; ++y) {
+      acc.x += sh_cs[y * blockDim.x + w].x;
+      acc.y += sh_cs[y * blockDim.x + w].y;
+    }
+    atomicAdd(wsum + 2 * w, acc.x);
+    atomicAdd(wsum + 2 * w + 1, acc.y);
+  }
 }
 
 static CAREL_DEVINL void split3(float h, __nv_bfloat16& h1, __nv_bfloat16& h2, __nv_bfloat16& h3) {
@@ -236,72 +258,100 @@ static CAREL_DEVINL void split3(float h, __nv_bfloat16& h1, __nv_bfloat16& h2, _
   h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
 }
 
-// Combine the pass-F partials of a row (one warp per row): lse_i, power sums, dense loss term and
-// S_i = sum_j u_ij; writes -lse (3-way bf16 split) into the h columns of ZA.  Rows outside the series'
-// range are flagged (row_flag / tile_flag) and contribute nothing here.
-constexpr int kCombineWarps = 8;
-static __global__ void __launch_bounds__(kCombineWarps * 32)
+// Combine the pass-F partials of the rows: lse_i, power sums, dense loss term and S_i = sum_j u_ij; writes
+// -lse (3-way bf16 split) into the h columns of ZA.  Rows outside the series' range are flagged (row_flag /
+// tile_flag[1 + tile], tile_flag[0] = any) and contribute nothing here.
+// Block = 32 rows x 8 partial groups: thread (r, g) folds partials g, g + 8, ... of row r online (consecutive
+// threads read consecutive rows: coalesced), the 8 groups meet in shared memory, then warp w finishes rows
+// 4w .. 4w + 3 (sum_j x_ij = ZA_i . wsum needs a warp per row).
+constexpr int kCombineRows = 32, kCombineGroups = 8;
+static __global__ void __launch_bounds__(kCombineRows * kCombineGroups)
 bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ part2, int ntp, int Npad, int N,
                    int V, int K, int ldk, float c, const float* __restrict__ wsum, __nv_bfloat16* __restrict__ ZA,
-                   float* __restrict__ neg_lse, float* __restrict__ srow, double* __restrict__ lossacc,
-                   int* __restrict__ row_flag, int* __restrict__ tile_flag) {
-  __shared__ double sh_loss[kCombineWarps];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int r = blockIdx.x * kCombineWarps + wid;
-  double f = 0.0;
-  if (r < N) {
-    float M = -INFINITY;
-    for (int t = lane; t < ntp; t += 32) M = fmaxf(M, part4[size_t(t) * Npad + r].x);
-    M = warp_max(M);
-    float T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f, mn = INFINITY;
-    for (int t = lane; t < ntp; t += 32) {
+                   float* __restrict__ neg_lse, float* __restrict__ nlse2, float* __restrict__ srow,
+                   double* __restrict__ lossacc, int* __restrict__ row_flag, int* __restrict__ tile_flag) {
+  __shared__ float sh[kCombineGroups][6][kCombineRows];
+  __shared__ double sh_loss[kCombineGroups];
+  const int rl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int r = blockIdx.x * kCombineRows + rl;          // r < Npad always (Npad is a multiple of 128)
+  {
+    float M = -INFINITY, T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f, mn = INFINITY;
+    for (int t = g; t < ntp; t += kCombineGroups) {
       const float4 a = part4[size_t(t) * Npad + r];
       const float2 b = part2[size_t(t) * Npad + r];
+      mn = fminf(mn, b.y);
       if (a.y > 0.f) {
+        if (a.x > M) {          // rescale the running sums to the new reference
+          const float w = __expf(M - a.x), w2 = w * w;
+          T1 *= w; T2 *= w2; T3 *= w2 * w; T4 *= w2 * w2;
+          M = a.x;
+        }
         const float w = __expf(a.x - M), w2 = w * w;
         T1 = fmaf(a.y, w, T1);
         T2 = fmaf(a.z, w2, T2);
         T3 = fmaf(a.w, w2 * w, T3);
         T4 = fmaf(b.x, w2 * w2, T4);
       }
-      mn = fminf(mn, b.y);
     }
-    T1 = warp_sum(T1); T2 = warp_sum(T2); T3 = warp_sum(T3); T4 = warp_sum(T4);
+    sh[g][0][rl] = M; sh[g][1][rl] = T1; sh[g][2][rl] = T2; sh[g][3][rl] = T3; sh[g][4][rl] = T4; sh[g][5][rl] = mn;
+  }
+  __syncthreads();
+  // warp g finishes rows 4g .. 4g+3
+  const int lane = rl;
+  double f = 0.0;
+  for (int q = 0; q < kCombineRows / kCombineGroups; ++q) {
+    const int row_l = g * (kCombineRows / kCombineGroups) + q;
+    const int row = blockIdx.x * kCombineRows + row_l;
+    if (row >= N) {
+      if (lane == 0) { nlse2[row] = 0.f; srow[row] = 0.f; }      // padding rows read by the backward chains
+      continue;
+    }
+    // lanes 0..7 hold the 8 groups
+    float M = -INFINITY, T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f, mn = INFINITY;
+    if (lane < kCombineGroups) {
+      M = sh[lane][0][row_l]; T1 = sh[lane][1][row_l]; T2 = sh[lane][2][row_l]; T3 = sh[lane][3][row_l];
+      T4 = sh[lane][4][row_l]; mn = sh[lane][5][row_l];
+    }
+    const float Mx = warp_max(M);
+    const float w = (T1 > 0.f) ? __expf(M - Mx) : 0.f, w2 = w * w;
+    T1 = warp_sum(T1 * w); T2 = warp_sum(T2 * w2); T3 = warp_sum(T3 * w2 * w); T4 = warp_sum(T4 * w2 * w2);
     mn = -warp_max(-mn);
     // sum_j x_ij from the column sums of the packed operand (the h columns of ZA are still zero here)
     float sx = 0.f;
-    const __nv_bfloat16* zrow = ZA + size_t(r) * ldk;
+    const __nv_bfloat16* zrow = ZA + size_t(row) * ldk;
     for (int k = lane; k < ldk; k += 32) sx = fmaf(__bfloat162float(zrow[k]), __ldg(wsum + k), sx);
     sx = warp_sum(sx);
     if (lane == 0) {
-      const float lse = M + logf(T1);
+      const float lse = Mx + logf(T1);
       const float i1 = 1.f / T1, i2 = i1 * i1;
       const float S2 = T2 * i2, S3 = T3 * i2 * i1, S4 = T4 * i2 * i2;
       const bool valid = (i1 < 0.03125f) && (mn - lse > -27.f);
       float u = 0.f;
       if (valid) {
-        f = double(c) * (double(sx) - double(V) * double(lse)) -
-            double(1.f - c) * (1.0 + double(0.5f * S2 + (1.f / 3.f) * S3 + 0.25f * S4));
+        f += double(c) * (double(sx) - double(V) * double(lse)) -
+             double(1.f - c) * (1.0 + double(0.5f * S2 + (1.f / 3.f) * S3 + 0.25f * S4));
         u = (1.f + S2 + S3 + S4) - c * (float(V) + 1.f + S2 + S3);
       } else {
-        tile_flag[r >> 7] = 1;
+        tile_flag[0] = 1;
+        tile_flag[1 + (row >> 7)] = 1;
       }
-      row_flag[r] = valid ? 0 : 1;
-      srow[r] = u;
+      row_flag[row] = valid ? 0 : 1;
+      srow[row] = u;
       const float nl = -lse;
-      neg_lse[r] = nl;
+      neg_lse[row] = nl;
+      nlse2[row] = nl * kLog2e;
       __nv_bfloat16 h1, h2, h3;
       split3(nl, h1, h2, h3);
-      ZA[size_t(r) * ldk + K] = h1;
-      ZA[size_t(r) * ldk + K + 1] = h2;
-      ZA[size_t(r) * ldk + K + 2] = h3;
+      ZA[size_t(row) * ldk + K] = h1;
+      ZA[size_t(row) * ldk + K + 1] = h2;
+      ZA[size_t(row) * ldk + K + 2] = h3;
     }
   }
-  if (lane == 0) sh_loss[wid] = f;
+  if (lane == 0) sh_loss[g] = f;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int i = 0; i < kCombineWarps; ++i) t += sh_loss[i];
+    for (int i = 0; i < kCombineGroups; ++i) t += sh_loss[i];
     if (t != 0.0) atomicAdd(lossacc, t);
   }
 }
@@ -324,6 +374,8 @@ struct EpiBowLossParams {
   double* lossacc;
   float* srow;
   const int* row_flag;   // optional: only flagged rows contribute (exact redo of the rows pass F could not take)
+  const float* bl2e;     // [Vpad]  b_j log2(e)
+  const float* nlse2;    // [Npad]  -lse_i log2(e)
   int N, V;
   float c;
 };
@@ -340,10 +392,21 @@ struct EpiBowLoss {
     const bool full = c0 + HALF <= p.V;
     float sx = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, cnt = 0.f, fex = 0.f, uex = 0.f;
     const float c = p.c;
+    // Plain operands: log p = (acc log2(e) + b_j log2(e) - lse_i log2(e)) ln 2, evaluated with EXACTLY the
+    // operations of bow_dlogit16 (backward): for p -> 1 the gradient u_j - p_j S_i cancels catastrophically and
+    // is only right if S_i (here) and u_j (there) come from bit-identical log p.
+    const float rc = __ldg(p.nlse2 + min(ctx.row, p.N - 1));
+    const float2 l2e = make_float2(kLog2e, kLog2e), rc2 = make_float2(rc, rc);
     for_each_chunk16(ctx.taddr + ctx.half * HALF, HALF / 16, [&](int ch, const uint32_t (&r)[16]) {
       float x[16];
+      const float* ccp = p.bl2e + c0 + ch * 16;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
+      for (int i = 0; i < 16; i += 2) {
+        const float2 t = __fadd2_rn(__ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), l2e,
+                                               make_float2(__ldg(ccp + i), __ldg(ccp + i + 1))), rc2);
+        x[i] = t.x * kLn2;
+        x[i + 1] = t.y * kLn2;
+      }
       float mx = fmaxf(x[0], x[1]), mn = fminf(x[0], x[1]);
 #pragma unroll
       for (int i = 2; i < 16; ++i) { mx = fmaxf(mx, x[i]); mn = fminf(mn, x[i]); }
@@ -574,29 +637,40 @@ static __global__ void csc_count_kernel(const int* __restrict__ cols, const int*
     if (n <= cap && q < n) atomicAdd(cnt + cols[t], 1);
   }
 }
-// cnt may alias fillpos (each thread reads its own range before overwriting it)
-static __global__ void csc_scan_kernel(const int* cnt, int V, int* colptr, int* fillpos) {
+// Exclusive scan of the per-word counts (one block; cnt may alias fillpos).  The counts are staged through
+// shared memory in chunks of 8 per thread so that every global access is coalesced.
+static __global__ void __launch_bounds__(1024) csc_scan_kernel(const int* cnt, int V, int* colptr, int* fillpos) {
+  constexpr int PER = 8, CH = 1024 * PER;
+  __shared__ int buf[CH];
   __shared__ int part[1024];
-  const int per = (V + blockDim.x - 1) / blockDim.x;
-  const int b = threadIdx.x * per, e = min(b + per, V);
-  int s = 0;
-  for (int i = b; i < e; ++i) s += cnt[i];
-  part[threadIdx.x] = s;
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int off = 1; off < blockDim.x; off <<= 1) {
-    const int v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0;
+  for (int base = 0; base < V; base += CH) {
+    for (int i = threadIdx.x; i < CH; i += 1024) buf[i] = (base + i < V) ? cnt[base + i] : 0;
     __syncthreads();
-    part[threadIdx.x] += v;
+    int loc[PER], s = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { loc[i] = s; s += buf[threadIdx.x * PER + i]; }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      const int v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0;
+      __syncthreads();
+      part[threadIdx.x] += v;
+      __syncthreads();
+    }
+    const int run = carry + part[threadIdx.x] - s;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) buf[threadIdx.x * PER + i] = run + loc[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < CH; i += 1024)
+      if (base + i < V) { colptr[base + i] = buf[i]; fillpos[base + i] = buf[i]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += part[1023];
     __syncthreads();
   }
-  int run = part[threadIdx.x] - s;
-  for (int i = b; i < e; ++i) {
-    const int c = cnt[i];
-    colptr[i] = run;
-    fillpos[i] = run;
-    run += c;
-  }
-  if (threadIdx.x == blockDim.x - 1) colptr[V] = part[threadIdx.x];
+  if (threadIdx.x == 0) colptr[V] = carry;
 }
 static __global__ void csc_fill_kernel(const int* __restrict__ cols, const int* __restrict__ nnz, int N,
                                        int cap, int* __restrict__ fillpos, int* __restrict__ csc_row,
@@ -708,6 +782,8 @@ static __global__ void bow_loss_finalize_kernel(const double* __restrict__ lossa
 // ---------------------------------------------------------------------------------------------
 struct BowBwdParams {
   const float* srow;     // [Npad]  S_i (zero beyond N)
+  const float* nlse2;    // [Npad]  -lse_i log2(e)
+  const float* bl2e;     // [Vpad]  b_j log2(e)
   const float* grad_out;
   float* dWacc;          // [V, ldk]     (W policy)
   float* grad_z;         // [N, ldgz]    (Z policy)
@@ -716,24 +792,31 @@ struct BowBwdParams {
   float c, inv_nv;
 };
 
-// d[16] from 16 log-probabilities; Sn[i] = -S * scale per element
-static CAREL_DEVINL void bow_dlogit16(const uint32_t (&r)[16], const float (&Sn)[16], float c, float scale,
-                                      bool in_range, int n_valid, float (&d)[16]) {
-  float x[16];
+// d[16] from 16 accumulators acc = z_i . w_j (plain operands, no augmentation columns):
+//   log2 p = acc log2(e) + cc[col] + rc      (cc: per-column constant, rc: per-row constant)
+// Sn[i] = -S * scale per element.
+static CAREL_DEVINL void bow_dlogit16(const uint32_t (&r)[16], const float (&cc)[16], float rc, const float (&Sn)[16],
+                                      float c, float scale, bool in_range, int n_valid, float (&d)[16]) {
+  const float2 l2e = make_float2(kLog2e, kLog2e), rc2 = make_float2(rc, rc);
+  float t[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
-  float mx = fmax3(x[0], x[1], x[2]), mn = fmin3(x[0], x[1], x[2]);
+  for (int i = 0; i < 16; i += 2) {
+    const float2 v = __fadd2_rn(__ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), l2e,
+                                           make_float2(cc[i], cc[i + 1])), rc2);
+    t[i] = v.x;
+    t[i + 1] = v.y;
+  }
+  float mx = fmax3(t[0], t[1], t[2]), mn = fmin3(t[0], t[1], t[2]);
 #pragma unroll
-  for (int i = 3; i < 15; i += 2) { mx = fmax3(mx, x[i], x[i + 1]); mn = fmin3(mn, x[i], x[i + 1]); }
-  mx = fmaxf(mx, x[15]);
-  mn = fminf(mn, x[15]);
-  if (in_range && mx < kTinyLogP && mn > -27.f) {
-    const float2 l2e = make_float2(kLog2e, kLog2e), one = make_float2(1.f, 1.f);
+  for (int i = 3; i < 15; i += 2) { mx = fmax3(mx, t[i], t[i + 1]); mn = fmin3(mn, t[i], t[i + 1]); }
+  mx = fmaxf(mx, t[15]);
+  mn = fminf(mn, t[15]);
+  if (in_range && mx < -10.f && mn > -27.f * kLog2e) {          // all p in (e^-27, 2^-10)
+    const float2 one = make_float2(1.f, 1.f);
     const float2 sc = make_float2(scale, scale), mcs = make_float2(-c * scale, -c * scale);
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
-      const float2 t = __fmul2_rn(make_float2(x[i], x[i + 1]), l2e);
-      const float2 pv = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+      const float2 pv = make_float2(ex2_approx(t[i]), ex2_approx(t[i + 1]));
       const float2 q = __ffma2_rn(pv, __fadd2_rn(pv, one), one);              // 1 + p + p^2
       const float2 a = __ffma2_rn(pv, sc, mcs);                               // (p - c) scale
       const float2 m = __fmul2_rn(pv, make_float2(Sn[i], Sn[i + 1]));         // -p S scale
@@ -744,9 +827,10 @@ static CAREL_DEVINL void bow_dlogit16(const uint32_t (&r)[16], const float (&Sn)
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
+      const float x = t[i] * kLn2;
       float f, u;
-      bow_exact_terms(x[i], c, f, u);
-      d[i] = (i < n_valid) ? fmaf(u, scale, __expf(x[i]) * Sn[i]) : 0.f;
+      bow_exact_terms(x, c, f, u);
+      d[i] = (i < n_valid) ? fmaf(u, scale, __expf(x) * Sn[i]) : 0.f;
     }
   }
 }
@@ -755,19 +839,22 @@ struct PolBowBwdW {
   using Params = BowBwdParams;
   static constexpr bool kHiLo = false;    // measured decoder gradients are 6e-5..3e-4 with a single bf16 P
   const Params& p;
-  float scale, dbsum;
-  float Sn[16];
-  CAREL_DEVINL PolBowBwdW(const Params& p_, const ChainCtx&) : p(p_), scale(0.f), dbsum(0.f) {}
-  CAREL_DEVINL void begin_item(const ChainCtx&) {
+  float scale, dbsum, rc;
+  float Sn[16], cc[16];
+  CAREL_DEVINL PolBowBwdW(const Params& p_, const ChainCtx&) : p(p_), scale(0.f), dbsum(0.f), rc(0.f) {}
+  CAREL_DEVINL void begin_item(const ChainCtx& ctx) {
     scale = __ldg(p.grad_out) * p.inv_nv;
     dbsum = 0.f;
+    rc = __ldg(p.bl2e + min(ctx.row, p.V - 1));         // this thread's word: b_v log2(e)
   }
   CAREL_DEVINL void prefetch(const ChainCtx&, int i0) {
     const float4* s4 = reinterpret_cast<const float4*>(p.srow + i0);
+    const float4* l4 = reinterpret_cast<const float4*>(p.nlse2 + i0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 v = __ldg(s4 + i);
+      const float4 v = __ldg(s4 + i), l = __ldg(l4 + i);
       Sn[4 * i] = -v.x * scale; Sn[4 * i + 1] = -v.y * scale; Sn[4 * i + 2] = -v.z * scale; Sn[4 * i + 3] = -v.w * scale;
+      cc[4 * i] = l.x; cc[4 * i + 1] = l.y; cc[4 * i + 2] = l.z; cc[4 * i + 3] = l.w;
     }
   }
   CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
@@ -778,7 +865,7 @@ struct PolBowBwdW {
       for (int i = 0; i < 16; ++i) d[i] = 0.f;
       return;
     }
-    bow_dlogit16(r, Sn, p.c, scale, i0 + 16 <= p.N, p.N - i0, d);
+    bow_dlogit16(r, cc, rc, Sn, p.c, scale, i0 + 16 <= p.N, p.N - i0, d);
     float t = 0.f;                       // db_v: thread-local column sum (fp32, before the bf16 rounding)
 #pragma unroll
     for (int i = 0; i < 16; ++i) t += d[i];
@@ -810,20 +897,29 @@ struct PolBowBwdZ {
   using Params = BowBwdParams;
   static constexpr bool kHiLo = false;
   const Params& p;
-  float scale;
-  float Sn[16];
-  CAREL_DEVINL PolBowBwdZ(const Params& p_, const ChainCtx&) : p(p_), scale(0.f) {}
+  float scale, rc;
+  float Sn[16], cc[16];
+  CAREL_DEVINL PolBowBwdZ(const Params& p_, const ChainCtx&) : p(p_), scale(0.f), rc(0.f) {}
   CAREL_DEVINL void begin_item(const ChainCtx& ctx) {
     scale = __ldg(p.grad_out) * p.inv_nv;
-    const float sn = (ctx.row < p.N) ? -__ldg(p.srow + ctx.row) * scale : 0.f;
+    const bool ok = ctx.row < p.N;
+    const float sn = ok ? -__ldg(p.srow + ctx.row) * scale : 0.f;
+    rc = ok ? __ldg(p.nlse2 + ctx.row) : 0.f;           // this thread's clause: -lse_i log2(e)
 #pragma unroll
     for (int i = 0; i < 16; ++i) Sn[i] = sn;
   }
-  CAREL_DEVINL void prefetch(const ChainCtx&, int) {}
+  CAREL_DEVINL void prefetch(const ChainCtx&, int v0) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bl2e + v0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 l = __ldg(b4 + i);
+      cc[4 * i] = l.x; cc[4 * i + 1] = l.y; cc[4 * i + 2] = l.z; cc[4 * i + 3] = l.w;
+    }
+  }
   CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
   CAREL_DEVINL void weights16(const ChainCtx&, int v0, const uint32_t (&r)[16], const uint32_t (&)[16],
                               float (&d)[16]) {
-    bow_dlogit16(r, Sn, p.c, scale, v0 + 16 <= p.V, p.V - v0, d);
+    bow_dlogit16(r, cc, rc, Sn, p.c, scale, v0 + 16 <= p.V, p.V - v0, d);
   }
   CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
   CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
@@ -895,6 +991,11 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   CAREL_LAUNCHED();
   pack_rows_kernel<<<int(std::min<int64_t>((V + 7) / 8, 148 * 32)), 256, 0, st>>>(dec_w, int(V), int(K), int(K), nullptr, w.WB, w.ldk, 0, 1, nullptr, dec_b);
   CAREL_LAUNCHED();
+  {
+    const int Vpad = int(round_up64(V, 64));
+    bow_bias_kernel<<<(Vpad + 255) / 256, 256, 0, st>>>(dec_b, int(V), Vpad, w.bl2e);
+    CAREL_LAUNCHED();
+  }
   // ---- sparse target ----
   if (ell_cols_in != nullptr) {
     CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_cols, ell_cols_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, st));
@@ -911,22 +1012,31 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   GemmSched s = make_sched(N, V, w.ldk, 256, 1, TILE_FULL);
   // ---- pass F: the one dense pass (online max, power sums) + per-row combine ----
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.wsum, 0, size_t(w.ldk) * 4, st));
-  CAREL_CHECK_CUDA(cudaMemsetAsync(w.tile_flag, 0, size_t(w.Npad / 128) * 4, st));
-  bow_colsum_kernel<<<148 * 4, (w.ldk / 2 + 31) / 32 * 32, 0, st>>>(w.WB, int(V), w.ldk, w.wsum);
+  CAREL_CHECK_CUDA(cudaMemsetAsync(w.tile_flag, 0, (size_t(w.Npad / 128) + 1) * 4, st));
+  {
+    const dim3 blk((w.ldk / 2 + 31) / 32 * 32, 4);
+    bow_colsum_kernel<<<148 * 4, blk, blk.x * blk.y * sizeof(float2), st>>>(w.WB, int(V), w.ldk, w.wsum);
+  }
   CAREL_LAUNCHED();
   EpiBowFusedParams e1;
   e1.part4 = w.part4; e1.part2 = w.part2; e1.N = int(N); e1.V = int(V); e1.Npad = w.Npad;
   if (int rc = launch_gemm<EpiBowFused<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e1, st, "bow_passF")) return rc;
-  bow_combine_kernel<<<int((N + kCombineWarps - 1) / kCombineWarps), kCombineWarps * 32, 0, st>>>(
+  bow_combine_kernel<<<w.Npad / kCombineRows, kCombineRows * kCombineGroups, 0, st>>>(
       w.part4, w.part2, w.ntp, w.Npad, int(N), int(V), int(K), w.ldk, label_smoothing / float(V), w.wsum, w.ZA,
-      w.lse, w.srow, w.lossacc, w.row_flag, w.tile_flag);
+      w.lse, w.nlse2, w.srow, w.lossacc, w.row_flag, w.tile_flag);
   CAREL_LAUNCHED();
   // ---- exact redo of the flagged rows (skips every row tile without a flag: normally all of them) ----
   EpiBowLossParams e2;
-  e2.lossacc = w.lossacc; e2.srow = w.srow; e2.row_flag = w.row_flag; e2.N = int(N); e2.V = int(V);
-  e2.c = label_smoothing / float(V);
-  s.row_tile_flags = w.tile_flag;
-  if (int rc = launch_gemm<EpiBowLoss<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e2, st, "bow_pass2_exact")) return rc;
+  e2.lossacc = w.lossacc; e2.srow = w.srow; e2.row_flag = w.row_flag; e2.bl2e = w.bl2e; e2.nlse2 = w.nlse2;
+  e2.N = int(N); e2.V = int(V); e2.c = label_smoothing / float(V);
+  {
+    CUtensorMap ta2, tb2;      // plain operands: columns [0, K) of ZA / WB
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta2, w.ZA, N, K, w.ldk, 128) == 0, "carel_bow_fwd: tensor map Z failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb2, w.WB, V, K, w.ldk, 128) == 0, "carel_bow_fwd: tensor map W failed");
+    GemmSched s2 = make_sched(N, V, K, 256, 1, TILE_FULL);
+    s2.row_tile_flags = w.tile_flag;      // [0] = any flagged row at all, [1 + tile] per row tile
+    if (int rc = launch_gemm<EpiBowLoss<256>, 256, 1, false, false>(ta2, tb2, ta2, tb2, s2, e2, st, "bow_pass2_exact")) return rc;
+  }
   // ---- sparse corrections ----
   BowSparseArgs sa;
   sa.ZA = w.ZA; sa.WB = w.WB; sa.ell_cols = w.ell_cols; sa.ell_vals = w.ell_vals; sa.ell_nnz = w.ell_nnz;
@@ -981,29 +1091,33 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
     bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
     CAREL_LAUNCHED();
   }
-  const int k16 = w.ldk / 16;
+  // The chains use the PLAIN operands (columns [0, K) of ZA / WB; bias and -lse are added in the epilogue), so
+  // K = 4 full 64-wide blocks: A 64 KB + 5 ring stages of 32 KB, and 4 accumulator buffers in flight.
+  const int k16 = int(K / 16);
   BowBwdParams bp;
-  bp.srow = w.srow; bp.grad_out = grad_out; bp.dWacc = w.dWacc; bp.grad_z = grad_z; bp.ldgz = ldgz;
+  bp.srow = w.srow; bp.nlse2 = w.nlse2; bp.bl2e = w.bl2e; bp.grad_out = grad_out; bp.dWacc = w.dWacc;
+  bp.grad_z = grad_z; bp.ldgz = ldgz;
   bp.N = int(N); bp.V = int(V); bp.K = int(K); bp.ldk = w.ldk;
   bp.c = label_smoothing / float(V); bp.inv_nv = inv_nv;
-  using Cfg = ChainCfg<1, 64>;
+  constexpr int NB = 4;
+  using Cfg = ChainCfg<1, 64, NB>;
   // ---- pass 3 (vocabulary-major): dense dlogits -> [dW | db] accumulated in TMEM per 128 words ----
   if (need_w) {
     CUtensorMap ta, tb;
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.WB, V, w.ldk, w.ldk, 128) == 0, "carel_bow_bwd: tensor map W failed");
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.ZA, N, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.WB, V, K, w.ldk, 128) == 0, "carel_bow_bwd: tensor map W failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.ZA, N, K, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z failed");
     ChainSched cs = make_chain_sched(0, int((V + 127) / 128), int((N + 63) / 64), k16, Cfg::stages_for(k16), 16);
     cs.n2_16 = int(K / 16);
-    if (int rc = launch_chain<PolBowBwdW, 1, 64>(ta, tb, ta, tb, cs, bp, st, "bow_pass3_dw")) return rc;
+    if (int rc = launch_chain<PolBowBwdW, 1, 64, NB>(ta, tb, ta, tb, cs, bp, st, "bow_pass3_dw")) return rc;
   }
   // ---- pass 4 (clause-major): dense dlogits -> dZ accumulated in TMEM per 128 clauses ----
   {
     CUtensorMap ta, tb;
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.ZA, N, w.ldk, w.ldk, 128) == 0, "carel_bow_bwd: tensor map Z failed");
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.ZA, N, K, w.ldk, 128) == 0, "carel_bow_bwd: tensor map Z failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, K, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
     ChainSched cs = make_chain_sched(0, int((N + 127) / 128), int((V + 63) / 64), k16, Cfg::stages_for(k16), 64);
     cs.n2_16 = int(K / 16);
-    if (int rc = launch_chain<PolBowBwdZ, 1, 64>(ta, tb, ta, tb, cs, bp, st, "bow_pass4_dz")) return rc;
+    if (int rc = launch_chain<PolBowBwdZ, 1, 64, NB>(ta, tb, ta, tb, cs, bp, st, "bow_pass4_dz")) return rc;
   }
   if (need_w) {
     bow_scatter_grads_kernel<<<148 * 4, 256, 0, st>>>(w.dWacc, w.ldk, int(V), int(K), grad_w, grad_b);

@@ -34,14 +34,14 @@ inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int k16
   return s;
 }
 
-template <class Pol, int NG, int BN1>
+template <class Pol, int NG, int BN1, int NB = 2>
 int launch_chain(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1,
                  const CUtensorMap& b1, const ChainSched& s, const typename Pol::Params& pp,
                  cudaStream_t st, const char* tag = "chain_tc") {
-  using Cfg = ChainCfg<NG, BN1>;
-  auto kern = chain_tc_kernel<Pol, NG, BN1>;
+  using Cfg = ChainCfg<NG, BN1, NB>;
+  auto kern = chain_tc_kernel<Pol, NG, BN1, NB>;
   CAREL_REQUIRE(16 * s.n2_16 <= Cfg::kMaxN2, "chain kernel: operand width %d exceeds the TMEM budget (%d)", 16 * s.n2_16, Cfg::kMaxN2);
-  CAREL_REQUIRE(s.stages >= 2, "chain kernel: operand too wide for the shared-memory ring");
+  CAREL_REQUIRE(s.stages >= NB, "chain kernel: operand too wide for the shared-memory ring (%d stages, %d needed)", s.stages, NB);
   const int smem_bytes = Cfg::smem_bytes(s.k16, s.stages);
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {

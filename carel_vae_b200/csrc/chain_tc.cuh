@@ -14,7 +14,7 @@
 //
 // 128*kChainSplit + 64 threads: 4*kChainSplit epilogue warps (warp w: TMEM lanes 32*(w%4).., column part w/4 of the
 // inner tile), then the TMEM allocator + TMA producer warp and the MMA issuer warp (highest ids: scheduler priority).
-// TMEM columns: acc1 2 buffers x NG x BN1 | acc2 16*n2_16   (<= 512).  Within an acc1 buffer the half
+// TMEM columns: acc1 NB buffers x NG x BN1 | acc2 16*n2_16   (<= 512).  Within an acc1 buffer the half
 // part h of product 0 (columns [h R, (h+1) R), R = BN1/kChainSplit) is overwritten by its own thread with
 // P_hi (R/2 columns of packed bf16 pairs) followed by P_lo (R/2 columns).
 // Ordering: tcgen05.mma instructions of one thread execute in issue order, so GEMM-1 of tile t+2
@@ -78,13 +78,15 @@ struct ChainCtx {
   uint32_t acc2_taddr;  // TMEM address (lane quarter applied) of acc2 column 0
 };
 
-template <int NG, int BN1>
+template <int NG, int BN1, int NB = 2>
 struct ChainCfg {
   static_assert(BN1 == 64 || BN1 == 128, "BN1");
+  static_assert(NB >= 2 && NB <= 4, "acc1 buffers");
   static constexpr int kAcc1Cols = NG * BN1;       // per buffer
-  static constexpr int kAcc2Base = 2 * kAcc1Cols;
+  static constexpr int kAcc2Base = NB * kAcc1Cols;
+  static_assert(kAcc2Base < 512, "TMEM budget");
   static constexpr int kMaxN2 = (512 - kAcc2Base) < 256 ? (512 - kAcc2Base) : 256;
-  static constexpr int kMaxStages = 4;
+  static constexpr int kMaxStages = 6;
   static __host__ __device__ int kb(int k16) { return (k16 + 3) / 4; }
   static __host__ __device__ int a_bytes(int k16) { return NG * kb(k16) * 16384; }
   static __host__ __device__ int b_bytes(int k16) { return NG * kb(k16) * BN1 * 128; }
@@ -98,13 +100,13 @@ struct ChainCfg {
   }
 };
 
-template <class Pol, int NG, int BN1>
+template <class Pol, int NG, int BN1, int NB = 2>
 __global__ void __launch_bounds__(kChainThreads, 1)
 chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                 const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                 const __grid_constant__ ChainSched sched,
                 const __grid_constant__ typename Pol::Params pp) {
-  using Cfg = ChainCfg<NG, BN1>;
+  using Cfg = ChainCfg<NG, BN1, NB>;
   constexpr int MAXST = Cfg::kMaxStages;
   constexpr int R = BN1 / kChainSplit;       // columns of the inner tile per epilogue thread
   constexpr bool HILO = Pol::kHiLo;
@@ -123,9 +125,9 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint64_t* b_empty = bars + MAXST;          // [MAXST]
   uint64_t* a_full = bars + 2 * MAXST;       // [1]
   uint64_t* a_empty = a_full + 1;            // [1]
-  uint64_t* acc1_full = a_empty + 1;         // [2]
-  uint64_t* p_full = acc1_full + 2;          // [2]
-  uint64_t* acc2_full = p_full + 2;          // [1]
+  uint64_t* acc1_full = a_empty + 1;         // [NB]
+  uint64_t* p_full = acc1_full + NB;         // [NB]
+  uint64_t* acc2_full = p_full + NB;         // [1]
   uint64_t* acc2_empty = acc2_full + 1;      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
@@ -149,7 +151,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NB; ++i) {
       mbar_init(&acc1_full[i], 1);
       mbar_init(&p_full[i], 4 * kChainSplit);
     }
@@ -202,7 +204,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     int g1_stage = 0; uint32_t g1_phase = 0;   // smem stage of the next GEMM-1
     int g2_stage = 0;                          // smem stage of the next GEMM-2
     int g1_buf = 0;                            // acc1 buffer of the next GEMM-1
-    int g2_buf = 0; uint32_t p_phase0 = 0, p_phase1 = 0;
+    int g2_buf = 0; uint32_t p_phases = 0;     // bit b = phase of p_full[b]
     uint32_t aphase = 0, acc2_phase = 0;
     int trace_g1 = 0, trace_g2 = 0; (void)trace_g1; (void)trace_g2;
     constexpr uint32_t idesc1 = make_idesc_bf16(128, BN1, 0, 0);
@@ -237,11 +239,11 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         CAREL_TRACE(6, trace_g1 - 1);
         umma_commit(&acc1_full[g1_buf]);
         if (++g1_stage == STAGES) { g1_stage = 0; g1_phase ^= 1; }
-        g1_buf ^= 1;
+        if (++g1_buf == NB) g1_buf = 0;
       };
       auto issue_g2 = [&]() {
-        if (g2_buf == 0) { mbar_wait(&p_full[0], p_phase0); p_phase0 ^= 1; }
-        else { mbar_wait(&p_full[1], p_phase1); p_phase1 ^= 1; }
+        mbar_wait(&p_full[g2_buf], (p_phases >> g2_buf) & 1u);
+        p_phases ^= 1u << g2_buf;
         if (first_g2) mbar_wait(acc2_empty, acc2_phase ^ 1);
         CAREL_TRACE(2, trace_g2); ++trace_g2;
         tc_fence_after();
@@ -262,12 +264,15 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         CAREL_TRACE(7, trace_g2 - 1);
         umma_commit(&b_empty[g2_stage]);
         if (++g2_stage == STAGES) g2_stage = 0;
-        g2_buf ^= 1;
+        if (++g2_buf == NB) g2_buf = 0;
       };
-      if (it.t1 > it.t0) issue_g1();
+      // GEMM-1 runs NB - 1 inner tiles ahead of GEMM-2 (needs STAGES >= NB, checked by the launcher)
+      int next_g1 = it.t0;
+#pragma unroll 1
+      for (; next_g1 < it.t1 && next_g1 < it.t0 + NB - 1; ++next_g1) issue_g1();
 #pragma unroll 1
       for (int t = it.t0; t < it.t1; ++t) {
-        if (t + 1 < it.t1) issue_g1();
+        if (next_g1 < it.t1) { issue_g1(); ++next_g1; }
         issue_g2();
       }
       umma_commit(acc2_full);
@@ -286,7 +291,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     ChainIter iter(sched);
     ChainItem it;
     int buf = 0;
-    uint32_t full_phase0 = 0, full_phase1 = 0;
+    uint32_t full_phases = 0;                  // bit b = phase of acc1_full[b]
     uint32_t acc2_phase = 0;
     int trace_e = 0; (void)trace_e;
     const bool tracer = (threadIdx.x == 0); (void)tracer;
@@ -301,8 +306,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll 1
       for (int t = it.t0; t < it.t1; ++t) {
         pol.prefetch(ctx, t * BN1 + ctx.half * R);       // loads that do not depend on acc1: issued before the wait
-        if (buf == 0) { mbar_wait(&acc1_full[0], full_phase0); full_phase0 ^= 1; }
-        else { mbar_wait(&acc1_full[1], full_phase1); full_phase1 ^= 1; }
+        mbar_wait(&acc1_full[buf], (full_phases >> buf) & 1u);
+        full_phases ^= 1u << buf;
         if (tracer) CAREL_TRACE(3, trace_e);
         tc_fence_after();
         // this thread's region of product 0 (product 1 sits BN1 columns further)
@@ -341,7 +346,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[buf]);
         if (tracer) { CAREL_TRACE(5, trace_e); ++trace_e; }
-        buf ^= 1;
+        if (++buf == NB) buf = 0;
       }
       mbar_wait(acc2_full, acc2_phase);
       acc2_phase ^= 1;

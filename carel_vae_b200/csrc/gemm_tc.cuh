@@ -49,7 +49,7 @@ struct GemmSched {
   int num_items;  // total work items
   int m_tile0;    // first row tile owned by this launch (row-block sharding across GPUs)
   int n_cols;     // if > 0: logical N; the last column tile issues a narrower MMA (multiple of 16)
-  const int* row_tile_flags;  // optional (device): only row tiles with a non-zero flag are processed
+  const int* row_tile_flags;  // optional (device): flags[0] = any work at all, flags[1 + tm] = process row tile tm
 };
 
 // Sequential decoder of the persistent schedule; every role of a CTA walks the same items.
@@ -59,12 +59,14 @@ struct TileIter {
   int tri_tm, tri_base;
   int tm, tn, kb0, kb1;
   CAREL_DEVINL explicit TileIter(const GemmSched& s_)
-      : s(s_), item(blockIdx.x), tri_tm(0), tri_base(0) {}
+      : s(s_), item(blockIdx.x), tri_tm(0), tri_base(0) {
+    if (s.row_tile_flags != nullptr && s.row_tile_flags[0] == 0) item = s.num_items;   // nothing flagged
+  }
   CAREL_DEVINL int tri_count(int t) const { return s.n_tiles - ((s.m_tile0 + t) >> 1); }
   CAREL_DEVINL bool next() {
     for (;;) {
       if (!decode()) return false;
-      if (s.row_tile_flags == nullptr || s.row_tile_flags[tm] != 0) return true;
+      if (s.row_tile_flags == nullptr || s.row_tile_flags[1 + tm] != 0) return true;
     }
   }
   CAREL_DEVINL bool decode() {

@@ -177,3 +177,11 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   pp.inv_w_scale = 1.f;
   return mmd_bwd_launch<128>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
 }
+
+#ifdef CAREL_CHAIN_TRACE
+// debug: chain-kernel timeline of this translation unit (see chain_tc.cuh)
+extern "C" int carel_debug_chain_trace_mmd(long long* host_dst) {
+  CAREL_CHECK_CUDA(cudaMemcpyFromSymbol(host_dst, carel::g_chain_trace, sizeof(long long) * 8 * 256));
+  return 0;
+}
+#endif

@@ -14,15 +14,19 @@ idx = torch.randint(0, V, (n, 24), device="cuda")
 bow = torch.zeros(n, V, device="cuda")
 bow.scatter_add_(1, idx, torch.ones(n, 24, device="cuda"))
 bow = bow / bow.sum(1, keepdim=True).clamp_min(1)
-for _ in range(2):
-    o = F.bow_reconstruction_loss(Z, W, b, bow)
-    o.backward()
+if which == "mmd":
+    x = torch.tanh(torch.randn(n, d, device="cuda")).requires_grad_(True)
+    y = torch.tanh(torch.randn(n, d, device="cuda")).requires_grad_(True)
+    for _ in range(2):
+        F.mmd(x, y, [0.1]).backward()
+else:
+    for _ in range(2):
+        o = F.bow_reconstruction_loss(Z, W, b, bow)
+        o.backward()
 torch.cuda.synchronize()
-L = _lib.lib()._handle if hasattr(_lib.lib(), "_handle") else None
-h = C.CDLL(str(_lib.LIB_PATH)) if hasattr(_lib, "LIB_PATH") else None
 lib = C.CDLL("carel_vae_b200/libcarel_head.so")
 buf = (C.c_longlong * (8 * 256))()
-assert lib.carel_debug_chain_trace(buf) == 0
+assert (lib.carel_debug_chain_trace_mmd if which == 'mmd' else lib.carel_debug_chain_trace)(buf) == 0
 ev = [[buf[s * 256 + i] for i in range(256)] for s in range(8)]
 t0 = min(v for v in ev[0] if v > 0)
 names = ["load_issue", "g1_issue", "g2_issue", "epi_acc1_ready", "epi_ld_done", "epi_p_arrive", "g1_issued", "g2_issued"]
