@@ -872,22 +872,38 @@ struct PolBowBwdW {
     dbsum += t;
   }
   CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
-  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
+  // acc2 -> registers (this thread's K / kChainSplit columns of its row), release the accumulator, THEN reduce
+  // into global memory: GEMM-2 of the next item does not wait for the reductions.
+  template <class Release>
+  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid, Release&& release) {
+    constexpr int kMaxQ = 256 / 16 / kChainSplit;   // chunks per thread at K = 256
     const int n16 = p.K / 16;                       // feature columns only
     const int q0 = (n16 * ctx.half) / kChainSplit, q1 = (n16 * (ctx.half + 1)) / kChainSplit;
     const bool row_ok = valid && ctx.row < p.V;
     float* dst = p.dWacc + size_t(min(ctx.row, p.V - 1)) * p.ldk;
+    (void)kMaxQ;
+    // two chunks (32 registers) at a time: holding all of this thread's columns at once spills
 #pragma unroll 1
-    for (int q = q0; q < q1; ++q) {
-      uint32_t r[16];
-      tmem_ld16(ctx.acc2_taddr + q * 16, r);
+    for (int q = q0; q < q1; q += 2) {
+      uint32_t ra[16], rb[16];
+      const bool two = q + 1 < q1;
+      tmem_ld16(ctx.acc2_taddr + q * 16, ra);
+      if (two) tmem_ld16(ctx.acc2_taddr + (q + 1) * 16, rb);
       tmem_ld_wait();
+      if (q + 2 >= q1) release();                 // last read of acc2 by this thread
       if (!row_ok) continue;
 #pragma unroll
       for (int i = 0; i < 16; i += 4)
-        red_add_v4(dst + q * 16 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                   __uint_as_float(r[i + 3]));
+        red_add_v4(dst + q * 16 + i, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]), __uint_as_float(ra[i + 2]),
+                   __uint_as_float(ra[i + 3]));
+      if (two) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          red_add_v4(dst + (q + 1) * 16 + i, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]),
+                     __uint_as_float(rb[i + 2]), __uint_as_float(rb[i + 3]));
+      }
     }
+    if (q0 >= q1) release();
     if (row_ok && dbsum != 0.f) atomicAdd(dst + p.K + 3, dbsum);    // every column part adds its share
   }
   CAREL_DEVINL void finish() {}
@@ -922,28 +938,46 @@ struct PolBowBwdZ {
     bow_dlogit16(r, cc, rc, Sn, p.c, scale, v0 + 16 <= p.V, p.V - v0, d);
   }
   CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
-  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
+  template <class Release>
+  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid, Release&& release) {
+    constexpr int kMaxQ = 256 / 16 / kChainSplit;
     const int n16 = p.K / 16;
     const int q0 = (n16 * ctx.half) / kChainSplit, q1 = (n16 * (ctx.half + 1)) / kChainSplit;
     const bool row_ok = valid && ctx.row < p.N;
     float* dst = p.grad_z + size_t(min(ctx.row, p.N - 1)) * p.ldgz;
     const bool vec = ((p.ldgz & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.grad_z) & 15) == 0);
+    (void)kMaxQ;
 #pragma unroll 1
-    for (int q = q0; q < q1; ++q) {
-      uint32_t r[16];
-      tmem_ld16(ctx.acc2_taddr + q * 16, r);
+    for (int q = q0; q < q1; q += 2) {
+      uint32_t ra[16], rb[16];
+      const bool two = q + 1 < q1;
+      tmem_ld16(ctx.acc2_taddr + q * 16, ra);
+      if (two) tmem_ld16(ctx.acc2_taddr + (q + 1) * 16, rb);
       tmem_ld_wait();
+      if (q + 2 >= q1) release();                 // last read of acc2 by this thread
       if (!row_ok) continue;
+      float* o = dst + q * 16;
       if (vec) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
-          red_add_v4(dst + q * 16 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                     __uint_as_float(r[i + 3]));
+          red_add_v4(o + i, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]), __uint_as_float(ra[i + 2]),
+                     __uint_as_float(ra[i + 3]));
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            red_add_v4(o + 16 + i, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]), __uint_as_float(rb[i + 2]),
+                       __uint_as_float(rb[i + 3]));
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(dst + q * 16 + i, __uint_as_float(r[i]));
+        for (int i = 0; i < 16; ++i) atomicAdd(o + i, __uint_as_float(ra[i]));
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(o + 16 + i, __uint_as_float(rb[i]));
+        }
       }
     }
+    if (q0 >= q1) release();
   }
   CAREL_DEVINL void finish() {}
 };

@@ -5,10 +5,8 @@
 
 namespace carel {
 
-// Split the inner range so that the number of work items fills whole waves of the persistent
-// grid: pick nsplit in [1, max_split] maximising items / (ceil(items / SMs) * SMs); ties go to
-// the smaller split (less atomic traffic).
-inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int k16, int stages, int max_split) {
+// Equal contiguous unit ranges per CTA (see ChainIter).  `max_split` is kept for source compatibility.
+inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int k16, int stages, int /*max_split*/) {
   ChainSched s;
   s.owner0 = owner0;
   s.n_owner = n_owner;
@@ -16,21 +14,14 @@ inline ChainSched make_chain_sched(int owner0, int n_owner, int n_inner, int k16
   s.k16 = k16;
   s.n2_16 = k16;
   s.stages = stages;
+  s.total_units = n_owner * n_inner;
   const int sms = sm_count();
-  int best = 1;
-  double best_eff = -1.0;
-  for (int sp = 1; sp <= max_split && sp <= (n_inner > 0 ? n_inner : 1); ++sp) {
-    const int per = (n_inner + sp - 1) / sp;
-    if (per * (sp - 1) >= n_inner && sp > 1) continue;  // would create an empty split
-    const long long items = 1LL * n_owner * sp;
-    const long long waves = (items + sms - 1) / sms;
-    // every wave costs `per` inner tiles plus a fixed per-item overhead (~2 tiles)
-    const double cost = double(waves) * (per + 2.0);
-    const double eff = 1.0 / cost;
-    if (eff > best_eff * 1.0001) { best_eff = eff; best = sp; }
-  }
-  s.nsplit = best;
-  s.num_items = n_owner * best;
+  int grid = s.total_units < sms ? s.total_units : sms;
+  if (grid < 1) grid = 1;
+  s.upc = (s.total_units + grid - 1) / grid;
+  if (s.upc < 1) s.upc = 1;
+  s.num_items = (s.total_units + s.upc - 1) / s.upc;
+  s.nsplit = (n_inner > 0 && s.upc % n_inner == 0) ? 1 : 2;
   return s;
 }
 

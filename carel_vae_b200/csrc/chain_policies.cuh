@@ -96,7 +96,8 @@ struct PolMmdBwd {
     }
   }
   CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
-  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
+  template <class Release>
+  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid, Release&& release) {
     // row sum of the rounded W: the ones column of the B operand
     const uint32_t rtot_bits = tmem_ld1(ctx.acc2_taddr + (p.split ? 2 * p.kp : p.dim));
     tmem_ld_wait();
@@ -148,12 +149,16 @@ struct PolMmdBwd {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (f0 + i < p.dim) dst[f0 + i] = v[i];
+      } else if (f0 + 16 <= p.dim && ((reinterpret_cast<uintptr_t>(dst + f0) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) red_add_v4(dst + f0 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (f0 + i < p.dim) atomicAdd(dst + f0 + i, v[i]);
       }
     }
+    release();
   }
   CAREL_DEVINL void finish() {}
 };

@@ -39,30 +39,37 @@ struct ChainSched {
   int n_owner;     // owner tiles (128 rows) in this launch
   int owner0;      // first owner tile index (row-block sharding)
   int n_inner;     // inner tiles (BN1 rows each) in total
-  int nsplit;      // inner range split factor; item = owner * nsplit + split
-  int num_items;
+  int nsplit;      // 1: every owner tile is processed whole by one CTA (plain stores allowed); 2: pieces
+  int num_items;   // persistent grid size (CTAs with work)
+  int total_units; // n_owner * n_inner (owner tile, inner tile) units, owner-major
+  int upc;         // units per CTA: CTA b owns units [b * upc, (b + 1) * upc)
   int k16;         // operand width in 16-wide steps (GEMM-1 K)
   int n2_16;       // GEMM-2 N in 16-column groups (<= k16; acc2 columns = 16 * n2_16)
-  int stages;      // B ring depth (2..4), chosen by the host from the smem budget
+  int stages;      // B ring depth, chosen by the host from the smem budget
 };
 
 struct ChainItem {
   int owner, t0, t1;
 };
 
+// Stream-K style decomposition: the (owner, inner) units are cut into equal contiguous ranges, one per CTA, so
+// the load is balanced to one inner tile whatever the owner count, a CTA touches at most
+// 1 + ceil(upc / n_inner) owners (that many accumulator write-outs) and the write-outs of different CTAs fall
+// at different times instead of colliding in one burst of reductions.
 struct ChainIter {
   const ChainSched& s;
-  int item;
-  CAREL_DEVINL explicit ChainIter(const ChainSched& s_) : s(s_), item(blockIdx.x) {}
+  int pos, end;
+  CAREL_DEVINL explicit ChainIter(const ChainSched& s_) : s(s_) {
+    pos = blockIdx.x * s.upc;
+    end = min(pos + s.upc, s.total_units);
+  }
   CAREL_DEVINL bool next(ChainItem& it) {
-    if (item >= s.num_items) return false;
-    const int o = item / s.nsplit;
-    const int sp = item - o * s.nsplit;
-    const int per = (s.n_inner + s.nsplit - 1) / s.nsplit;
+    if (pos >= end) return false;
+    const int o = pos / s.n_inner;
     it.owner = s.owner0 + o;
-    it.t0 = sp * per;
-    it.t1 = min(it.t0 + per, s.n_inner);
-    item += gridDim.x;
+    it.t0 = pos - o * s.n_inner;
+    it.t1 = min(s.n_inner, it.t0 + (end - pos));
+    pos += it.t1 - it.t0;
     return true;
   }
 };
@@ -351,10 +358,12 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       mbar_wait(acc2_full, acc2_phase);
       acc2_phase ^= 1;
       tc_fence_after();
-      pol.final(ctx, it.t1 > it.t0);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc2_empty);
+      // the policy calls release() once, as soon as it no longer reads acc2 (e.g. after moving it to registers)
+      pol.final(ctx, it.t1 > it.t0, [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc2_empty);
+      });
     }
     pol.finish();
   }

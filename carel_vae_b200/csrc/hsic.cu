@@ -186,7 +186,8 @@ struct PolHsicBwd {
     }
   }
   CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
-  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid) {
+  template <class Release>
+  CAREL_DEVINL void final(const ChainCtx& ctx, bool valid, Release&& release) {
     const uint32_t rtot_bits = tmem_ld1(ctx.acc2_taddr + p.dim);   // ones column: sum_j w_ij
     tmem_ld_wait();
     const float rtot = __uint_as_float(rtot_bits);
@@ -213,6 +214,7 @@ struct PolHsicBwd {
         if (f + 1 < p.dim) atomicAdd(dst + f + 1, g * (rtot * s2.y - __uint_as_float(r[2 * h + 1])));
       }
     }
+    release();
   }
   CAREL_DEVINL void finish() {}
 };
