@@ -45,7 +45,8 @@ struct BowWs {
   float* nlse2;         // [Npad]  -lse log2(e) (0 beyond N)
   float* bl2e;          // [V rounded up to 64]  b log2(e) (0 beyond V)
   float* srow;          // [Npad]  S_i = N V s_i
-  float* dWacc;         // [V, ldk] fp32 accumulation of dlogit^T [Z | 1]
+  float* dWacc;         // [V, ldk] scratch target of dW when the caller does not want grad_w
+  float* dbacc;         // [V]      scratch target of db when the caller does not want grad_b
   double* lossacc;      // [2] dense, sparse
   int* ell_cols;        // [N, cap]
   float* ell_vals;      // [N, cap]
@@ -78,6 +79,7 @@ static BowWs carve_bow(void* ws, int64_t N, int64_t K, int64_t V, int64_t cap) {
   r.bl2e = w.take<float>(size_t(round_up64(V, 64)));
   r.srow = w.take<float>(size_t(r.Npad));
   r.dWacc = w.take<float>(size_t(V) * r.ldk);
+  r.dbacc = w.take<float>(size_t(V));
   r.lossacc = w.take<double>(2);
   r.ell_cols = w.take<int>(size_t(N) * cap);
   r.ell_vals = w.take<float>(size_t(N) * cap);
@@ -144,8 +146,9 @@ static __global__ void bow_pack_ell_kernel(const float* __restrict__ bow, int64_
 // 2 FADD2, 2 FFMA2 and one FMNMX3 each for max and min.
 // ---------------------------------------------------------------------------------------------
 struct EpiBowFusedParams {
-  float4* part4;   // [ntp][Npad]  (m, T1, T2, T3)
+  float4* part4;   // [ntp][Npad]  (m, T1, T2, T3)     m, mn in log2 units
   float2* part2;   // [ntp][Npad]  (T4, mn)
+  const float* bl2e;   // [Vpad]  b_j log2(e)
   int N, V, Npad;
 };
 template <int BN>
@@ -153,6 +156,7 @@ struct EpiBowFused {
   using Params = EpiBowFusedParams;
   const Params& p;
   CAREL_DEVINL EpiBowFused(const Params& p_, const TileCtx&) : p(p_) {}
+  CAREL_DEVINL void prefetch(const TileCtx&) {}
   CAREL_DEVINL void tile(const TileCtx& ctx) {
     constexpr int HALF = BN / kColSplit;
     const int c0 = ctx.col0 + ctx.half * HALF;
@@ -161,32 +165,41 @@ struct EpiBowFused {
     if (c0 < p.V) {
       const bool full = c0 + HALF <= p.V;
       const float2 l2e = make_float2(kLog2e, kLog2e);
+      const float4* cc4 = reinterpret_cast<const float4*>(p.bl2e + c0);
       for_each_chunk16(ctx.taddr + ctx.half * HALF, HALF / 16, [&](int c, const uint32_t (&r)[16]) {
-        float x[16];
+        // y = log2-domain logit: acc log2(e) + b_j log2(e)   (plain operands; the bias is a per-column constant)
+        float y[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 4; ++i) {
+          const float4 b4 = __ldg(cc4 + c * 4 + i);
+          const float2 y0 = __ffma2_rn(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), l2e,
+                                       make_float2(b4.x, b4.y));
+          const float2 y1 = __ffma2_rn(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), l2e,
+                                       make_float2(b4.z, b4.w));
+          y[4 * i] = y0.x; y[4 * i + 1] = y0.y; y[4 * i + 2] = y1.x; y[4 * i + 3] = y1.y;
+        }
         float cm, cn;
         if (full) {
-          cm = fmax3(x[0], x[1], x[2]);
-          cn = fmin3(x[0], x[1], x[2]);
+          cm = fmax3(y[0], y[1], y[2]);
+          cn = fmin3(y[0], y[1], y[2]);
 #pragma unroll
-          for (int i = 3; i < 15; i += 2) { cm = fmax3(cm, x[i], x[i + 1]); cn = fmin3(cn, x[i], x[i + 1]); }
-          cm = fmaxf(cm, x[15]);
-          cn = fminf(cn, x[15]);
+          for (int i = 3; i < 15; i += 2) { cm = fmax3(cm, y[i], y[i + 1]); cn = fmin3(cn, y[i], y[i + 1]); }
+          cm = fmaxf(cm, y[15]);
+          cn = fminf(cn, y[15]);
         } else {
           cm = -INFINITY;
           cn = INFINITY;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const bool ok = c0 + c * 16 + i < p.V;
-            cn = fminf(cn, ok ? x[i] : INFINITY);
-            x[i] = ok ? x[i] : -INFINITY;
-            cm = fmaxf(cm, x[i]);
+            cn = fminf(cn, ok ? y[i] : INFINITY);
+            y[i] = ok ? y[i] : -INFINITY;
+            cm = fmaxf(cm, y[i]);
           }
         }
         mn = fminf(mn, cn);
         if (cm > m) {          // rescale the running sums to the new reference (rare after the first chunks)
-          const float sc = ex2_approx((m - cm) * kLog2e), sc2 = sc * sc;
+          const float sc = ex2_approx(m - cm), sc2 = sc * sc;
           t1.x *= sc; t1.y *= sc;
           t2.x *= sc2; t2.y *= sc2;
           t3.x *= sc2 * sc; t3.y *= sc2 * sc;
@@ -194,11 +207,10 @@ struct EpiBowFused {
           m = cm;
         }
         if (m > -INFINITY) {
-          const float nm = -m * kLog2e;
-          const float2 nm2 = make_float2(nm, nm);
+          const float2 nm2 = make_float2(-m, -m);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const float2 t = __ffma2_rn(make_float2(x[i], x[i + 1]), l2e, nm2);
+            const float2 t = __fadd2_rn(make_float2(y[i], y[i + 1]), nm2);
             const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
             const float2 e2 = __fmul2_rn(e, e);
             t1 = __fadd2_rn(t1, e);
@@ -282,11 +294,11 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
       mn = fminf(mn, b.y);
       if (a.y > 0.f) {
         if (a.x > M) {          // rescale the running sums to the new reference
-          const float w = __expf(M - a.x), w2 = w * w;
+          const float w = ex2_approx(M - a.x), w2 = w * w;
           T1 *= w; T2 *= w2; T3 *= w2 * w; T4 *= w2 * w2;
           M = a.x;
         }
-        const float w = __expf(a.x - M), w2 = w * w;
+        const float w = ex2_approx(a.x - M), w2 = w * w;
         T1 = fmaf(a.y, w, T1);
         T2 = fmaf(a.z, w2, T2);
         T3 = fmaf(a.w, w2 * w, T3);
@@ -313,7 +325,7 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
       T4 = sh[lane][4][row_l]; mn = sh[lane][5][row_l];
     }
     const float Mx = warp_max(M);
-    const float w = (T1 > 0.f) ? __expf(M - Mx) : 0.f, w2 = w * w;
+    const float w = (T1 > 0.f) ? ex2_approx(M - Mx) : 0.f, w2 = w * w;
     T1 = warp_sum(T1 * w); T2 = warp_sum(T2 * w2); T3 = warp_sum(T3 * w2 * w); T4 = warp_sum(T4 * w2 * w2);
     mn = -warp_max(-mn);
     // sum_j x_ij from the column sums of the packed operand (the h columns of ZA are still zero here)
@@ -322,10 +334,11 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
     for (int k = lane; k < ldk; k += 32) sx = fmaf(__bfloat162float(zrow[k]), __ldg(wsum + k), sx);
     sx = warp_sum(sx);
     if (lane == 0) {
-      const float lse = Mx + logf(T1);
+      const float lse2 = Mx + log2f(T1);                 // the partials carry log2-domain maxima / minima
+      const float lse = lse2 * kLn2;
       const float i1 = 1.f / T1, i2 = i1 * i1;
       const float S2 = T2 * i2, S3 = T3 * i2 * i1, S4 = T4 * i2 * i2;
-      const bool valid = (i1 < 0.03125f) && (mn - lse > -27.f);
+      const bool valid = (i1 < 0.03125f) && (mn - lse2 > -27.f * kLog2e);
       float u = 0.f;
       if (valid) {
         f += double(c) * (double(sx) - double(V) * double(lse)) -
@@ -339,7 +352,7 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
       srow[row] = u;
       const float nl = -lse;
       neg_lse[row] = nl;
-      nlse2[row] = nl * kLog2e;
+      nlse2[row] = -lse2;
       __nv_bfloat16 h1, h2, h3;
       split3(nl, h1, h2, h3);
       ZA[size_t(row) * ldk + K] = h1;
@@ -385,6 +398,7 @@ struct EpiBowLoss {
   const Params& p;
   double loss;
   CAREL_DEVINL EpiBowLoss(const Params& p_, const TileCtx&) : p(p_), loss(0.0) {}
+  CAREL_DEVINL void prefetch(const TileCtx&) {}
   CAREL_DEVINL void tile(const TileCtx& ctx) {
     constexpr int HALF = BN / kColSplit;
     const int c0 = ctx.col0 + ctx.half * HALF;
@@ -452,7 +466,7 @@ struct EpiBowLoss {
 //   x = ZA[i] . WB[j]  (same rounded operands as the tensor-core passes)
 //   fwd (mode 0):  lossacc[1] += sum (1-ls) t (A - B) ;  S_i += sum -(1-ls) t p / max(p(1-p),1e-12)
 //   bwd (mode 1):  e = -(1-ls) t p / max(p(1-p),1e-12) * g/(N V);
-//                  dZ[i,:] += e w_j ; dWacc[j,:K] += e z_i ; dWacc[j, K+3] += e   (db column)
+//                  dZ[i,:] += e w_j ; dW[j,:] += e z_i ; db[j] += e
 // ---------------------------------------------------------------------------------------------
 struct BowSparseArgs {
   const __nv_bfloat16* ZA;
@@ -471,7 +485,8 @@ struct BowSparseArgs {
   const float* grad_out;
   float* grad_z;
   int64_t ldgz;
-  float* dWacc;
+  float* gw;             // [V, K] dW target (accumulated)
+  float* gb;             // [V]    db target (accumulated)
 };
 
 // One warp per row; 4 non-zeros in flight (one per 8-lane group); the row's own operand (ZA[i], 8-element
@@ -484,6 +499,9 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
   const int nchunk = a.ldk >> 3;
   const float scale = (a.mode == 1) ? __ldg(a.grad_out) / (float(a.N) * float(a.V)) : 0.f;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < a.N; r += gridDim.x * wpb) {
+    const int nnz = a.ell_nnz[r];
+    const bool dense_scan = nnz > a.cap;
+    if (a.mode == 1 && a.overflow_only && !dense_scan) continue;
     const __nv_bfloat16* zrow = a.ZA + size_t(r) * a.ldk;
     uint4 zreg[kSparseChunks];
 #pragma unroll
@@ -491,9 +509,6 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
       const int c = gl + 8 * k;
       zreg[k] = (c < nchunk) ? __ldg(reinterpret_cast<const uint4*>(zrow) + c) : make_uint4(0, 0, 0, 0);
     }
-    const int nnz = a.ell_nnz[r];
-    const bool dense_scan = nnz > a.cap;
-    if (a.mode == 1 && a.overflow_only && !dense_scan) continue;
     float dloss = 0.f, du = 0.f;
     float dz[kSparseChunks][8];
     if (a.mode == 1) {
@@ -541,7 +556,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
         }
       } else {
         const float e = ev * scale;
-        float* dwrow = a.dWacc + size_t(j) * a.ldk;
+        float* dwrow = a.gw + size_t(j) * a.K;
 #pragma unroll
         for (int k = 0; k < kSparseChunks; ++k) {
           const int c = gl + 8 * k;
@@ -559,7 +574,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
             }
           }
         }
-        if (gl == 0) atomicAdd(dwrow + a.K + 3, e);
+        if (gl == 0) atomicAdd(a.gb + j, e);
       }
     };
     if (!dense_scan) {
@@ -723,17 +738,18 @@ static __global__ void bow_sparse_dz_kernel(const __nv_bfloat16* __restrict__ WB
   }
 }
 
-// sparse part of [dW | db]: one warp per vocabulary word, gather over the rows that contain it.
+// sparse part of [dW | db]: one warp per vocabulary word, gather over the rows that contain it.  This kernel
+// INITIALISES gw[j, :] and gb[j] (plain stores, zeros for words nobody uses), so the dense passes that follow
+// can accumulate into the caller's gradient tensors directly: no memset, no staging buffer, no scatter pass.
 static __global__ void bow_sparse_dw_kernel(const __nv_bfloat16* __restrict__ ZA, int ldk, int K,
                                             const int* __restrict__ colptr, const int* __restrict__ csc_row,
                                             const int* __restrict__ csc_slot, const float* __restrict__ ev,
                                             int V, const float* __restrict__ grad_out, float inv_nv,
-                                            float* __restrict__ dWacc) {
+                                            float* __restrict__ gw, float* __restrict__ gb) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const float scale = __ldg(grad_out) * inv_nv;
   for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < V; j += gridDim.x * wpb) {
     const int p0 = colptr[j], p1 = colptr[j + 1];
-    if (p1 == p0) continue;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float esum = 0.f;
     const bool act = lane * 8 < K;
@@ -752,13 +768,18 @@ static __global__ void bow_sparse_dw_kernel(const __nv_bfloat16* __restrict__ ZA
         }
       }
     }
-    float* dw = dWacc + size_t(j) * ldk;
+    float* dw = gw + size_t(j) * K;
     if (act) {
+      if (lane * 8 + 8 <= K && (reinterpret_cast<uintptr_t>(dw) & 15) == 0) {
+        reinterpret_cast<float4*>(dw + lane * 8)[0] = make_float4(acc[0] * scale, acc[1] * scale, acc[2] * scale, acc[3] * scale);
+        reinterpret_cast<float4*>(dw + lane * 8)[1] = make_float4(acc[4] * scale, acc[5] * scale, acc[6] * scale, acc[7] * scale);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (lane * 8 + i < K) atomicAdd(dw + lane * 8 + i, acc[i] * scale);
+        for (int i = 0; i < 8; ++i)
+          if (lane * 8 + i < K) dw[lane * 8 + i] = acc[i] * scale;
+      }
     }
-    if (lane == 0) atomicAdd(dw + K + 3, esum * scale);
+    if (lane == 0) gb[j] = esum * scale;
   }
 }
 
@@ -785,7 +806,8 @@ struct BowBwdParams {
   const float* nlse2;    // [Npad]  -lse_i log2(e)
   const float* bl2e;     // [Vpad]  b_j log2(e)
   const float* grad_out;
-  float* dWacc;          // [V, ldk]     (W policy)
+  float* gw;             // [V, K]  dW target (W policy; initialised by bow_sparse_dw_kernel)
+  float* gb;             // [V]     db target
   float* grad_z;         // [N, ldgz]    (Z policy)
   int64_t ldgz;
   int N, V, K, ldk;
@@ -880,7 +902,7 @@ struct PolBowBwdW {
     const int n16 = p.K / 16;                       // feature columns only
     const int q0 = (n16 * ctx.half) / kChainSplit, q1 = (n16 * (ctx.half + 1)) / kChainSplit;
     const bool row_ok = valid && ctx.row < p.V;
-    float* dst = p.dWacc + size_t(min(ctx.row, p.V - 1)) * p.ldk;
+    float* dst = p.gw + size_t(min(ctx.row, p.V - 1)) * p.K;
     (void)kMaxQ;
     // two chunks (32 registers) at a time: holding all of this thread's columns at once spills
 #pragma unroll 1
@@ -904,7 +926,7 @@ struct PolBowBwdW {
       }
     }
     if (q0 >= q1) release();
-    if (row_ok && dbsum != 0.f) atomicAdd(dst + p.K + 3, dbsum);    // every column part adds its share
+    if (row_ok && dbsum != 0.f) atomicAdd(p.gb + ctx.row, dbsum);    // every column part adds its share
   }
   CAREL_DEVINL void finish() {}
 };
@@ -982,22 +1004,6 @@ struct PolBowBwdZ {
   CAREL_DEVINL void finish() {}
 };
 
-// scatter [V, ldk] accumulation buffer into grad_w [V, K] and grad_b [V] (column K+3 = ones column of ZA)
-static __global__ void bow_scatter_grads_kernel(const float* __restrict__ acc, int ldk, int V, int K,
-                                                float* __restrict__ gw, float* __restrict__ gb) {
-  const long long total = 1LL * V * (K + 1);
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int c = int(t % (K + 1));
-    const int r = int(t / (K + 1));
-    if (c < K) {
-      if (gw) gw[size_t(r) * K + c] = acc[size_t(r) * ldk + c];
-    } else if (gb) {
-      gb[r] = acc[size_t(r) * ldk + K + 3];
-    }
-  }
-}
-
 }  // namespace carel
 
 using namespace carel;
@@ -1040,10 +1046,6 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
     CAREL_LAUNCHED();
   }
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.lossacc, 0, 2 * sizeof(double), st));
-  CUtensorMap ta, tb;
-  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.ZA, N, w.ldk, w.ldk, 128) == 0, "carel_bow_fwd: tensor map Z failed");
-  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.WB, V, w.ldk, w.ldk, 128) == 0, "carel_bow_fwd: tensor map W failed");
-  GemmSched s = make_sched(N, V, w.ldk, 256, 1, TILE_FULL);
   // ---- pass F: the one dense pass (online max, power sums) + per-row combine ----
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.wsum, 0, size_t(w.ldk) * 4, st));
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.tile_flag, 0, (size_t(w.Npad / 128) + 1) * 4, st));
@@ -1052,9 +1054,14 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
     bow_colsum_kernel<<<148 * 4, blk, blk.x * blk.y * sizeof(float2), st>>>(w.WB, int(V), w.ldk, w.wsum);
   }
   CAREL_LAUNCHED();
+  // plain operands (columns [0, K) of ZA / WB) through the A-stationary GEMM: bias is added in the epilogue
+  CUtensorMap ta2, tb2;
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&ta2, w.ZA, N, K, w.ldk, 128) == 0, "carel_bow_fwd: tensor map Z failed");
+  CAREL_REQUIRE(make_tmap_bf16_sw128(&tb2, w.WB, V, K, w.ldk, 128) == 0, "carel_bow_fwd: tensor map W failed");
+  AsSched as = make_as_sched(N, V, K, sm_count());
   EpiBowFusedParams e1;
-  e1.part4 = w.part4; e1.part2 = w.part2; e1.N = int(N); e1.V = int(V); e1.Npad = w.Npad;
-  if (int rc = launch_gemm<EpiBowFused<256>, 256, 1, false, false>(ta, tb, ta, tb, s, e1, st, "bow_passF")) return rc;
+  e1.part4 = w.part4; e1.part2 = w.part2; e1.bl2e = w.bl2e; e1.N = int(N); e1.V = int(V); e1.Npad = w.Npad;
+  if (int rc = launch_gemm_as<EpiBowFused<256>>(ta2, tb2, as, e1, st, "bow_passF")) return rc;
   bow_combine_kernel<<<w.Npad / kCombineRows, kCombineRows * kCombineGroups, 0, st>>>(
       w.part4, w.part2, w.ntp, w.Npad, int(N), int(V), int(K), w.ldk, label_smoothing / float(V), w.wsum, w.ZA,
       w.lse, w.nlse2, w.srow, w.lossacc, w.row_flag, w.tile_flag);
@@ -1063,21 +1070,15 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   EpiBowLossParams e2;
   e2.lossacc = w.lossacc; e2.srow = w.srow; e2.row_flag = w.row_flag; e2.bl2e = w.bl2e; e2.nlse2 = w.nlse2;
   e2.N = int(N); e2.V = int(V); e2.c = label_smoothing / float(V);
-  {
-    CUtensorMap ta2, tb2;      // plain operands: columns [0, K) of ZA / WB
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta2, w.ZA, N, K, w.ldk, 128) == 0, "carel_bow_fwd: tensor map Z failed");
-    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb2, w.WB, V, K, w.ldk, 128) == 0, "carel_bow_fwd: tensor map W failed");
-    GemmSched s2 = make_sched(N, V, K, 256, 1, TILE_FULL);
-    s2.row_tile_flags = w.tile_flag;      // [0] = any flagged row at all, [1 + tile] per row tile
-    if (int rc = launch_gemm<EpiBowLoss<256>, 256, 1, false, false>(ta2, tb2, ta2, tb2, s2, e2, st, "bow_pass2_exact")) return rc;
-  }
+  as.row_tile_flags = w.tile_flag;      // [0] = any flagged row at all, [1 + tile] per row tile
+  if (int rc = launch_gemm_as<EpiBowLoss<256>>(ta2, tb2, as, e2, st, "bow_pass2_exact")) return rc;
   // ---- sparse corrections ----
   BowSparseArgs sa;
   sa.ZA = w.ZA; sa.WB = w.WB; sa.ell_cols = w.ell_cols; sa.ell_vals = w.ell_vals; sa.ell_nnz = w.ell_nnz;
   sa.bow_dense = bow_dense; sa.ld_bow = ld_bow; sa.N = int(N); sa.V = int(V); sa.K = int(K); sa.ldk = w.ldk;
   sa.cap = cap; sa.mode = 0; sa.one_minus_ls = 1.f - label_smoothing; sa.lossacc = w.lossacc; sa.srow = w.srow;
   sa.ell_ev = w.ell_ev; sa.overflow_only = 0;
-  sa.grad_out = nullptr; sa.grad_z = nullptr; sa.ldgz = 0; sa.dWacc = nullptr;
+  sa.grad_out = nullptr; sa.grad_z = nullptr; sa.ldgz = 0; sa.gw = nullptr; sa.gb = nullptr;
   bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
   CAREL_LAUNCHED();
   bow_loss_finalize_kernel<<<1, 32, 0, st>>>(w.lossacc, 1.0 / (double(N) * double(V)), loss_out);
@@ -1102,8 +1103,10 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_bow_bwd: workspace too small");
   CAREL_REQUIRE(grad_z != nullptr, "carel_bow_bwd: grad_z is required");
   const bool need_w = grad_w != nullptr || grad_b != nullptr;
-  // grad_z[r, 0:K] is fully written (not accumulated) by the sparse kernel, pass 3 then adds to it
-  if (need_w) CAREL_CHECK_CUDA(cudaMemsetAsync(w.dWacc, 0, size_t(V) * w.ldk * 4, st));
+  // grad_z[r, 0:K] and (if wanted) grad_w / grad_b are fully written (not accumulated) by the sparse gather
+  // kernels; the dense passes then add to them.  A gradient the caller does not want lands in scratch.
+  float* gw = grad_w != nullptr ? grad_w : w.dWacc;
+  float* gb = grad_b != nullptr ? grad_b : w.dbacc;
   // ---- sparse part: gathers through the ELL (rows) and CSC (words) views; rows that overflowed the ELL
   // list fall back to the scan + atomics kernel ----
   const float inv_nv = float(1.0 / (double(N) * double(V)));
@@ -1112,7 +1115,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   CAREL_LAUNCHED();
   if (need_w) {
     bow_sparse_dw_kernel<<<148 * 16, 256, 0, st>>>(w.ZA, w.ldk, int(K), w.colptr, w.csc_row, w.csc_slot, w.ell_ev,
-                                                  int(V), grad_out, inv_nv, w.dWacc);
+                                                  int(V), grad_out, inv_nv, gw, gb);
     CAREL_LAUNCHED();
   }
   if (bow_dense != nullptr) {
@@ -1121,7 +1124,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
     sa.ell_ev = nullptr; sa.overflow_only = 1;
     sa.bow_dense = bow_dense; sa.ld_bow = ld_bow; sa.N = int(N); sa.V = int(V); sa.K = int(K); sa.ldk = w.ldk;
     sa.cap = int(ell_cap); sa.mode = 1; sa.one_minus_ls = 1.f - label_smoothing; sa.lossacc = nullptr; sa.srow = nullptr;
-    sa.grad_out = grad_out; sa.grad_z = grad_z; sa.ldgz = ldgz; sa.dWacc = w.dWacc;
+    sa.grad_out = grad_out; sa.grad_z = grad_z; sa.ldgz = ldgz; sa.gw = gw; sa.gb = gb;
     bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
     CAREL_LAUNCHED();
   }
@@ -1129,7 +1132,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   // K = 4 full 64-wide blocks: A 64 KB + 5 ring stages of 32 KB, and 4 accumulator buffers in flight.
   const int k16 = int(K / 16);
   BowBwdParams bp;
-  bp.srow = w.srow; bp.nlse2 = w.nlse2; bp.bl2e = w.bl2e; bp.grad_out = grad_out; bp.dWacc = w.dWacc;
+  bp.srow = w.srow; bp.nlse2 = w.nlse2; bp.bl2e = w.bl2e; bp.grad_out = grad_out; bp.gw = gw; bp.gb = gb;
   bp.grad_z = grad_z; bp.ldgz = ldgz;
   bp.N = int(N); bp.V = int(V); bp.K = int(K); bp.ldk = w.ldk;
   bp.c = label_smoothing / float(V); bp.inv_nv = inv_nv;
@@ -1152,10 +1155,6 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
     ChainSched cs = make_chain_sched(0, int((N + 127) / 128), int((V + 63) / 64), k16, Cfg::stages_for(k16), 64);
     cs.n2_16 = int(K / 16);
     if (int rc = launch_chain<PolBowBwdZ, 1, 64, NB>(ta, tb, ta, tb, cs, bp, st, "bow_pass4_dz")) return rc;
-  }
-  if (need_w) {
-    bow_scatter_grads_kernel<<<148 * 4, 256, 0, st>>>(w.dWacc, w.ldk, int(V), int(K), grad_w, grad_b);
-    CAREL_LAUNCHED();
   }
   return 0;
 }

@@ -25,16 +25,6 @@
 
 namespace carel {
 
-// Debug timeline (build with CAREL_EXTRA_FLAGS=-DCAREL_CHAIN_TRACE): block 0 records clock64() of the main
-// pipeline events of its first 256 inner tiles; read back with carel_debug_chain_trace().
-#ifdef CAREL_CHAIN_TRACE
-static __device__ long long g_chain_trace[8 * 256];
-#define CAREL_TRACE(slot, idx) \
-  do { if (blockIdx.x == 0 && (idx) < 256) g_chain_trace[(slot) * 256 + (idx)] = clock64(); } while (0)
-#else
-#define CAREL_TRACE(slot, idx) do {} while (0)
-#endif
-
 struct ChainSched {
   int n_owner;     // owner tiles (128 rows) in this launch
   int owner0;      // first owner tile index (row-block sharding)

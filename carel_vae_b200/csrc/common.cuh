@@ -335,6 +335,16 @@ CAREL_DEVINL void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Debug timeline (build with CAREL_EXTRA_FLAGS=-DCAREL_CHAIN_TRACE): block 0 records clock64() of the main
+// pipeline events of its first 256 inner tiles; read back with carel_debug_chain_trace().
+#ifdef CAREL_CHAIN_TRACE
+static __device__ long long g_chain_trace[8 * 256];
+#define CAREL_TRACE(slot, idx) \
+  do { if (blockIdx.x == 0 && (idx) < 256) g_chain_trace[(slot) * 256 + (idx)] = clock64(); } while (0)
+#else
+#define CAREL_TRACE(slot, idx) do {} while (0)
+#endif
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

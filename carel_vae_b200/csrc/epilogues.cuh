@@ -45,9 +45,14 @@ struct EpiStore {
       }
       float* o = p.out + size_t(ctx.row) * p.ld + col;
       if (p.atomic) {
+        if (col + 32 <= p.N && (p.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col + i < p.N) atomicAdd(o + i, v[i]);
+          for (int i = 0; i < 32; i += 4) red_add_v4(o + i, v[i], v[i + 1], v[i + 2], v[i + 3]);   // 16-byte reductions
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col + i < p.N) atomicAdd(o + i, v[i]);
+        }
       } else if (col + 32 <= p.N && (p.ld & 3) == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)

@@ -1,6 +1,7 @@
 // gemm_launch.cuh — host-side launcher of gemm_tc_kernel (persistent grid = min(items, #SM)).
 #pragma once
 #include "api_common.cuh"
+#include "gemm_as.cuh"
 #include "gemm_tc.cuh"
 
 namespace carel {
@@ -35,6 +36,41 @@ inline void set_ksplit(GemmSched& s, int desired) {
   const int per = (num_kb + desired - 1) / desired;
   s.ksplit = (num_kb + per - 1) / per;
   s.num_items = s.m_tiles * s.n_tiles * s.ksplit;
+}
+
+template <class Epi>
+int launch_gemm_as(const CUtensorMap& a, const CUtensorMap& b, const AsSched& s, const typename Epi::Params& ep,
+                   cudaStream_t st, const char* tag = "gemm_as") {
+  auto kern = gemm_as_kernel<Epi>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAsSmemBytes));
+    attr_done = true;
+  }
+  CAREL_REQUIRE(s.num_k16 >= 1 && s.num_k16 <= 16, "A-stationary GEMM: K must be <= 256");
+  const int grid = (s.total + s.tpc - 1) / s.tpc;
+  if (grid <= 0) return 0;
+  timing_begin(tag, st);
+  kern<<<grid, kGemmThreads, kAsSmemBytes, st>>>(a, b, s, ep);
+  timing_end(st);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
+// Split-K factor that fills whole waves of the persistent grid: minimise waves * (k-blocks per item + a fixed
+// per-item cost of ~3 k-blocks for the accumulator write-out); ties go to the smaller split (fewer reductions).
+inline void set_ksplit_auto(GemmSched& s, int max_split = 32) {
+  const int num_kb = (s.num_k16 + 3) / 4;
+  const int tiles = s.m_tiles * s.n_tiles, sms = sm_count();
+  int best = 1;
+  long long best_cost = -1;
+  for (int ks = 1; ks <= max_split && ks <= num_kb; ++ks) {
+    const long long items = 1LL * tiles * ks;
+    const long long waves = (items + sms - 1) / sms;
+    const long long cost = waves * ((num_kb + ks - 1) / ks + 3);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ks; }
+  }
+  set_ksplit(s, best);
 }
 
 inline GemmSched make_sched(int64_t M, int64_t N, int64_t K, int BN, int ksplit, int mode) {

@@ -65,6 +65,29 @@ static __global__ void pack_x_ones_kernel(const float* __restrict__ x, int N, in
   }
 }
 
+// The four [L, D] projection weights -> bf16 rows of Wp, stacked twice (rows [0, 4L) and [ldd, ldd + 4L)), and
+// the four [L] biases -> one contiguous [4L] vector: one launch instead of eight packs and four copies.
+struct PackW4Args {
+  const float* w[4];
+  const float* b[4];
+};
+static __global__ void pack_w4_kernel(const PackW4Args a, int L, int D, __nv_bfloat16* __restrict__ Wp, int ldw,
+                                      int ldd, float* __restrict__ bias4) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < 4 * L; r += gridDim.x * wpb) {
+    const int i = r / L, rr = r - i * L;
+    const float* s = a.w[i] + size_t(rr) * D;
+    __nv_bfloat16* o0 = Wp + size_t(r) * ldw;
+    __nv_bfloat16* o1 = Wp + size_t(ldd + r) * ldw;
+    for (int k = lane; k < ldw; k += 32) {
+      const __nv_bfloat16 v = __float2bfloat16_rn(k < D ? __ldg(s + k) : 0.f);
+      o0[k] = v;
+      o1[k] = v;
+    }
+    if (lane == 0) bias4[r] = __ldg(a.b[i] + rr);
+  }
+}
+
 // One thread per 4 latent dims of one row and one space.  pre layout: [mu_e | lv_e | mu_c | lv_c].
 // Writes z = [z_e | z_c] and accumulates the two KL sums (double) with one atomic per warp.
 static __global__ void reparam_kl_fwd_kernel(const float* __restrict__ pre, int ldp,
@@ -196,12 +219,11 @@ extern "C" int carel_latent_fwd(const float* x, int64_t ldx, int64_t N, int64_t 
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_latent_fwd: workspace too small");
   pack_x_ones_kernel<<<int((N + 7) / 8), 256, 0, st>>>(x, int(N), int(D), int(ldx), w.Xp, w.ldx);
   CAREL_LAUNCHED();
-  for (int i = 0; i < 4; ++i) {
-    pack_rows_kernel<<<int((L + 7) / 8), 256, 0, st>>>(w4[i], int(L), int(D), int(D), w.Wp, nullptr,
-                                                       w.ldw, int(i * L), 0, nullptr);
-    CAREL_LAUNCHED();
-    pack_rows_kernel<<<int((L + 7) / 8), 256, 0, st>>>(w4[i], int(L), int(D), int(D), w.Wp, nullptr,
-                                                       w.ldw, int(w.ldd + i * L), 0, nullptr);
+  float* bias4 = w.dW;     // contiguous [4L] staging vector at the head of the dW buffer (free during forward)
+  {
+    PackW4Args pa;
+    for (int i = 0; i < 4; ++i) { pa.w[i] = w4[i]; pa.b[i] = b4[i]; }
+    pack_w4_kernel<<<int((4 * L + 7) / 8), 256, 0, st>>>(pa, int(L), int(D), w.Wp, w.ldw, w.ldd, bias4);
     CAREL_LAUNCHED();
   }
   // bias: the four [L] vectors are gathered into pre's first row region by the epilogue via a
@@ -210,9 +232,6 @@ extern "C" int carel_latent_fwd(const float* x, int64_t ldx, int64_t N, int64_t 
     CAREL_CHECK_CUDA(cudaMemsetAsync(w.Wp + size_t(4 * L) * w.ldw, 0, size_t(w.ldd - 4 * L) * w.ldw * 2, st));
     CAREL_CHECK_CUDA(cudaMemsetAsync(w.Wp + size_t(w.ldd + 4 * L) * w.ldw, 0, size_t(w.ldd - 4 * L) * w.ldw * 2, st));
   }
-  float* bias4 = w.dW;
-  for (int i = 0; i < 4; ++i)
-    CAREL_CHECK_CUDA(cudaMemcpyAsync(bias4 + i * L, b4[i], size_t(L) * 4, cudaMemcpyDeviceToDevice, st));
   CUtensorMap ta, tb;
   CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.Xp, N, D, w.ldx, 128) == 0, "carel_latent_fwd: tensor map X failed");
   CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.Wp, 4 * L, D, w.ldw, 128) == 0, "carel_latent_fwd: tensor map W failed");
@@ -267,8 +286,7 @@ extern "C" int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* 
     CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.dpre, N, K2, K2, 64) == 0, "carel_latent_bwd: tensor map dpre^T failed");
     CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.Xp, N, D + 1, w.ldx, 64) == 0, "carel_latent_bwd: tensor map X failed");
     GemmSched s = make_sched(K2, D + 1, N, 256, 1, TILE_FULL);
-    const int tiles = s.m_tiles * s.n_tiles;
-    set_ksplit(s, (2 * sm_count() + tiles - 1) / tiles);
+    set_ksplit_auto(s);
     CAREL_CHECK_CUDA(cudaMemsetAsync(w.dW, 0, size_t(K2) * w.ldx * 4, st));
     EpiStore<256>::Params ep;
     ep.out = w.dW; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(K2); ep.N = int(D + 1);

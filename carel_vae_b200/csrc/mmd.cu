@@ -73,9 +73,8 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
   double* acc = partial_sums ? partial_sums : w.accum;
 
   if (!precision) {
-    pack_rows_kernel<<<int((n1 + 7) / 8), 256, 0, st>>>(x, int(n1), int(dim), int(ldx), w.SA, w.SB, ldp, 0, 1, nullptr);
-    CAREL_LAUNCHED();
-    pack_rows_kernel<<<int((n2 + 7) / 8), 256, 0, st>>>(y, int(n2), int(dim), int(ldy), w.SA, w.SB, ldp, int(n1), 1, nullptr);
+    pack_rows_kernel<<<int((M + 7) / 8), 256, 0, st>>>(x, int(M), int(dim), int(ldx), w.SA, w.SB, ldp, 0, 1, nullptr,
+                                                      nullptr, y, int(n1), int(ldy));
     CAREL_LAUNCHED();
   } else {
     const Pack3Out oa{w.SA, 0, 0}, ob{w.SB, 1, 1};

@@ -22,17 +22,20 @@ inline __host__ __device__ int aug_width(int K) { return (K + 6 + 15) / 16 * 16;
 static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows, int K, int ld,
                                         __nv_bfloat16* __restrict__ A, __nv_bfloat16* __restrict__ B,
                                         int ldp, int dst_row0, int aug, float* __restrict__ norms,
-                                        const float* __restrict__ hvec = nullptr) {
+                                        const float* __restrict__ hvec = nullptr,
+                                        const float* __restrict__ src1 = nullptr, int rows0 = 0, int ld1 = 0) {
+  // optional second source: rows [rows0, rows) come from src1 (stacked samples cat(x, y) in ONE launch)
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows;
        r += gridDim.x * warps_per_block) {
-    const float* s = src + size_t(r) * ld;
+    const bool second = src1 != nullptr && r >= rows0;
+    const float* s = second ? src1 + size_t(r - rows0) * ld1 : src + size_t(r) * ld;
     __nv_bfloat16* a = (A != nullptr) ? A + size_t(dst_row0 + r) * ldp : nullptr;
     __nv_bfloat16* b = (B != nullptr) ? B + size_t(dst_row0 + r) * ldp : nullptr;
     float nrm = 0.f;
-    const bool vec = ((K & 3) == 0) && ((ld & 3) == 0) && ((ldp & 3) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const bool vec = ((K & 3) == 0) && (((second ? ld1 : ld) & 3) == 0) && ((ldp & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(second ? src1 : src) & 15) == 0);
     if (vec) {
       for (int k = lane * 4; k < K; k += 128) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(s + k));

@@ -22,17 +22,21 @@ if which == "mmd":
 else:
     for _ in range(2):
         o = F.bow_reconstruction_loss(Z, W, b, bow)
-        o.backward()
+        if which != "fwd":
+            o.backward()
 torch.cuda.synchronize()
 lib = C.CDLL("carel_vae_b200/libcarel_head.so")
 buf = (C.c_longlong * (8 * 256))()
 assert (lib.carel_debug_chain_trace_mmd if which == 'mmd' else lib.carel_debug_chain_trace)(buf) == 0
 ev = [[buf[s * 256 + i] for i in range(256)] for s in range(8)]
 t0 = min(v for v in ev[0] if v > 0)
-names = ["load_issue", "g1_issue", "g2_issue", "epi_acc1_ready", "epi_ld_done", "epi_p_arrive", "g1_issued", "g2_issued"]
+if which == "fwd":
+    names = ["tile_load", "mma_start", "mma_issued", "epi_start", "epi_done", "-", "-", "-"]
+else:
+  names = ["load_issue", "g1_issue", "g2_issue", "epi_acc1_ready", "epi_ld_done", "epi_p_arrive", "g1_issued", "g2_issued"]
 print("tile " + " ".join(f"{n:>14s}" for n in names))
-for i in list(range(0, 8)) + list(range(100, 112)):
+for i in list(range(0, 8)) + (list(range(20, 40)) if which == 'fwd' else list(range(100, 112))):
     print(f"{i:4d} " + " ".join(f"{ev[s][i] - t0:14d}" for s in range(8)))
 for s in range(8):
-    d_ = [ev[s][i + 1] - ev[s][i] for i in range(20, 120)]
+    d_ = [ev[s][i + 1] - ev[s][i] for i in (range(10, 45) if which == 'fwd' else range(20, 100))]
     print(names[s], "mean period", sum(d_) / len(d_))
