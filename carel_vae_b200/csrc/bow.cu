@@ -178,14 +178,24 @@ struct EpiBowFused {
                                        make_float2(b4.z, b4.w));
           y[4 * i] = y0.x; y[4 * i + 1] = y0.y; y[4 * i + 2] = y1.x; y[4 * i + 3] = y1.y;
         }
+        // Speculative exponentials against the CURRENT reference m (not yet the chunk maximum): they do not wait
+        // for the max chain below.  The reference only moves when the chunk maximum exceeds it by more than 2^8
+        // (then e <= 2^8, e^4 <= 2^32: no overflow), in which case the chunk is redone against the new one.
+        const float2 nm2 = make_float2(-m, -m);
+        float2 e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 t = __fadd2_rn(make_float2(y[2 * i], y[2 * i + 1]), nm2);
+          e[i] = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+        }
         float cm, cn;
         if (full) {
-          cm = fmax3(y[0], y[1], y[2]);
-          cn = fmin3(y[0], y[1], y[2]);
-#pragma unroll
-          for (int i = 3; i < 15; i += 2) { cm = fmax3(cm, y[i], y[i + 1]); cn = fmin3(cn, y[i], y[i + 1]); }
-          cm = fmaxf(cm, y[15]);
-          cn = fminf(cn, y[15]);
+          const float ma = fmax3(y[0], y[1], y[2]), mb = fmax3(y[3], y[4], y[5]);
+          const float mc = fmax3(y[6], y[7], y[8]), md = fmax3(y[9], y[10], y[11]);
+          const float na = fmin3(y[0], y[1], y[2]), nb = fmin3(y[3], y[4], y[5]);
+          const float nc = fmin3(y[6], y[7], y[8]), nd = fmin3(y[9], y[10], y[11]);
+          cm = fmax3(fmax3(ma, mb, mc), md, fmax3(y[12], y[13], fmaxf(y[14], y[15])));
+          cn = fmin3(fmin3(na, nb, nc), nd, fmin3(y[12], y[13], fminf(y[14], y[15])));
         } else {
           cm = -INFINITY;
           cn = INFINITY;
@@ -198,26 +208,29 @@ struct EpiBowFused {
           }
         }
         mn = fminf(mn, cn);
-        if (cm > m) {          // rescale the running sums to the new reference (rare after the first chunks)
-          const float sc = ex2_approx(m - cm), sc2 = sc * sc;
-          t1.x *= sc; t1.y *= sc;
-          t2.x *= sc2; t2.y *= sc2;
-          t3.x *= sc2 * sc; t3.y *= sc2 * sc;
-          t4.x *= sc2 * sc2; t4.y *= sc2 * sc2;
-          m = cm;
-        }
-        if (m > -INFINITY) {
-          const float2 nm2 = make_float2(-m, -m);
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float2 t = __fadd2_rn(make_float2(y[i], y[i + 1]), nm2);
-            const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
-            const float2 e2 = __fmul2_rn(e, e);
-            t1 = __fadd2_rn(t1, e);
-            t2 = __fadd2_rn(t2, e2);
-            t3 = __ffma2_rn(e2, e, t3);
-            t4 = __ffma2_rn(e2, e2, t4);
+        if (cm > m + 8.f || !full) {          // move the reference (rare after the first chunk) and redo the chunk
+          if (cm > m) {
+            const float sc = ex2_approx(m - cm), sc2 = sc * sc;
+            t1.x *= sc; t1.y *= sc;
+            t2.x *= sc2; t2.y *= sc2;
+            t3.x *= sc2 * sc; t3.y *= sc2 * sc;
+            t4.x *= sc2 * sc2; t4.y *= sc2 * sc2;
+            m = cm;
           }
+          const float2 nm = make_float2(-m, -m);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 t = __fadd2_rn(make_float2(y[2 * i], y[2 * i + 1]), nm);
+            e[i] = (m > -INFINITY) ? make_float2(ex2_approx(t.x), ex2_approx(t.y)) : make_float2(0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 e2 = __fmul2_rn(e[i], e[i]);
+          t1 = __fadd2_rn(t1, e[i]);
+          t2 = __fadd2_rn(t2, e2);
+          t3 = __ffma2_rn(e2, e[i], t3);
+          t4 = __ffma2_rn(e2, e2, t4);
         }
       });
     }
@@ -338,7 +351,8 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
       const float lse = lse2 * kLn2;
       const float i1 = 1.f / T1, i2 = i1 * i1;
       const float S2 = T2 * i2, S3 = T3 * i2 * i1, S4 = T4 * i2 * i2;
-      const bool valid = (i1 < 0.03125f) && (mn - lse2 > -27.f * kLog2e);
+      // max_j p_ij <= S4^(1/4): S4 < 2^-20 guarantees every p < 2^-5 (the partial maxima are only references)
+      const bool valid = (T1 > 0.f) && (S4 < 9.5367431640625e-07f) && (mn - lse2 > -27.f * kLog2e);
       float u = 0.f;
       if (valid) {
         f += double(c) * (double(sx) - double(V) * double(lse)) -

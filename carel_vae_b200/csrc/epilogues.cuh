@@ -146,6 +146,7 @@ struct EpiMMD {
   const Params& p;
   double acc0, acc1, acc2;
   CAREL_DEVINL EpiMMD(const Params& p_, const TileCtx&) : p(p_), acc0(0.0), acc1(0.0), acc2(0.0) {}
+  CAREL_DEVINL void prefetch(const TileCtx&) {}
 
   CAREL_DEVINL float kmulti(float a) const {
     float k = 0.f;

@@ -14,12 +14,14 @@
 namespace carel {
 
 struct AsSched {
-  int m_tiles, n_tiles;   // 128-row and 256-column tiles
+  int m_tile0, m_tiles;   // row tiles [m_tile0, m_tile0 + m_tiles) of 128 rows (row-block sharding across GPUs)
+  int n_tiles;            // 256-column tiles
+  int tri;                // 1: only tiles on / above the diagonal of a square problem (tn >= tm / 2)
   int num_k16;            // K in 16-wide steps (<= 16)
-  int total;              // m_tiles * n_tiles
-  int tpc;                // tiles per CTA: CTA b owns tiles [b * tpc, (b + 1) * tpc) in row-major order
+  int total;              // number of scheduled tiles
+  int tpc;                // tiles per CTA: CTA b owns tiles [b * tpc, (b + 1) * tpc) of the row-major tile list
   int n_cols;             // logical N (the last column tile issues a narrower MMA)
-  const int* row_tile_flags;   // optional (device): flags[0] = any work at all, flags[1 + tm] = process row tile tm
+  const int* row_tile_flags;   // optional (device, full mode): flags[0] = any work at all, flags[1 + tm] per row tile
 };
 
 constexpr int kAsStages = 5;
@@ -27,28 +29,52 @@ constexpr int kAsBytesA = 4 * 16384;                     // 4 k-blocks of [128 x
 constexpr int kAsStageB = 256 * 128;                     // one k-block of [256 x 64] bf16
 constexpr int kAsSmemBytes = kAsBytesA + kAsStages * kAsStageB + 1024 + 256;
 
-// Walks the CTA's tile range; every role uses the same iterator.  `new_row` is true on the first tile of a row
-// tile (A has to be (re)loaded), `last_of_row` on the last one this CTA processes for that row tile.
+// Walks the CTA's range of the tile list; every role uses the same iterator.  `new_row` is true on the first
+// tile of a row tile (A has to be (re)loaded), `last_of_row` on the last one this CTA processes for it.
 struct AsIter {
   const AsSched& s;
-  int t, end, prev_tm;
+  int remaining, cur_tm, cur_tn, prev_tm;
   int tm, tn;
   bool new_row, last_of_row;
+  CAREL_DEVINL int first_tn(int m) const { return s.tri ? (m >> 1) : 0; }
   CAREL_DEVINL explicit AsIter(const AsSched& s_) : s(s_), prev_tm(-1) {
-    t = blockIdx.x * s.tpc;
-    end = min(t + s.tpc, s.total);
-    if (s.row_tile_flags != nullptr && s.row_tile_flags[0] == 0) t = end;
+    int t = blockIdx.x * s.tpc;
+    remaining = min(s.tpc, s.total - t);
+    if (s.row_tile_flags != nullptr && s.row_tile_flags[0] == 0) remaining = 0;
+    cur_tm = s.m_tile0;
+    cur_tn = first_tn(cur_tm);
+    if (remaining > 0) {
+      if (!s.tri) {
+        cur_tm = s.m_tile0 + t / s.n_tiles;
+        cur_tn = t % s.n_tiles;
+      } else {
+        while (t >= s.n_tiles - first_tn(cur_tm)) {       // at most m_tiles steps, once per CTA
+          t -= s.n_tiles - first_tn(cur_tm);
+          ++cur_tm;
+        }
+        cur_tn = first_tn(cur_tm) + t;
+      }
+    }
   }
-  CAREL_DEVINL bool flagged(int m) const { return s.row_tile_flags == nullptr || s.row_tile_flags[1 + m] != 0; }
   CAREL_DEVINL bool next() {
-    while (t < end && !flagged(t / s.n_tiles)) t = (t / s.n_tiles + 1) * s.n_tiles;   // skip unflagged row tiles
-    if (t >= end) return false;
-    tm = t / s.n_tiles;
-    tn = t - tm * s.n_tiles;
+    if (s.row_tile_flags != nullptr) {                     // skip unflagged row tiles
+      while (remaining > 0 && s.row_tile_flags[1 + cur_tm] == 0) {
+        remaining -= s.n_tiles - cur_tn;
+        ++cur_tm;
+        cur_tn = first_tn(cur_tm);
+      }
+    }
+    if (remaining <= 0) return false;
+    tm = cur_tm;
+    tn = cur_tn;
     new_row = tm != prev_tm;
     prev_tm = tm;
-    ++t;
-    last_of_row = (t >= end) || (t / s.n_tiles != tm);
+    --remaining;
+    if (++cur_tn == s.n_tiles) {
+      ++cur_tm;
+      cur_tn = first_tn(cur_tm);
+    }
+    last_of_row = (remaining <= 0) || (cur_tm != tm);
     return true;
   }
 };
@@ -198,15 +224,21 @@ gemm_as_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == kEpi) tmem_dealloc(tmem_base, 512);
 }
 
-inline AsSched make_as_sched(int64_t M, int64_t N, int64_t K, int sms) {
+inline AsSched make_as_sched(int64_t M, int64_t N, int64_t K, int sms, int tri = 0, int m_tile0 = 0, int m_tile1 = -1) {
   AsSched s;
-  s.m_tiles = int((M + 127) / 128);
+  const int all_m = int((M + 127) / 128);
+  if (m_tile1 < 0 || m_tile1 > all_m) m_tile1 = all_m;
+  s.m_tile0 = m_tile0;
+  s.m_tiles = m_tile1 > m_tile0 ? m_tile1 - m_tile0 : 0;
   s.n_tiles = int((N + 255) / 256);
+  s.tri = tri;
   s.num_k16 = int((K + 15) / 16);
-  s.total = s.m_tiles * s.n_tiles;
+  s.total = 0;
+  for (int m = m_tile0; m < m_tile0 + s.m_tiles; ++m) s.total += s.n_tiles - (tri ? (m >> 1) : 0);
   int grid = s.total < sms ? s.total : sms;
   if (grid < 1) grid = 1;
   s.tpc = (s.total + grid - 1) / grid;
+  if (s.tpc < 1) s.tpc = 1;
   s.n_cols = int(N);
   s.row_tile_flags = nullptr;
   return s;

@@ -125,10 +125,17 @@ static __global__ void reparam_kl_fwd_kernel(const float* __restrict__ pre, int 
     }
     kl_local[sp] += s;
   }
+  // warp shuffle, then one shared-memory hop per block: two double atomics per BLOCK (per warp they serialise on
+  // the two addresses and cost more than the pass itself)
+  __shared__ float sh_kl[2][32];
   const float k0 = warp_sum(kl_local[0]), k1 = warp_sum(kl_local[1]);
-  if ((threadIdx.x & 31) == 0) {
-    if (k0 != 0.f) atomicAdd(klacc + 0, double(k0));
-    if (k1 != 0.f) atomicAdd(klacc + 1, double(k1));
+  const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sh_kl[0][wid] = k0; sh_kl[1][wid] = k1; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += double(sh_kl[threadIdx.x][i]);
+    if (t != 0.0) atomicAdd(klacc + threadIdx.x, t);
   }
 }
 

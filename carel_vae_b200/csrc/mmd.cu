@@ -108,7 +108,13 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
     ep.a_scale[i] = -2.f * a * kLog2e;
     ep.a_shift[i] = -a * eps * kLog2e;
   }
-  if (int rc = launch_gemm<EpiMMD<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st, "mmd_gram_fwd")) return rc;
+  if (ldp <= 256) {
+    // short K (latent-sized samples): A-stationary schedule, only the column operand is streamed
+    AsSched as = make_as_sched(M, M, ldp, sm_count(), tri, t0, t1);
+    if (int rc = launch_gemm_as<EpiMMD<256>>(ta, tb, as, ep, st, "mmd_gram_fwd")) return rc;
+  } else if (int rc = launch_gemm<EpiMMD<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st, "mmd_gram_fwd")) {
+    return rc;
+  }
   if (out_mmd != nullptr) return carel_mmd_finalize(acc, n1, n2, out_mmd, stream);
   return 0;
 }
