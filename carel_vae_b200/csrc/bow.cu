@@ -286,10 +286,10 @@ static CAREL_DEVINL void split3(float h, __nv_bfloat16& h1, __nv_bfloat16& h2, _
 // Combine the pass-F partials of the rows: lse_i, power sums, dense loss term and S_i = sum_j u_ij; writes
 // -lse (3-way bf16 split) into the h columns of ZA.  Rows outside the series' range are flagged (row_flag /
 // tile_flag[1 + tile], tile_flag[0] = any) and contribute nothing here.
-// Block = 32 rows x 8 partial groups: thread (r, g) folds partials g, g + 8, ... of row r online (consecutive
+// Block = 32 rows x 16 partial groups: thread (r, g) folds partials g, g + 16, ... of row r online (consecutive
 // threads read consecutive rows: coalesced), the 8 groups meet in shared memory, then warp w finishes rows
-// 4w .. 4w + 3 (sum_j x_ij = ZA_i . wsum needs a warp per row).
-constexpr int kCombineRows = 32, kCombineGroups = 8;
+// 2w, 2w + 1 (sum_j x_ij = ZA_i . wsum needs a warp per row).
+constexpr int kCombineRows = 32, kCombineGroups = 16;
 static __global__ void __launch_bounds__(kCombineRows * kCombineGroups)
 bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ part2, int ntp, int Npad, int N,
                    int V, int K, int ldk, float c, const float* __restrict__ wsum, __nv_bfloat16* __restrict__ ZA,
@@ -301,6 +301,7 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
   const int r = blockIdx.x * kCombineRows + rl;          // r < Npad always (Npad is a multiple of 128)
   {
     float M = -INFINITY, T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f, mn = INFINITY;
+#pragma unroll 4
     for (int t = g; t < ntp; t += kCombineGroups) {
       const float4 a = part4[size_t(t) * Npad + r];
       const float2 b = part2[size_t(t) * Npad + r];
@@ -321,7 +322,7 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
     sh[g][0][rl] = M; sh[g][1][rl] = T1; sh[g][2][rl] = T2; sh[g][3][rl] = T3; sh[g][4][rl] = T4; sh[g][5][rl] = mn;
   }
   __syncthreads();
-  // warp g finishes rows 4g .. 4g+3
+  // warp g finishes rows g * (32 / groups) ..
   const int lane = rl;
   double f = 0.0;
   for (int q = 0; q < kCombineRows / kCombineGroups; ++q) {
@@ -331,7 +332,7 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
       if (lane == 0) { nlse2[row] = 0.f; srow[row] = 0.f; }      // padding rows read by the backward chains
       continue;
     }
-    // lanes 0..7 hold the 8 groups
+    // lanes 0 .. groups-1 hold the partial groups
     float M = -INFINITY, T1 = 0.f, T2 = 0.f, T3 = 0.f, T4 = 0.f, mn = INFINITY;
     if (lane < kCombineGroups) {
       M = sh[lane][0][row_l]; T1 = sh[lane][1][row_l]; T2 = sh[lane][2][row_l]; T3 = sh[lane][3][row_l];
@@ -876,7 +877,8 @@ struct PolBowBwdW {
   static constexpr bool kHiLo = false;    // measured decoder gradients are 6e-5..3e-4 with a single bf16 P
   const Params& p;
   float scale, dbsum, rc;
-  float Sn[16], cc[16];
+  float4 sraw[4], lraw[4];        // prefetched S_i and -lse_i log2(e) of this thread's 16 columns (raw: no use before
+                                  // the accumulator barrier, so the L2 latency of the loads hides behind the wait)
   CAREL_DEVINL PolBowBwdW(const Params& p_, const ChainCtx&) : p(p_), scale(0.f), dbsum(0.f), rc(0.f) {}
   CAREL_DEVINL void begin_item(const ChainCtx& ctx) {
     scale = __ldg(p.grad_out) * p.inv_nv;
@@ -888,9 +890,8 @@ struct PolBowBwdW {
     const float4* l4 = reinterpret_cast<const float4*>(p.nlse2 + i0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 v = __ldg(s4 + i), l = __ldg(l4 + i);
-      Sn[4 * i] = -v.x * scale; Sn[4 * i + 1] = -v.y * scale; Sn[4 * i + 2] = -v.z * scale; Sn[4 * i + 3] = -v.w * scale;
-      cc[4 * i] = l.x; cc[4 * i + 1] = l.y; cc[4 * i + 2] = l.z; cc[4 * i + 3] = l.w;
+      sraw[i] = __ldg(s4 + i);
+      lraw[i] = __ldg(l4 + i);
     }
   }
   CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
@@ -901,11 +902,18 @@ struct PolBowBwdW {
       for (int i = 0; i < 16; ++i) d[i] = 0.f;
       return;
     }
-    bow_dlogit16(r, cc, rc, Sn, p.c, scale, i0 + 16 <= p.N, p.N - i0, d);
-    float t = 0.f;                       // db_v: thread-local column sum (fp32, before the bf16 rounding)
+    float Sn[16], cc[16];
+    const float ns = -scale;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) t += d[i];
-    dbsum += t;
+    for (int i = 0; i < 4; ++i) {
+      Sn[4 * i] = sraw[i].x * ns; Sn[4 * i + 1] = sraw[i].y * ns; Sn[4 * i + 2] = sraw[i].z * ns; Sn[4 * i + 3] = sraw[i].w * ns;
+      cc[4 * i] = lraw[i].x; cc[4 * i + 1] = lraw[i].y; cc[4 * i + 2] = lraw[i].z; cc[4 * i + 3] = lraw[i].w;
+    }
+    bow_dlogit16(r, cc, rc, Sn, p.c, scale, i0 + 16 <= p.N, p.N - i0, d);
+    float2 t = make_float2(0.f, 0.f);    // db_v: thread-local column sum (fp32, before the bf16 rounding)
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) t = __fadd2_rn(t, make_float2(d[i], d[i + 1]));
+    dbsum += t.x + t.y;
   }
   CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
   // acc2 -> registers (this thread's K / kChainSplit columns of its row), release the accumulator, THEN reduce
@@ -949,28 +957,30 @@ struct PolBowBwdZ {
   using Params = BowBwdParams;
   static constexpr bool kHiLo = false;
   const Params& p;
-  float scale, rc;
-  float Sn[16], cc[16];
-  CAREL_DEVINL PolBowBwdZ(const Params& p_, const ChainCtx&) : p(p_), scale(0.f), rc(0.f) {}
+  float scale, rc, sn;
+  float4 braw[4];                 // prefetched b_j log2(e) of this thread's 16 columns
+  CAREL_DEVINL PolBowBwdZ(const Params& p_, const ChainCtx&) : p(p_), scale(0.f), rc(0.f), sn(0.f) {}
   CAREL_DEVINL void begin_item(const ChainCtx& ctx) {
     scale = __ldg(p.grad_out) * p.inv_nv;
     const bool ok = ctx.row < p.N;
-    const float sn = ok ? -__ldg(p.srow + ctx.row) * scale : 0.f;
+    sn = ok ? -__ldg(p.srow + ctx.row) * scale : 0.f;
     rc = ok ? __ldg(p.nlse2 + ctx.row) : 0.f;           // this thread's clause: -lse_i log2(e)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) Sn[i] = sn;
   }
   CAREL_DEVINL void prefetch(const ChainCtx&, int v0) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bl2e + v0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 l = __ldg(b4 + i);
-      cc[4 * i] = l.x; cc[4 * i + 1] = l.y; cc[4 * i + 2] = l.z; cc[4 * i + 3] = l.w;
-    }
+    for (int i = 0; i < 4; ++i) braw[i] = __ldg(b4 + i);
   }
   CAREL_DEVINL void begin_tile(const ChainCtx&, int, int) {}
   CAREL_DEVINL void weights16(const ChainCtx&, int v0, const uint32_t (&r)[16], const uint32_t (&)[16],
                               float (&d)[16]) {
+    float Sn[16], cc[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cc[4 * i] = braw[i].x; cc[4 * i + 1] = braw[i].y; cc[4 * i + 2] = braw[i].z; cc[4 * i + 3] = braw[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Sn[i] = sn;
     bow_dlogit16(r, cc, rc, Sn, p.c, scale, v0 + 16 <= p.V, p.V - v0, d);
   }
   CAREL_DEVINL void store16(const ChainCtx&, int, const uint32_t (&)[8]) {}
