@@ -105,20 +105,31 @@ static __global__ void bow_pack_ell_kernel(const float* __restrict__ bow, int64_
     int count = 0;
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(bow) & 15) == 0);
     const int V4 = vec ? (V & ~3) : 0;
-    for (int base = 0; base < V4; base += 128) {
-      const int j = base + lane * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < V4) v = __ldg(reinterpret_cast<const float4*>(row + j));
-      const float e[4] = {v.x, v.y, v.z, v.w};
+    // four 128-bit loads per lane in flight (512 floats of the row per iteration): the ballots below serialise, so
+    // without the batch one warp never has more than one load outstanding
+    for (int base = 0; base < V4; base += 512) {
+      float4 v[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const bool nz = e[q] != 0.f;
-        const unsigned m = __ballot_sync(0xffffffffu, nz);
-        if (nz) {
-          const int pos = count + __popc(m & ((1u << lane) - 1u));
-          if (pos < cap) { cols[size_t(r) * cap + pos] = j + q; vals[size_t(r) * cap + pos] = e[q]; }
+      for (int u = 0; u < 4; ++u) {
+        const int j = base + u * 128 + lane * 4;
+        v[u] = (j < V4) ? __ldcs(reinterpret_cast<const float4*>(row + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = base + u * 128 + lane * 4;
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const bool any_nz = (e[0] != 0.f) || (e[1] != 0.f) || (e[2] != 0.f) || (e[3] != 0.f);
+        if (__ballot_sync(0xffffffffu, any_nz) == 0u) continue;      // the common case: 128 zeros
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool nz = e[q] != 0.f;
+          const unsigned m = __ballot_sync(0xffffffffu, nz);
+          if (nz) {
+            const int pos = count + __popc(m & ((1u << lane) - 1u));
+            if (pos < cap) { cols[size_t(r) * cap + pos] = j + q; vals[size_t(r) * cap + pos] = e[q]; }
+          }
+          count += __popc(m);
         }
-        count += __popc(m);
       }
     }
     for (int base = V4; base < V; base += 32) {

@@ -81,6 +81,7 @@ inline GemmSched make_sched(int64_t M, int64_t N, int64_t K, int BN, int ksplit,
   s.mode = mode;
   set_ksplit(s, ksplit);
   s.m_tile0 = 0;
+  s.tri_rows = s.m_tiles;
   s.n_cols = int(N);
   s.row_tile_flags = nullptr;
   return s;

@@ -48,21 +48,33 @@ struct GemmSched {
   int mode;       // TileMode; TILE_TRI requires BN == 256 and a square problem
   int num_items;  // total work items
   int m_tile0;    // first row tile owned by this launch (row-block sharding across GPUs)
+  int tri_rows;   // TILE_TRI: number of row tiles of this launch
   int n_cols;     // if > 0: logical N; the last column tile issues a narrower MMA (multiple of 16)
   const int* row_tile_flags;  // optional (device): flags[0] = any work at all, flags[1 + tm] = process row tile tm
 };
 
 // Sequential decoder of the persistent schedule; every role of a CTA walks the same items.
+// TILE_TRI orders the tiles in BANDS of kTriBand row tiles, column tile outermost inside a band: the CTAs that run
+// concurrently then share ~148 / kTriBand column tiles across kTriBand row tiles, so a column-operand tile fetched
+// from HBM is reused kTriBand times out of L2.  (Row-major order streams the whole column operand once per row
+// tile: at N = 131072, d = 768 that is 2048 x 411 MB and the Gram kernel becomes HBM-bound.)
+constexpr int kTriBand = 8;
 struct TileIter {
   const GemmSched& s;
   int item;
-  int tri_tm, tri_base;
+  int band, band_base;
   int tm, tn, kb0, kb1;
   CAREL_DEVINL explicit TileIter(const GemmSched& s_)
-      : s(s_), item(blockIdx.x), tri_tm(0), tri_base(0) {
+      : s(s_), item(blockIdx.x), band(0), band_base(0) {
     if (s.row_tile_flags != nullptr && s.row_tile_flags[0] == 0) item = s.num_items;   // nothing flagged
   }
-  CAREL_DEVINL int tri_count(int t) const { return s.n_tiles - ((s.m_tile0 + t) >> 1); }
+  CAREL_DEVINL int first_tn(int t) const { return (s.m_tile0 + t) >> 1; }
+  CAREL_DEVINL int band_count(int b) const {
+    const int r0 = b * kTriBand, r1 = min(r0 + kTriBand, s.tri_rows);
+    int c = 0;
+    for (int r = r0; r < r1; ++r) c += s.n_tiles - first_tn(r);
+    return c;
+  }
   CAREL_DEVINL bool next() {
     for (;;) {
       if (!decode()) return false;
@@ -77,12 +89,29 @@ struct TileIter {
       tm = tile / s.n_tiles;
       tn = tile - tm * s.n_tiles;
     } else {
-      while (tile >= tri_base + tri_count(tri_tm)) {
-        tri_base += tri_count(tri_tm);
-        ++tri_tm;
+      int c = band_count(band);
+      while (tile >= band_base + c) {
+        band_base += c;
+        ++band;
+        c = band_count(band);
       }
-      tm = tri_tm;
-      tn = ((s.m_tile0 + tri_tm) >> 1) + (tile - tri_base);
+      int l = tile - band_base;
+      const int r0 = band * kTriBand, nr = min(kTriBand, s.tri_rows - r0), last = r0 + nr - 1;
+      const int fl = first_tn(last), cmin = s.n_tiles - fl;
+      if (l < nr * cmin) {            // common columns of the band: column-major
+        const int q = l / nr;
+        tn = fl + q;
+        tm = r0 + (l - q * nr);
+      } else {                        // the few near-diagonal tiles a row has beyond the band's common columns
+        l -= nr * cmin;
+        tm = last;
+        tn = fl;
+        for (int r = r0; r <= last; ++r) {
+          const int cnt = fl - first_tn(r);
+          if (l < cnt) { tm = r; tn = first_tn(r) + l; break; }
+          l -= cnt;
+        }
+      }
     }
     tm += s.m_tile0;
     const int num_kb = (s.num_k16 + 3) >> 2;

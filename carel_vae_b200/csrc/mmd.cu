@@ -94,6 +94,7 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
   const int t1 = int((row_tile_end < 0 || row_tile_end > s.m_tiles) ? s.m_tiles : row_tile_end);
   CAREL_REQUIRE(t0 <= t1, "carel_mmd_fwd: bad row tile range");
   s.m_tile0 = t0;
+  s.tri_rows = t1 - t0;
   if (tri) {
     int items = 0;
     for (int t = t0; t < t1; ++t) items += s.n_tiles - (t >> 1);
