@@ -32,6 +32,13 @@ _SIGNATURES = {
     "carel_mmd_finalize": (C.c_int, [c_ptr, i64, i64, c_ptr, c_ptr]),
     "carel_mmd_bwd": (C.c_int, [c_ptr, i64, i64, i64, C.POINTER(C.c_float), C.c_int, C.c_float, i64, i64,
                                 c_ptr, i64, c_ptr, i64, c_ptr, C.c_size_t, C.c_int, c_ptr]),
+    "carel_heads_workspace_bytes": (C.c_size_t, [i64, i64]),
+    "carel_heads_fwd": (C.c_int, [c_ptr, i64, i64, i64, i64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_ptr,
+                                  c_ptr, c_ptr, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                  C.POINTER(C.c_float), c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "carel_heads_bwd": (C.c_int, [c_ptr, c_ptr, i64, i64, i64, i64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                  c_ptr, c_ptr, c_ptr, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                  C.POINTER(C.c_float), c_ptr, i64, C.POINTER(C.c_void_p), c_ptr, C.c_size_t, c_ptr]),
     "carel_latent_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "carel_latent_fwd": (C.c_int, [c_ptr, i64, i64, i64, i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_ptr,
                                    c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),

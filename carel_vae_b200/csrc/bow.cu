@@ -524,6 +524,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
   const int grp = lane >> 3, gl = lane & 7;
   const int nchunk = a.ldk >> 3;
   const float scale = (a.mode == 1) ? __ldg(a.grad_out) / (float(a.N) * float(a.V)) : 0.f;
+  double loss_warp = 0.0;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < a.N; r += gridDim.x * wpb) {
     const int nnz = a.ell_nnz[r];
     const bool dense_scan = nnz > a.cap;
@@ -645,7 +646,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
       du += __shfl_xor_sync(0xffffffffu, du, 8);
       du += __shfl_xor_sync(0xffffffffu, du, 16);
       if (lane == 0) {
-        if (dloss != 0.f) atomicAdd(a.lossacc + 1, double(dloss));
+        loss_warp += double(dloss);          // reduced per block below (one double atomic per row serialises)
         if (du != 0.f) atomicAdd(a.srow + r, du);
       }
     } else {
@@ -662,6 +663,16 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
           if (grp == 0 && c * 8 + i < a.K) gz[c * 8 + i] = v;
         }
       }
+    }
+  }
+  if (a.mode == 0) {          // block-level sum of the loss corrections: one double atomic per block
+    __shared__ double sh_l[8];
+    if (lane == 0) sh_l[threadIdx.x >> 5] = loss_warp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < wpb; ++w) t += sh_l[w];
+      if (t != 0.0) atomicAdd(a.lossacc + 1, t);
     }
   }
 }

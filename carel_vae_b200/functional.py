@@ -89,6 +89,46 @@ class _MMDFn(torch.autograd.Function):
         return gx.to(dtx), gy.to(dty), None, None, None, None, None
 
 
+class _MMDHalvesFn(torch.autograd.Function):
+    """MMD^2 between the two column halves of ONE tensor z = [x | y] (the head's z_e / z_c): same kernels as _MMDFn
+    on strided views, but the backward writes both gradient halves into one [N, 2L] tensor, so autograd needs no
+    slice-backward zero-fill / copy / add for them."""
+
+    @staticmethod
+    def forward(ctx, z, L, alphas, eps, prec):
+        _require_cuda(z)
+        zf = _rowmajor_f32(z)
+        N = zf.shape[0]
+        if zf.shape[1] != 2 * L:
+            raise ValueError("z must be [N, 2L]")
+        lb = lib()
+        ws = _workspace(lb.carel_mmd_workspace_bytes(N, N, L, prec), zf.device)
+        out = torch.empty((), dtype=torch.float32, device=zf.device)
+        al = float_array(alphas)
+        x, y = zf[:, :L], zf[:, L:]
+        check(lb.carel_mmd_fwd(_p(x), zf.stride(0), _p(y), zf.stride(0), N, N, L, al, len(alphas), float(eps), 0, 0, -1,
+                               _p(None), _p(out), _p(ws), ws.numel(), prec, _stream()), "carel_mmd_fwd")
+        ctx.ws = ws
+        ctx.meta = (N, L, tuple(float(a) for a in alphas), float(eps), z.dtype, prec)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, L, alphas, eps, dtz, prec = ctx.meta
+        ws = ctx.ws
+        g = g.reshape(()).float().contiguous()
+        gz = torch.empty((N, 2 * L), dtype=torch.float32, device=ws.device)
+        check(lib().carel_mmd_bwd(_p(g), N, N, L, float_array(alphas), len(alphas), eps, 0, -1, _p(gz[:, :L]), 2 * L,
+                                  _p(gz[:, L:]), 2 * L, _p(ws), ws.numel(), prec, _stream()), "carel_mmd_bwd")
+        return gz.to(dtz), None, None, None, None
+
+
+def mmd_halves(z: torch.Tensor, L: int, alphas: Sequence[float], eps: float = 1e-5,
+               precision: str | None = None) -> torch.Tensor:
+    """mmd(z[:, :L], z[:, L:], alphas) with a single [N, 2L] gradient (see _MMDHalvesFn)."""
+    return _MMDHalvesFn.apply(z, int(L), tuple(alphas), eps, _lib.precision_code(precision))
+
+
 def mmd(sample_1: torch.Tensor, sample_2: torch.Tensor, alphas: Sequence[float], eps: float = 1e-5,
         full_gram: bool = False, precision: str | None = None) -> torch.Tensor:
     """Unbiased multi-bandwidth RBF MMD^2 (reference MMDStatistic.__call__,
@@ -189,6 +229,70 @@ def latent(x, eps_e, eps_c, w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_c
     """Fused latent layer.  Returns (z [N, 2L] = [z_e | z_c], kl [2] = (kl_e, kl_c), pre [N, 4L] =
     [mu_e | lv_e | mu_c | lv_c] (detached))."""
     return _LatentFn.apply(x, eps_e, eps_c, w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_clv)
+
+
+# --------------------------------------------------------------------------------------------
+# classifier heads: three tiny Linear + loss heads in two kernels
+# --------------------------------------------------------------------------------------------
+class _HeadsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, m_e, m_c, m_p, w_e, b_e, w_c, b_c, w_p, b_p, emo_labels, cau_labels, pair_labels, cfg):
+        emo_mode, ls, n_e, n_c, n_p, guard, wts = cfg
+        _require_cuda(z, w_e, w_c, w_p)
+        zf = _rowmajor_f32(z)
+        N, twoL = zf.shape
+        L = twoL // 2
+        C_e = w_e.shape[0]
+        masks = [None if m is None else m.detach().float().contiguous() for m in (m_e, m_c, m_p)]
+        weights = [t.detach().float().contiguous() for t in (w_e, b_e, w_c, b_c, w_p, b_p)]
+        emo = (emo_labels.reshape(-1).long() if emo_mode == 0 else emo_labels.reshape(-1).float()).contiguous()
+        cau = cau_labels.reshape(-1).float().contiguous()
+        pair = pair_labels.reshape(-1).float().contiguous()
+        lb = lib()
+        ws = _workspace(lb.carel_heads_workspace_bytes(N, C_e), zf.device)
+        losses = torch.empty(4, dtype=torch.float32, device=zf.device)
+        wv = float_array(wts)
+        check(lb.carel_heads_fwd(_p(zf), zf.stride(0), N, L, C_e, int(emo_mode), _ptr_array(masks), _ptr_array(weights),
+                                 _p(emo), _p(cau), _p(pair), float(ls), float(n_e), float(n_c), float(n_p), int(guard),
+                                 wv, _p(losses), _p(ws), ws.numel(), _stream()), "carel_heads_fwd")
+        ctx.keep = (zf, masks, weights, emo, cau, pair, ws)
+        ctx.meta = (N, L, C_e, int(emo_mode), float(ls), float(n_e), float(n_c), float(n_p), int(guard), tuple(wts),
+                    z.dtype, [t.dtype for t in (w_e, b_e, w_c, b_c, w_p, b_p)],
+                    [tuple(t.shape) for t in (w_e, b_e, w_c, b_c, w_p, b_p)])
+        ctx.mark_non_differentiable(losses)
+        return losses[3].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g, _g_losses):
+        zf, masks, weights, emo, cau, pair, ws = ctx.keep
+        N, L, C_e, emo_mode, ls, n_e, n_c, n_p, guard, wts, zdt, wdts, wshapes = ctx.meta
+        g = g.reshape(()).float().contiguous()
+        need = ctx.needs_input_grad
+        gz = torch.empty((N, 2 * L), dtype=torch.float32, device=zf.device)
+        gws = [torch.empty(shape, dtype=torch.float32, device=zf.device) if need[4 + i] else None
+               for i, shape in enumerate(wshapes)]
+        check(lib().carel_heads_bwd(_p(g), _p(zf), zf.stride(0), N, L, C_e, emo_mode, _ptr_array(masks),
+                                    _ptr_array(weights), _p(emo), _p(cau), _p(pair), ls, n_e, n_c, n_p, guard,
+                                    float_array(wts), _p(gz), 2 * L, _ptr_array(gws), _p(ws), ws.numel(), _stream()),
+              "carel_heads_bwd")
+        out = [gz.to(zdt) if need[0] else None, None, None, None]
+        out += [None if t is None else t.to(dt) for t, dt in zip(gws, wdts)]
+        out += [None, None, None, None]
+        return tuple(out)
+
+
+def classifier_heads(z, masks, emotion_classifier, cause_classifier, pair_classifier, emotion_labels, cause_labels,
+                     pair_labels, emo_mode: int, label_smoothing: float, n_e: float, n_c: float, n_p: float,
+                     guard_inf: bool, loss_weights: Sequence[float]):
+    """The three classifier heads + their weighted sum (reference get_emotion_mul_loss / get_cause_mul_loss /
+    get_pair_mul_loss, drl_classifier_ec_mmd_final_mul.py:461-513, and the head terms of the loss assembly :256-261).
+    `masks` = (m_e [N,L], m_c [N,L], m_p [N,2L]) scaled dropout masks or None.  Returns (weighted sum — differentiable
+    w.r.t. z and the six parameters —, losses[4] = emotion, cause, pair, weighted sum (detached))."""
+    m_e, m_c, m_p = masks if masks is not None else (None, None, None)
+    cfg = (emo_mode, label_smoothing, n_e, n_c, n_p, bool(guard_inf), tuple(float(w) for w in loss_weights))
+    return _HeadsFn.apply(z, m_e, m_c, m_p, emotion_classifier.weight, emotion_classifier.bias,
+                          cause_classifier.weight, cause_classifier.bias, pair_classifier.weight, pair_classifier.bias,
+                          emotion_labels, cause_labels, pair_labels, cfg)
 
 
 # --------------------------------------------------------------------------------------------

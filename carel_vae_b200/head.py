@@ -9,7 +9,8 @@ after `.pooler_output` runs on the sm_100a kernels of libcarel_head.so:
     MMD / HSIC independence losses                 -> losses.MMDStatistic / losses.HSIC
     BoW decoder + softmax + BCE                    -> functional.bow_reconstruction_loss
 
-The tiny classifier heads (<= 6 outputs) stay in PyTorch.  Hyper-parameters
+The three classifier heads + their weighted sum -> functional.classifier_heads
+    (carel_heads_fwd/bwd; the per-head methods keep the reference's PyTorch form for external callers).  Hyper-parameters
 are read from the `opt` passed to __init__ (the reference reads a module-global `opt`).
 
 RNG order per forward matches the reference: randn(L) for emotion, randn(L) for
@@ -185,6 +186,50 @@ class _DrlClassifierBase(nn.Module):
         pos_weight = (len(pair_labels) - torch.sum(pair_labels)) / torch.sum(pair_labels)
         return TF.binary_cross_entropy_with_logits(preds, t, pos_weight=pos_weight)
 
+    # ---- the three heads fused into two CUDA kernels ------------------------------
+    _emo_mode = 1          # 0: cross-entropy over the emotion classes, 1: sigmoid + BCE (base / hsic / gan)
+    _guard_inf = False     # reference mmd:510-511 only
+
+    def _fused_heads_ok(self):
+        o = self.opt
+        return (getattr(o, "fused_heads", True) and o.ec_dim <= 128 and self.cause_classifier.out_features == 1 and
+                self.pair_classifier.out_features == 1 and
+                (self.emotion_classifier.out_features == 1 if self._emo_mode == 1
+                 else self.emotion_classifier.out_features <= 8))
+
+    def _mask(self, n, k, device):
+        """Scaled dropout mask with the RNG consumption of `self.dropout(x)` on a contiguous [n, k] tensor (the
+        mask torch draws depends on shape and layout only), or None in eval mode / p = 0."""
+        if self.training and self.dropout.p > 0:
+            return self.dropout(torch.ones((n, k), device=device))
+        return None
+
+    def _head_weights(self):
+        o = self.opt
+        return (o.ec_mul_loss_weight, o.ec_mul_loss_weight, o.pair_mul_loss_weight)
+
+    def _heads(self, z, emotion_labels, cause_labels, pair_labels, masks=None):
+        """w_e emo_mul_loss + w_c cau_mul_loss + w_p pair_mul_loss: fused kernels when the shapes fit, the reference's
+        per-head methods otherwise.  `masks` = pre-drawn (m_e, m_c, m_p) if the caller had to interleave other
+        dropout draws (GAN); otherwise they are drawn here in the reference order emotion, cause, pair."""
+        w = self._head_weights()
+        L = self.opt.ec_dim
+        if not self._fused_heads_ok():
+            return (w[0] * self.get_emotion_mul_loss(z[:, :L], emotion_labels) +
+                    w[1] * self.get_cause_mul_loss(z[:, L:], cause_labels) +
+                    w[2] * self.get_pair_mul_loss(z, pair_labels))
+        if masks is None:
+            n = z.shape[0]
+            masks = (self._mask(n, L, z.device), self._mask(n, L, z.device), self._mask(n, 2 * L, z.device))
+        o = self.opt
+        total, parts = F.classifier_heads(z, masks, self.emotion_classifier, self.cause_classifier, self.pair_classifier,
+                                          emotion_labels, cause_labels, pair_labels, self._emo_mode, o.label_smoothing,
+                                          self._label_classes() if self._emo_mode == 1 else 1,
+                                          self._cause_label_classes(), self._pair_label_classes(),
+                                          self._guard_inf, w)
+        self.last_head_losses = parts          # (emotion, cause, pair, weighted sum), detached, on the device
+        return total
+
     # ---- inference -----------------------------------------------------------------------
     def get_pair_preds_tensor(self, input_ids, att_masks, token_type_ids):
         """Device-side result of get_pair_preds (no host round trip): sigmoid(pair logits) [N, 1]."""
@@ -204,6 +249,12 @@ class _DrlClassifierBase(nn.Module):
 class DrlClassifierMMD(_DrlClassifierBase):
     """drl_classifier_ec_mmd_final_mul.py (and its newsplit / emnlp siblings with --adapter false)."""
     variant = "mmd"
+    _emo_mode = 0
+    _guard_inf = True
+
+    def _head_weights(self):
+        o = self.opt
+        return (o.emo_mul_loss_weight, o.cau_mul_loss_weight, o.pair_mul_loss_weight)
 
     def _emotion_classes(self, opt):
         return opt.e_num_class
@@ -235,12 +286,8 @@ class DrlClassifierMMD(_DrlClassifierBase):
         if side is not None:
             side.wait_stream(main)
         with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
-            emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
-            cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
-            pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
-            heads = (o.emo_mul_loss_weight * emo_mul_loss + o.cau_mul_loss_weight * cau_mul_loss +
-                     o.pair_mul_loss_weight * pair_mul_loss)
-        mmd_loss = -MMDStatistic(input_ids.shape[0], input_ids.shape[0])(z_e, z_c, [0.1])
+            heads = self._heads(z, emotion_labels, cause_labels, pair_labels)
+        mmd_loss = -MMDStatistic(input_ids.shape[0], input_ids.shape[0]).halves(z, [0.1])
         kl_e, kl_c = self._kl_terms(kl, iteration)
         reconstruction_loss = self._reconstruction(z, content_bow)
         if side is not None:
@@ -261,14 +308,11 @@ class DrlClassifierHSIC(_DrlClassifierBase):
         o, L = self.opt, self.opt.ec_dim
         z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
         z_e, z_c = z[:, :L], z[:, L:]
-        emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
-        cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
+        heads = self._heads(z, emotion_labels, cause_labels, pair_labels)
         hsic_loss = HSIC(z_e, z_c)
-        pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
         kl_e, kl_c = self._kl_terms(kl, iteration)
         reconstruction_loss = self._reconstruction(z, content_bow)
-        return (hsic_loss + o.ec_mul_loss_weight * (emo_mul_loss + cau_mul_loss) +
-                o.pair_mul_loss_weight * pair_mul_loss + kl_e + kl_c + reconstruction_loss)
+        return hsic_loss + heads + kl_e + kl_c + reconstruction_loss
 
     def get_params(self):
         return self._core_params()
@@ -277,6 +321,7 @@ class DrlClassifierHSIC(_DrlClassifierBase):
 class DrlClassifierVI(_DrlClassifierBase):
     """drl_classifier_ec_vi_final.py / drl_classifier_ec_vi.py: KL + CLUB upper bound."""
     variant = "vi"
+    _emo_mode = 0
 
     def _build_variant_modules(self, opt):
         L = opt.ec_dim
@@ -309,14 +354,11 @@ class DrlClassifierVI(_DrlClassifierBase):
         o, L = self.opt, self.opt.ec_dim
         z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
         z_e, z_c = z[:, :L], z[:, L:]
-        emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
-        cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
+        heads = self._heads(z, emotion_labels, cause_labels, pair_labels)
         ec_aprx_loss = self.get_ec_aprx_loss(z_e, z_c)
-        pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
         kl_e, kl_c = self._kl_terms(kl, iteration)
         reconstruction_loss = self._reconstruction(z, content_bow)
-        loss = (o.ec_mul_loss_weight * (emo_mul_loss + cau_mul_loss) + o.pair_mul_loss_weight * pair_mul_loss +
-                kl_e + kl_c + reconstruction_loss)
+        loss = heads + kl_e + kl_c + reconstruction_loss
         return z_e, z_c, ec_aprx_loss, loss
 
     def get_params(self):
@@ -351,19 +393,29 @@ class DrlClassifierGAN(_DrlClassifierBase):
         o, L = self.opt, self.opt.ec_dim
         z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
         z_e, z_c = z[:, :L], z[:, L:]
+        # dropout draws in the reference's order: ec_disc, emotion head, ce_disc, cause head, pair head
+        n, fused = z.shape[0], self._fused_heads_ok()
         ec_disc_preds = self.get_ec_disc_preds(z_c)
         ec_disc_loss = self.get_ec_disc_loss(ec_disc_preds, emotion_labels)
         ec_entropy_loss = self.get_entropy_loss(ec_disc_preds)
-        emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
+        if fused:
+            m_e = self._mask(n, L, z.device)
+        else:
+            emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
         ce_disc_preds = self.get_ce_disc_preds(z_e)
         ce_disc_loss = self.get_ec_disc_loss(ce_disc_preds, cause_labels)
         ce_entropy_loss = self.get_entropy_loss(ce_disc_preds)
-        cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
-        pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
+        if fused:
+            m_c = self._mask(n, L, z.device)
+            m_p = self._mask(n, 2 * L, z.device)
+            heads = self._heads(z, emotion_labels, cause_labels, pair_labels, masks=(m_e, m_c, m_p))
+        else:
+            cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
+            pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
+            heads = o.ec_mul_loss_weight * (emo_mul_loss + cau_mul_loss) + o.pair_mul_loss_weight * pair_mul_loss
         kl_e, kl_c = self._kl_terms(kl, iteration)
         reconstruction_loss = self._reconstruction(z, content_bow)
-        loss = (o.ecce_adv_loss_weight * (ec_entropy_loss + ce_entropy_loss) +
-                o.ec_mul_loss_weight * (emo_mul_loss + cau_mul_loss) + o.pair_mul_loss_weight * pair_mul_loss +
+        loss = (o.ecce_adv_loss_weight * (ec_entropy_loss + ce_entropy_loss) + heads +
                 kl_e + kl_c + reconstruction_loss)
         return ec_disc_loss, ce_disc_loss, loss
 

@@ -38,6 +38,13 @@ class MMDStatistic:
             return mmd, F.pairwise(s, s, 0, list(alphas), 1e-5)
         return mmd
 
+    def halves(self, z: torch.Tensor, alphas: Sequence[float]):
+        """self(z[:, :L], z[:, L:], alphas) for z = [sample_1 | sample_2] stored side by side (the head's latent
+        tensor): identical value, one [N, 2L] gradient instead of two sliced ones."""
+        if z.shape[0] != self.n_1 or self.n_1 != self.n_2 or z.shape[1] % 2:
+            raise ValueError("halves() needs z of shape [n, 2L] with n == n_1 == n_2")
+        return F.mmd_halves(z, z.shape[1] // 2, list(alphas))
+
     def pval(self, distances, n_permutations=1000):
         """Dead in the reference too: permutation_test_mat is a stub returning None (:599-600)."""
         return permutation_test_mat(distances, self.n_1, self.n_2, n_permutations,

@@ -148,6 +148,34 @@ int carel_hsic_bwd(const float* grad_out, int64_t m, int64_t dx, int64_t dy, flo
                    int64_t row_tile_begin, int64_t row_tile_end, float* grad_x, int64_t ldgx,
                    float* grad_y, int64_t ldgy, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Classifier heads — replaces get_emotion_mul_loss / get_cause_mul_loss / get_pair_mul_loss
+ * (drl_classifier_ec_mmd_final_mul.py:461-513; drl_classifier_ec_hsic.py:459-505 for emo_mode 1) and their weighted
+ * sum in the loss assembly (:256-261):
+ *   emotion: W_e (z_e (.) m_e) + b_e -> CrossEntropy over C_e classes (emo_mode 0, int64 labels [N]) or
+ *            sigmoid + BCELoss against y (1-ls) + ls / n_e (emo_mode 1, float labels [N]);
+ *   cause:   w_c . (z_c (.) m_c) + b_c -> sigmoid + BCELoss against y (1-ls) + ls / n_c;
+ *   pair:    w_p . (z (.) m_p) + b_p  -> BCEWithLogits(., y (1-ls) + ls / n_p, pos_weight = (N - sum y) / sum y),
+ *            an infinite pair loss is replaced by 0 if guard_inf (reference :510-511).
+ * z [N, 2L] = [z_e | z_c]; masks3 = {m_e [N,L], m_c [N,L], m_p [N,2L]}: dropout masks already scaled by 1/(1-p)
+ * (host array of three device pointers; NULL or NULL entries = no dropout); weights6 = {W_e [C_e,L], b_e [C_e],
+ * W_c [L], b_c [1], W_p [2L], b_p [1]} (host array of device pointers).  losses4 (device) = emotion, cause, pair and
+ * loss_weights3_host . (emotion, cause, pair).  The backward takes d/d(losses4[3]) and writes grad_z [N, 2L]
+ * (all three heads) and the six weight gradients (grad_weights6 entries may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+size_t carel_heads_workspace_bytes(int64_t N, int64_t C_e);
+int carel_heads_fwd(const float* z, int64_t ldz, int64_t N, int64_t L, int64_t C_e, int emo_mode,
+                    const float* const* masks3, const float* const* weights6, const void* emo_labels,
+                    const float* cau_labels, const float* pair_labels, float label_smoothing, float n_e,
+                    float n_c, float n_p, int guard_inf, const float* loss_weights3_host, float* losses4,
+                    void* ws, size_t ws_bytes, void* stream);
+int carel_heads_bwd(const float* grad_out, const float* z, int64_t ldz, int64_t N, int64_t L, int64_t C_e,
+                    int emo_mode, const float* const* masks3, const float* const* weights6,
+                    const void* emo_labels, const float* cau_labels, const float* pair_labels,
+                    float label_smoothing, float n_e, float n_c, float n_p, int guard_inf,
+                    const float* loss_weights3_host, float* grad_z, int64_t ldgz,
+                    float* const* grad_weights6, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

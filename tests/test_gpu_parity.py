@@ -341,3 +341,68 @@ def test_mmd_fp32_mode(n1, n2, d, alphas):
     gx, gy = torch.autograd.grad(out, (x, y))
     assert relv(out, ref) < 1e-5
     assert rel(gx, rgx) < 1e-5 and rel(gy, rgy) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# fused classifier heads (carel_heads_fwd/bwd) vs the reference's PyTorch formulas in fp64
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,L,Ce,mode,drop", [(1, 24, 6, 0, False), (64, 24, 6, 0, True), (300, 128, 6, 0, True),
+                                              (257, 64, 1, 1, True), (8192, 128, 6, 0, True), (40, 100, 3, 0, False)])
+def test_classifier_heads_vs_torch(N, L, Ce, mode, drop):
+    import torch.nn as nn
+    import torch.nn.functional as TF
+    torch.manual_seed(N + L)
+    z = torch.randn(N, 2 * L, device=DEV, requires_grad=True)
+    ec, cc, pc = nn.Linear(L, Ce).to(DEV), nn.Linear(L, 1).to(DEV), nn.Linear(2 * L, 1).to(DEV)
+    emo = torch.randint(0, Ce, (N, 1), device=DEV) if mode == 0 else (torch.rand(N, 1, device=DEV) < 0.4).float()
+    cau = (torch.rand(N, 1, device=DEV) < 0.5).float()
+    pair = (torch.rand(N, 1, device=DEV) < 0.3).float()
+    if N > 1:
+        pair[0], pair[1 % N] = 1.0, 0.0                     # both classes present: finite pos_weight
+    else:
+        pair[0] = 1.0
+    masks = None
+    if drop:
+        masks = tuple(TF.dropout(torch.ones(N, k, device=DEV), 0.5, True) for k in (L, L, 2 * L))
+    ls, n_e, n_c, n_p, w = 0.1, 1.0, 1.0, 1.0, (10.0, 7.0, 30.0)
+    total, parts = F.classifier_heads(z, masks, ec, cc, pc, emo, cau, pair, mode, ls, n_e, n_c, n_p, True, w)
+    total.backward()
+    got = [z.grad.clone()] + [p_.grad.clone() for m in (ec, cc, pc) for p_ in (m.weight, m.bias)]
+    # reference formulas (mmd:461-513 / hsic:459-505) in fp64
+    zd = z.detach().double().requires_grad_(True)
+    mods = [nn.Linear(L, Ce).to(DEV).double(), nn.Linear(L, 1).to(DEV).double(), nn.Linear(2 * L, 1).to(DEV).double()]
+    for md, ms in zip(mods, (ec, cc, pc)):
+        md.load_state_dict({k: v.double() for k, v in ms.state_dict().items()})
+    me, mc, mp = (m.double() for m in masks) if masks is not None else (1.0, 1.0, 1.0)
+    xe, xc, xp = mods[0](zd[:, :L] * me), mods[1](zd[:, L:] * mc), mods[2](zd * mp)
+    if mode == 0:
+        le = TF.cross_entropy(xe, emo.flatten())
+    else:
+        le = TF.binary_cross_entropy(torch.sigmoid(xe), emo.double() * (1 - ls) + ls / n_e)
+    lc = TF.binary_cross_entropy(torch.sigmoid(xc), cau.double() * (1 - ls) + ls / n_c)
+    pw = (len(pair) - pair.sum()) / pair.sum()
+    lp = TF.binary_cross_entropy_with_logits(xp, pair.double() * (1 - ls) + ls / n_p, pos_weight=pw.double())
+    ref = w[0] * le + w[1] * lc + w[2] * lp
+    ref.backward()
+    want = [zd.grad] + [p_.grad for m in mods for p_ in (m.weight, m.bias)]
+    assert relv(total, ref) < 1e-5
+    for a_, b_ in zip((le, lc, lp), parts[:3]):
+        assert relv(b_, a_) < 1e-5
+    for a_, b_ in zip(got, want):
+        assert rel(a_, b_) < 2e-5
+
+
+def test_classifier_heads_infinite_pair_loss_guard():
+    """No positive pair label: pos_weight = N / 0 = inf -> the reference replaces the infinite loss by 0 (mmd:510-511)."""
+    import torch.nn as nn
+    torch.manual_seed(3)
+    N, L = 32, 24
+    z = torch.randn(N, 2 * L, device=DEV, requires_grad=True)
+    ec, cc, pc = nn.Linear(L, 6).to(DEV), nn.Linear(L, 1).to(DEV), nn.Linear(2 * L, 1).to(DEV)
+    emo = torch.randint(0, 6, (N, 1), device=DEV)
+    cau = (torch.rand(N, 1, device=DEV) < 0.5).float()
+    pair = torch.zeros(N, 1, device=DEV)
+    total, parts = F.classifier_heads(z, None, ec, cc, pc, emo, cau, pair, 0, 0.1, 1.0, 1.0, 1.0, True, (1.0, 1.0, 1.0))
+    total.backward()
+    assert float(parts[2]) == 0.0 and torch.isfinite(total) and torch.isfinite(z.grad).all()
+    assert pc.weight.grad.abs().max().item() == 0.0
