@@ -135,7 +135,11 @@ def run_ours(args):
     pinned = {k: v.pin_memory() for k, v in host.items()}
     static = {k: v.to(dev) for k, v in host.items()}            # device-resident inputs (value) / H2D targets (e2e)
     params = model.get_params()
-    bucket = FlatGradBucket(params)
+    # N = 1: no bucket (autograd assigns fresh gradient tensors: no 31 MB zero-fill + accumulate per step).
+    # N > 1: one flat fp32 bucket -> ONE NCCL all-reduce (31 MB) between the fwd+bwd graph and the Adam graph.
+    # (Launching the decoder-weight slice from a post-accumulate hook inside the capture, to hide it under the rest
+    #  of the backward pass, dead-locked on this stack and is left for a later round.)
+    bucket = FlatGradBucket(params) if world > 1 else None
     # the four latent projections receive gradients but are not stepped (reference get_params, mmd:292-297)
     optim = torch.optim.Adam(params, lr=1e-5, capturable=True, fused=True)
     loss_buf = torch.zeros((), device=dev)
@@ -144,7 +148,11 @@ def run_ours(args):
     def make_stepper(target):
         """(eager step, graph-replaying step) for a BoW target given as static device tensor(s)."""
         def compute():
-            bucket.zero_()
+            if bucket is not None:
+                bucket.zero_()
+            else:
+                for p in params:
+                    p.grad = None
             for p in model.parameters():
                 if p.grad is not None and not any(p is q for q in params):
                     p.grad = None
@@ -157,7 +165,8 @@ def run_ours(args):
 
         def step():
             compute()
-            bucket.allreduce_mean()          # one flat NCCL all-reduce (no-op at N = 1)
+            if bucket is not None:
+                bucket.allreduce_mean()          # one flat NCCL all-reduce
             update()
 
         for _ in range(3):
