@@ -120,11 +120,11 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
   return 0;
 }
 
-template <int BN1>
+template <int BN1, int NB>
 static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, int n2_16, int t0, int t1,
                           float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy, int64_t n1, int64_t n2,
                           int64_t dim, cudaStream_t st) {
-  using Cfg = ChainCfg<1, BN1>;
+  using Cfg = ChainCfg<1, BN1, NB>;
   CUtensorMap ta, tb;
   CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.SA, M, ldp, ldp, 128) == 0, "carel_mmd_bwd: tensor map A failed");
   CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.SB, M, ldp, ldp, BN1) == 0, "carel_mmd_bwd: tensor map B failed");
@@ -138,7 +138,7 @@ static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, i
     CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_x, size_t(ldgx) * 4, 0, size_t(dim) * 4, size_t(n1), st));
     CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_y, size_t(ldgy) * 4, 0, size_t(dim) * 4, size_t(n2), st));
   }
-  return launch_chain<PolMmdBwd, 1, BN1>(ta, tb, ta, tb, s, pp, st, "mmd_gram_bwd");
+  return launch_chain<PolMmdBwd, 1, BN1, NB>(ta, tb, ta, tb, s, pp, st, "mmd_gram_bwd");
 }
 
 extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int64_t dim,
@@ -181,7 +181,11 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   (void)asum;
   pp.w_scale = 1.f;
   pp.inv_w_scale = 1.f;
-  return mmd_bwd_launch<128>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
+#ifdef CAREL_MMD_BWD_BN64
+  return mmd_bwd_launch<64, 4>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
+#else
+  return mmd_bwd_launch<128, 2>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
+#endif
 }
 
 #ifdef CAREL_CHAIN_TRACE
