@@ -12,12 +12,14 @@
 //   g = (p - t) / max(p (1-p), 1e-12) / (N V)   (torch's BCELoss backward),  s_i = sum_j g_ij p_ij,
 //   dlogit = p (g - s_i)  =  [u - p S_i] / (N V)  +  sparse,    u = p (p - c) / max(p (1-p), 1e-12).
 //
-// Operands are augmented: ZA = [z, -lse split(3), 1 1 1], WB = [w, 1 1 1, b split(3)], so the
-// accumulator is  log p_ij = z_i.w_j + b_j - lse_i  directly (lse columns are 0 during pass F).
-//   pass F  gemm_tc + EpiBowFused  ONE dense pass: per-row online max + power sums -> lse, dense loss, S_i
+// Operands: ZA = [z, -lse split(3), 1 1 1], WB = [w, 1 1 1, b split(3)] (bf16, pack_rows_kernel).  The tensor-core
+// passes use the PLAIN columns [0, K) and add b_j log2(e) / -lse_i log2(e) in the epilogue (K = 256 is four full
+// 64-wide TMA boxes); the augmented columns serve the O(nnz) sparse kernels, whose dot product ZA_i . WB_j is log p_ij.
+//   pass F  gemm_as + EpiBowFused  ONE dense pass: per-row running reference + power sums -> lse, dense loss, S_i
 //           (bow_combine_kernel); rows outside the series' range are flagged and redone exactly by
-//   pass 2  gemm_tc + EpiBowLoss   (skips every row tile without a flagged row)
-//   sparse  bow_sparse_kernel     corrections of loss, S_i (fwd) and of dZ, dW, db (bwd)
+//   pass 2  gemm_as + EpiBowLoss   (skips every row tile without a flagged row: normally all of them)
+//   sparse  bow_sparse_kernel      corrections of loss and S_i (fwd); bow_sparse_dz / bow_sparse_dw gathers (bwd),
+//                                  which also initialise grad_z / grad_w / grad_b
 //   pass 3  chain_tc + PolBowBwdW  owner = vocabulary tile: dlogit tile -> bf16 (TMEM only), dW += dlogit^T Z, db
 //   pass 4  chain_tc + PolBowBwdZ  owner = clause tile:     dlogit tile recomputed,          dZ += dlogit W_d
 #include <algorithm>
@@ -148,13 +150,14 @@ static __global__ void bow_pack_ell_kernel(const float* __restrict__ bow, int64_
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass F epilogue (the ONE dense forward pass): per row and per 64-column part, with m = running max,
-//   T_k = sum_j exp(k (x_ij - m)), k = 1..4,   and   mn = min_j x_ij.
+// pass F epilogue (the ONE dense forward pass): per row and per 64-column part, with y = log2-domain logit
+// (acc log2 e + b_j log2 e) and m = a running reference (moved when a chunk maximum exceeds it by more than 2^8):
+//   T_k = sum_j 2^(k (y_ij - m)), k = 1..4,   and   mn = min_j y_ij.
 // From these the combine kernel gets lse_i, the power sums S_k = sum_j p_ij^k = T_k / T_1^k and with them
 //   sum_j log1p(-p) = -(S1 + S2/2 + S3/3 + S4/4 + ...),   sum_j (p - c)/(1 - p) = (S1+S2+S3+S4+..) - c (V + S1+S2+S3+..)
-// (S1 = 1), valid to 2^-20 whenever max_j p_ij < 2^-5; rows beyond that (or with a clamped log) are flagged
-// and redone exactly by the EpiBowLoss pass.  Hot loop per PAIR of elements: FFMA2, 2 MUFU.EX2, FMUL2,
-// 2 FADD2, 2 FFMA2 and one FMNMX3 each for max and min.
+// (S1 = 1), valid to 2^-20 whenever max_j p_ij < 2^-5 (certified by S4 < 2^-20); rows beyond that (or with a
+// clamped log) are flagged and redone exactly by the EpiBowLoss pass.  Hot loop per PAIR of elements: FFMA2 (y),
+// FADD2 (y - m), 2 MUFU.EX2 issued before the chunk's max / min chains, FMUL2, 2 FADD2, 2 FFMA2, 2 x 1/2 FMNMX3.
 // ---------------------------------------------------------------------------------------------
 struct EpiBowFusedParams {
   float4* part4;   // [ntp][Npad]  (m, T1, T2, T3)     m, mn in log2 units
