@@ -165,3 +165,28 @@ def test_train_steps_reduce_loss():
     assert losses[-1] < losses[0]
     assert all(p.grad is not None for p in model.emotion_mu.parameters())   # projections receive gradients ...
     assert not any(p is q for p in model.get_params() for q in model.emotion_mu.parameters())  # ... but are not stepped
+
+
+def test_full_size_mmd_head_step_matches_oracle():
+    """BASELINE configs[1] at its real size (N = 8192 clauses, d = 768, latent 128, vocab 30000, dropout off):
+    loss and gradients of one forward/backward against the fp64 oracle."""
+    variant, N, L, V, D = "mmd", 8192, 128, 30000, 768
+    opt, model, b = _setup(variant, N, L, V, D, 0.0, seed=5)
+    model.train()
+    X = b["X"].clone().requires_grad_(True)
+    torch.manual_seed(99)
+    loss = model(X, None, None, b["emo"], b["cau"], b["pair"], b["bow"], 3)
+    params = dict(model.named_parameters())
+    grads = torch.autograd.grad(loss, [X] + list(params.values()), allow_unused=True)
+    p64 = {k: v.detach().double().requires_grad_(True) for k, v in params.items()}
+    X64 = b["X"].double().requires_grad_(True)
+    torch.manual_seed(99)
+    ref = ho.HeadOracle(opt, variant).forward(p64, X64, b["emo"], b["cau"].double(), b["pair"].double(),
+                                              b["bow"].double(), 3)
+    rgrads = torch.autograd.grad(ref, [X64] + list(p64.values()), allow_unused=True)
+    assert rel(loss.detach(), ref.detach()) < 1e-4
+    assert rel(grads[0], rgrads[0]) < 2e-3, ("grad X", rel(grads[0], rgrads[0]))
+    for (k, g), r in zip(zip(params.keys(), grads[1:]), rgrads[1:]):
+        if r is None:
+            continue
+        assert rel(g, r) < 2e-3, (k, rel(g, r))

@@ -406,3 +406,31 @@ def test_classifier_heads_infinite_pair_loss_guard():
     total.backward()
     assert float(parts[2]) == 0.0 and torch.isfinite(total) and torch.isfinite(z.grad).all()
     assert pc.weight.grad.abs().max().item() == 0.0
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json's full decoder size (N = 8192 clauses, 2L = 256, V = 30000): every row tile, the stream-K unit
+# ranges of both backward chains (each CTA spans several owner tiles) and the partial combine at their real shapes
+# ------------------------------------------------------------------------------------------
+def test_bow_full_size_vs_oracle():
+    torch.manual_seed(11)
+    N, K, V = 8192, 256, 30000
+    Z = bf(torch.randn(N, K, device=DEV) * 1.1).requires_grad_(True)
+    W = bf((torch.rand(V, K, device=DEV) * 2 - 1) / K ** 0.5).requires_grad_(True)
+    b = bf((torch.rand(V, device=DEV) * 2 - 1) / K ** 0.5).requires_grad_(True)
+    bow = ho.synthetic_batch(N, V, D=8, nnz=24, seed=2, device=DEV)["bow"]
+    loss = F.bow_reconstruction_loss(Z, W, b, bow, 0.1)
+    loss.backward()
+    # fp64 oracle in row blocks (the [N, V] fp64 intermediates of one shot would be ~20 GB)
+    Zd, Wd, bd = (t.detach().double().requires_grad_(True) for t in (Z, W, b))
+    ref = torch.zeros((), dtype=torch.float64, device=DEV)
+    for r0 in range(0, N, 1024):
+        # ho.bow_reconstruction takes the mean over its block: re-weight to the mean over all N rows
+        part = ho.bow_reconstruction(Zd[r0:r0 + 1024], Wd, bd, bow[r0:r0 + 1024].double(), 0.1) * (1024 / N)
+        part.backward()
+        ref = ref + part.detach()
+    assert relv(loss, ref) < 1e-5
+    assert rel(Z.grad, Zd.grad) < 1e-3 and rel(W.grad, Wd.grad) < 1e-3 and rel(b.grad, bd.grad) < 1e-3
+    # size-independent property: the loss is invariant under a shift of all logits of a row (softmax), so the
+    # gradient w.r.t. the bias sums to zero over the vocabulary
+    assert abs(float(b.grad.double().sum())) < 1e-6 * float(b.grad.double().abs().sum())
