@@ -175,10 +175,17 @@ struct EpiMMD {
       float s = 0.f;
       if (p.n_alpha == 1) {
         const float sc = p.a_scale[0], sh = p.a_shift[0];
-        for_each_chunk16(taddr, HALF / 16, [&](int, const uint32_t (&r)[16]) {
+        float s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent accumulation chains
+        for_each_chunk32(taddr, HALF / 32, [&](int, const uint32_t (&r)[32]) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) s += ex2_approx(fmaf(fabsf(__uint_as_float(r[i])), sc, sh));
+          for (int i = 0; i < 32; i += 4) {
+            s += ex2_approx(fmaf(fabsf(__uint_as_float(r[i])), sc, sh));
+            s1 += ex2_approx(fmaf(fabsf(__uint_as_float(r[i + 1])), sc, sh));
+            s2 += ex2_approx(fmaf(fabsf(__uint_as_float(r[i + 2])), sc, sh));
+            s3 += ex2_approx(fmaf(fabsf(__uint_as_float(r[i + 3])), sc, sh));
+          }
         });
+        s += (s1 + s2) + s3;
       } else {
         for_each_chunk16(taddr, HALF / 16, [&](int, const uint32_t (&r)[16]) {
 #pragma unroll

@@ -321,4 +321,21 @@ CAREL_DEVINL void for_each_chunk16(uint32_t taddr, int n16, F&& f) {
   }
 }
 
+// Same walk in chunks of 32 columns (tcgen05.ld 32x32b.x32): half as many TMEM loads / waits per tile, for
+// epilogues light enough to keep two 32-register buffers.  n32 must be even.
+template <class F>
+CAREL_DEVINL void for_each_chunk32(uint32_t taddr, int n32, F&& f) {
+  uint32_t ra[32], rb[32];
+  tmem_ld32(taddr, ra);
+#pragma unroll 1
+  for (int c = 0; c < n32; c += 2) {
+    tmem_ld_wait();
+    tmem_ld32(taddr + (c + 1) * 32, rb);
+    f(c, ra);
+    tmem_ld_wait();
+    if (c + 2 < n32) tmem_ld32(taddr + (c + 2) * 32, ra);
+    f(c + 1, rb);
+  }
+}
+
 }  // namespace carel

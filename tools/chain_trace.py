@@ -14,7 +14,12 @@ idx = torch.randint(0, V, (n, 24), device="cuda")
 bow = torch.zeros(n, V, device="cuda")
 bow.scatter_add_(1, idx, torch.ones(n, 24, device="cuda"))
 bow = bow / bow.sum(1, keepdim=True).clamp_min(1)
-if which == "mmd":
+if which == "mmdfwd":
+    x = torch.tanh(torch.randn(n, d, device="cuda"))
+    y = torch.tanh(torch.randn(n, d, device="cuda"))
+    for _ in range(2):
+        F.mmd(x, y, [0.1])
+elif which == "mmd":
     x = torch.tanh(torch.randn(n, d, device="cuda")).requires_grad_(True)
     y = torch.tanh(torch.randn(n, d, device="cuda")).requires_grad_(True)
     for _ in range(2):
@@ -27,16 +32,16 @@ else:
 torch.cuda.synchronize()
 lib = C.CDLL("carel_vae_b200/libcarel_head.so")
 buf = (C.c_longlong * (8 * 256))()
-assert (lib.carel_debug_chain_trace_mmd if which == 'mmd' else lib.carel_debug_chain_trace)(buf) == 0
+assert (lib.carel_debug_chain_trace_mmd if which.startswith('mmd') else lib.carel_debug_chain_trace)(buf) == 0
 ev = [[buf[s * 256 + i] for i in range(256)] for s in range(8)]
 t0 = min(v for v in ev[0] if v > 0)
-if which == "fwd":
+if which in ("fwd", "mmdfwd"):
     names = ["tile_load", "mma_start", "mma_issued", "epi_start", "epi_done", "-", "-", "-"]
 else:
   names = ["load_issue", "g1_issue", "g2_issue", "epi_acc1_ready", "epi_ld_done", "epi_p_arrive", "g1_issued", "g2_issued"]
 print("tile " + " ".join(f"{n:>14s}" for n in names))
-for i in list(range(0, 8)) + (list(range(20, 40)) if which == 'fwd' else list(range(100, 112))):
+for i in list(range(0, 8)) + (list(range(8, 29)) if which in ('fwd', 'mmdfwd') else list(range(100, 112))):
     print(f"{i:4d} " + " ".join(f"{ev[s][i] - t0:14d}" for s in range(8)))
 for s in range(8):
-    d_ = [ev[s][i + 1] - ev[s][i] for i in (range(10, 45) if which == 'fwd' else range(20, 100))]
+    d_ = [ev[s][i + 1] - ev[s][i] for i in (range(4, 26) if which in ('fwd', 'mmdfwd') else range(20, 100))]
     print(names[s], "mean period", sum(d_) / len(d_))
