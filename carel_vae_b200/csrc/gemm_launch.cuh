@@ -1,6 +1,7 @@
 // gemm_launch.cuh — host-side launcher of gemm_tc_kernel (persistent grid = min(items, #SM)).
 #pragma once
 #include "api_common.cuh"
+#include "gemm_2sm.cuh"
 #include "gemm_as.cuh"
 #include "gemm_tc.cuh"
 
@@ -52,6 +53,23 @@ int launch_gemm_as(const CUtensorMap& a, const CUtensorMap& b, const AsSched& s,
   if (grid <= 0) return 0;
   timing_begin(tag, st);
   kern<<<grid, kGemmThreads, kAsSmemBytes, st>>>(a, b, s, ep);
+  timing_end(st);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
+template <class Epi>
+int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, const PairSched& s, const typename Epi::Params& ep,
+                    cudaStream_t st, const char* tag = "gemm_2sm") {
+  auto kern = gemm_2sm_kernel<Epi>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    attr_done = true;
+  }
+  if (s.total <= 0) return 0;
+  timing_begin(tag, st);
+  kern<<<2 * s.clusters, kGemmThreads, kPairSmemBytes, st>>>(a, b, s, ep);     // __cluster_dims__(2, 1, 1)
   timing_end(st);
   CAREL_LAUNCHED();
   return 0;

@@ -113,6 +113,10 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
     // short K (latent-sized samples): A-stationary schedule, only the column operand is streamed
     AsSched as = make_as_sched(M, M, ldp, sm_count(), tri, t0, t1);
     if (int rc = launch_gemm_as<EpiMMD<256>>(ta, tb, as, ep, st, "mmd_gram_fwd")) return rc;
+  } else if ((t0 & 1) == 0 && ((t1 & 1) == 0 || t1 == s.m_tiles) && !(flags & CAREL_MMD_NO_PAIRS)) {
+    // long K (the d = 768 Gram sweep): CTA pairs, one M = 256 UMMA across two SMs (gemm_2sm.cuh)
+    PairSched ps = make_pair_sched(M, M, ldp, tri, t0, t1, sm_count());
+    if (int rc = launch_gemm_2sm<EpiMMD<256>>(ta, tb, ps, ep, st, "mmd_gram_fwd")) return rc;
   } else if (int rc = launch_gemm<EpiMMD<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st, "mmd_gram_fwd")) {
     return rc;
   }

@@ -6,6 +6,7 @@ the memory and the stream.  Tensors must live on a CUDA device — there is no C
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Sequence
 
 import torch
@@ -133,7 +134,7 @@ def mmd(sample_1: torch.Tensor, sample_2: torch.Tensor, alphas: Sequence[float],
         full_gram: bool = False, precision: str | None = None) -> torch.Tensor:
     """Unbiased multi-bandwidth RBF MMD^2 (reference MMDStatistic.__call__,
     drl_classifier_ec_mmd_final_mul.py:547-569).  0-dim fp32 tensor, differentiable w.r.t. both samples."""
-    flags = 1 if full_gram else 0
+    flags = (1 if full_gram else 0) | (2 if os.environ.get("CAREL_MMD_NO_PAIRS") else 0)
     return _MMDFn.apply(sample_1, sample_2, tuple(alphas), eps, flags, (0, -1), _lib.precision_code(precision))
 
 

@@ -28,6 +28,7 @@ extern "C" {
 
 /* flags */
 #define CAREL_MMD_FULL_GRAM 1 /* compute all (2N)^2 entries like the reference instead of j > i */
+#define CAREL_MMD_NO_PAIRS 2 /* long-K Gram on single CTAs (gemm_tc) instead of cta_group::2 pairs (debug / A-B) */
 #define CAREL_BF16 0
 #define CAREL_FP32 1
 
