@@ -323,12 +323,12 @@ def run_ours(args):
             ms = rep["mmd_gram_fwd"][0] / rep["mmd_gram_fwd"][1]
             res[name] = ms
         achieved = GRAM_FLOPS / (res["triangular"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiMMD> (MMD Gram forward, N=8192, d=768, j>i schedule)",
+        roof = {"bound": "tensor", "kernel": "gemm_2sm_kernel<EpiMMD> (MMD Gram forward on CTA pairs, N=8192, d=768, j>i schedule)",
                 "achieved": round(achieved, 1), "peak": pk["bf16_burst"], "unit": "TFLOP/s",
                 "frac": round(achieved / pk["bf16_burst"], 3),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                # (profiles/r01_final_ncu_summary.txt): 51.47 MB + 0.56 MB per launch; algorithmic 2 x 25.7 MB operands
-                "traffic": 52.03e6, "traffic_unit": "bytes/launch (ncu, profiles/r01_final_ncu_summary.txt)",
+                # (profiles/r01_final_ncu_summary.txt): 51.47 MB + 0.90 MB per launch; algorithmic 2 x 25.7 MB operands
+                "traffic": 52.37e6, "traffic_unit": "bytes/launch (ncu, profiles/r01_final_ncu_summary.txt)",
                 "peak_source": pk["source"],
                 "note": "algorithmic FLOPs = 2*(2N)^2*d (full Gram, SURVEY §8d); the kernel executes the j>i half, "
                         "so executed-FLOP tensor utilisation is ~half of frac; full_gram variant below executes all of it",
