@@ -45,6 +45,10 @@ def balanced_tri_ranges(n_rows: int, world: int, tile: int = 128, col_tile: int 
             t1 += 1
         if r == world - 1:
             t1 = tiles
+        elif (t1 & 1) and t1 < tiles:
+            # keep rank boundaries on 256-row (CTA-pair) tiles: the long-K Gram kernel pairs two row tiles
+            acc += work[t1]
+            t1 += 1
         ranges.append((t0, t1))
         t0 = t1
     return ranges
