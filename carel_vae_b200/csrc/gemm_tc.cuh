@@ -48,7 +48,7 @@ struct GemmSched {
   int mode;       // TileMode; TILE_TRI requires BN == 256 and a square problem
   int num_items;  // total work items
   int m_tile0;    // first row tile owned by this launch (row-block sharding across GPUs)
-  int tri_rows;   // TILE_TRI: number of row tiles of this launch
+  int tri_rows;   // number of row tiles of this launch (m_tiles unless a row block [m_tile0, m_tile0 + tri_rows) is set)
   int n_cols;     // if > 0: logical N; the last column tile issues a narrower MMA (multiple of 16)
   const int* row_tile_flags;  // optional (device): flags[0] = any work at all, flags[1 + tm] = process row tile tm
 };
@@ -86,8 +86,12 @@ struct TileIter {
     const int tile = item / s.ksplit;
     const int ks = item - tile * s.ksplit;
     if (s.mode == TILE_FULL) {
-      tm = tile / s.n_tiles;
-      tn = tile - tm * s.n_tiles;
+      // bands of kTriBand row tiles, column tile outermost inside a band (same L2 argument as below)
+      const int band_tiles = kTriBand * s.n_tiles;
+      const int b = tile / band_tiles, l = tile - b * band_tiles;
+      const int r0 = b * kTriBand, nr = min(kTriBand, s.tri_rows - r0);
+      tn = l / nr;
+      tm = r0 + (l - tn * nr);
     } else {
       int c = band_count(band);
       while (tile >= band_base + c) {

@@ -276,6 +276,7 @@ extern "C" int carel_hsic_fwd(const float* x, int64_t ldx, const float* y, int64
   const int t1 = int((row_tile_end < 0 || row_tile_end > s.m_tiles) ? s.m_tiles : row_tile_end);
   CAREL_REQUIRE(t0 <= t1, "carel_hsic_fwd: bad row tile range");
   s.m_tile0 = t0;
+  s.tri_rows = t1 - t0;
   s.num_items = (t1 - t0) * s.n_tiles;
   EpiHsicParams ep;
   ep.rK = w.rK; ep.rL = w.rL; ep.acc = w.acc; ep.m = int(m);

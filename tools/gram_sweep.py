@@ -22,7 +22,9 @@ if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
 D = 768
-sizes = [int(a) for a in sys.argv[1:]] or [4096, 8192, 16384, 32768, 65536, 131072]
+hsic_mode = "--hsic" in sys.argv
+sizes = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or ([4096, 8192, 16384, 32768, 65536] if hsic_mode else
+                                                                    [4096, 8192, 16384, 32768, 65536, 131072])
 ref = {}
 for N in sizes:
     g = torch.Generator(device="cpu").manual_seed(N)
@@ -33,8 +35,10 @@ for N in sizes:
         for r0 in range(0, N, 16384):
             blk = torch.tanh(torch.randn(min(16384, N - r0), D, generator=g))
             t[r0:r0 + blk.shape[0]] = (blk / blk.norm(dim=1, keepdim=True)).to(dev)
+    sig = 2.0                      # unit-norm rows: squared distances in [0, 4]
+    fn = (lambda: par.sharded_hsic(x, y, sig, sig)) if hsic_mode else (lambda: par.sharded_mmd(x, y, [0.1]))
     for _ in range(2):
-        v = par.sharded_mmd(x, y, [0.1])
+        v = fn()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier(device_ids=[local])
@@ -42,16 +46,16 @@ for N in sizes:
     reps = 5 if N <= 32768 else 2
     e0.record()
     for _ in range(reps):
-        v = par.sharded_mmd(x, y, [0.1])
+        v = fn()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
-        flops = 2.0 * (2 * N) ** 2 * D
-        print(json.dumps({"metric": "mmd_gram_sweep", "N": N, "d": D, "n_gpus": world, "ms": round(float(ms), 3),
-                          "algorithmic_tflops": round(flops / (float(ms) * 1e-3) / 1e12, 1), "mmd": float(v),
+        flops = 2.0 * 2.0 * N ** 2 * D if hsic_mode else 2.0 * (2 * N) ** 2 * D     # HSIC: two N x N Grams
+        print(json.dumps({"metric": "hsic_gram_sweep" if hsic_mode else "mmd_gram_sweep", "N": N, "d": D, "n_gpus": world, "ms": round(float(ms), 3),
+                          "algorithmic_tflops": round(flops / (float(ms) * 1e-3) / 1e12, 1), "value": float(v),
                           "includes": "pack of both samples to bf16 + Gram tiles (j>i schedule) + all-reduce + finalize"}),
               flush=True)
     del x, y
