@@ -755,17 +755,30 @@ static __global__ void bow_sparse_dz_kernel(const __nv_bfloat16* __restrict__ WB
     if (n > cap) continue;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const bool act = lane * 8 < K;
-    for (int q = 0; q < n; ++q) {
-      const int j = __ldg(cols + size_t(r) * cap + q);
-      const float e = __ldg(ev + size_t(r) * cap + q);
-      if (act) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(WB + size_t(j) * ldk) + lane);
-        const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+    // the lanes fetch the (column, weight) pairs of the row once; the gather then keeps FOUR decoder rows in flight
+    for (int base = 0; base < n; base += 32) {
+      const int cnt = min(32, n - base);
+      const int my_j = (lane < cnt) ? __ldg(cols + size_t(r) * cap + base + lane) : 0;
+      const float my_e = (lane < cnt) ? __ldg(ev + size_t(r) * cap + base + lane) : 0.f;
+      for (int q4 = 0; q4 < cnt; q4 += 4) {
+        uint4 w[4];
+        float e[4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
-          acc[2 * h] = fmaf(e, f.x, acc[2 * h]);
-          acc[2 * h + 1] = fmaf(e, f.y, acc[2 * h + 1]);
+        for (int u = 0; u < 4; ++u) {
+          const int src = (q4 + u) & 31;
+          const int j = __shfl_sync(0xffffffffu, my_j, src);
+          e[u] = (q4 + u < cnt) ? __shfl_sync(0xffffffffu, my_e, src) : 0.f;
+          w[u] = act ? __ldg(reinterpret_cast<const uint4*>(WB + size_t(j) * ldk) + lane) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t v[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[h]));
+            acc[2 * h] = fmaf(e[u], f.x, acc[2 * h]);
+            acc[2 * h + 1] = fmaf(e[u], f.y, acc[2 * h + 1]);
+          }
         }
       }
     }
@@ -793,18 +806,30 @@ static __global__ void bow_sparse_dw_kernel(const __nv_bfloat16* __restrict__ ZA
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float esum = 0.f;
     const bool act = lane * 8 < K;
-    for (int pz = p0; pz < p1; ++pz) {
-      const int r = __ldg(csc_row + pz);
-      const float e = __ldg(ev + __ldg(csc_slot + pz));
-      esum += e;
-      if (act) {
-        const uint4 z = __ldg(reinterpret_cast<const uint4*>(ZA + size_t(r) * ldk) + lane);
-        const uint32_t u[4] = {z.x, z.y, z.z, z.w};
+    for (int base = p0; base < p1; base += 32) {
+      const int cnt = min(32, p1 - base);
+      const int my_r = (lane < cnt) ? __ldg(csc_row + base + lane) : 0;
+      const float my_e = (lane < cnt) ? __ldg(ev + __ldg(csc_slot + base + lane)) : 0.f;
+      for (int q4 = 0; q4 < cnt; q4 += 4) {
+        uint4 z[4];
+        float e[4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
-          acc[2 * h] = fmaf(e, f.x, acc[2 * h]);
-          acc[2 * h + 1] = fmaf(e, f.y, acc[2 * h + 1]);
+        for (int u = 0; u < 4; ++u) {
+          const int src = (q4 + u) & 31;
+          const int r = __shfl_sync(0xffffffffu, my_r, src);
+          e[u] = (q4 + u < cnt) ? __shfl_sync(0xffffffffu, my_e, src) : 0.f;
+          z[u] = act ? __ldg(reinterpret_cast<const uint4*>(ZA + size_t(r) * ldk) + lane) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          esum += e[u];
+          const uint32_t v[4] = {z[u].x, z[u].y, z[u].z, z[u].w};
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[h]));
+            acc[2 * h] = fmaf(e[u], f.x, acc[2 * h]);
+            acc[2 * h + 1] = fmaf(e[u], f.y, acc[2 * h + 1]);
+          }
         }
       }
     }
