@@ -257,36 +257,37 @@ struct EpiBowFused {
   CAREL_DEVINL void finish() {}
 };
 
-// b log2(e) for the backward chains (zero padded to a multiple of 64)
-static __global__ void bow_bias_kernel(const float* __restrict__ b, int V, int Vpad, float* __restrict__ bl2e) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < Vpad) bl2e[j] = (j < V) ? __ldg(b + j) * kLog2e : 0.f;
-}
-
-// column sums of the packed decoder operand WB [V, ldk] (bf16 -> fp32): sum_j x_ij = ZA_i . wsum
-// block = (ldk/2 pair columns rounded to 32) x 4 row lanes; grid-stride over rows, one atomicAdd per column and block
-static __global__ void bow_colsum_kernel(const __nv_bfloat16* __restrict__ WB, int V, int ldk,
-                                         float* __restrict__ wsum) {
-  extern __shared__ float2 sh_cs[];          // [blockDim.y][blockDim.x]
-  const int w = threadIdx.x;                 // bf16 pair index
-  const bool act = w * 2 < ldk;
-  float2 acc = make_float2(0.f, 0.f);
-  if (act) {
+// Column sums of the packed decoder operand WB [V, ldk] (bf16 -> fp32: sum_j x_ij = ZA_i . wsum) and
+// bl2e[j] = b_j log2(e) (zero padded to a multiple of 64) for the plain-operand passes, in one launch.
+// Block = (ldk / 8 chunks of 8 bf16) x 16 row lanes, 128-bit loads; one atomicAdd per column and block.
+static __global__ void bow_colsum_bias_kernel(const __nv_bfloat16* __restrict__ WB, int V, int ldk,
+                                              float* __restrict__ wsum, const float* __restrict__ b, int Vpad,
+                                              float* __restrict__ bl2e) {
+  extern __shared__ float sh_cs[];           // [blockDim.y][ldk]
+  const int nx = ldk >> 3;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
+  for (int j = blockIdx.x * nthreads + tid; j < Vpad; j += gridDim.x * nthreads)
+    bl2e[j] = (j < V) ? __ldg(b + j) * kLog2e : 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (threadIdx.x < nx) {
     for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < V; r += gridDim.x * blockDim.y) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(WB + size_t(r) * ldk + 2 * w));
-      acc.x += f.x;
-      acc.y += f.y;
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(WB + size_t(r) * ldk) + threadIdx.x);
+      const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
+        acc[2 * h] += f.x;
+        acc[2 * h + 1] += f.y;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sh_cs[threadIdx.y * ldk + threadIdx.x * 8 + i] = acc[i];
   }
-  sh_cs[threadIdx.y * blockDim.x + w] = acc;
   __syncthreads();
-  if (threadIdx.y == 0 && act) {
-    for (int y = 1; y < blockDim.y; ++y) {
-      acc.x += sh_cs[y * blockDim.x + w].x;
-      acc.y += sh_cs[y * blockDim.x + w].y;
-    }
-    atomicAdd(wsum + 2 * w, acc.x);
-    atomicAdd(wsum + 2 * w + 1, acc.y);
+  for (int k = tid; k < ldk; k += nthreads) {
+    float t = 0.f;
+    for (int y = 0; y < blockDim.y; ++y) t += sh_cs[y * ldk + k];
+    atomicAdd(wsum + k, t);
   }
 }
 
@@ -1105,11 +1106,6 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   CAREL_LAUNCHED();
   pack_rows_kernel<<<int(std::min<int64_t>((V + 7) / 8, 148 * 32)), 256, 0, st>>>(dec_w, int(V), int(K), int(K), nullptr, w.WB, w.ldk, 0, 1, nullptr, dec_b);
   CAREL_LAUNCHED();
-  {
-    const int Vpad = int(round_up64(V, 64));
-    bow_bias_kernel<<<(Vpad + 255) / 256, 256, 0, st>>>(dec_b, int(V), Vpad, w.bl2e);
-    CAREL_LAUNCHED();
-  }
   // ---- sparse target ----
   if (ell_cols_in != nullptr) {
     CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_cols, ell_cols_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, st));
@@ -1124,8 +1120,9 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.wsum, 0, size_t(w.ldk) * 4, st));
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.tile_flag, 0, (size_t(w.Npad / 128) + 1) * 4, st));
   {
-    const dim3 blk((w.ldk / 2 + 31) / 32 * 32, 4);
-    bow_colsum_kernel<<<148 * 4, blk, blk.x * blk.y * sizeof(float2), st>>>(w.WB, int(V), w.ldk, w.wsum);
+    const dim3 blk((w.ldk / 8 + 7) / 8 * 8, 16);
+    bow_colsum_bias_kernel<<<148 * 2, blk, size_t(blk.y) * w.ldk * sizeof(float), st>>>(
+        w.WB, int(V), w.ldk, w.wsum, dec_b, int(round_up64(V, 64)), w.bl2e);
   }
   CAREL_LAUNCHED();
   // plain operands (columns [0, K) of ZA / WB) through the A-stationary GEMM: bias is added in the epilogue
