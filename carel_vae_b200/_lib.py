@@ -26,6 +26,8 @@ _SIGNATURES = {
     "carel_timing_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "carel_gemm_bf16": (C.c_int, [c_ptr, i64, C.c_int, c_ptr, i64, C.c_int, i64, i64, i64, c_ptr, i64,
                                   c_ptr, C.c_int, c_ptr]),
+    "carel_gemm_bf16_2sm": (C.c_int, [c_ptr, i64, C.c_int, c_ptr, i64, C.c_int, i64, i64, i64, c_ptr, i64,
+                                      c_ptr, C.c_int, c_ptr]),
     "carel_mmd_workspace_bytes": (C.c_size_t, [i64, i64, i64, C.c_int]),
     "carel_mmd_fwd": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.POINTER(C.c_float), C.c_int,
                                 C.c_float, C.c_int, i64, i64, c_ptr, c_ptr, c_ptr, C.c_size_t, C.c_int, c_ptr]),

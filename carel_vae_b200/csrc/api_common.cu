@@ -116,6 +116,31 @@ extern "C" int carel_gemm_bf16(const void* a, int64_t lda, int a_mn, const void*
   return launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st);
 }
 
+// Same product on CTA pairs (gemm_2sm.cuh, cta_group::2); tiles of 256 x 256, optional split-K.
+extern "C" int carel_gemm_bf16_2sm(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb,
+                                   int b_mn, int64_t M, int64_t N, int64_t K, float* c, int64_t ldc,
+                                   const float* bias, int ksplit, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(M > 0 && N > 0 && K > 0, "carel_gemm_bf16_2sm: empty problem");
+  CAREL_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, "carel_gemm_bf16_2sm: lda/ldb must be multiples of 8");
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = make_tmap_bf16_sw128(&ta, a, M, K, lda, 128);
+  else rc = make_tmap_bf16_sw128(&ta, a, K, M, lda, 64);
+  CAREL_REQUIRE(rc == 0, "carel_gemm_bf16_2sm: tensor map A failed (%d)", rc);
+  if (!b_mn) rc = make_tmap_bf16_sw128(&tb, b, N, K, ldb, 128);
+  else rc = make_tmap_bf16_sw128(&tb, b, K, N, ldb, 64);
+  CAREL_REQUIRE(rc == 0, "carel_gemm_bf16_2sm: tensor map B failed (%d)", rc);
+  PairSched s = make_pair_sched(M, N, K, 0, 0, int((M + 127) / 128), sm_count(), ksplit);
+  EpiStore<256>::Params ep;
+  ep.out = c; ep.bias = bias; ep.out_bf16 = nullptr; ep.M = int(M); ep.N = int(N);
+  ep.ld = int(ldc); ep.ld_bf16 = 0; ep.atomic = s.ksplit > 1; ep.scale = 1.f;
+  if (!a_mn && !b_mn) return launch_gemm_2sm<EpiStore<256>, false, false>(ta, tb, s, ep, st);
+  if (!a_mn && b_mn) return launch_gemm_2sm<EpiStore<256>, false, true>(ta, tb, s, ep, st);
+  if (a_mn && !b_mn) return launch_gemm_2sm<EpiStore<256>, true, false>(ta, tb, s, ep, st);
+  return launch_gemm_2sm<EpiStore<256>, true, true>(ta, tb, s, ep, st);
+}
+
 // ------------------------------------------------------------------------------------------
 // dense pairwise matrices (API completeness; materialises [n1, n2])
 // ------------------------------------------------------------------------------------------

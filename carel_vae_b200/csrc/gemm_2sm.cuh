@@ -25,7 +25,8 @@ struct PairSched {
   int n_tiles;            // 256-column tiles
   int tri;                // 1: only tiles on / above the diagonal (tn >= pair-row index)
   int num_k16;            // K in 16-wide steps
-  int total;              // scheduled pair tiles
+  int ksplit;             // split-K factor (items = pair tiles x ksplit; the epilogue then accumulates atomically)
+  int total;              // scheduled items
   int clusters;           // persistent grid = 2 * clusters CTAs
 };
 
@@ -39,7 +40,7 @@ constexpr int kPairBand = 4;                     // pair-row tiles per band (col
 struct PairIter {
   const PairSched& s;
   int item, band, band_base;
-  int pm, tn;
+  int pm, tn, kb0, kb1;
   CAREL_DEVINL explicit PairIter(const PairSched& s_) : s(s_), item(blockIdx.x >> 1), band(0), band_base(0) {}
   CAREL_DEVINL int first_tn(int p) const { return s.tri ? (s.p_tile0 + p) : 0; }
   CAREL_DEVINL int band_count(int b) const {
@@ -50,13 +51,14 @@ struct PairIter {
   }
   CAREL_DEVINL bool next() {
     if (item >= s.total) return false;
+    const int tile = item / s.ksplit, ks = item - tile * s.ksplit;
     int c = band_count(band);
-    while (item >= band_base + c) {
+    while (tile >= band_base + c) {
       band_base += c;
       ++band;
       c = band_count(band);
     }
-    int l = item - band_base;
+    int l = tile - band_base;
     const int r0 = band * kPairBand, nr = min(kPairBand, s.p_tiles - r0), last = r0 + nr - 1;
     const int fl = first_tn(last), cmin = s.n_tiles - fl;
     if (l < nr * cmin) {
@@ -74,12 +76,15 @@ struct PairIter {
       }
     }
     pm += s.p_tile0;
+    const int num_kb = (s.num_k16 + 3) >> 2, per = (num_kb + s.ksplit - 1) / s.ksplit;
+    kb0 = ks * per;
+    kb1 = min(kb0 + per, num_kb);
     item += s.clusters;
     return true;
   }
 };
 
-template <class Epi>
+template <class Epi, bool A_MN = false, bool B_MN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ PairSched sched, const __grid_constant__ typename Epi::Params ep) {
@@ -97,7 +102,6 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int kEpi = 4 * kColSplit;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int num_kb = (sched.num_k16 + 3) >> 2;
 
   if (threadIdx.x == (kEpi + 1) * 32) {
     tma_prefetch_desc(&tmA);
@@ -126,13 +130,24 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t phase = 0;
     while (it.next()) {
 #pragma unroll 1
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sA = smem + stage * kPairStageBytes;
         uint8_t* sB = sA + 16384;
         if (leader) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
-        tma_load_2d_2sm(sA, &tmA, &full_bar[stage], kb * 64, it.pm * 256 + int(rank) * 128);
-        tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kb * 64, it.tn * BN + int(rank) * 128);
+        const int m0 = it.pm * 256 + int(rank) * 128, n0 = it.tn * BN + int(rank) * 128;
+        if (!A_MN) {
+          tma_load_2d_2sm(sA, &tmA, &full_bar[stage], kb * 64, m0);
+        } else {                     // MN-major: two [64 k x 64 m] chunks
+          tma_load_2d_2sm(sA, &tmA, &full_bar[stage], m0, kb * 64);
+          tma_load_2d_2sm(sA + 8192, &tmA, &full_bar[stage], m0 + 64, kb * 64);
+        }
+        if (!B_MN) {
+          tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kb * 64, n0);
+        } else {
+          tma_load_2d_2sm(sB, &tmB, &full_bar[stage], n0, kb * 64);
+          tma_load_2d_2sm(sB + 8192, &tmB, &full_bar[stage], n0 + 64, kb * 64);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -143,22 +158,24 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t phase = 0;
     int buf = 0;
     uint32_t bphase = 0;
-    constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     while (it.next()) {
       mbar_wait(&tempty_bar[buf], bphase ^ 1);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + buf * BN;
 #pragma unroll 1
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + stage * kPairStageBytes);
-        const uint64_t da0 = make_sdesc_sw128(a_base, 16, 1024);
-        const uint64_t db0 = make_sdesc_sw128(a_base + 16384, 16, 1024);
+        const uint64_t da0 = A_MN ? make_sdesc_sw128(a_base, 8192, 1024) : make_sdesc_sw128(a_base, 16, 1024);
+        const uint64_t db0 = B_MN ? make_sdesc_sw128(a_base + 16384, 8192, 1024) : make_sdesc_sw128(a_base + 16384, 16, 1024);
         const int nk = min(4, sched.num_k16 - kb * 4);
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16)
-          if (k16 < nk) umma_ss_2sm(d_addr, sdesc_advance(da0, k16 * 32), sdesc_advance(db0, k16 * 32), idesc, (kb | k16) ? 1u : 0u);
+          if (k16 < nk)
+            umma_ss_2sm(d_addr, sdesc_advance(da0, k16 * (A_MN ? 2048 : 32)), sdesc_advance(db0, k16 * (B_MN ? 2048 : 32)),
+                        idesc, (kb > it.kb0 || k16 > 0) ? 1u : 0u);
         umma_commit_2sm(&empty_bar[stage], 0b11);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -180,8 +197,8 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       ctx.tn = it.tn;
       ctx.row = ctx.tm * 128 + q * 32 + lane;
       ctx.col0 = it.tn * BN;
-      ctx.kb0 = 0;
-      ctx.kb1 = num_kb;
+      ctx.kb0 = it.kb0;
+      ctx.kb1 = it.kb1;
       mbar_wait(&tfull_bar[buf], bphase);
       tc_fence_after();
       ctx.taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * BN;
@@ -202,15 +219,22 @@ gemm_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == kEpi) tmem_dealloc_2sm(tmem_base, 512);
 }
 
-inline PairSched make_pair_sched(int64_t M, int64_t N, int64_t K, int tri, int row_tile0, int row_tile1, int sms) {
+inline PairSched make_pair_sched(int64_t M, int64_t N, int64_t K, int tri, int row_tile0, int row_tile1, int sms,
+                                 int ksplit = 1) {
   PairSched s;
   s.p_tile0 = row_tile0 / 2;
   s.p_tiles = (row_tile1 - row_tile0 + 1) / 2;
   s.n_tiles = int((N + 255) / 256);
   s.tri = tri;
   s.num_k16 = int((K + 15) / 16);
+  const int num_kb = (s.num_k16 + 3) / 4;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > num_kb) ksplit = num_kb;
+  const int per = (num_kb + ksplit - 1) / ksplit;
+  s.ksplit = (num_kb + per - 1) / per;          // no empty splits
   s.total = 0;
   for (int p = 0; p < s.p_tiles; ++p) s.total += s.n_tiles - (tri ? (s.p_tile0 + p) : 0);
+  s.total *= s.ksplit;
   int cl = sms / 2;
   if (s.total < cl) cl = s.total;
   if (cl < 1) cl = 1;

@@ -58,10 +58,10 @@ int launch_gemm_as(const CUtensorMap& a, const CUtensorMap& b, const AsSched& s,
   return 0;
 }
 
-template <class Epi>
+template <class Epi, bool A_MN = false, bool B_MN = false>
 int launch_gemm_2sm(const CUtensorMap& a, const CUtensorMap& b, const PairSched& s, const typename Epi::Params& ep,
                     cudaStream_t st, const char* tag = "gemm_2sm") {
-  auto kern = gemm_2sm_kernel<Epi>;
+  auto kern = gemm_2sm_kernel<Epi, A_MN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
     CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));

@@ -154,7 +154,7 @@ def pairwise(a: torch.Tensor, b: torch.Tensor, mode: int, alphas: Sequence[float
 
 
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias=None,
-              ksplit: int = 1) -> torch.Tensor:
+              ksplit: int = 1, pairs: bool = False) -> torch.Tensor:
     """Debug entry: C = op(A) op(B)^T on the tcgen05 core.  a: [M,K] (or [K,M] if a_mn), bf16."""
     _require_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
@@ -162,8 +162,9 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool =
     M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
     N = b.shape[1] if b_mn else b.shape[0]
     c = torch.zeros((M, N), dtype=torch.float32, device=a.device)
-    check(lib().carel_gemm_bf16(_p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
-                                _p(c), N, _p(bias), ksplit, _stream()), "carel_gemm_bf16")
+    fn = lib().carel_gemm_bf16_2sm if pairs else lib().carel_gemm_bf16
+    check(fn(_p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K,
+             _p(c), N, _p(bias), ksplit, _stream()), "carel_gemm_bf16")
     return c
 
 

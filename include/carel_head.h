@@ -52,6 +52,9 @@ int carel_timing_report(char* buf, size_t n);
 int carel_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn,
                     int64_t M, int64_t N, int64_t K, float* c, int64_t ldc, const float* bias,
                     int ksplit, void* stream);
+/* The same product on CTA pairs (cluster of 2, tcgen05 cta_group::2; 256 x 256 tiles). */
+int carel_gemm_bf16_2sm(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, int64_t M,
+                        int64_t N, int64_t K, float* c, int64_t ldc, const float* bias, int ksplit, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * MMD  — replaces MMDStatistic.__call__ + pdist

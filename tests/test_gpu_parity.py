@@ -54,6 +54,19 @@ def test_gemm_core_layouts(a_mn, b_mn, ks):
     assert rel(F.gemm_bf16(aa, bb, bool(a_mn), bool(b_mn), ksplit=ks), ref) < 1e-5
 
 
+@pytest.mark.parametrize("a_mn,b_mn,ks,M,N,K", [(0, 0, 1, 304, 520, 208), (0, 1, 2, 304, 520, 208), (1, 0, 1, 304, 520, 208),
+                                                (1, 1, 3, 304, 520, 208), (1, 1, 5, 1000, 256, 2048), (0, 1, 4, 768, 256, 1000)])
+def test_gemm_core_cta_pairs(a_mn, b_mn, ks, M, N, K):
+    """The same products on CTA pairs (cta_group::2 UMMA of M = 256, split-K, K-major and MN-major operands)."""
+    torch.manual_seed(1)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = torch.randn(N, K, device=DEV).bfloat16()
+    ref = a.float() @ b.float().T
+    aa = a.T.contiguous() if a_mn else a
+    bb = b.T.contiguous() if b_mn else b
+    assert rel(F.gemm_bf16(aa, bb, bool(a_mn), bool(b_mn), ksplit=ks, pairs=True), ref) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------
 # MMD
 # ------------------------------------------------------------------------------------------
