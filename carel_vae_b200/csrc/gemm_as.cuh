@@ -204,6 +204,8 @@ gemm_as_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ctx.col0 = it.tn * BN;
       ctx.kb0 = 0;
       ctx.kb1 = KB;
+      ctx.first_of_row = it.new_row;
+      ctx.last_of_row = it.last_of_row;
       epi.prefetch(ctx);                               // loads that do not depend on the accumulator
       mbar_wait(&tfull_bar[buf], bphase);
       if (tracer) CAREL_TRACE(3, trace_n);

@@ -136,6 +136,7 @@ struct TileCtx {
   int half;        // column part handled by this warp: columns [half*BN/kColSplit, (half+1)*BN/kColSplit)
   int kb0, kb1;    // k-block range that was accumulated (split-K)
   int epi_tid;     // 0..255 within the epilogue warps
+  bool first_of_row, last_of_row;   // A-stationary kernel only: first / last tile this CTA runs on row tile tm
 };
 
 template <int BN, int NG>
