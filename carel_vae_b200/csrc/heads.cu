@@ -344,3 +344,52 @@ extern "C" int carel_heads_bwd(const float* grad_out, const float* z, int64_t ld
   CAREL_LAUNCHED();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Loss assembly: out = sum_i w_i t_i over device scalars (the reference's chain of python-level scalar ops,
+// drl_classifier_ec_mmd_final_mul.py:256-261).  Products and sums are rounded separately and taken left to right,
+// so the value is bit-identical to the torch chain it replaces; one launch instead of ~10 forward and ~10 backward.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWsumMax = 16;
+struct WsumArgs {
+  const float* t[kWsumMax];
+  float w[kWsumMax];
+  int n;
+};
+static __global__ void wsum_fwd_kernel(const WsumArgs a, float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  float acc = __fmul_rn(a.w[0], *a.t[0]);
+  for (int i = 1; i < a.n; ++i) acc = __fadd_rn(acc, __fmul_rn(a.w[i], *a.t[i]));
+  *out = acc;
+}
+static __global__ void wsum_bwd_kernel(const WsumArgs a, const float* __restrict__ g, float* __restrict__ grads) {
+  const int i = threadIdx.x;
+  if (i < a.n) grads[i] = __fmul_rn(a.w[i], *g);
+}
+
+extern "C" int carel_wsum_fwd(const float* const* terms_host, const float* weights_host, int n, float* out,
+                              void* stream) {
+  CAREL_REQUIRE(n >= 1 && n <= kWsumMax, "carel_wsum_fwd: 1..%d terms supported, got %d", kWsumMax, n);
+  CAREL_REQUIRE(terms_host != nullptr && weights_host != nullptr && out != nullptr, "carel_wsum_fwd: null argument");
+  WsumArgs a{};
+  a.n = n;
+  for (int i = 0; i < n; ++i) {
+    CAREL_REQUIRE(terms_host[i] != nullptr, "carel_wsum_fwd: term %d is null", i);
+    a.t[i] = terms_host[i];
+    a.w[i] = weights_host[i];
+  }
+  wsum_fwd_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a, out);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int carel_wsum_bwd(const float* grad_out, const float* weights_host, int n, float* grads, void* stream) {
+  CAREL_REQUIRE(n >= 1 && n <= kWsumMax, "carel_wsum_bwd: 1..%d terms supported, got %d", kWsumMax, n);
+  CAREL_REQUIRE(grad_out != nullptr && weights_host != nullptr && grads != nullptr, "carel_wsum_bwd: null argument");
+  WsumArgs a{};
+  a.n = n;
+  for (int i = 0; i < n; ++i) a.w[i] = weights_host[i];
+  wsum_bwd_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a, grad_out, grads);
+  CAREL_LAUNCHED();
+  return 0;
+}

@@ -298,6 +298,53 @@ def classifier_heads(z, masks, emotion_classifier, cause_classifier, pair_classi
 
 
 # --------------------------------------------------------------------------------------------
+# loss assembly: one launch for the weighted sum of the loss terms
+# --------------------------------------------------------------------------------------------
+class _WeightedSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, *tensors):
+        _require_cuda(*tensors)
+        flat = [t.detach().float().contiguous() for t in tensors]
+        ptrs, wts = [], []
+        for t, w in zip(flat, weights):
+            if t.numel() != len(w):
+                raise ValueError(f"weighted_sum: {t.numel()} elements but {len(w)} weights")
+            for j, wj in enumerate(w):
+                ptrs.append(t.data_ptr() + 4 * j)
+                wts.append(float(wj))
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        out = torch.empty((), dtype=torch.float32, device=flat[0].device)
+        check(lib().carel_wsum_fwd(arr, float_array(wts), len(ptrs), _p(out), _stream()), "carel_wsum_fwd")
+        ctx.wts = wts
+        ctx.meta = [(tuple(t.shape), t.dtype) for t in tensors]
+        ctx.keep = flat            # the kernel reads them on the stream: keep them alive until it has run
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.reshape(()).float().contiguous()
+        grads = torch.empty(len(ctx.wts), dtype=torch.float32, device=g.device)
+        check(lib().carel_wsum_bwd(_p(g), float_array(ctx.wts), len(ctx.wts), _p(grads), _stream()), "carel_wsum_bwd")
+        out, off = [None], 0
+        for i, (shape, dt) in enumerate(ctx.meta):
+            n = 1
+            for d in shape:
+                n *= d
+            out.append(grads[off:off + n].view(shape).to(dt) if ctx.needs_input_grad[1 + i] else None)
+            off += n
+        return tuple(out)
+
+
+def weighted_sum(tensors, weights) -> torch.Tensor:
+    """sum_i w_i t_i over small device tensors in ONE launch (and one in the backward): the loss assembly of the
+    trainers (drl_classifier_ec_mmd_final_mul.py:256-261 and its siblings).  `tensors[i]` is a 0-dim or short 1-D fp32
+    tensor, `weights[i]` a float (0-dim) or a sequence with one float per element; at most 16 elements in total.
+    Products and sums are rounded separately, left to right: bit-identical to the torch expression."""
+    ws = tuple(tuple(float(x) for x in w) if isinstance(w, (tuple, list)) else (float(w),) for w in weights)
+    return _WeightedSumFn.apply(ws, *tensors)
+
+
+# --------------------------------------------------------------------------------------------
 # BoW reconstruction: decoder GEMM fused with softmax + BCE
 # --------------------------------------------------------------------------------------------
 DEFAULT_ELL_CAP = 64

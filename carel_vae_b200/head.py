@@ -137,12 +137,14 @@ class _DrlClassifierBase(nn.Module):
         target = content_bow * (1 - o.label_smoothing) + o.label_smoothing / o.pair_bow_dim
         return TF.binary_cross_entropy(reconstruct_pred, target)
 
-    def _kl_terms(self, kl, iteration):
-        kl_e, kl_c = kl[0], kl[1]
+    def _assemble(self, leading, kl, iteration, reconstruction_loss):
+        """leading terms + w KL_e + w KL_c + reconstruction in ONE launch (F.weighted_sum): `leading` = [(tensor,
+        weight), ...] in the reference's order of addition; the value is bit-identical to the chain of scalar ops."""
+        w = 1.0
         if iteration < self.opt.kl_ann_iterations:
             w = self.get_annealed_weight(iteration, self.opt.ec_kl_lambda)
-            kl_e, kl_c = w * kl_e, w * kl_c
-        return kl_e, kl_c
+        return F.weighted_sum([t for t, _ in leading] + [kl, reconstruction_loss],
+                              [wt for _, wt in leading] + [(w, w), 1.0])
 
     def _reconstruction(self, z, content_bow):
         """`content_bow` is the reference's dense [N, V] fp32 target, or — SURVEY §8f.1 — the compact
@@ -287,12 +289,12 @@ class DrlClassifierMMD(_DrlClassifierBase):
             side.wait_stream(main)
         with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
             heads = self._heads(z, emotion_labels, cause_labels, pair_labels)
-        mmd_loss = -MMDStatistic(input_ids.shape[0], input_ids.shape[0]).halves(z, [0.1])
-        kl_e, kl_c = self._kl_terms(kl, iteration)
+        mmd = MMDStatistic(input_ids.shape[0], input_ids.shape[0]).halves(z, [0.1])
         reconstruction_loss = self._reconstruction(z, content_bow)
         if side is not None:
             main.wait_stream(side)
-        return o.mmd_loss_weight * mmd_loss + heads + kl_e + kl_c + reconstruction_loss
+        # mmd_loss_weight * (-mmd) + heads + kl_e + kl_c + reconstruction_loss   (:256-261)
+        return self._assemble([(mmd, -float(o.mmd_loss_weight)), (heads, 1.0)], kl, iteration, reconstruction_loss)
 
     def get_params(self):
         """The four latent projections are NOT handed to the optimiser, as in the reference (:284-297)."""
@@ -310,9 +312,8 @@ class DrlClassifierHSIC(_DrlClassifierBase):
         z_e, z_c = z[:, :L], z[:, L:]
         heads = self._heads(z, emotion_labels, cause_labels, pair_labels)
         hsic_loss = HSIC(z_e, z_c)
-        kl_e, kl_c = self._kl_terms(kl, iteration)
         reconstruction_loss = self._reconstruction(z, content_bow)
-        return hsic_loss + heads + kl_e + kl_c + reconstruction_loss
+        return self._assemble([(hsic_loss, 1.0), (heads, 1.0)], kl, iteration, reconstruction_loss)
 
     def get_params(self):
         return self._core_params()
@@ -356,9 +357,8 @@ class DrlClassifierVI(_DrlClassifierBase):
         z_e, z_c = z[:, :L], z[:, L:]
         heads = self._heads(z, emotion_labels, cause_labels, pair_labels)
         ec_aprx_loss = self.get_ec_aprx_loss(z_e, z_c)
-        kl_e, kl_c = self._kl_terms(kl, iteration)
         reconstruction_loss = self._reconstruction(z, content_bow)
-        loss = heads + kl_e + kl_c + reconstruction_loss
+        loss = self._assemble([(heads, 1.0)], kl, iteration, reconstruction_loss)
         return z_e, z_c, ec_aprx_loss, loss
 
     def get_params(self):
@@ -413,10 +413,9 @@ class DrlClassifierGAN(_DrlClassifierBase):
             cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
             pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
             heads = o.ec_mul_loss_weight * (emo_mul_loss + cau_mul_loss) + o.pair_mul_loss_weight * pair_mul_loss
-        kl_e, kl_c = self._kl_terms(kl, iteration)
         reconstruction_loss = self._reconstruction(z, content_bow)
-        loss = (o.ecce_adv_loss_weight * (ec_entropy_loss + ce_entropy_loss) + heads +
-                kl_e + kl_c + reconstruction_loss)
+        loss = self._assemble([(ec_entropy_loss + ce_entropy_loss, float(o.ecce_adv_loss_weight)), (heads, 1.0)],
+                              kl, iteration, reconstruction_loss)
         return ec_disc_loss, ce_disc_loss, loss
 
     def get_params(self):

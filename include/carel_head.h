@@ -180,6 +180,18 @@ int carel_heads_bwd(const float* grad_out, const float* z, int64_t ldz, int64_t 
                     const float* loss_weights3_host, float* grad_z, int64_t ldgz,
                     float* const* grad_weights6, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Loss assembly — replaces the chain of scalar tensor ops that forms the training loss
+ * (drl_classifier_ec_mmd_final_mul.py:256-261: 30 (-mmd) + heads + w KL_e + w KL_c + recon; drl_classifier_ec_hsic.py:
+ * 253-258; drl_classifier_ec_vi_final.py:261-266; drl_classifier_ec_gan.py:275-281).
+ *   out = sum_i weights_host[i] * *terms_host[i]      (fp32, left to right, products and sums rounded separately:
+ *                                                      bit-identical to the torch expression it replaces)
+ * terms_host = host array of n device pointers to fp32 scalars, n <= 16.  The backward writes
+ * grads[i] = weights_host[i] * *grad_out.
+ * ------------------------------------------------------------------------------------------ */
+int carel_wsum_fwd(const float* const* terms_host, const float* weights_host, int n, float* out, void* stream);
+int carel_wsum_bwd(const float* grad_out, const float* weights_host, int n, float* grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -190,3 +190,26 @@ def test_full_size_mmd_head_step_matches_oracle():
         if r is None:
             continue
         assert rel(g, r) < 2e-3, (k, rel(g, r))
+
+
+def test_weighted_sum_is_bit_identical_to_the_scalar_chain():
+    """F.weighted_sum (loss assembly, mmd:256-261) against the torch expression it replaces: value bit-exact,
+    gradients exact (w_i * g), 1-D terms (the two KL sums) get a gradient of their own shape."""
+    from carel_vae_b200 import functional as F
+    torch.manual_seed(5)
+    mmd = (torch.rand((), device=DEV) * 1e-2).requires_grad_()
+    heads = (torch.rand((), device=DEV) * 50).requires_grad_()
+    kl = (torch.rand(2, device=DEV) * 30).requires_grad_()
+    recon = (torch.rand((), device=DEV) * 1e-3).requires_grad_()
+    w = 7.412e-6
+    ours = F.weighted_sum([mmd, heads, kl, recon], [-30.0, 1.0, (w, w), 1.0])
+    ref = 30 * (-mmd) + heads + w * kl[0] + w * kl[1] + recon
+    assert ours.shape == () and torch.equal(ours.detach(), ref.detach())
+    g_ours = torch.autograd.grad(ours * 3.0, [mmd, heads, kl, recon])
+    g_ref = torch.autograd.grad(ref * 3.0, [mmd, heads, kl, recon])
+    for a, b in zip(g_ours, g_ref):
+        assert a.shape == b.shape and torch.equal(a, b)
+    with pytest.raises(ValueError):
+        F.weighted_sum([kl], [1.0])
+    with pytest.raises(cv._lib.CarelError):
+        F.weighted_sum([torch.ones(17, device=DEV)], [tuple([1.0] * 17)])
