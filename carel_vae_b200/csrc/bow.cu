@@ -539,16 +539,19 @@ struct BowSparseArgs {
 // chunks c = (lane & 7) + 8 k) stays in registers for all of its non-zeros.
 constexpr int kSparseChunks = 5;     // 8 lanes x 5 chunks x 8 elements = 320 >= ldk (<= 272)
 
-static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseArgs a) {
+// MODE is a template parameter: the forward instance does not carry the dz accumulators (160 -> <= 80 registers,
+// 1 -> 3 blocks per SM; the kernel is latency-bound on the gathers, so occupancy is what it needs).
+template <int MODE>
+static __global__ void __launch_bounds__(256, MODE == 0 ? 3 : 1) bow_sparse_kernel(const BowSparseArgs a) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int grp = lane >> 3, gl = lane & 7;
   const int nchunk = a.ldk >> 3;
-  const float scale = (a.mode == 1) ? __ldg(a.grad_out) / (float(a.N) * float(a.V)) : 0.f;
+  const float scale = (MODE == 1) ? __ldg(a.grad_out) / (float(a.N) * float(a.V)) : 0.f;
   double loss_warp = 0.0;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < a.N; r += gridDim.x * wpb) {
     const int nnz = a.ell_nnz[r];
     const bool dense_scan = nnz > a.cap;
-    if (a.mode == 1 && a.overflow_only && !dense_scan) continue;
+    if (MODE == 1 && a.overflow_only && !dense_scan) continue;
     const __nv_bfloat16* zrow = a.ZA + size_t(r) * a.ldk;
     uint4 zreg[kSparseChunks];
 #pragma unroll
@@ -558,7 +561,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
     }
     float dloss = 0.f, du = 0.f;
     float dz[kSparseChunks][8];
-    if (a.mode == 1) {
+    if (MODE == 1) {
 #pragma unroll
       for (int k = 0; k < kSparseChunks; ++k)
 #pragma unroll
@@ -594,7 +597,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
       const float p = __expf(x);
       const float den = fmaxf(p * (1.f - p), 1e-12f);
       const float ev = -a.one_minus_ls * t * p / den;
-      if (a.mode == 0) {
+      if (MODE == 0) {
         if (gl == 0) {
           if (slot >= 0) a.ell_ev[slot] = ev;
           const float A = fmaxf(x, -100.f), B = fmaxf(log1pf(-p), -100.f);
@@ -659,7 +662,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
         }
       }
     }
-    if (a.mode == 0) {
+    if (MODE == 0) {
       // combine the four group leaders
       dloss += __shfl_xor_sync(0xffffffffu, dloss, 8);
       dloss += __shfl_xor_sync(0xffffffffu, dloss, 16);
@@ -685,7 +688,7 @@ static __global__ void __launch_bounds__(256) bow_sparse_kernel(const BowSparseA
       }
     }
   }
-  if (a.mode == 0) {          // block-level sum of the loss corrections: one double atomic per block
+  if (MODE == 0) {          // block-level sum of the loss corrections: one double atomic per block
     __shared__ double sh_l[8];
     if (lane == 0) sh_l[threadIdx.x >> 5] = loss_warp;
     __syncthreads();
@@ -710,36 +713,42 @@ static __global__ void csc_count_kernel(const int* __restrict__ cols, const int*
   }
 }
 // Exclusive scan of the per-word counts (one block; cnt may alias fillpos).  The counts are staged through
-// shared memory in chunks of 8 per thread so that every global access is coalesced.
+// shared memory in chunks of 8 per thread so that every global access is coalesced; the 1024 thread totals of a
+// chunk are scanned with warp shuffles (two block barriers instead of the twenty of a shared-memory ladder).
 static __global__ void __launch_bounds__(1024) csc_scan_kernel(const int* cnt, int V, int* colptr, int* fillpos) {
   constexpr int PER = 8, CH = 1024 * PER;
   __shared__ int buf[CH];
-  __shared__ int part[1024];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
+  __shared__ int wtot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int carry = 0;                                  // every thread tracks the running total
   for (int base = 0; base < V; base += CH) {
     for (int i = threadIdx.x; i < CH; i += 1024) buf[i] = (base + i < V) ? cnt[base + i] : 0;
     __syncthreads();
     int loc[PER], s = 0;
 #pragma unroll
     for (int i = 0; i < PER; ++i) { loc[i] = s; s += buf[threadIdx.x * PER + i]; }
-    part[threadIdx.x] = s;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      const int v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0;
-      __syncthreads();
-      part[threadIdx.x] += v;
-      __syncthreads();
+    int incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
     }
-    const int run = carry + part[threadIdx.x] - s;
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    int wv = wtot[lane];                          // every warp scans the 32 warp totals itself
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wv, off);
+      if (lane >= off) wv += v;
+    }
+    const int before = __shfl_sync(0xffffffffu, wv, (warp + 31) & 31);
+    const int run = carry + (warp > 0 ? before : 0) + incl - s;
+    carry += __shfl_sync(0xffffffffu, wv, 31);
 #pragma unroll
     for (int i = 0; i < PER; ++i) buf[threadIdx.x * PER + i] = run + loc[i];
     __syncthreads();
     for (int i = threadIdx.x; i < CH; i += 1024)
       if (base + i < V) { colptr[base + i] = buf[i]; fillpos[base + i] = buf[i]; }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += part[1023];
     __syncthreads();
   }
   if (threadIdx.x == 0) colptr[V] = carry;
@@ -1169,7 +1178,7 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   sa.cap = cap; sa.mode = 0; sa.one_minus_ls = 1.f - label_smoothing; sa.lossacc = w.lossacc; sa.srow = w.srow;
   sa.ell_ev = w.ell_ev; sa.overflow_only = 0;
   sa.grad_out = nullptr; sa.grad_z = nullptr; sa.ldgz = 0; sa.gw = nullptr; sa.gb = nullptr;
-  bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
+  bow_sparse_kernel<0><<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
   CAREL_LAUNCHED();
   bow_loss_finalize_kernel<<<1, 32, 0, st>>>(w.lossacc, 1.0 / (double(N) * double(V)), loss_out);
   CAREL_LAUNCHED();
@@ -1215,7 +1224,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
     sa.bow_dense = bow_dense; sa.ld_bow = ld_bow; sa.N = int(N); sa.V = int(V); sa.K = int(K); sa.ldk = w.ldk;
     sa.cap = int(ell_cap); sa.mode = 1; sa.one_minus_ls = 1.f - label_smoothing; sa.lossacc = nullptr; sa.srow = nullptr;
     sa.grad_out = grad_out; sa.grad_z = grad_z; sa.ldgz = ldgz; sa.gw = gw; sa.gb = gb;
-    bow_sparse_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
+    bow_sparse_kernel<1><<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(sa);
     CAREL_LAUNCHED();
   }
   // The chains use the PLAIN operands (columns [0, K) of ZA / WB; bias and -lse are added in the epilogue), so
