@@ -115,6 +115,10 @@ def synthetic_batch(device, seed=0):
     return dict(X=X, emo=emo, cau=pair.clone(), pair=pair, bow=bow, ell_cols=cols, ell_vals=vals, ell_nnz=nnz)
 
 
+WORKLOAD = ("drl_classifier_ec_mmd_final_mul MMD-VAE head + BoW reconstruction, N=8192 clauses/GPU, d=768, latent=128, "
+            "vocab=30000, Adam(get_params)")
+
+
 def run_ours(args):
     import torch.distributed as dist
     import carel_vae_b200 as cv
@@ -350,8 +354,7 @@ def run_ours(args):
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": "drl_classifier_ec_mmd_final_mul MMD-VAE head + BoW reconstruction, "
-                                      "N=8192 clauses/GPU, d=768, latent=128, vocab=30000, Adam(get_params)",
+               "config": {"workload": WORKLOAD,
                           "global_batch": N_ROWS * world, "parallelism": f"dp{world}", "cuda_graph": use_graph,
                           "l2": "inputs larger than L2 (dense BoW target 983 MB/step is re-read every step)"},
                "clocks": clocks,
@@ -420,8 +423,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / cpu["value"], 2),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "drl_classifier_ec_mmd_final_mul MMD-VAE head + BoW reconstruction, N=8192 clauses, "
-                                  "d=768, latent=128, vocab=30000, Adam(get_params) — CPU, host cores"},
+           "config": {"workload": WORKLOAD, "global_batch": N_ROWS, "parallelism": "host cores (rank 0 only)",
+                      "cuda_graph": False, "l2": "n/a (CPU)"},
            "cpu_baseline": cpu,
            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

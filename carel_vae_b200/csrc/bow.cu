@@ -98,18 +98,22 @@ static BowWs carve_bow(void* ws, int64_t N, int64_t K, int64_t V, int64_t cap) {
 // ---------------------------------------------------------------------------------------------
 // dense BoW target -> ELL (one warp per row, 128-bit loads; HBM-bound)
 // ---------------------------------------------------------------------------------------------
-static __global__ void bow_pack_ell_kernel(const float* __restrict__ bow, int64_t ld, int N, int V,
-                                           int cap, int* __restrict__ cols, float* __restrict__ vals,
-                                           int* __restrict__ nnz) {
+// Measured and rejected (a two-stream probe on B200): a small-footprint form (U = 12, 128 threads, 72 registers, one block
+// per SM, max-shared carve-out) on a forked stream, meant to stream the target underneath the latent GEMM / MMD forward /
+// pass F.  By the resource arithmetic it is co-resident with the 576-thread, 96-register, 225 KB tensor-core CTAs, but
+// the two never share an SM in practice (MMD forward x3: 263 us alone, 543 us with the 380 us background pack).
+template <int U, int THREADS, int MINB>
+static __global__ void __launch_bounds__(THREADS, MINB)
+bow_pack_ell_kernel(const float* __restrict__ bow, int64_t ld, int N, int V, int cap, int* __restrict__ cols,
+                    float* __restrict__ vals, int* __restrict__ nnz) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < N; r += gridDim.x * wpb) {
     const float* row = bow + size_t(r) * ld;
     int count = 0;
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(bow) & 15) == 0);
     const int V4 = vec ? (V & ~3) : 0;
-    // eight 128-bit loads per lane in flight (1024 floats of the row per iteration) and ONE ballot for the common
-    // all-zero batch: 4 loads + a ballot per load measured 5.69 TB/s, this form 6.72 TB/s (tools/pack_rate.cu)
-    constexpr int U = 8;
+    // U 128-bit loads per lane in flight (128 U floats of the row per iteration) and ONE ballot for the common
+    // all-zero batch: 4 loads + a ballot per load measured 5.69 TB/s, U = 8 in this form 6.72 TB/s (tools/pack_rate.cu)
     for (int base = 0; base < V4; base += 128 * U) {
       float4 v[U];
 #pragma unroll
@@ -1112,8 +1116,18 @@ extern "C" size_t carel_bow_workspace_bytes(int64_t N, int64_t K, int64_t V, int
   return carve_bow(nullptr, N, K, V, ell_cap).bytes;
 }
 
-// Pack a dense [N, V] target into the ELL arrays of a workspace (also done implicitly by
-// carel_bow_fwd when bow_dense != NULL).
+// Dense [N, V] target -> ELL arrays (also done implicitly by carel_bow_fwd when it gets a dense target only).
+extern "C" int carel_bow_pack_ell(const float* bow_dense, int64_t ld_bow, int64_t N, int64_t V, int64_t ell_cap,
+                                  int32_t* ell_cols, float* ell_vals, int32_t* ell_nnz, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(N > 0 && V > 0 && ell_cap > 0, "carel_bow_pack_ell: empty problem");
+  CAREL_REQUIRE(bow_dense && ell_cols && ell_vals && ell_nnz, "carel_bow_pack_ell: null argument");
+  bow_pack_ell_kernel<8, 256, 1><<<int(std::min<int64_t>((N + 7) / 8, 148 * 32)), 256, 0, st>>>(
+      bow_dense, ld_bow, int(N), int(V), int(ell_cap), ell_cols, ell_vals, ell_nnz);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
 extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, const float* dec_b,
                              const float* bow_dense, int64_t ld_bow, const int32_t* ell_cols_in,
                              const float* ell_vals_in, const int32_t* ell_nnz_in, int64_t N,
@@ -1137,7 +1151,7 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
     CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_vals, ell_vals_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, st));
     CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_nnz, ell_nnz_in, size_t(N) * 4, cudaMemcpyDeviceToDevice, st));
   } else {
-    bow_pack_ell_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 32)), 256, 0, st>>>(bow_dense, ld_bow, int(N), int(V), cap, w.ell_cols, w.ell_vals, w.ell_nnz);
+    bow_pack_ell_kernel<8, 256, 1><<<int(std::min<int64_t>((N + 7) / 8, 148 * 32)), 256, 0, st>>>(bow_dense, ld_bow, int(N), int(V), cap, w.ell_cols, w.ell_vals, w.ell_nnz);
     CAREL_LAUNCHED();
   }
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.lossacc, 0, 2 * sizeof(double), st));

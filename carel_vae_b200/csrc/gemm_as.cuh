@@ -24,7 +24,10 @@ struct AsSched {
   const int* row_tile_flags;   // optional (device, full mode): flags[0] = any work at all, flags[1 + tm] per row tile
 };
 
-constexpr int kAsStages = 5;
+#ifndef CAREL_AS_STAGES
+#define CAREL_AS_STAGES 5
+#endif
+constexpr int kAsStages = CAREL_AS_STAGES;
 constexpr int kAsBytesA = 4 * 16384;                     // 4 k-blocks of [128 x 64] bf16
 constexpr int kAsStageB = 256 * 128;                     // one k-block of [256 x 64] bf16
 constexpr int kAsSmemBytes = kAsBytesA + kAsStages * kAsStageB + 1024 + 256;

@@ -395,6 +395,20 @@ class _BowFn(torch.autograd.Function):
                 None if gb is None else gb.to(dtb), None, None, None, None)
 
 
+def bow_pack_ell(content_bow: torch.Tensor, ell_cap: int = DEFAULT_ELL_CAP):
+    """Dense [N, V] BoW target -> ELL triple (cols int32 [N, C], vals fp32 [N, C], nnz int32 [N]) on the current
+    stream; `nnz` may exceed C (the row then needs the dense target next to the list)."""
+    _require_cuda(content_bow)
+    bd = _rowmajor_f32(content_bow)
+    N, V = bd.shape
+    cols = torch.empty((N, ell_cap), dtype=torch.int32, device=bd.device)
+    vals = torch.empty((N, ell_cap), dtype=torch.float32, device=bd.device)
+    nnz = torch.empty((N,), dtype=torch.int32, device=bd.device)
+    check(lib().carel_bow_pack_ell(_p(bd), bd.stride(0), N, V, int(ell_cap), _p(cols), _p(vals), _p(nnz), _stream()),
+          "carel_bow_pack_ell")
+    return cols, vals, nnz
+
+
 def bow_reconstruction_loss(z, dec_w, dec_b, content_bow=None, label_smoothing: float = 0.1, ell=None,
                             ell_cap: int = DEFAULT_ELL_CAP):
     """BCELoss(softmax(z dec_w^T + dec_b), content_bow (1 - ls) + ls / V) without materialising [N, V]

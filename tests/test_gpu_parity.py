@@ -248,6 +248,26 @@ def test_bow_sparse_equals_dense_target():
     assert relv(sparse, dense) < 1e-6
 
 
+@pytest.mark.parametrize("N,V,nnz,cap", [(1, 7, 3, 4), (37, 1001, 5, 8), (300, 30000, 24, 64), (64, 2050, 40, 8)])
+def test_bow_pack_ell_matches_nonzero(N, V, nnz, cap):
+    """carel_bow_pack_ell (bit-exact index / byte work): ascending column order, values copied verbatim, nnz counts the
+    whole row even when it overflows the list (cap = 8 with 40 draws per row); ragged V (no 128-bit alignment) too.
+    The list handed back together with the dense rows gives the same loss as the dense target alone."""
+    bow = ho.synthetic_batch(N, V, D=8, nnz=nnz, seed=N + V, device=DEV)["bow"]
+    cols, vals, cnt = F.bow_pack_ell(bow, cap)
+    assert cols.dtype == torch.int32 and vals.dtype == torch.float32 and cnt.dtype == torch.int32
+    for i in range(N):
+        nz = bow[i].nonzero().flatten()
+        assert int(cnt[i]) == len(nz)
+        k = min(len(nz), cap)
+        assert torch.equal(cols[i, :k].long(), nz[:k]) and torch.equal(vals[i, :k], bow[i, nz[:k]])
+    torch.manual_seed(1)
+    Z, W, b = torch.randn(N, 64, device=DEV), torch.randn(V, 64, device=DEV) / 8, torch.randn(V, device=DEV) / 8
+    dense = F.bow_reconstruction_loss(Z, W, b, bow, 0.1, ell_cap=cap)
+    both = F.bow_reconstruction_loss(Z, W, b, bow, 0.1, ell=(cols, vals, cnt))
+    assert torch.equal(dense, both)
+
+
 def test_bow_extreme_logits_take_the_exact_path():
     """Peaked softmax rows (p up to ~0.99, log p << -27 elsewhere) leave the series' range and take
     the exact per-element path.  (Not pushed to p -> 1 - 1e-8: there log(1 - p) is ill-conditioned in
