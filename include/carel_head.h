@@ -124,10 +124,10 @@ int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* grad_kl, co
 size_t carel_bow_workspace_bytes(int64_t N, int64_t K, int64_t V, int64_t ell_cap);
 /* Dense target -> ELL list on its own (what ECPEDataset._get_bow_representations + the H2D copy hand over,
  * :100-119, :830): cols / vals [N, ell_cap], nnz [N] (nnz may exceed ell_cap: such rows are re-scanned from the dense
- * rows by carel_bow_fwd / carel_bow_bwd).  background = 1 launches the one-small-block-per-SM form that is co-resident
- * with the tensor-core kernels (for a forked stream); 0 the stand-alone form (HBM roofline). */
+ * rows by carel_bow_fwd / carel_bow_bwd).  HBM-bound: N V 4 bytes read once (6.6 TB/s measured at N = 8192,
+ * V = 30000). */
 int carel_bow_pack_ell(const float* bow_dense, int64_t ld_bow, int64_t N, int64_t V, int64_t ell_cap,
-                       int32_t* ell_cols, float* ell_vals, int32_t* ell_nnz, int background, void* stream);
+                       int32_t* ell_cols, float* ell_vals, int32_t* ell_nnz, void* stream);
 int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, const float* dec_b,
                   const float* bow_dense, int64_t ld_bow, const int32_t* ell_cols,
                   const float* ell_vals, const int32_t* ell_nnz, int64_t N, int64_t K, int64_t V,

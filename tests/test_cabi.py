@@ -36,6 +36,19 @@ def test_library_exports_every_declared_symbol():
     assert not [s for s in _lib._SIGNATURES if not hasattr(handle, s)]
 
 
+def test_ctypes_signatures_match_the_header():
+    """Every entry point bound in _lib._SIGNATURES takes as many arguments as include/carel_head.h declares (a stale
+    binding would otherwise shift the stream pointer into garbage)."""
+    import re
+    from carel_vae_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "carel_head.h").read_text(), flags=re.S)
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(carel_\w+)\s*\(([^;{]*?)\)\s*;", text)}
+    for name, (_, args) in _lib._SIGNATURES.items():
+        assert name in decl, f"{name} is bound but not declared in the header"
+        params = [p for p in decl[name].split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), f"{name}: header has {len(params)} parameters, ctypes binding {len(args)}"
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly on CPU tensors instead of silently computing elsewhere."""
     import carel_vae_b200 as cv
