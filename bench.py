@@ -344,6 +344,24 @@ def run_ours(args):
         roof_step = {"bound": "tensor", "achieved": round(step_tflops, 1), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": round(step_tflops / pk["bf16_sustained"], 3),
                      "note": "whole step, algorithmic 6.03e11 FLOP / step time vs sustained bf16 peak"}
+        # ---- HBM roofline of the step's one bandwidth-bound kernel: dense BoW target -> ELL (N*V*4 bytes read once) ----
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            F.bow_pack_ell(static["bow"], 64)
+        ev0.record()
+        for _ in range(20):
+            F.bow_pack_ell(static["bow"], 64)
+        ev1.record()
+        torch.cuda.synchronize()
+        pack_us = ev0.elapsed_time(ev1) / 20 * 1e3
+        pack_bytes = N_ROWS * VOCAB * 4
+        roof_hbm = {"bound": "hbm", "kernel": "bow_pack_ell_kernel (dense [N,V] fp32 BoW target -> ELL list, once per step)",
+                    "achieved": round(pack_bytes / (pack_us * 1e-6) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(pack_bytes / (pack_us * 1e-6) / 1e9 / pk["hbm_gbs"], 3),
+                    # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/r01h_ncu_summary_hbm_and_forward.txt)
+                    "traffic": 988.1e6, "traffic_unit": "bytes/launch (ncu); algorithmic N*V*4 = 983.0e6",
+                    "us_per_launch": round(pack_us, 1), "peak_source": pk["source"],
+                    "note": "the target is larger than L2 (983 MB), 20 back-to-back launches timed with CUDA events"}
 
     # ---- cpu baseline (rank 0, N = 1 only): the oracle port of the reference step on the host cores ----
     cpu = None
@@ -366,7 +384,7 @@ def run_ours(args):
                            "resident_ms_per_step": round(ell_resident_ms, 4),
                            "note": "BoW target passed as an ELL non-zero list (cols/vals [N,32], nnz [N]) instead of dense rows"},
                "gpu_launches": int(launches_eager) * args.steps, "gpu_launches_per_step": int(launches_eager),
-               "roofline": roof, "roofline_step": roof_step, "gram": gram, "kernels_us": kernels,
+               "roofline": roof, "roofline_step": roof_step, "roofline_hbm": roof_hbm, "gram": gram, "kernels_us": kernels,
                "cpu_baseline": cpu}
         print(json.dumps(out))
     if world > 1:

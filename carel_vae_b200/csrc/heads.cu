@@ -345,6 +345,7 @@ extern "C" int carel_heads_bwd(const float* grad_out, const float* z, int64_t ld
   return 0;
 }
 
+namespace carel {
 // ---------------------------------------------------------------------------------------------
 // Loss assembly: out = sum_i w_i t_i over device scalars (the reference's chain of python-level scalar ops,
 // drl_classifier_ec_mmd_final_mul.py:256-261).  Products and sums are rounded separately and taken left to right,
@@ -366,6 +367,7 @@ static __global__ void wsum_bwd_kernel(const WsumArgs a, const float* __restrict
   const int i = threadIdx.x;
   if (i < a.n) grads[i] = __fmul_rn(a.w[i], *g);
 }
+}  // namespace carel
 
 extern "C" int carel_wsum_fwd(const float* const* terms_host, const float* weights_host, int n, float* out,
                               void* stream) {
