@@ -343,11 +343,47 @@ class DrlClassifierVI(_DrlClassifierBase):
         ec_mu, ec_log_var = self.get_ec_emb(c_embedding.detach())
         return -((-(ec_mu - e_embedding) ** 2 / ec_log_var.exp() - ec_log_var).sum(dim=1).mean(dim=0))
 
+    # ---- CLUB negative sampling ---------------------------------------------------------------
+    def _negative_slots(self, n):
+        """Two pinned host buffers per batch size: the permutation is drawn on the CPU generator exactly like the
+        reference's `torch.randperm(N)` (vi_final:433) and reaches the GPU by an ASYNC copy from pinned memory — no
+        host sync, and under CUDA-graph capture the copy becomes a graph node that re-reads slot 0 on every replay."""
+        slots = self.__dict__.setdefault("_perm_slots", {})
+        if n not in slots:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("run one eager step (or redraw_negative_index) before capturing the VI step")
+            slots[n] = {"host": [torch.empty(n, dtype=torch.long).pin_memory() for _ in range(2)],
+                        "busy": [None, None], "next": 0}
+        return slots[n]
+
+    def redraw_negative_index(self, n):
+        """For CUDA-graph users: draw the next permutation into the slot the captured copy reads (call between replays,
+        once the previous replay's copy has run)."""
+        torch.randperm(n, out=self._negative_slots(n)["host"][0])
+
+    def _negative_index(self, n, device):
+        s = self._negative_slots(n)
+        if torch.cuda.is_current_stream_capturing():
+            torch.randperm(n, out=s["host"][0])
+            return s["host"][0].to(device, non_blocking=True)
+        k = s["next"]
+        s["next"] ^= 1
+        if s["busy"][k] is not None:
+            s["busy"][k].synchronize()              # the copy issued two calls ago has long finished
+        torch.randperm(n, out=s["host"][k])
+        idx = s["host"][k].to(device, non_blocking=True)
+        s["busy"][k] = torch.cuda.Event()
+        s["busy"][k].record()
+        return idx
+
     def get_ec_upper_loss(self, e_embedding, c_embedding):
         ec_mu, ec_log_var = self.get_ec_emb(c_embedding)
-        random_index = torch.randperm(e_embedding.shape[0]).long()          # CPU generator, as the reference
+        if e_embedding.is_cuda:
+            random_index = self._negative_index(e_embedding.shape[0], e_embedding.device)
+        else:
+            random_index = torch.randperm(e_embedding.shape[0]).long()      # CPU generator, as the reference
         positive = -(ec_mu - e_embedding) ** 2 / ec_log_var.exp()
-        negative = -(ec_mu - e_embedding[random_index.to(e_embedding.device)]) ** 2 / ec_log_var.exp()
+        negative = -(ec_mu - e_embedding[random_index]) ** 2 / ec_log_var.exp()
         return (positive.sum(dim=-1) - negative.sum(dim=-1)).mean() / 2.0
 
     def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,

@@ -213,3 +213,37 @@ def test_weighted_sum_is_bit_identical_to_the_scalar_chain():
         F.weighted_sum([kl], [1.0])
     with pytest.raises(cv._lib.CarelError):
         F.weighted_sum([torch.ones(17, device=DEV)], [tuple([1.0] * 17)])
+
+
+def test_vi_step_is_graph_capturable_and_draws_the_reference_permutation():
+    """CLUB negatives: same CPU-generator permutation as `torch.randperm(N)` (vi_final:433), delivered by an async copy
+    from pinned memory, so the VI train step can be replayed as a CUDA graph; the replay picks up the permutation
+    drawn by redraw_negative_index."""
+    opt, model, b = _setup("vi", 128, 24, 1000, 768, 0.0, seed=3)
+    z_e, z_c = torch.randn(128, 24, device=DEV), torch.randn(128, 24, device=DEV)
+    torch.manual_seed(11)
+    ours = model.get_ec_upper_loss(z_e, z_c)
+    torch.manual_seed(11)
+    perm = torch.randperm(128).to(DEV)
+    mu, lv = model.get_ec_emb(z_c)
+    ref = ((-(mu - z_e) ** 2 / lv.exp()).sum(-1) - (-(mu - z_e[perm]) ** 2 / lv.exp()).sum(-1)).mean() / 2.0
+    assert torch.equal(ours, ref)
+    out = torch.zeros((), device=DEV)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        out.copy_(model.get_ec_upper_loss(z_e, z_c).detach())
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.graph(g):
+        out.copy_(model.get_ec_upper_loss(z_e, z_c))
+    for seed in (5, 6):
+        torch.manual_seed(seed)
+        model.redraw_negative_index(128)
+        g.replay()
+        torch.cuda.synchronize()
+        torch.manual_seed(seed)
+        perm = torch.randperm(128).to(DEV)
+        ref = ((-(mu - z_e) ** 2 / lv.exp()).sum(-1) - (-(mu - z_e[perm]) ** 2 / lv.exp()).sum(-1)).mean() / 2.0
+        assert torch.allclose(out, ref.detach(), rtol=1e-6, atol=1e-7)
