@@ -43,6 +43,8 @@ _SIGNATURES = {
                                   C.POINTER(C.c_float), c_ptr, i64, C.POINTER(C.c_void_p), c_ptr, C.c_size_t, c_ptr]),
     "carel_wsum_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_float), C.c_int, c_ptr, c_ptr]),
     "carel_wsum_bwd": (C.c_int, [c_ptr, C.POINTER(C.c_float), C.c_int, c_ptr, c_ptr]),
+    "carel_club_fwd": (C.c_int, [c_ptr, c_ptr, c_ptr, i64, c_ptr, i64, i64, c_ptr, c_ptr, c_ptr]),
+    "carel_club_bwd": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, i64, c_ptr, i64, i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "carel_latent_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "carel_latent_fwd": (C.c_int, [c_ptr, i64, i64, i64, i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_ptr,
                                    c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),

@@ -151,9 +151,58 @@ static __global__ void reparam_kl_bwd_kernel(const float* __restrict__ pre, int 
                                              const float* __restrict__ gz, int ldgz,
                                              const float* __restrict__ gkl, int N, int L,
                                              __nv_bfloat16* __restrict__ dpre, int ldd) {
-  const long long total = 1LL * N * 2 * L;
   const float invN = 1.f / float(N);
   const float g0 = gkl ? __ldg(gkl) : 0.f, g1 = gkl ? __ldg(gkl + 1) : 0.f;
+  // one element: gradient pair + its two-term bf16 split
+  auto one = [&](float mu, float lv, float eps, float dz, float g, float& dmu, float& dlv) {
+    const float e = __expf(lv);
+    dmu = dz + g * mu * invN;
+    dlv = dz * eps * e - 0.5f * g * (1.f - e) * invN;
+  };
+  const bool vec = ((L & 3) == 0) && ((ldp & 3) == 0) && ((ldd & 3) == 0) && (gz == nullptr || (ldgz & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(pre) & 15) == 0) && ((reinterpret_cast<uintptr_t>(gz) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(eps_e) & 15) == 0) && ((reinterpret_cast<uintptr_t>(eps_c) & 15) == 0);
+  if (vec) {
+    // four latent dims per thread: 128-bit loads, 64-bit bf16x4 stores, 32-bit index arithmetic
+    const int L4 = L >> 2;
+    const unsigned total = unsigned(N) * 2u * unsigned(L4);       // < 2^32 for every shape the GEMMs accept
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+      const unsigned c4 = t % unsigned(L4), rs = t / unsigned(L4);
+      const int sp = int(rs & 1u), row = int(rs >> 1), c = int(c4) * 4;
+      const float* base = pre + size_t(row) * ldp + sp * 2 * L + c;
+      const float4 m4 = *reinterpret_cast<const float4*>(base);
+      const float4 l4 = *reinterpret_cast<const float4*>(base + L);
+      const float4 e4 = __ldg(reinterpret_cast<const float4*>((sp ? eps_c : eps_e) + c));
+      const float4 d4 = gz ? *reinterpret_cast<const float4*>(gz + size_t(row) * ldgz + sp * L + c)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float g = sp ? g1 : g0;
+      float dm[4], dl[4];
+      one(m4.x, l4.x, e4.x, d4.x, g, dm[0], dl[0]);
+      one(m4.y, l4.y, e4.y, d4.y, g, dm[1], dl[1]);
+      one(m4.z, l4.z, e4.z, d4.z, g, dm[2], dl[2]);
+      one(m4.w, l4.w, e4.w, d4.w, g, dm[3], dl[3]);
+      auto split4 = [](const float (&v)[4], uint2& hi, uint2& lo) {
+        __nv_bfloat16 h[4];
+        float r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h[i] = __float2bfloat16_rn(v[i]); r[i] = v[i] - __bfloat162float(h[i]); }
+        hi.x = pack_bf16x2(__bfloat162float(h[0]), __bfloat162float(h[1]));
+        hi.y = pack_bf16x2(__bfloat162float(h[2]), __bfloat162float(h[3]));
+        lo.x = pack_bf16x2(r[0], r[1]);
+        lo.y = pack_bf16x2(r[2], r[3]);
+      };
+      uint2 mh, ml, lh, ll;
+      split4(dm, mh, ml);
+      split4(dl, lh, ll);
+      __nv_bfloat16* o = dpre + size_t(row) * 2 * ldd + sp * 2 * L + c;
+      *reinterpret_cast<uint2*>(o) = mh;
+      *reinterpret_cast<uint2*>(o + L) = lh;
+      *reinterpret_cast<uint2*>(o + ldd) = ml;
+      *reinterpret_cast<uint2*>(o + ldd + L) = ll;
+    }
+    return;
+  }
+  const long long total = 1LL * N * 2 * L;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     const int c = int(t % L);
@@ -163,10 +212,8 @@ static __global__ void reparam_kl_bwd_kernel(const float* __restrict__ pre, int 
     const float lv = pre[size_t(row) * ldp + sp * 2 * L + L + c];
     const float eps = __ldg((sp ? eps_c : eps_e) + c);
     const float dz = gz ? gz[size_t(row) * ldgz + sp * L + c] : 0.f;
-    const float g = sp ? g1 : g0;
-    const float e = __expf(lv);
-    const float dmu = dz + g * mu * invN;
-    const float dlv = dz * eps * e - 0.5f * g * (1.f - e) * invN;
+    float dmu, dlv;
+    one(mu, lv, eps, dz, sp ? g1 : g0, dmu, dlv);
     __nv_bfloat16* o = dpre + size_t(row) * 2 * ldd + sp * 2 * L;
     const __nv_bfloat16 mh = __float2bfloat16_rn(dmu), lh = __float2bfloat16_rn(dlv);
     o[c] = mh;

@@ -345,6 +345,53 @@ def weighted_sum(tensors, weights) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------
+# CLUB terms of the VI variant (elementwise tails after the two small MLPs)
+# --------------------------------------------------------------------------------------------
+class _ClubFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu_hat, lv_hat, e, perm):
+        _require_cuda(mu_hat, lv_hat, e)
+        mf, lf = mu_hat.detach().float().contiguous(), lv_hat.detach().float().contiguous()
+        ef = _rowmajor_f32(e.detach())
+        N, L = mf.shape
+        if lf.shape != (N, L) or ef.shape != (N, L):
+            raise ValueError(f"club: shapes {tuple(mf.shape)}, {tuple(lf.shape)}, {tuple(ef.shape)} do not match")
+        pf = None
+        if perm is not None:
+            pf = perm.to(device=mf.device, dtype=torch.int64).contiguous()
+            if pf.shape != (N,):
+                raise ValueError(f"club: perm must have shape ({N},), got {tuple(pf.shape)}")
+        out = torch.empty((), dtype=torch.float32, device=mf.device)
+        acc = torch.empty(1, dtype=torch.float64, device=mf.device)
+        check(lib().carel_club_fwd(_p(mf), _p(lf), _p(ef), ef.stride(0), _p(pf), N, L, _p(out), _p(acc), _stream()),
+              "carel_club_fwd")
+        ctx.keep = (mf, lf, ef, pf)
+        ctx.dts = (mu_hat.dtype, lv_hat.dtype, e.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        mf, lf, ef, pf = ctx.keep
+        N, L = mf.shape
+        g = g.reshape(()).float().contiguous()
+        need = ctx.needs_input_grad
+        gs = [torch.empty((N, L), dtype=torch.float32, device=mf.device) if need[i] else None for i in range(3)]
+        check(lib().carel_club_bwd(_p(g), _p(mf), _p(lf), _p(ef), ef.stride(0), _p(pf), N, L, _p(gs[0]), _p(gs[1]),
+                                   _p(gs[2]), _stream()), "carel_club_bwd")
+        return tuple(None if t is None else t.to(dt) for t, dt in zip(gs, ctx.dts)) + (None,)
+
+
+def club_aprx_loss(mu_hat, lv_hat, e_embedding) -> torch.Tensor:
+    """-mean_i sum_d [-(mu - e)^2 / exp(lv) - lv]  (get_ec_aprx_loss, drl_classifier_ec_vi_final.py:421-426, after the MLPs)."""
+    return _ClubFn.apply(mu_hat, lv_hat, e_embedding, None)
+
+
+def club_upper_bound(mu_hat, lv_hat, e_embedding, perm) -> torch.Tensor:
+    """mean_i [sum_d -(mu - e)^2/exp(lv) - sum_d -(mu - e[perm])^2/exp(lv)] / 2  (get_ec_upper_loss, :428-439)."""
+    return _ClubFn.apply(mu_hat, lv_hat, e_embedding, perm)
+
+
+# --------------------------------------------------------------------------------------------
 # BoW reconstruction: decoder GEMM fused with softmax + BCE
 # --------------------------------------------------------------------------------------------
 DEFAULT_ELL_CAP = 64

@@ -341,6 +341,8 @@ class DrlClassifierVI(_DrlClassifierBase):
 
     def get_ec_aprx_loss(self, e_embedding, c_embedding):
         ec_mu, ec_log_var = self.get_ec_emb(c_embedding.detach())
+        if e_embedding.is_cuda:
+            return F.club_aprx_loss(ec_mu, ec_log_var, e_embedding)
         return -((-(ec_mu - e_embedding) ** 2 / ec_log_var.exp() - ec_log_var).sum(dim=1).mean(dim=0))
 
     # ---- CLUB negative sampling ---------------------------------------------------------------
@@ -380,8 +382,8 @@ class DrlClassifierVI(_DrlClassifierBase):
         ec_mu, ec_log_var = self.get_ec_emb(c_embedding)
         if e_embedding.is_cuda:
             random_index = self._negative_index(e_embedding.shape[0], e_embedding.device)
-        else:
-            random_index = torch.randperm(e_embedding.shape[0]).long()      # CPU generator, as the reference
+            return F.club_upper_bound(ec_mu, ec_log_var, e_embedding, random_index)
+        random_index = torch.randperm(e_embedding.shape[0]).long()          # CPU generator, as the reference
         positive = -(ec_mu - e_embedding) ** 2 / ec_log_var.exp()
         negative = -(ec_mu - e_embedding[random_index]) ** 2 / ec_log_var.exp()
         return (positive.sum(dim=-1) - negative.sum(dim=-1)).mean() / 2.0

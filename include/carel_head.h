@@ -198,6 +198,22 @@ int carel_heads_bwd(const float* grad_out, const float* z, int64_t ldz, int64_t 
 int carel_wsum_fwd(const float* const* terms_host, const float* weights_host, int n, float* out, void* stream);
 int carel_wsum_bwd(const float* grad_out, const float* weights_host, int n, float* grads, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * CLUB terms of the VI variant — replace the elementwise tails of get_ec_aprx_loss / get_ec_upper_loss
+ * (drl_classifier_ec_vi_final.py:421-426, :428-439); the two small MLPs ec_mu / ec_log_var stay with the caller.
+ *   mu_hat, lv_hat [N, L] contiguous; e = e_embedding [N, L] with row pitch lde (a column view of z is fine);
+ *   perm == NULL:  out = mean_i sum_d [ (mu - e)^2 / exp(lv) + lv ]                               (aprx loss)
+ *   perm != NULL:  out = mean_i sum_d [ (mu - e[perm[i]])^2 - (mu - e)^2 ] / exp(lv) / 2          (upper bound; perm =
+ *                  the caller's torch.randperm(N) as int64 on the device, a permutation of 0..N-1)
+ *   acc: 8 bytes of device scratch.  The backward writes grad_mu / grad_lv / grad_e [N, L] contiguous (each may be
+ *   NULL) for d(out) = *grad_out.
+ * ------------------------------------------------------------------------------------------ */
+int carel_club_fwd(const float* mu_hat, const float* lv_hat, const float* e, int64_t lde, const int64_t* perm,
+                   int64_t N, int64_t L, float* out, double* acc, void* stream);
+int carel_club_bwd(const float* grad_out, const float* mu_hat, const float* lv_hat, const float* e, int64_t lde,
+                   const int64_t* perm, int64_t N, int64_t L, float* grad_mu, float* grad_lv, float* grad_e,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
