@@ -32,7 +32,7 @@ club_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, cons
       const float dp = m - er[d];
       if (UPPER) {
         const float dn = m - ep[d];
-        s += dn * dn / den - dp * dp / den;
+        s += (dn - dp) * (dn + dp) / den;          // = (dn^2 - dp^2) / den without the cancellation
       } else {
         s += dp * dp / den + l;
       }
@@ -69,11 +69,12 @@ club_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ mu
       const float dp = m - er[d];
       if (UPPER) {
         const float dn = m - ep[d];
-        if (g_mu) g_mu[o + d] = 2.f * inv * (dn - dp) * g;
-        if (g_lv) g_lv[o + d] = -inv * (dn * dn - dp * dp) * g;
+        const float w = inv * g, w2 = 2.f * w;         // shared factors: a fixed point pi(i) = i cancels exactly
+        if (g_mu) g_mu[o + d] = w2 * (dn - dp);
+        if (g_lv) g_lv[o + d] = -w * ((dn - dp) * (dn + dp));
         if (g_e) {
-          atomicAdd(g_e + o + d, 2.f * inv * dp * g);
-          atomicAdd(g_e + size_t(pr) * L + d, -2.f * inv * dn * g);
+          atomicAdd(g_e + o + d, w2 * dp);
+          atomicAdd(g_e + size_t(pr) * L + d, -(w2 * dn));
         }
       } else {
         const float t = 2.f * inv * dp * g;
