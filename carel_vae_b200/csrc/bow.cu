@@ -710,59 +710,76 @@ static __global__ void __launch_bounds__(256, MODE == 0 ? 3 : 1) bow_sparse_kern
 // ---------------------------------------------------------------------------------------------
 static __global__ void csc_count_kernel(const int* __restrict__ cols, const int* __restrict__ nnz, int N,
                                         int cap, int* __restrict__ cnt) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < 1LL * N * cap;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int r = int(t / cap), q = int(t % cap), n = nnz[r];
+  // N * cap < 2^31 for every workspace this library carves (the ELL arrays are int-indexed)
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < unsigned(N) * unsigned(cap); t += gridDim.x * blockDim.x) {
+    const int r = int(t / unsigned(cap)), q = int(t % unsigned(cap)), n = nnz[r];
     if (n <= cap && q < n) atomicAdd(cnt + cols[t], 1);
   }
 }
-// Exclusive scan of the per-word counts (one block; cnt may alias fillpos).  The counts are staged through
-// shared memory in chunks of 8 per thread so that every global access is coalesced; the 1024 thread totals of a
-// chunk are scanned with warp shuffles (two block barriers instead of the twenty of a shared-memory ladder).
+// Exclusive scan of the per-word counts (one block; cnt may alias fillpos).  Each thread owns 32 consecutive counts
+// (eight 128-bit loads straight from L2, scanned in registers), the 1024 thread totals are scanned with warp
+// shuffles: one pass and two block barriers per 32768 words (V = 30000: a single pass).
 static __global__ void __launch_bounds__(1024) csc_scan_kernel(const int* cnt, int V, int* colptr, int* fillpos) {
-  constexpr int PER = 8, CH = 1024 * PER;
-  __shared__ int buf[CH];
+  constexpr int PER = 32, CH = 1024 * PER;
   __shared__ int wtot[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool vec = ((reinterpret_cast<uintptr_t>(cnt) | reinterpret_cast<uintptr_t>(colptr) |
+                     reinterpret_cast<uintptr_t>(fillpos)) & 15) == 0;
   int carry = 0;                                  // every thread tracks the running total
   for (int base = 0; base < V; base += CH) {
-    for (int i = threadIdx.x; i < CH; i += 1024) buf[i] = (base + i < V) ? cnt[base + i] : 0;
-    __syncthreads();
-    int loc[PER], s = 0;
+    const int i0 = base + threadIdx.x * PER;
+    int v[PER];
+    if (vec && i0 + PER <= V) {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { loc[i] = s; s += buf[threadIdx.x * PER + i]; }
+      for (int q = 0; q < PER / 4; ++q) {
+        const int4 t = *reinterpret_cast<const int4*>(cnt + i0 + 4 * q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < PER; ++i) v[i] = (i0 + i < V) ? cnt[i0 + i] : 0;
+    }
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { const int t = v[i]; v[i] = s; s += t; }      // thread-local exclusive scan
     int incl = s;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += v;
+      const int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
     }
+    __syncthreads();                              // wtot of the previous chunk has been read by everyone
     if (lane == 31) wtot[warp] = incl;
     __syncthreads();
     int wv = wtot[lane];                          // every warp scans the 32 warp totals itself
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, wv, off);
-      if (lane >= off) wv += v;
+      const int t = __shfl_up_sync(0xffffffffu, wv, off);
+      if (lane >= off) wv += t;
     }
     const int before = __shfl_sync(0xffffffffu, wv, (warp + 31) & 31);
     const int run = carry + (warp > 0 ? before : 0) + incl - s;
     carry += __shfl_sync(0xffffffffu, wv, 31);
+    if (vec && i0 + PER <= V) {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) buf[threadIdx.x * PER + i] = run + loc[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < CH; i += 1024)
-      if (base + i < V) { colptr[base + i] = buf[i]; fillpos[base + i] = buf[i]; }
-    __syncthreads();
+      for (int q = 0; q < PER / 4; ++q) {
+        const int4 t = make_int4(run + v[4 * q], run + v[4 * q + 1], run + v[4 * q + 2], run + v[4 * q + 3]);
+        *reinterpret_cast<int4*>(colptr + i0 + 4 * q) = t;
+        *reinterpret_cast<int4*>(fillpos + i0 + 4 * q) = t;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < PER; ++i)
+        if (i0 + i < V) { colptr[i0 + i] = run + v[i]; fillpos[i0 + i] = run + v[i]; }
+    }
   }
   if (threadIdx.x == 0) colptr[V] = carry;
 }
 static __global__ void csc_fill_kernel(const int* __restrict__ cols, const int* __restrict__ nnz, int N,
                                        int cap, int* __restrict__ fillpos, int* __restrict__ csc_row,
                                        int* __restrict__ csc_slot) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < 1LL * N * cap;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int r = int(t / cap), q = int(t % cap), n = nnz[r];
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < unsigned(N) * unsigned(cap); t += gridDim.x * blockDim.x) {
+    const int r = int(t / unsigned(cap)), q = int(t % unsigned(cap)), n = nnz[r];
     if (n <= cap && q < n) {
       const int pos = atomicAdd(fillpos + cols[t], 1);
       csc_row[pos] = r;
@@ -1135,6 +1152,7 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
                              float* loss_out, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CAREL_REQUIRE(N > 0 && K > 0 && V > 0 && ell_cap > 0, "carel_bow_fwd: empty problem");
+  CAREL_REQUIRE(N * ell_cap < (int64_t(1) << 31), "carel_bow_fwd: N * ell_cap must stay below 2^31 (int-indexed ELL / CSC arrays)");
   CAREL_REQUIRE(K % 16 == 0 && K <= 256, "carel_bow_fwd: decoder input width (2 * ec_dim) must be a multiple of 16 and <= 256, got %lld", (long long)K);
   CAREL_REQUIRE(bow_dense != nullptr || (ell_cols_in && ell_vals_in && ell_nnz_in), "carel_bow_fwd: need a dense or an ELL target");
   BowWs w = carve_bow(ws, N, K, V, ell_cap);

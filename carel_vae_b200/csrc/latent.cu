@@ -234,25 +234,20 @@ static __global__ void zero_pad_cols_kernel(__nv_bfloat16* p, int rows, int c0, 
   }
 }
 
-// scatter the fp32 [4L, ldx] accumulation buffer into the eight nn.Linear gradients
+// scatter the fp32 [4L, ldx] accumulation buffer (hi rows + lo rows) into the eight nn.Linear gradients:
+// one block per output row (the target pointers are block-uniform), coalesced columns
 static __global__ void latent_scatter_grads_kernel(const float* __restrict__ dW, int ldx, int ldd, int L, int D,
                                                    float* gw0, float* gw1, float* gw2, float* gw3,
                                                    float* gb0, float* gb1, float* gb2, float* gb3) {
-  float* gw[4] = {gw0, gw1, gw2, gw3};
-  float* gb[4] = {gb0, gb1, gb2, gb3};
-  const long long total = 4LL * L * (D + 1);
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int c = int(t % (D + 1));
-    const int r = int(t / (D + 1));
-    const int blk = r / L, rr = r - blk * L;
-    const float v = dW[size_t(r) * ldx + c] + dW[size_t(ldd + r) * ldx + c];
-    if (c < D) {
-      if (gw[blk]) gw[blk][size_t(rr) * D + c] = v;
-    } else if (gb[blk]) {
-      gb[blk][rr] = v;
-    }
-  }
+  const int r = blockIdx.x;                     // 0 .. 4L-1
+  const int blk = r / L, rr = r - blk * L;
+  float* gw = blk == 0 ? gw0 : blk == 1 ? gw1 : blk == 2 ? gw2 : gw3;
+  float* gb = blk == 0 ? gb0 : blk == 1 ? gb1 : blk == 2 ? gb2 : gb3;
+  const float* hi = dW + size_t(r) * ldx;
+  const float* lo = dW + size_t(ldd + r) * ldx;
+  if (gw != nullptr)
+    for (int c = threadIdx.x; c < D; c += blockDim.x) gw[size_t(rr) * D + c] = hi[c] + lo[c];
+  if (gb != nullptr && threadIdx.x == 0) gb[rr] = hi[D] + lo[D];
 }
 
 }  // namespace carel
@@ -346,7 +341,7 @@ extern "C" int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* 
     ep.out = w.dW; ep.bias = nullptr; ep.out_bf16 = nullptr; ep.M = int(K2); ep.N = int(D + 1);
     ep.ld = w.ldx; ep.ld_bf16 = 0; ep.atomic = 1; ep.scale = 1.f;
     if (int rc = launch_gemm<EpiStore<256>, 256, 1, true, true>(ta, tb, ta, tb, s, ep, st, "latent_dw")) return rc;
-    latent_scatter_grads_kernel<<<148, 256, 0, st>>>(w.dW, w.ldx, w.ldd, int(L), int(D), grad_w4[0], grad_w4[1],
+    latent_scatter_grads_kernel<<<int(4 * L), 256, 0, st>>>(w.dW, w.ldx, w.ldd, int(L), int(D), grad_w4[0], grad_w4[1],
                                                     grad_w4[2], grad_w4[3], grad_b4[0], grad_b4[1],
                                                     grad_b4[2], grad_b4[3]);
     CAREL_LAUNCHED();
