@@ -43,7 +43,16 @@ struct HeadsArgs {
 
 static CAREL_DEVINL float softplus_neg(float x) { return log1pf(__expf(-fabsf(x))) + fmaxf(-x, 0.f); }   // log(1 + e^-x)
 
-static __global__ void __launch_bounds__(256) heads_fwd_kernel(const HeadsArgs a) {
+CAREL_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+CAREL_DEVINL float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+CAREL_DEVINL float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+CAREL_DEVINL float dot4(float4 a, float4 b, float acc) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc)))); }
+
+// VEC: L % 4 == 0 and every pointer / pitch 16-byte aligned: lane l owns latent dims 4l .. 4l+3 of each half, so a
+// row is six 128-bit loads per lane, all in flight at once (the scalar form issues 24 dependent-address 32-bit loads
+// and needed 1160 instructions per row; ncu: long-scoreboard bound at 3 blocks per SM).
+template <bool VEC>
+static __global__ void __launch_bounds__(256, 4) heads_fwd_kernel(const HeadsArgs a) {
   __shared__ double sh[8][5];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int L = a.L, nk = (L + 31) / 32;          // per-lane elements of each half
@@ -53,6 +62,23 @@ static __global__ void __launch_bounds__(256) heads_fwd_kernel(const HeadsArgs a
     float acc_e[kHeadsMaxC], acc_c = 0.f, acc_p = 0.f;
 #pragma unroll
     for (int c = 0; c < kHeadsMaxC; ++c) acc_e[c] = 0.f;
+    if (VEC) {
+      const int k = lane * 4;
+      if (k < L) {
+        const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 ze = ld4(zr + k), zc = ld4(zr + L + k);
+        const float4 me = a.m_e ? ld4(a.m_e + size_t(r) * L + k) : one;
+        const float4 mc = a.m_c ? ld4(a.m_c + size_t(r) * L + k) : one;
+        const float4 mpe = a.m_p ? ld4(a.m_p + size_t(r) * 2 * L + k) : one;
+        const float4 mpc = a.m_p ? ld4(a.m_p + size_t(r) * 2 * L + L + k) : one;
+        const float4 xe = mul4(ze, me), xc = mul4(zc, mc), pe = mul4(ze, mpe), pc = mul4(zc, mpc);
+#pragma unroll
+        for (int c = 0; c < kHeadsMaxC; ++c)
+          if (c < a.C_e) acc_e[c] = dot4(xe, ldg4(a.W_e + size_t(c) * L + k), 0.f);
+        acc_c = dot4(xc, ldg4(a.W_c + k), 0.f);
+        acc_p = dot4(pe, ldg4(a.W_p + k), dot4(pc, ldg4(a.W_p + L + k), 0.f));
+      }
+    } else
 #pragma unroll 4
     for (int q = 0; q < nk; ++q) {
       const int k = q * 32 + lane;
@@ -138,11 +164,21 @@ static __global__ void heads_finalize_kernel(const double* __restrict__ sums, in
   losses[3] = w_e * losses[0] + w_c * losses[1] + w_p * lp;
 }
 
-static __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsArgs a) {
-  __shared__ float sh_w[8][kHeadsMaxC + 3][kHeadsMaxK * 32 / 2 + 1];   // per warp: dW_e rows | dW_c | dW_p (two halves)
-  __shared__ float sh_b[8][kHeadsMaxC + 2];
+// Weight gradients accumulate in ONE shared-memory tile per block (float atomics, lanes on distinct addresses) instead
+// of per-warp register accumulators + a per-warp shared slice: 168 -> <= 64 registers and 46 KB -> 6 KB of shared
+// memory, so 4 blocks (32 warps) per SM instead of 1 block (8 warps); ncu had the old form long-scoreboard bound at
+// 12 % of the warp slots.  Each block ends with one global atomic per non-zero weight-gradient element.
+template <bool VEC>
+static __global__ void __launch_bounds__(256, 4) heads_bwd_kernel(const HeadsArgs a) {
+  constexpr int kRows = kHeadsMaxC + 3;                      // dW_e rows | dW_c | dW_p (emotion half) | dW_p (cause half)
+  constexpr int kW = kHeadsMaxK * 32 / 2;                    // 128 = max L
+  __shared__ float sh_w[kRows][kW];
+  __shared__ float sh_b[kHeadsMaxC + 2];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int L = a.L, nk = (L + 31) / 32;
+  for (int i = threadIdx.x; i < kRows * kW; i += blockDim.x) (&sh_w[0][0])[i] = 0.f;
+  if (threadIdx.x < kHeadsMaxC + 2) sh_b[threadIdx.x] = 0.f;
+  __syncthreads();
   const float invN = 1.f / float(a.N);
   const float g0 = __ldg(a.g);
   const float ge = g0 * a.wgt[0], gc = g0 * a.wgt[1], gp = g0 * a.wgt[2];
@@ -150,16 +186,7 @@ static __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsArgs a
   // the guard zeroes the pair loss when it is infinite: then it has no gradient either
   float lp_chk = (float(a.sums[2]) + (pw - 1.f) * float(a.sums[3])) * invN;
   const bool pair_dead = a.guard_inf && isinf(lp_chk);
-  float gw_e[kHeadsMaxC][kHeadsMaxK / 2], gw_c[kHeadsMaxK / 2], gw_p[kHeadsMaxK];
   float gb[kHeadsMaxC + 2];
-#pragma unroll
-  for (int c = 0; c < kHeadsMaxC; ++c)
-#pragma unroll
-    for (int q = 0; q < kHeadsMaxK / 2; ++q) gw_e[c][q] = 0.f;
-#pragma unroll
-  for (int q = 0; q < kHeadsMaxK / 2; ++q) gw_c[q] = 0.f;
-#pragma unroll
-  for (int q = 0; q < kHeadsMaxK; ++q) gw_p[q] = 0.f;
 #pragma unroll
   for (int c = 0; c < kHeadsMaxC + 2; ++c) gb[c] = 0.f;
 
@@ -205,50 +232,63 @@ static __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsArgs a
     gb[kHeadsMaxC + 1] += dl_p;
     const float* zr = a.z + size_t(r) * a.ldz;
     float* dzr = a.dz + size_t(r) * a.lddz;
+    // one latent dim k of both halves: its dz pair and its eleven weight-gradient contributions
+    auto one = [&](int k, float ze, float zc, float me, float mc, float mpe, float mpc, float& dze, float& dzc) {
+      float de = 0.f;
 #pragma unroll
-    for (int q = 0; q < kHeadsMaxK / 2; ++q) {
-      const int k = q * 32 + lane;
-      if (q < nk && k < L) {
-        const float ze = zr[k], zc = zr[L + k];
-        const float me = a.m_e ? a.m_e[size_t(r) * L + k] : 1.f;
-        const float mc = a.m_c ? a.m_c[size_t(r) * L + k] : 1.f;
-        const float mpe = a.m_p ? a.m_p[size_t(r) * 2 * L + k] : 1.f;
-        const float mpc = a.m_p ? a.m_p[size_t(r) * 2 * L + L + k] : 1.f;
-        float de = 0.f;
-#pragma unroll
-        for (int c = 0; c < kHeadsMaxC; ++c) {
-          if (c < a.C_e) {
-            de = fmaf(dl_e[c], __ldg(a.W_e + size_t(c) * L + k), de);
-            gw_e[c][q] = fmaf(dl_e[c], ze * me, gw_e[c][q]);
-          }
+      for (int c = 0; c < kHeadsMaxC; ++c) {
+        if (c < a.C_e) {
+          de = fmaf(dl_e[c], __ldg(a.W_e + size_t(c) * L + k), de);
+          atomicAdd(&sh_w[c][k], dl_e[c] * (ze * me));
         }
-        gw_c[q] = fmaf(dl_c, zc * mc, gw_c[q]);
-        gw_p[q] = fmaf(dl_p, ze * mpe, gw_p[q]);
-        gw_p[kHeadsMaxK / 2 + q] = fmaf(dl_p, zc * mpc, gw_p[kHeadsMaxK / 2 + q]);
-        dzr[k] = de * me + dl_p * __ldg(a.W_p + k) * mpe;
-        dzr[L + k] = dl_c * __ldg(a.W_c + k) * mc + dl_p * __ldg(a.W_p + L + k) * mpc;
+      }
+      atomicAdd(&sh_w[kHeadsMaxC][k], dl_c * (zc * mc));
+      atomicAdd(&sh_w[kHeadsMaxC + 1][k], dl_p * (ze * mpe));
+      atomicAdd(&sh_w[kHeadsMaxC + 2][k], dl_p * (zc * mpc));
+      dze = de * me + dl_p * __ldg(a.W_p + k) * mpe;
+      dzc = dl_c * __ldg(a.W_c + k) * mc + dl_p * __ldg(a.W_p + L + k) * mpc;
+    };
+    if (VEC) {
+      const int k = lane * 4;
+      if (k < L) {
+        const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 ze = ld4(zr + k), zc = ld4(zr + L + k);
+        const float4 me = a.m_e ? ld4(a.m_e + size_t(r) * L + k) : one4;
+        const float4 mc = a.m_c ? ld4(a.m_c + size_t(r) * L + k) : one4;
+        const float4 mpe = a.m_p ? ld4(a.m_p + size_t(r) * 2 * L + k) : one4;
+        const float4 mpc = a.m_p ? ld4(a.m_p + size_t(r) * 2 * L + L + k) : one4;
+        float4 de, dc;
+        one(k, ze.x, zc.x, me.x, mc.x, mpe.x, mpc.x, de.x, dc.x);
+        one(k + 1, ze.y, zc.y, me.y, mc.y, mpe.y, mpc.y, de.y, dc.y);
+        one(k + 2, ze.z, zc.z, me.z, mc.z, mpe.z, mpc.z, de.z, dc.z);
+        one(k + 3, ze.w, zc.w, me.w, mc.w, mpe.w, mpc.w, de.w, dc.w);
+        *reinterpret_cast<float4*>(dzr + k) = de;
+        *reinterpret_cast<float4*>(dzr + L + k) = dc;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kHeadsMaxK / 2; ++q) {
+        const int k = q * 32 + lane;
+        if (q < nk && k < L) {
+          const float me = a.m_e ? a.m_e[size_t(r) * L + k] : 1.f;
+          const float mc = a.m_c ? a.m_c[size_t(r) * L + k] : 1.f;
+          const float mpe = a.m_p ? a.m_p[size_t(r) * 2 * L + k] : 1.f;
+          const float mpc = a.m_p ? a.m_p[size_t(r) * 2 * L + L + k] : 1.f;
+          one(k, zr[k], zr[L + k], me, mc, mpe, mpc, dzr[k], dzr[L + k]);
+        }
       }
     }
   }
-  // ---- weight gradients: warps -> shared -> one atomic per element and block ----
-#pragma unroll
-  for (int q = 0; q < kHeadsMaxK / 2; ++q) {
-    const int k = q * 32 + lane;
-#pragma unroll
-    for (int c = 0; c < kHeadsMaxC; ++c) sh_w[wid][c][k] = gw_e[c][q];
-    sh_w[wid][kHeadsMaxC][k] = gw_c[q];
-    sh_w[wid][kHeadsMaxC + 1][k] = gw_p[q];
-    sh_w[wid][kHeadsMaxC + 2][k] = gw_p[kHeadsMaxK / 2 + q];
-  }
   if (lane == 0) {
 #pragma unroll
-    for (int c = 0; c < kHeadsMaxC + 2; ++c) sh_b[wid][c] = gb[c];
+    for (int c = 0; c < kHeadsMaxC + 2; ++c)
+      if (gb[c] != 0.f) atomicAdd(&sh_b[c], gb[c]);
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < (kHeadsMaxC + 3) * L; idx += blockDim.x) {
+  // ---- block tile -> one global atomic per non-zero element ----
+  for (int idx = threadIdx.x; idx < kRows * L; idx += blockDim.x) {
     const int row = idx / L, k = idx - row * L;
-    float t = 0.f;
-    for (int w = 0; w < wpb; ++w) t += sh_w[w][row][k];
+    const float t = sh_w[row][k];
     if (t == 0.f) continue;
     if (row < kHeadsMaxC) {
       if (row < a.C_e && a.dW_e) atomicAdd(a.dW_e + size_t(row) * L + k, t);
@@ -259,8 +299,7 @@ static __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsArgs a
     }
   }
   if (threadIdx.x < kHeadsMaxC + 2) {
-    float t = 0.f;
-    for (int w = 0; w < wpb; ++w) t += sh_b[w][threadIdx.x];
+    const float t = sh_b[threadIdx.x];
     const int c = threadIdx.x;
     if (c < kHeadsMaxC) {
       if (c < a.C_e && a.db_e && t != 0.f) atomicAdd(a.db_e + c, t);
@@ -275,6 +314,13 @@ static __global__ void __launch_bounds__(256) heads_bwd_kernel(const HeadsArgs a
 }  // namespace carel
 
 using namespace carel;
+
+// 128-bit path: L a multiple of 4 and every row pointer 16-byte aligned
+static bool heads_vec_ok(const HeadsArgs& a, const float* dz, int64_t lddz) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (a.L % 4 == 0) && (a.ldz % 4 == 0) && al(a.z) && al(a.m_e) && al(a.m_c) && al(a.m_p) && al(a.W_e) &&
+         al(a.W_c) && al(a.W_p) && (dz == nullptr || (al(dz) && lddz % 4 == 0));
+}
 
 extern "C" size_t carel_heads_workspace_bytes(int64_t N, int64_t C_e) {
   return align_up(size_t(N) * size_t(C_e + 2) * 4, 256) + 256;
@@ -312,7 +358,10 @@ extern "C" int carel_heads_fwd(const float* z, int64_t ldz, int64_t N, int64_t L
   if (int rc = heads_fill(a, z, ldz, N, L, C_e, emo_mode, masks3, weights6, emo_labels, cau_labels, pair_labels,
                           label_smoothing, n_e, n_c, n_p, guard_inf, loss_weights3_host, ws, ws_bytes)) return rc;
   CAREL_CHECK_CUDA(cudaMemsetAsync(a.sums, 0, 5 * sizeof(double), st));
-  heads_fwd_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 8)), 256, 0, st>>>(a);
+  if (heads_vec_ok(a, nullptr, 0))
+    heads_fwd_kernel<true><<<int(std::min<int64_t>((N + 7) / 8, 148 * 8)), 256, 0, st>>>(a);
+  else
+    heads_fwd_kernel<false><<<int(std::min<int64_t>((N + 7) / 8, 148 * 8)), 256, 0, st>>>(a);
   CAREL_LAUNCHED();
   heads_finalize_kernel<<<1, 32, 0, st>>>(a.sums, int(N), int(C_e), emo_mode, guard_inf, a.wgt[0], a.wgt[1], a.wgt[2], losses4);
   CAREL_LAUNCHED();
@@ -334,13 +383,34 @@ extern "C" int carel_heads_bwd(const float* grad_out, const float* z, int64_t ld
   a.dz = grad_z; a.lddz = ldgz;
   a.dW_e = grad_weights6[0]; a.db_e = grad_weights6[1]; a.dW_c = grad_weights6[2]; a.db_c = grad_weights6[3];
   a.dW_p = grad_weights6[4]; a.db_p = grad_weights6[5];
-  if (a.dW_e) CAREL_CHECK_CUDA(cudaMemsetAsync(a.dW_e, 0, size_t(C_e) * L * 4, st));
-  if (a.db_e) CAREL_CHECK_CUDA(cudaMemsetAsync(a.db_e, 0, size_t(C_e) * 4, st));
-  if (a.dW_c) CAREL_CHECK_CUDA(cudaMemsetAsync(a.dW_c, 0, size_t(L) * 4, st));
-  if (a.db_c) CAREL_CHECK_CUDA(cudaMemsetAsync(a.db_c, 0, 4, st));
-  if (a.dW_p) CAREL_CHECK_CUDA(cudaMemsetAsync(a.dW_p, 0, size_t(2 * L) * 4, st));
-  if (a.db_p) CAREL_CHECK_CUDA(cudaMemsetAsync(a.db_p, 0, 4, st));
-  heads_bwd_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148)), 256, 0, st>>>(a);     // one block per SM: 148 atomics per weight
+  // zero the accumulation targets: ONE memset when the caller carved them back to back out of one buffer (the Python
+  // wrapper does), else one each
+  {
+    float* ptr[6] = {a.dW_e, a.db_e, a.dW_c, a.db_c, a.dW_p, a.db_p};
+    const size_t cnt[6] = {size_t(C_e) * L, size_t(C_e), size_t(L), 1, size_t(2 * L), 1};
+    float* first = nullptr;
+    float* end = nullptr;
+    bool packed = true;
+    size_t total = 0;
+    for (int i = 0; i < 6; ++i) {
+      if (!ptr[i]) continue;
+      if (first == nullptr) first = ptr[i];
+      else if (ptr[i] != end) packed = false;
+      end = ptr[i] + cnt[i];
+      total += cnt[i];
+    }
+    if (first != nullptr && packed) {
+      CAREL_CHECK_CUDA(cudaMemsetAsync(first, 0, total * 4, st));
+    } else {
+      for (int i = 0; i < 6; ++i)
+        if (ptr[i]) CAREL_CHECK_CUDA(cudaMemsetAsync(ptr[i], 0, cnt[i] * 4, st));
+    }
+  }
+  const int blocks = int(std::min<int64_t>((N + 7) / 8, 148 * 4));      // 4 blocks per SM: 592 atomics per weight element
+  if (heads_vec_ok(a, grad_z, ldgz))
+    heads_bwd_kernel<true><<<blocks, 256, 0, st>>>(a);
+  else
+    heads_bwd_kernel<false><<<blocks, 256, 0, st>>>(a);
   CAREL_LAUNCHED();
   return 0;
 }

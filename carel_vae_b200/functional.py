@@ -271,8 +271,13 @@ class _HeadsFn(torch.autograd.Function):
         g = g.reshape(()).float().contiguous()
         need = ctx.needs_input_grad
         gz = torch.empty((N, 2 * L), dtype=torch.float32, device=zf.device)
-        gws = [torch.empty(shape, dtype=torch.float32, device=zf.device) if need[4 + i] else None
-               for i, shape in enumerate(wshapes)]
+        # the six weight gradients are carved back to back out of one buffer: the library zeroes them with one memset
+        counts = [int(torch.Size(shape).numel()) if need[4 + i] else 0 for i, shape in enumerate(wshapes)]
+        flat = torch.empty(sum(counts), dtype=torch.float32, device=zf.device)
+        gws, off = [], 0
+        for n, shape in zip(counts, wshapes):
+            gws.append(flat[off:off + n].view(shape) if n else None)
+            off += n
         check(lib().carel_heads_bwd(_p(g), _p(zf), zf.stride(0), N, L, C_e, emo_mode, _ptr_array(masks),
                                     _ptr_array(weights), _p(emo), _p(cau), _p(pair), ls, n_e, n_c, n_p, guard,
                                     float_array(wts), _p(gz), 2 * L, _ptr_array(gws), _p(ws), ws.numel(), _stream()),

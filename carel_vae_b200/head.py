@@ -101,11 +101,14 @@ class _DrlClassifierBase(nn.Module):
     def _sentence_emb(self, input_ids, att_masks, token_type_ids):
         return self.encoder(input_ids, attention_mask=att_masks, token_type_ids=token_type_ids).pooler_output
 
-    def _latents(self, sentence_emb):
-        """Fused path.  Returns (z [N, 2L], kl [2], pre [N, 4L])."""
+    def _latents(self, sentence_emb, after_noise=None):
+        """Fused path.  Returns (z [N, 2L], kl [2], pre [N, 4L]).  `after_noise()` runs between the two noise draws
+        and the latent kernels: host-side RNG order is still randn, randn, <whatever it draws>, as in the reference."""
         L = self.opt.ec_dim
         eps_e = torch.randn(L, device=sentence_emb.device)      # same two draws, same order as
         eps_c = torch.randn(L, device=sentence_emb.device)      # sample_prior(emotion), sample_prior(cause)
+        if after_noise is not None:
+            after_noise()
         return F.latent(sentence_emb, eps_e, eps_c,
                         self.emotion_mu.weight, self.emotion_mu.bias,
                         self.emotion_log_var.weight, self.emotion_log_var.bias,
@@ -203,7 +206,12 @@ class _DrlClassifierBase(nn.Module):
         """Scaled dropout mask with the RNG consumption of `self.dropout(x)` on a contiguous [n, k] tensor (the
         mask torch draws depends on shape and layout only), or None in eval mode / p = 0."""
         if self.training and self.dropout.p > 0:
-            return self.dropout(torch.ones((n, k), device=device))
+            # the all-ones input is a constant: keep one per shape instead of filling [n, k] three times a step
+            cache = self.__dict__.setdefault("_ones_cache", {})
+            key = (n, k, str(device))
+            if key not in cache:
+                cache[key] = torch.ones((n, k), device=device)
+            return self.dropout(cache[key])
         return None
 
     def _head_weights(self):
@@ -282,13 +290,27 @@ class DrlClassifierMMD(_DrlClassifierBase):
     def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,
                 iteration):
         o, L = self.opt, self.opt.ec_dim
-        z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
+        emb = self._sentence_emb(input_ids, att_masks, token_type_ids)
+        side, main = self._side(emb.device), torch.cuda.current_stream()
+        masks = []
+
+        def draw_masks():
+            # The three dropout masks depend on nothing but the generator: drawn here (after the two noise draws, in the
+            # reference's order emotion, cause, pair) on the side stream, they run underneath the latent layer's small
+            # kernels instead of in front of the heads.
+            if side is None or not self._fused_heads_ok():
+                return
+            n = emb.shape[0]
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                masks.extend((self._mask(n, L, emb.device), self._mask(n, L, emb.device), self._mask(n, 2 * L, emb.device)))
+
+        z, kl, _ = self._latents(emb, after_noise=draw_masks)
         z_e, z_c = z[:, :L], z[:, L:]
-        side, main = self._side(z.device), torch.cuda.current_stream()
         if side is not None:
             side.wait_stream(main)
         with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
-            heads = self._heads(z, emotion_labels, cause_labels, pair_labels)
+            heads = self._heads(z, emotion_labels, cause_labels, pair_labels, masks=tuple(masks) if masks else None)
         mmd = MMDStatistic(input_ids.shape[0], input_ids.shape[0]).halves(z, [0.1])
         reconstruction_loss = self._reconstruction(z, content_bow)
         if side is not None:
