@@ -101,6 +101,35 @@ class _DrlClassifierBase(nn.Module):
     def _sentence_emb(self, input_ids, att_masks, token_type_ids):
         return self.encoder(input_ids, attention_mask=att_masks, token_type_ids=token_type_ids).pooler_output
 
+    def _latents_and_heads(self, emb, emotion_labels, cause_labels, pair_labels):
+        """Latent layer on the current stream and the classifier heads on the forked side stream (see _side).
+        Returns (z, kl, heads, join): call join() before the heads' loss is consumed on the current stream.
+        The three dropout masks depend on nothing but the generator: they are drawn right after the two noise draws
+        (reference order: randn, randn, emotion / cause / pair masks) on the side stream, so they run underneath
+        the latent layer's small kernels instead of in front of the heads."""
+        L = self.opt.ec_dim
+        side, main = self._side(emb.device), torch.cuda.current_stream()
+        masks = []
+
+        def draw_masks():
+            if side is None or not self._fused_heads_ok():
+                return
+            n = emb.shape[0]
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                masks.extend((self._mask(n, L, emb.device), self._mask(n, L, emb.device), self._mask(n, 2 * L, emb.device)))
+
+        z, kl, _ = self._latents(emb, after_noise=draw_masks)
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            heads = self._heads(z, emotion_labels, cause_labels, pair_labels, masks=tuple(masks) if masks else None)
+
+        def join():
+            if side is not None:
+                main.wait_stream(side)
+        return z, kl, heads, join
+
     def _latents(self, sentence_emb, after_noise=None):
         """Fused path.  Returns (z [N, 2L], kl [2], pre [N, 4L]).  `after_noise()` runs between the two noise draws
         and the latent kernels: host-side RNG order is still randn, randn, <whatever it draws>, as in the reference."""
@@ -289,32 +318,12 @@ class DrlClassifierMMD(_DrlClassifierBase):
 
     def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,
                 iteration):
-        o, L = self.opt, self.opt.ec_dim
+        o = self.opt
         emb = self._sentence_emb(input_ids, att_masks, token_type_ids)
-        side, main = self._side(emb.device), torch.cuda.current_stream()
-        masks = []
-
-        def draw_masks():
-            # The three dropout masks depend on nothing but the generator: drawn here (after the two noise draws, in the
-            # reference's order emotion, cause, pair) on the side stream, they run underneath the latent layer's small
-            # kernels instead of in front of the heads.
-            if side is None or not self._fused_heads_ok():
-                return
-            n = emb.shape[0]
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                masks.extend((self._mask(n, L, emb.device), self._mask(n, L, emb.device), self._mask(n, 2 * L, emb.device)))
-
-        z, kl, _ = self._latents(emb, after_noise=draw_masks)
-        z_e, z_c = z[:, :L], z[:, L:]
-        if side is not None:
-            side.wait_stream(main)
-        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
-            heads = self._heads(z, emotion_labels, cause_labels, pair_labels, masks=tuple(masks) if masks else None)
+        z, kl, heads, join = self._latents_and_heads(emb, emotion_labels, cause_labels, pair_labels)
         mmd = MMDStatistic(input_ids.shape[0], input_ids.shape[0]).halves(z, [0.1])
         reconstruction_loss = self._reconstruction(z, content_bow)
-        if side is not None:
-            main.wait_stream(side)
+        join()
         # mmd_loss_weight * (-mmd) + heads + kl_e + kl_c + reconstruction_loss   (:256-261)
         return self._assemble([(mmd, -float(o.mmd_loss_weight)), (heads, 1.0)], kl, iteration, reconstruction_loss)
 
@@ -330,11 +339,12 @@ class DrlClassifierHSIC(_DrlClassifierBase):
     def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,
                 iteration):
         o, L = self.opt, self.opt.ec_dim
-        z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
+        emb = self._sentence_emb(input_ids, att_masks, token_type_ids)
+        z, kl, heads, join = self._latents_and_heads(emb, emotion_labels, cause_labels, pair_labels)
         z_e, z_c = z[:, :L], z[:, L:]
-        heads = self._heads(z, emotion_labels, cause_labels, pair_labels)
         hsic_loss = HSIC(z_e, z_c)
         reconstruction_loss = self._reconstruction(z, content_bow)
+        join()
         return self._assemble([(hsic_loss, 1.0), (heads, 1.0)], kl, iteration, reconstruction_loss)
 
     def get_params(self):
@@ -413,11 +423,12 @@ class DrlClassifierVI(_DrlClassifierBase):
     def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,
                 iteration):
         o, L = self.opt, self.opt.ec_dim
-        z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
+        emb = self._sentence_emb(input_ids, att_masks, token_type_ids)
+        z, kl, heads, join = self._latents_and_heads(emb, emotion_labels, cause_labels, pair_labels)
         z_e, z_c = z[:, :L], z[:, L:]
-        heads = self._heads(z, emotion_labels, cause_labels, pair_labels)
         ec_aprx_loss = self.get_ec_aprx_loss(z_e, z_c)
         reconstruction_loss = self._reconstruction(z, content_bow)
+        join()
         loss = self._assemble([(heads, 1.0)], kl, iteration, reconstruction_loss)
         return z_e, z_c, ec_aprx_loss, loss
 
