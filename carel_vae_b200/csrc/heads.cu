@@ -179,6 +179,9 @@ static __global__ void __launch_bounds__(256, 4) heads_bwd_kernel(const HeadsArg
   for (int i = threadIdx.x; i < kRows * kW; i += blockDim.x) (&sh_w[0][0])[i] = 0.f;
   if (threadIdx.x < kHeadsMaxC + 2) sh_b[threadIdx.x] = 0.f;
   __syncthreads();
+  // shared-memory column of latent dim k: in the 128-bit form lane l owns dims 4l..4l+3, which would put the lanes of
+  // one atomic instruction 4 words apart (4-way bank conflicts); (k & 3) * 32 + (k >> 2) puts them on 32 banks
+  auto slot = [](int k) { return VEC ? ((k & 3) * 32 + (k >> 2)) : k; };
   const float invN = 1.f / float(a.N);
   const float g0 = __ldg(a.g);
   const float ge = g0 * a.wgt[0], gc = g0 * a.wgt[1], gp = g0 * a.wgt[2];
@@ -234,17 +237,18 @@ static __global__ void __launch_bounds__(256, 4) heads_bwd_kernel(const HeadsArg
     float* dzr = a.dz + size_t(r) * a.lddz;
     // one latent dim k of both halves: its dz pair and its eleven weight-gradient contributions
     auto one = [&](int k, float ze, float zc, float me, float mc, float mpe, float mpc, float& dze, float& dzc) {
+      const int sl = slot(k);
       float de = 0.f;
 #pragma unroll
       for (int c = 0; c < kHeadsMaxC; ++c) {
         if (c < a.C_e) {
           de = fmaf(dl_e[c], __ldg(a.W_e + size_t(c) * L + k), de);
-          atomicAdd(&sh_w[c][k], dl_e[c] * (ze * me));
+          atomicAdd(&sh_w[c][sl], dl_e[c] * (ze * me));
         }
       }
-      atomicAdd(&sh_w[kHeadsMaxC][k], dl_c * (zc * mc));
-      atomicAdd(&sh_w[kHeadsMaxC + 1][k], dl_p * (ze * mpe));
-      atomicAdd(&sh_w[kHeadsMaxC + 2][k], dl_p * (zc * mpc));
+      atomicAdd(&sh_w[kHeadsMaxC][sl], dl_c * (zc * mc));
+      atomicAdd(&sh_w[kHeadsMaxC + 1][sl], dl_p * (ze * mpe));
+      atomicAdd(&sh_w[kHeadsMaxC + 2][sl], dl_p * (zc * mpc));
       dze = de * me + dl_p * __ldg(a.W_p + k) * mpe;
       dzc = dl_c * __ldg(a.W_c + k) * mc + dl_p * __ldg(a.W_p + L + k) * mpc;
     };
@@ -288,7 +292,7 @@ static __global__ void __launch_bounds__(256, 4) heads_bwd_kernel(const HeadsArg
   // ---- block tile -> one global atomic per non-zero element ----
   for (int idx = threadIdx.x; idx < kRows * L; idx += blockDim.x) {
     const int row = idx / L, k = idx - row * L;
-    const float t = sh_w[row][k];
+    const float t = sh_w[row][slot(k)];
     if (t == 0.f) continue;
     if (row < kHeadsMaxC) {
       if (row < a.C_e && a.dW_e) atomicAdd(a.dW_e + size_t(row) * L + k, t);
