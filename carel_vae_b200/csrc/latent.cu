@@ -79,10 +79,21 @@ static __global__ void pack_w4_kernel(const PackW4Args a, int L, int D, __nv_bfl
     const float* s = a.w[i] + size_t(rr) * D;
     __nv_bfloat16* o0 = Wp + size_t(r) * ldw;
     __nv_bfloat16* o1 = Wp + size_t(ldd + r) * ldw;
-    for (int k = lane; k < ldw; k += 32) {
-      const __nv_bfloat16 v = __float2bfloat16_rn(k < D ? __ldg(s + k) : 0.f);
-      o0[k] = v;
-      o1[k] = v;
+    if (((D & 3) == 0) && ((ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.w[i]) & 15) == 0)) {
+      for (int k = lane * 4; k < ldw; k += 128) {          // 128-bit loads, 64-bit stores
+        const float4 v = (k < D) ? __ldg(reinterpret_cast<const float4*>(s + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint2 pk;
+        pk.x = pack_bf16x2(v.x, v.y);
+        pk.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(o0 + k) = pk;
+        *reinterpret_cast<uint2*>(o1 + k) = pk;
+      }
+    } else {
+      for (int k = lane; k < ldw; k += 32) {
+        const __nv_bfloat16 v = __float2bfloat16_rn(k < D ? __ldg(s + k) : 0.f);
+        o0[k] = v;
+        o1[k] = v;
+      }
     }
     if (lane == 0) bias4[r] = __ldg(a.b[i] + rr);
   }
@@ -272,7 +283,7 @@ extern "C" int carel_latent_fwd(const float* x, int64_t ldx, int64_t N, int64_t 
   {
     PackW4Args pa;
     for (int i = 0; i < 4; ++i) { pa.w[i] = w4[i]; pa.b[i] = b4[i]; }
-    pack_w4_kernel<<<int((4 * L + 7) / 8), 256, 0, st>>>(pa, int(L), int(D), w.Wp, w.ldw, w.ldd, bias4);
+    pack_w4_kernel<<<int((4 * L + 1) / 2), 64, 0, st>>>(pa, int(L), int(D), w.Wp, w.ldw, w.ldd, bias4);
     CAREL_LAUNCHED();
   }
   // bias: the four [L] vectors are gathered into pre's first row region by the epilogue via a
