@@ -731,7 +731,28 @@ static __global__ void __launch_bounds__(1024) csc_scan_kernel(const int* cnt, i
   auto pad = [](int j) { return j + (j >> 5); };
   int carry = 0;                                  // every thread tracks the running total
   for (int base = 0; base < V; base += CH) {
-    for (int j = threadIdx.x; j < CH; j += 1024) scan_buf[pad(j)] = (base + j < V) ? cnt[base + j] : 0;
+    // eight independent 128-bit loads per thread (a plain strided loop waits for each load in turn: 32 dependent
+    // round trips on the one SM this kernel runs on)
+    const bool vec = (reinterpret_cast<uintptr_t>(cnt) & 15) == 0;
+    int4 ld[PER / 4];
+#pragma unroll
+    for (int q = 0; q < PER / 4; ++q) {
+      const int j = (q * 1024 + threadIdx.x) * 4;
+      if (vec && base + j + 3 < V) {
+        ld[q] = *reinterpret_cast<const int4*>(cnt + base + j);
+      } else {
+        ld[q].x = (base + j < V) ? cnt[base + j] : 0;
+        ld[q].y = (base + j + 1 < V) ? cnt[base + j + 1] : 0;
+        ld[q].z = (base + j + 2 < V) ? cnt[base + j + 2] : 0;
+        ld[q].w = (base + j + 3 < V) ? cnt[base + j + 3] : 0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PER / 4; ++q) {
+      const int j = (q * 1024 + threadIdx.x) * 4;          // j % 32 <= 28: the four words share one padding offset
+      int* d = scan_buf + pad(j);
+      d[0] = ld[q].x; d[1] = ld[q].y; d[2] = ld[q].z; d[3] = ld[q].w;
+    }
     __syncthreads();
     int v[PER], s = 0;
 #pragma unroll
