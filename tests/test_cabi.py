@@ -59,6 +59,15 @@ def test_no_cpu_fallback():
         cv.HSIC(x, y)
     with pytest.raises(ZeroDivisionError):
         cv.MMDStatistic(1, 1)          # reference behaviour for a batch of one row (mmd:543)
+    from carel_vae_b200 import functional as F
+    with pytest.raises(cv.CarelError):
+        F.weighted_sum([torch.ones(()), torch.ones(2)], [1.0, (0.5, 0.5)])
+    with pytest.raises(cv.CarelError):
+        F.bow_pack_ell(torch.zeros(4, 16), 8)
+    with pytest.raises(cv.CarelError):
+        F.club_aprx_loss(torch.zeros(4, 8), torch.zeros(4, 8), torch.zeros(4, 8))
+    with pytest.raises(cv.CarelError):
+        F.club_upper_bound(torch.zeros(4, 8), torch.zeros(4, 8), torch.zeros(4, 8), torch.randperm(4))
 
 
 def test_product_does_not_import_oracle():
