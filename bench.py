@@ -258,8 +258,13 @@ def run_ours(args):
     l0 = _lib.launch_count()
     total_ms = timed(run_step, args.steps)
     launches_eager = None
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
+    # The timed region is a few tens of ms, shorter than nvidia-smi's sampling period: keep the SAME load running
+    # (untimed, same step, same count on every rank) for ~0.4 s so that the clock / throttle samples are taken under it.
+    for _ in range(min(2000, int(400.0 / max(ms_per_step, 0.05)))):
+        run_step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     value = world * 1e3 / ms_per_step
 
     # ---- e2e: host buffers -> H2D -> step -> D2H loss ----
