@@ -14,7 +14,9 @@ Printed JSON (rank 0, one line): value = aggregate 8192-clause steps/s with inpu
 e2e = the same through the drop-in call with HOST buffers (pinned H2D of X, labels and the dense
 [N, V] fp32 BoW target the reference layout prescribes, D2H of the loss) inside the timed region;
 roofline = the MMD Gram kernel at N = 8192, d = 768 (the kernel BASELINE.json's metric names) against
-the measured bf16 peak; cpu_baseline = the oracle port of the reference step on the host cores.
+the measured bf16 peak; roofline_hbm = the step's one bandwidth-bound kernel (dense BoW target -> non-zero list,
+N*V*4 bytes read once) against the measured copy bandwidth; roofline_step = the whole step's algorithmic FLOPs against
+the sustained bf16 peak; cpu_baseline = the oracle port of the reference step on the host cores.
 `--impl reference` times that CPU implementation alone.
 """
 from __future__ import annotations
