@@ -56,3 +56,44 @@ def test_bad_language_and_empty_file(tmp_path):
     empty.write_text("")
     df, sizes, unpred = ecpe.read_ECPE_data(empty)
     assert len(df) == 0 and list(df.columns) == ["pair", "label", "emotion"] and sizes == [] and unpred == 0
+
+
+REAL = [("Englishnovel_multiple/biography_num.txt", "en", None), ("Englishnovel_multiple/war_new_num.txt", "en", None),
+        ("THUCTC_multiple/society_num.txt", "zh", 2500)]
+
+
+@pytest.mark.parametrize("rel_path,language,max_lines", REAL)
+@pytest.mark.parametrize("test_mode", [False, True])
+def test_matches_reference_on_the_reference_corpora(rel_path, language, max_lines, test_mode, tmp_path):
+    """Build container only (skipped where /root/reference is absent): the reference's own reader, executed live, and
+    ours on real corpus files of the reference (a document-aligned prefix for the large zh file — the reference's
+    per-row DataFrame.append is quadratic), same `random` seed: identical frames, sizes and counters."""
+    import pandas as pd
+    from oracle import make_golden_ecpe as mg
+    src = Path("/root/reference/domains") / rel_path
+    if not src.exists():
+        pytest.skip("reference corpora are only present in the build container")
+    path = src
+    if max_lines is not None:
+        lines = src.read_text(encoding="utf8").splitlines(keepends=True)[:max_lines]
+        while lines and not ecpe._HEADER.search(lines[-1]):         # cut back to a document boundary
+            lines.pop()
+        lines.pop()                                                   # drop the dangling header itself
+        path = tmp_path / "prefix.txt"
+        path.write_text("".join(lines), encoding="utf8")
+    had = hasattr(pd.DataFrame, "append")
+    if not had:
+        pd.DataFrame.append = mg._append
+    try:
+        random.seed(42)
+        rdf, rsizes, runpred = mg.reference_reader(language)(str(path), test=test_mode)
+    finally:
+        if not had:
+            del pd.DataFrame.append
+    random.seed(42)
+    df, sizes, unpred = ecpe.read_ECPE_data(path, test=test_mode, language=language)
+    assert len(df) == len(rdf) > 50
+    assert list(df["pair"]) == [str(x) for x in rdf["pair"]]
+    assert [int(x) for x in df["label"]] == [int(x) for x in rdf["label"]]
+    assert [int(x) for x in df["emotion"]] == [int(x) for x in rdf["emotion"]]
+    assert sizes == [int(x) for x in rsizes] and unpred == int(runpred)
