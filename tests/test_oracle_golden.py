@@ -86,3 +86,57 @@ def test_head_forward_backward(golden_dir, variant):
         torch.manual_seed(5 + c["seed"])
         preds = ho.HeadOracle(opt, variant).pair_preds(st, b["X"]).round()
         assert torch.equal(preds, c["pair_preds"].reshape(preds.shape))
+
+
+@pytest.mark.parametrize("variant", ["mmd", "hsic", "vi", "gan"])
+@pytest.mark.parametrize("N,L,V,D,dropout,seed", [(33, 32, 301, 64, 0.5, 11), (7, 8, 40, 16, 0.0, 12)])
+def test_oracle_matches_the_live_reference_on_fresh_cases(variant, N, L, V, D, dropout, seed):
+    """Build container only (skipped where /root/reference is absent): the reference's own DrlClassifier, executed now
+    (oracle/reference_extract.py), against the restatement on shapes and seeds the golden files do not contain —
+    ragged N, dropout on, all outputs, the gradient w.r.t. the embeddings and every parameter, and for the VI variant
+    the CLUB upper bound with the CPU-generator permutation of vi_final:433."""
+    from oracle import reference_extract as rx
+    if not rx.available():
+        pytest.skip("the reference is only present in the build container")
+    opt = ho.default_opt(variant, ec_dim=L, pair_bow_dim=V, bert_dim=D, dropout=dropout)
+    ns = rx.load(variant, opt)
+    torch.manual_seed(1234 + seed)
+    model = ns["DrlClassifier"](opt)
+    model.train()
+    b = ho.synthetic_batch(N, V, D=D, seed=seed, emotion_float=variant in ("hsic", "gan"))
+    emo = b["emo"] if variant in ("mmd", "vi") else b["emo"].float()
+
+    def total_of(outs):
+        return outs[2] + outs[3] if variant == "vi" else (outs[0] + outs[1] + outs[2] if variant == "gan" else outs[0])
+
+    X = b["X"].clone().requires_grad_(True)
+    torch.manual_seed(77 + seed)
+    with rx.cpu_cuda_shim():
+        out = model(X, None, None, emo, b["cau"], b["pair"], b["bow"], 5)
+    r_outs = out if isinstance(out, tuple) else (out,)
+    names = [k for k, _ in model.named_parameters() if not k.startswith("encoder")]
+    r_params = dict(model.named_parameters())
+    r_grads = torch.autograd.grad(total_of(r_outs), [X] + [r_params[k] for k in names], allow_unused=True)
+
+    st = ho.init_state(opt, variant, seed=1234 + seed)
+    p = {k: v.clone().requires_grad_(True) for k, v in st.items()}
+    assert set(p) == set(names)
+    X2 = b["X"].clone().requires_grad_(True)
+    torch.manual_seed(77 + seed)
+    oracle = ho.HeadOracle(opt, variant)
+    out2 = oracle.forward(p, X2, emo, b["cau"], b["pair"], b["bow"], 5)
+    o_outs = out2 if isinstance(out2, tuple) else (out2,)
+    for o, r in zip(o_outs, r_outs):
+        _close(o, torch.as_tensor(r), rtol=3e-5)
+    o_grads = torch.autograd.grad(total_of(o_outs), [X2] + [p[k] for k in names], allow_unused=True)
+    for g, r in zip(o_grads, r_grads):
+        if r is None:
+            assert g is None or float(g.abs().max()) == 0.0
+        else:
+            _close(g, r, rtol=2e-4, atol=1e-8)
+    if variant == "vi":
+        z_e, z_c = torch.randn(N, L), torch.randn(N, L)
+        torch.manual_seed(3)
+        r_up = model.get_ec_upper_loss(z_e, z_c)
+        torch.manual_seed(3)
+        _close(oracle.ec_upper_loss(st, z_e, z_c), r_up, rtol=3e-5)
