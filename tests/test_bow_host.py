@@ -37,3 +37,27 @@ def test_bow_tokenize_matches_reference_rule():
     # survives as 'ġ' stays in the token (bow_util.py:43-47) — reproduced, not fixed.
     assert bow_tokenize("Hello, World!  it's Ġfine.") == ["hello", "world", "its", "ġfine"]
     assert bow_tokenize("a  b") == ["a", "b"]
+
+
+def test_bow_tokenize_matches_the_live_reference_function():
+    """Build container only: bow_util.py's own bow_tokenize (AST-extracted: the module imports jieba at the top) on
+    random punctuation / case / marker / whitespace mixes."""
+    import ast
+    import re
+    from pathlib import Path
+    import pytest
+    src = Path("/root/reference/bow_util.py")
+    if not src.exists():
+        pytest.skip("the reference is only present in the build container")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)          # the reference's un-raw regex strings
+        tree = ast.parse(src.read_text())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "bow_tokenize"]
+    ns = {"re": re}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), "bow_util.py", "exec"), ns)
+    rng = np.random.default_rng(1)
+    alphabet = list("abcXYZ09 _-.,!?'\"Ġġé中  \t")
+    for _ in range(300):
+        s = "".join(rng.choice(alphabet, size=rng.integers(0, 60)))
+        assert bow_tokenize(s) == ns["bow_tokenize"](s), repr(s)
