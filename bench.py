@@ -333,20 +333,27 @@ def run_ours(args):
             _lib.timing_enable(False)
             ms = rep["mmd_gram_fwd"][0] / rep["mmd_gram_fwd"][1]
             res[name] = ms
-        achieved = GRAM_FLOPS / (res["triangular"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_2sm_kernel<EpiMMD> (MMD Gram forward on CTA pairs, N=8192, d=768, j>i schedule)",
-                "achieved": round(achieved, 1), "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-                "frac": round(achieved / pk["bf16_burst"], 3),
+        # Primary roofline line: the launch that EXECUTES the algorithmic FLOPs (every tile of the Gram), so achieved / peak
+        # is a tensor-pipe utilisation <= 1.  The product's default schedule computes only the j > i tiles (the Gram is
+        # symmetric) and is reported next to it: same algorithmic FLOPs in about half the time.
+        full_tf = GRAM_FLOPS / (res["full_gram"] * 1e-3) / 1e12
+        tri_tf = GRAM_FLOPS / (res["triangular"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_2sm_kernel<EpiMMD> (MMD Gram forward on CTA pairs, N=8192, d=768, every tile executed)",
+                "achieved": round(full_tf, 1), "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                "frac": round(full_tf / pk["bf16_burst"], 3),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
                 # (profiles/r01_final_ncu_summary.txt): 51.47 MB + 0.90 MB per launch; algorithmic 2 x 25.7 MB operands
                 "traffic": 52.37e6, "traffic_unit": "bytes/launch (ncu, profiles/r01_final_ncu_summary.txt)",
                 "peak_source": pk["source"],
-                "note": "algorithmic FLOPs = 2*(2N)^2*d (full Gram, SURVEY §8d); the kernel executes the j>i half, "
-                        "so executed-FLOP tensor utilisation is ~half of frac; full_gram variant below executes all of it",
-                "full_gram_tflops": round(GRAM_FLOPS / (res["full_gram"] * 1e-3) / 1e12, 1),
-                "full_gram_frac": round(GRAM_FLOPS / (res["full_gram"] * 1e-3) / 1e12 / pk["bf16_burst"], 3),
+                "note": "algorithmic FLOPs = 2*(2N)^2*d = 4.12e11 (full Gram as the reference computes it, SURVEY §8d)",
+                "product_schedule": {"kernel": "same kernel, j>i tiles only (what MMDStatistic runs)",
+                                     "algorithmic_tflops": round(tri_tf, 1),
+                                     "algorithmic_frac": round(tri_tf / pk["bf16_burst"], 3),
+                                     "note": "half of the tiles are skipped by symmetry, so algorithmic FLOPs / time exceeds the peak; "
+                                             "executed-FLOP utilisation is about half of this figure"},
                 "us_per_launch": {k: round(v * 1e3, 1) for k, v in res.items()}}
-        gram = {"metric": "mmd_gram_tflops_n8192_d768", "value": round(achieved, 1), "unit": "TFLOP/s (algorithmic)"}
+        gram = {"metric": "mmd_gram_tflops_n8192_d768", "value": round(tri_tf, 1), "unit": "TFLOP/s (algorithmic, product schedule)",
+                "executed_tflops_full_gram": round(full_tf, 1)}
         step_tflops = STEP_FLOPS / (ms_per_step * 1e-3) / 1e12
         roof_step = {"bound": "tensor", "achieved": round(step_tflops, 1), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": round(step_tflops / pk["bf16_sustained"], 3),
