@@ -306,6 +306,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) |
          (uint32_t(b_mn_major) << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
+// Same with FP16 inputs (a_format = b_format = 0): 11 mantissa bits instead of 8 at the same MMA rate; used by the
+// BoW decoder, whose operands (latent sample, decoder weights, scaled dlogits) fit fp16's range.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) | (uint32_t(N >> 3) << 17) |
+         (uint32_t(M >> 4) << 24);
+}
 // Same, with A in FP16 (a_format = 0) and B in BF16: used when the A operand (a weight tile
 // written by an epilogue) needs 11 mantissa bits rather than 8.
 __host__ __device__ constexpr uint32_t make_idesc_f16a_bf16b(int M, int N, int a_mn_major,
@@ -372,6 +378,13 @@ CAREL_DEVINL uint32_t pack_f16x2(float lo, float hi) {
   __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// two fp32 -> packed fp16 pair, saturating to +-65504 instead of overflowing to inf (F2FP.SATFINITE.F16.F32.PACK_AB)
+CAREL_DEVINL uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+CAREL_DEVINL float2 unpack_f16x2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 CAREL_DEVINL float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 CAREL_DEVINL float warp_sum(float v) {

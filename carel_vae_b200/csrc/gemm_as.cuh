@@ -31,6 +31,10 @@ constexpr int kAsStages = CAREL_AS_STAGES;
 constexpr int kAsBytesA = 4 * 16384;                     // 4 k-blocks of [128 x 64] bf16
 constexpr int kAsStageB = 256 * 128;                     // one k-block of [256 x 64] bf16
 constexpr int kAsSmemBytes = kAsBytesA + kAsStages * kAsStageB + 1024 + 256;
+// With an epilogue staging area (EPI_SMEM bytes, e.g. tiles that are TMA-stored from shared memory) the B ring
+// gives up a stage.
+__host__ __device__ constexpr int as_stages(int epi_smem) { return epi_smem > 0 ? kAsStages - 1 : kAsStages; }
+__host__ __device__ constexpr int as_smem_bytes(int epi_smem) { return kAsBytesA + as_stages(epi_smem) * kAsStageB + epi_smem + 1024 + 256; }
 
 // Walks the CTA's range of the tile list; every role uses the same iterator.  `new_row` is true on the first
 // tile of a row tile (A has to be (re)loaded), `last_of_row` on the last one this CTA processes for it.
@@ -82,16 +86,19 @@ struct AsIter {
   }
 };
 
-template <class Epi>
+// F16: operands are fp16 instead of bf16 (same MMA rate, 11 mantissa bits).  EPI_SMEM: bytes of shared memory handed
+// to the epilogue (TileCtx::epi_smem, 1024-byte aligned).
+template <class Epi, bool F16 = false, int EPI_SMEM = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_as_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ AsSched sched, const __grid_constant__ typename Epi::Params ep) {
-  constexpr int BN = 256, STAGES = kAsStages;
+  constexpr int BN = 256, STAGES = as_stages(EPI_SMEM);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kAsBytesA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * kAsStageB);
+  uint8_t* sEpi = sB + STAGES * kAsStageB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + EPI_SMEM);
   uint64_t* b_full = bars;                       // [STAGES]
   uint64_t* b_empty = bars + STAGES;             // [STAGES]
   uint64_t* a_full = bars + 2 * STAGES;          // [1]
@@ -161,7 +168,7 @@ gemm_as_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int trace_n = 0; (void)trace_n;
     while (it.next()) {
       const int n_eff = min(BN, ((sched.n_cols - it.tn * BN + 15) >> 4) << 4);
-      const uint32_t idesc = make_idesc_bf16(128, n_eff, 0, 0);
+      const uint32_t idesc = F16 ? make_idesc_f16(128, n_eff, 0, 0) : make_idesc_bf16(128, n_eff, 0, 0);
       if (it.new_row) {
         mbar_wait(a_full, aphase);
         aphase ^= 1;
@@ -194,6 +201,7 @@ gemm_as_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     TileCtx ctx;
     ctx.half = warp >> 2;
     ctx.epi_tid = threadIdx.x;
+    ctx.epi_smem = sEpi;
     Epi epi(ep, ctx);
     AsIter it(sched);
     int buf = 0;

@@ -39,20 +39,21 @@ inline void set_ksplit(GemmSched& s, int desired) {
   s.num_items = s.m_tiles * s.n_tiles * s.ksplit;
 }
 
-template <class Epi>
+template <class Epi, bool F16 = false, int EPI_SMEM = 0>
 int launch_gemm_as(const CUtensorMap& a, const CUtensorMap& b, const AsSched& s, const typename Epi::Params& ep,
                    cudaStream_t st, const char* tag = "gemm_as") {
-  auto kern = gemm_as_kernel<Epi>;
+  auto kern = gemm_as_kernel<Epi, F16, EPI_SMEM>;
+  constexpr int kSmem = as_smem_bytes(EPI_SMEM);
   static bool attr_done = false;
   if (!attr_done) {
-    CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAsSmemBytes));
+    CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_done = true;
   }
   CAREL_REQUIRE(s.num_k16 >= 1 && s.num_k16 <= 16, "A-stationary GEMM: K must be <= 256");
   const int grid = (s.total + s.tpc - 1) / s.tpc;
   if (grid <= 0) return 0;
   timing_begin(tag, st);
-  kern<<<grid, kGemmThreads, kAsSmemBytes, st>>>(a, b, s, ep);
+  kern<<<grid, kGemmThreads, kSmem, st>>>(a, b, s, ep);
   timing_end(st);
   CAREL_LAUNCHED();
   return 0;

@@ -137,6 +137,7 @@ struct TileCtx {
   int kb0, kb1;    // k-block range that was accumulated (split-K)
   int epi_tid;     // 0..255 within the epilogue warps
   bool first_of_row, last_of_row;   // A-stationary kernel only: first / last tile this CTA runs on row tile tm
+  uint8_t* epi_smem;               // A-stationary kernel only: EPI_SMEM bytes of shared memory for the epilogue (or unset)
 };
 
 template <int BN, int NG>
