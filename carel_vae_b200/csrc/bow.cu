@@ -1080,16 +1080,18 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   yp.N = int(N); yp.V = int(V); yp.K = int(K);
   yp.c = label_smoothing / float(V); yp.inv_nv = inv_nv;
   CUtensorMap ty, tb;
-  CAREL_REQUIRE(make_tmap_f16_sw128(&ty, w.Y, N, V, w.ldy, 128) == 0, "carel_bow_bwd: tensor map Y failed");
-  if (need_w) {      // owner = 128 words, reduction over the clauses: dW += dlogit^T Z, db
-    CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.ZH, N, w.ldk, w.ldk, 128) == 0, "carel_bow_bwd: tensor map Z failed");
-    ChainSched cs = make_chain_sched(0, int((V + 127) / 128), int((N + 127) / 128), k16, 2, 0);
+  const int bst = yg_b_stages(k16);
+  if (need_w) {      // owner = 128 words, step = 128 clauses: dW += dlogit^T Z, db
+    CAREL_REQUIRE(make_tmap_f16_sw128(&ty, w.Y, N, V, w.ldy, 128) == 0, "carel_bow_bwd: tensor map Y failed");
+    CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.ZH, N, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z failed");
+    ChainSched cs = make_chain_sched(0, int((V + 127) / 128), int((N + 127) / 128), k16, bst, 0);
     yp.out = gw; yp.gb = gb; yp.ldo = K;
     if (int rc = launch_ygrad<true>(ty, tb, cs, yp, st, "bow_dw")) return rc;
   }
-  {                  // owner = 128 clauses, reduction over the vocabulary: dZ += dlogit W_d
-    CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.WH, V, w.ldk, w.ldk, 128) == 0, "carel_bow_bwd: tensor map W failed");
-    ChainSched cs = make_chain_sched(0, int((N + 127) / 128), int((V + 127) / 128), k16, 2, 0);
+  {                  // owner = 256 clauses, step = 64 words: dZ += dlogit W_d
+    CAREL_REQUIRE(make_tmap_f16_sw128(&ty, w.Y, N, V, w.ldy, 256) == 0, "carel_bow_bwd: tensor map Y failed");
+    CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.WH, V, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
+    ChainSched cs = make_chain_sched(0, int((N + 255) / 256), int((V + 63) / 64), k16, bst, 0);
     yp.out = grad_z; yp.gb = nullptr; yp.ldo = ldgz;
     if (int rc = launch_ygrad<false>(ty, tb, cs, yp, st, "bow_dz")) return rc;
   }
