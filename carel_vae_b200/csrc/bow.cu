@@ -30,6 +30,7 @@
 //             dW += dlogit^T Z (owner = 128 words) and dZ += dlogit W_d (owner = 128 clauses); the dlogit tile is
 //             formed in registers from the Y tile and goes to TMEM as the A operand.  No logit is recomputed.
 #include <algorithm>
+#include <cstdlib>
 
 #include "api_common.cuh"
 #include "chain_launch.cuh"
@@ -48,7 +49,8 @@ struct BowWs {
   float* wsum;          // [ldk + 4] column sums of WH; wsum[ldk] = sum_j b_j; wsum[ldk + 1] = max_j |w_j| (as bits)
   float* rm;            // [Npad]  row reference rm_i (log2 units; 0 beyond N)
   float2* rowenc;       // [Npad]  {a_i = log2(e) s_i, bmagic_i}: the encoder constants of pass F
-  float4* rowc;         // [Npad]  {1 / s_i, bmagic_i, -lse2_i, -S_i 2^10}: the decoder constants (0 beyond N)
+  float4* rowc;         // [2, Npad]  plane 0: {1 / s_i, bmagic_i, -lse2_i, -S_i 2^10}: the decoder constants (0 beyond N);
+                        //            plane 1: {a1, a2, a3, fast}: the backward fast-path polynomial (ygrad.cuh)
   int* row_flag;        // [Npad] 1: row needs the exact pass
   int* flag_list;       // [Npad] compact list of the flagged rows
   int* counters;        // [4]  [0] number of flagged rows, [1] ELL overflow without a dense target
@@ -83,7 +85,7 @@ static BowWs carve_bow(void* ws, int64_t N, int64_t K, int64_t V, int64_t cap) {
   r.wsum = w.take<float>(size_t(r.ldk) + 4);
   r.rm = w.take<float>(size_t(r.Npad));
   r.rowenc = w.take<float2>(size_t(r.Npad));
-  r.rowc = w.take<float4>(size_t(r.Npad));
+  r.rowc = w.take<float4>(size_t(2) * r.Npad);
   r.row_flag = w.take<int>(size_t(r.Npad));
   r.flag_list = w.take<int>(size_t(r.Npad));
   r.counters = w.take<int>(4);
@@ -490,7 +492,11 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
     const int row_l = g * (kCombineRows / kCombineGroups) + q;
     const int row = blockIdx.x * kCombineRows + row_l;
     if (row >= N) {
-      if (lane == 0) { rowc[row] = make_float4(0.f, 0.f, 0.f, 0.f); row_flag[row] = 0; }    // padding rows read by the backward kernels
+      if (lane == 0) {                       // padding rows read by the backward kernels
+        rowc[row] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rowc[Npad + row] = make_float4(0.f, 0.f, 0.f, 0.f);
+        row_flag[row] = 0;
+      }
       continue;
     }
     // lanes 0 .. groups-1 hold the partial groups
@@ -525,6 +531,9 @@ bow_combine_kernel(const float4* __restrict__ part4, const float2* __restrict__ 
       float* rc = reinterpret_cast<float*>(rowc + row);
       rc[2] = -lse2;
       rc[3] = -u * kYgScale;
+      // S4 < 2^-32 certifies every p < 2^-8: the whole row takes the backward kernels' unchecked polynomial path
+      // (quadratic in p: truncation p^2 / (1 - c - S) <= 1.5e-4 of an element's own dlogit at p = 2^-8, ~1e-8 typically)
+      rowc[Npad + row] = make_float4(0.f, 0.f, 0.f, (valid && S4 < 2.3283064365386963e-10f) ? 1.f : 0.f);
     }
   }
   if (lane == 0) sh_loss[g] = f;
@@ -615,7 +624,7 @@ bow_sparse_fwd_kernel(const uint16_t* __restrict__ Y, int ldy, const float* __re
                       float4* __restrict__ rowc, const int* __restrict__ ell_cols,
                       const float* __restrict__ ell_vals, const int* __restrict__ ell_nnz, float* __restrict__ ell_ev,
                       const float* __restrict__ bow_dense, int64_t ld_bow, int N, int V, int cap, float one_minus_ls,
-                      double* __restrict__ lossacc, int* __restrict__ counters) {
+                      float c, int Npad, double* __restrict__ lossacc, int* __restrict__ counters) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   double loss_warp = 0.0;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < N; r += gridDim.x * wpb) {
@@ -655,7 +664,13 @@ bow_sparse_fwd_kernel(const uint16_t* __restrict__ Y, int ldy, const float* __re
     if (lane == 0) {
       loss_warp += double(dloss);
       // this warp owns rowc[r].w (= -S_i 2^10) here: the combine / exact kernels ran before
-      if (du != 0.f) reinterpret_cast<float*>(rowc + r)[3] = rc4.w - du * kYgScale;
+      const float sn = rc4.w - du * kYgScale;
+      if (du != 0.f) reinterpret_cast<float*>(rowc + r)[3] = sn;
+      // S_i is final now: the polynomial of the backward fast path (ygrad.cuh),
+      //   d' = -c 2^10 + p' (a1 + p' (a2 + p' a3)),  p' = 2^(log2 p - rc),  P = 2^rc
+      const float P = exp2f(rc4.z), S = -sn * (1.f / kYgScale);
+      float4* pl = rowc + Npad + r;
+      *pl = make_float4(kYgScale * (1.f - c - S) * P, kYgScale * (1.f - c) * P * P, kYgScale * P * P * P, pl->w);
     }
   }
   __shared__ double sh_l[8];
@@ -1023,7 +1038,7 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   // ---- sparse corrections ----
   bow_sparse_fwd_kernel<<<int(std::min<int64_t>((N + 7) / 8, sms * 16)), 256, 0, st>>>(
       w.Y, w.ldy, w.bl2e, w.rowc, w.ell_cols, w.ell_vals, w.ell_nnz, w.ell_ev, bow_dense, ld_bow, int(N), int(V), cap,
-      1.f - label_smoothing, w.lossacc, w.counters);
+      1.f - label_smoothing, label_smoothing / float(V), w.Npad, w.lossacc, w.counters);
   CAREL_LAUNCHED();
   bow_loss_finalize_kernel<<<1, 32, 0, st>>>(w.lossacc, w.counters, 1.0 / (double(N) * double(V)), loss_out);
   CAREL_LAUNCHED();
@@ -1077,23 +1092,33 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   const int k16 = w.ldk / 16;
   YGradParams yp;
   yp.rowc = w.rowc; yp.bl2e = w.bl2e; yp.grad_out = grad_out;
-  yp.N = int(N); yp.V = int(V); yp.K = int(K);
+  yp.N = int(N); yp.V = int(V); yp.K = int(K); yp.Npad = w.Npad;
   yp.c = label_smoothing / float(V); yp.inv_nv = inv_nv;
   CUtensorMap ty, tb;
-  const int bst = yg_b_stages(k16);
   if (need_w) {      // owner = 128 words, step = 128 clauses: dW += dlogit^T Z, db
     CAREL_REQUIRE(make_tmap_f16_sw128(&ty, w.Y, N, V, w.ldy, 128) == 0, "carel_bow_bwd: tensor map Y failed");
     CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.ZH, N, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z failed");
-    ChainSched cs = make_chain_sched(0, int((V + 127) / 128), int((N + 127) / 128), k16, bst, 0);
+    ChainSched cs = make_chain_sched(0, int((V + 127) / 128), int((N + 127) / 128), k16, yg_b_stages(k16, true), 0);
     yp.out = gw; yp.gb = gb; yp.ldo = K;
     if (int rc = launch_ygrad<true>(ty, tb, cs, yp, st, "bow_dw")) return rc;
   }
+#ifdef CAREL_CHAIN_TRACE
+  if (getenv("CAREL_TRACE_SKIP_DZ") != nullptr) return 0;      // debug: keep the dW kernel's timeline
+#endif
   {                  // owner = 256 clauses, step = 64 words: dZ += dlogit W_d
     CAREL_REQUIRE(make_tmap_f16_sw128(&ty, w.Y, N, V, w.ldy, 256) == 0, "carel_bow_bwd: tensor map Y failed");
     CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.WH, V, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
-    ChainSched cs = make_chain_sched(0, int((N + 255) / 256), int((V + 63) / 64), k16, bst, 0);
+    ChainSched cs = make_chain_sched(0, int((N + 255) / 256), int((V + 63) / 64), k16, yg_b_stages(k16, false), 0);
     yp.out = grad_z; yp.gb = nullptr; yp.ldo = ldgz;
     if (int rc = launch_ygrad<false>(ty, tb, cs, yp, st, "bow_dz")) return rc;
   }
   return 0;
 }
+
+#ifdef CAREL_CHAIN_TRACE
+// debug: the clock64 timeline block 0 of the last traced kernel recorded (8 slots x 256 steps)
+extern "C" int carel_debug_chain_trace(long long* host_dst) {
+  CAREL_CHECK_CUDA(cudaMemcpyFromSymbol(host_dst, carel::g_chain_trace, sizeof(long long) * 8 * 256));
+  return 0;
+}
+#endif

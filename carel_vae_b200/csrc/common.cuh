@@ -104,6 +104,14 @@ CAREL_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* ba
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion counted on an mbarrier.
+CAREL_DEVINL void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // 2-D tiled store smem -> global (bulk group completion).
 CAREL_DEVINL void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t crd0,
                                int32_t crd1) {

@@ -15,11 +15,19 @@
 // in place -> MMA -> free), B pieces of 64 reduction rows (ldk / 64 x 8 KB each, up to 4).  Work split: stream-K units
 // of (owner, step) pairs (ChainSched).
 //
+// Per-step constants (b_j log2 e of the step's words; dW: also the two rowc planes of its 128 clauses) ride in the Y
+// ring as 1-D bulk copies on the same barrier, so the epilogue loop has no global load.
+//
 // dlogit (dense part; the O(nnz) sparse part is added by the gather kernels of bow.cu):
 //   log2 p = (float(Y16) - bmagic_i) inv_s_i + rc_i + cc_j,   rc_i = -lse2_i,   cc_j = b_j log2(e)
 //   (rowc[i] = {inv_s_i, bmagic_i, rc_i, -S_i 2^10}: the four per-clause constants in one 16-byte load)
 //   d' = (u - p S_i) 2^10,      u = p (p - c) / max(p (1 - p), 1e-12)        (torch's BCELoss backward rule)
-//   fast path (all 16 p in (e^-27, 2^-10)):  u = (p - c)(1 + p + p^2)
+//   series (p in (e^-27, 2^-10)):  u = (p - c)(1 + p + p^2), i.e.  u - p S = -c + p (1 - c - S + p (1 - c + p)).
+//   Rows the forward pass certified (rowc plane 1, .w = 1: every p of the row in (e^-27, 2^-8)) evaluate it as a polynomial in
+//   p' = 2^(log2 p - rc_i) with per-row coefficients (a1, a2, a3) = 2^10 ((1 - c - S) P, (1 - c) P^2, P^3), P = 2^rc_i
+//   (the cubic term, < 2^-20 of the linear one, is dropped): one FFMA2 for the exponent, 2 MUFU and 2 FFMA2 per PAIR
+//   of elements, no range test.  A warp with an uncertified
+//   row tests every 16-element chunk instead and falls back to the exact terms where needed.
 // The 2^10 puts d' (typically +-3e-5 before scaling) into fp16's normal range; the write-out multiplies the
 // accumulator by grad_out / (N V) 2^-10.
 #pragma once
@@ -30,10 +38,16 @@ namespace carel {
 constexpr float kYgScale = 1024.f;
 constexpr int kYgYStages = 3, kYgMaxBStages = 4;
 constexpr int kYgYBytes = 32768;                // one Y piece: [256 clauses x 64 words] or 2 x [128 clauses x 64 words]
-constexpr int kYgOnesBytes = 2048;              // [16 rows x 128 B] of fp16 1.0 (B operand of the db MMA)
+constexpr int kYgOnesBytes = 1024;              // [8 rows x 128 B] of fp16 1.0: B operand of the db MMA (N = 16: the
+                                                // second 8-row group aliases the first, SBO = 0)
+// per-stage constants: b log2 e of the 128 owner words (dW, 512 B) or of the step's 64 words (dZ, 256 B).  The two
+// rowc planes of a dW step's clauses are prefetched into registers one step ahead instead (8 KB per stage would cost
+// the fourth B stage).
+static __host__ __device__ constexpr int yg_c_bytes(bool trans) { return trans ? 512 : 256; }
 
 struct YGradParams {
   const float4* rowc;    // [Npad]  {inv_s_i, bmagic_i, -lse2_i, -S_i 2^10}  (zero beyond N)
+  int Npad;              // rows of one rowc plane; plane 1 = {a1, a2, a3, fast} (see above)
   const float* bl2e;     // [Vpad]  b_j log2(e)
   const float* grad_out; // device scalar
   float* out;            // TRANS: dW [V, ldo]; else dZ [N, ldo]   (accumulated with red.global.add)
@@ -45,13 +59,13 @@ struct YGradParams {
 
 // one B piece: 64 reduction rows x ldk features = ldk / 64 boxes of [64 rows x 128 B]
 static __host__ __device__ inline int yg_b_bytes(int k16) { return ((k16 + 3) / 4) * 8192; }
-static __host__ inline int yg_b_stages(int k16) {
-  const int budget = 227 * 1024 - kYgYStages * kYgYBytes - kYgOnesBytes - 256;
+static __host__ inline int yg_b_stages(int k16, bool trans) {
+  const int budget = 227 * 1024 - kYgYStages * (kYgYBytes + yg_c_bytes(trans)) - kYgOnesBytes - 256;
   const int st = budget / yg_b_bytes(k16);
   return st > kYgMaxBStages ? kYgMaxBStages : st;
 }
-static __host__ inline int yg_smem_bytes(int k16) {
-  return kYgYStages * kYgYBytes + yg_b_stages(k16) * yg_b_bytes(k16) + kYgOnesBytes + 256;
+static __host__ inline int yg_smem_bytes(int k16, bool trans) {
+  return kYgYStages * (kYgYBytes + yg_c_bytes(trans)) + yg_b_stages(k16, trans) * yg_b_bytes(k16) + kYgOnesBytes + 256;
 }
 
 // exact per-element terms (chunks that leave the series' range)
@@ -107,13 +121,15 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
   const int KB = (K16 + 3) / 4;
   const int b_bytes = yg_b_bytes(K16);
   const int BST = sched.stages;                   // B ring depth
+  constexpr int kCB = yg_c_bytes(TRANS);
   // the base of dynamic shared memory is 1024-byte aligned (no static shared memory in this kernel); checked below
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sY = smem;
   uint8_t* sB = smem + kYgYStages * kYgYBytes;
   uint8_t* sOnes = sB + BST * b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kYgOnesBytes);
-  uint64_t* y_full = bars;                        // [3]  TMA bytes
+  uint8_t* sC = sOnes + kYgOnesBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kYgYStages * kCB);
+  uint64_t* y_full = bars;                        // [3]  TMA bytes (Y piece + its constants)
   uint64_t* y_empty = y_full + kYgYStages;        // [3]  tcgen05.commit (the MMAs that read the piece are done)
   uint64_t* p_full = y_empty + kYgYStages;        // [3]  16 epilogue warps (dlogits written in place)
   uint64_t* b_full = p_full + kYgYStages;         // [4]
@@ -162,16 +178,21 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + bs * b_bytes + kb * 8192, &tmB, &b_full[bs], kb * 64, row0);
       if (++bs == BST) { bs = 0; bphase ^= 1; }
     };
+    int tn = 0;
     while (iter.next(it)) {
 #pragma unroll 1
-      for (int t = it.t0; t < it.t1; ++t) {
+      for (int t = it.t0; t < it.t1; ++t, ++tn) {
         mbar_wait(&y_empty[ys], yphase ^ 1);
-        mbar_expect_tx(&y_full[ys], kYgYBytes);
-        if (TRANS) {          // two boxes [128 clauses x 64 words]
+        CAREL_TRACE(0, tn);
+        mbar_expect_tx(&y_full[ys], kYgYBytes + kCB);
+        uint8_t* cst = sC + ys * kCB;
+        if (TRANS) {          // two boxes [128 clauses x 64 words]; rowc planes of the clauses; b of the owner's words
           tma_load_2d(sY + ys * kYgYBytes, &tmY, &y_full[ys], it.owner * 128, t * 128);
           tma_load_2d(sY + ys * kYgYBytes + 16384, &tmY, &y_full[ys], it.owner * 128 + 64, t * 128);
-        } else {              // one box [256 clauses x 64 words]
+          bulk_load_1d(cst, pp.bl2e + it.owner * 128, 512, &y_full[ys]);
+        } else {              // one box [256 clauses x 64 words]; b of the step's words
           tma_load_2d(sY + ys * kYgYBytes, &tmY, &y_full[ys], t * 64, it.owner * 256);
+          bulk_load_1d(cst, pp.bl2e + t * 64, 256, &y_full[ys]);
         }
         if (++ys == kYgYStages) { ys = 0; yphase ^= 1; }
         if (TRANS) {
@@ -180,24 +201,26 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         } else {
           load_b(t * 64);
         }
+        CAREL_TRACE(1, tn);
       }
     }
   } else if (warp == kEpi + 1 && elect_one()) {
     // ===================== MMA issuer =====================
     ChainIter iter(sched);
     ChainItem it;
-    int ys = 0, bs = 0;
+    int ys = 0, bs = 0, tn = 0;
     uint32_t yphase = 0, bphase = 0, acc_phase = 0;
     const uint32_t idesc = make_idesc_f16(128, 16 * K16, TRANS ? 1 : 0, 1);     // B MN-major (features contiguous)
     const uint32_t idesc_ones = make_idesc_f16(128, 16, 1, 0);
-    const uint64_t d_ones = make_sdesc_sw128(smem_u32(sOnes), 16, 1024);
+    const uint64_t d_ones = make_sdesc_sw128(smem_u32(sOnes), 16, 0);
     while (iter.next(it)) {
       mbar_wait(acc_empty, acc_phase ^ 1);
       acc_phase ^= 1;
       uint32_t accum = 0;
 #pragma unroll 1
-      for (int t = it.t0; t < it.t1; ++t) {
+      for (int t = it.t0; t < it.t1; ++t, ++tn) {
         mbar_wait(&p_full[ys], yphase);
+        CAREL_TRACE(4, tn);
         tc_fence_after();
         const uint32_t y_addr = smem_u32(sY + ys * kYgYBytes);
         if (TRANS) {
@@ -206,6 +229,7 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {
             mbar_wait(&b_full[bs], bphase);
+            if (hb == 1) CAREL_TRACE(5, tn);
             tc_fence_after();
             const uint64_t db0 = make_sdesc_sw128(smem_u32(sB + bs * b_bytes), 8192, 1024);
 #pragma unroll
@@ -222,6 +246,7 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           // A = dl, K-major: [256 clauses x 64 words], rows 128 B, the second accumulator's rows 16 KB further
           const uint64_t da0 = make_sdesc_sw128(y_addr, 16, 1024);
           mbar_wait(&b_full[bs], bphase);
+          CAREL_TRACE(5, tn);
           tc_fence_after();
           const uint64_t db0 = make_sdesc_sw128(smem_u32(sB + bs * b_bytes), 8192, 1024);
 #pragma unroll
@@ -235,6 +260,7 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           if (++bs == BST) { bs = 0; bphase ^= 1; }
         }
         umma_commit(&y_empty[ys]);
+        CAREL_TRACE(6, tn);
         if (++ys == kYgYStages) { ys = 0; yphase ^= 1; }
       }
       umma_commit(acc_full);
@@ -250,74 +276,108 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     ChainIter iter(sched);
     ChainItem it;
-    int ys = 0;
+    int ys = 0, tn = 0;
     uint32_t yphase = 0, acc_phase = 0;
     const float c = pp.c;
+    const float2 mc2 = make_float2(-c * kYgScale, -c * kYgScale);
     while (iter.next(it)) {
-      float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 own = make_float4(0.f, 0.f, 0.f, 0.f), pol = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 own_n = own, pol_n = pol;
       if (!TRANS) {
         const int clause = it.owner * 256 + r;
-        if (clause < pp.N) own = __ldg(pp.rowc + clause);
+        if (clause < pp.N) {
+          own = __ldg(pp.rowc + clause);
+          pol = __ldg(pp.rowc + pp.Npad + clause);
+        }
+      } else if (it.t0 < it.t1) {                 // rowc is padded to a multiple of 128 rows (zeros)
+        own_n = __ldg(pp.rowc + it.t0 * 128 + r);
+        pol_n = __ldg(pp.rowc + pp.Npad + it.t0 * 128 + r);
       }
 #pragma unroll 1
-      for (int t = it.t0; t < it.t1; ++t) {
+      for (int t = it.t0; t < it.t1; ++t, ++tn) {
         const int clause = TRANS ? t * 128 + r : it.owner * 256 + r;
         const int j0 = TRANS ? it.owner * 128 + seg * 32 : t * 64 + seg * 32;      // first word of this thread
-        // constants that do not depend on the tile are issued before the barrier wait
-        if (TRANS) own = __ldg(pp.rowc + clause);                  // rowc is padded to a multiple of 128 rows (zeros)
-        float4 ca[4];
-        auto load_consts = [&](int h) {
-          const float4* b4 = reinterpret_cast<const float4*>(pp.bl2e + j0 + h * 16);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) ca[i] = __ldg(b4 + i);
-        };
-        load_consts(0);
         mbar_wait(&y_full[ys], yphase);
+        if (threadIdx.x == 0) CAREL_TRACE(2, tn);
         uint8_t* rowp = sY + ys * kYgYBytes + tile_off;
-        uint32_t yh[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ch = (half * 4 + i) ^ (r & 7);
-          const uint4 v = *reinterpret_cast<const uint4*>(rowp + ch * 16);
-          yh[4 * i] = v.x; yh[4 * i + 1] = v.y; yh[4 * i + 2] = v.z; yh[4 * i + 3] = v.w;
+        const uint8_t* cst = sC + ys * kCB;
+        if (TRANS) {            // this step's clause constants were loaded a step ago; fetch the next step's
+          own = own_n;
+          pol = pol_n;
+          const int tn1 = min(t + 1, it.t1 - 1) * 128 + r;
+          own_n = __ldg(pp.rowc + tn1);
+          pol_n = __ldg(pp.rowc + pp.Npad + tn1);
         }
-        const bool row_dead = clause >= pp.N;
+        const float4* cc4 = reinterpret_cast<const float4*>(cst) + seg * 8;   // this thread's 32 words
         const float2 nb2 = make_float2(-own.y, -own.y), is2 = make_float2(own.x, own.x);
-        uint32_t ph[16];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h == 1) load_consts(1);
-          float tt[16], Sn[16], d[16];
+        if (__all_sync(0xffffffffu, pol.w != 0.f)) {
+          // ---- every row of this warp is certified: cubic in p', no range test (words beyond V meet zero-filled
+          //      operand rows or unwritten output rows; their values only have to be finite) ----
+          // (certified rows have every p < 2^-8; the p'^3 term is dropped, see bow_combine_kernel)
+          const float2 a1 = make_float2(pol.x, pol.x), a2 = make_float2(pol.y, pol.y);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 a4 = ca[i];
-            const uint32_t u0 = yh[h * 8 + 2 * i], u1 = yh[h * 8 + 2 * i + 1];
-            const float2 g0 = __fadd2_rn(make_float2(y16_lo(u0), y16_hi(u0)), nb2);     // exact: integers below 2^24
-            const float2 g1 = __fadd2_rn(make_float2(y16_lo(u1), y16_hi(u1)), nb2);
-            const float2 t0 = __ffma2_rn(g0, is2, make_float2(a4.x + own.z, a4.y + own.z));
-            const float2 t1 = __ffma2_rn(g1, is2, make_float2(a4.z + own.z, a4.w + own.z));
-            tt[4 * i] = t0.x; tt[4 * i + 1] = t0.y; tt[4 * i + 2] = t1.x; tt[4 * i + 3] = t1.y;
-            Sn[4 * i] = own.w; Sn[4 * i + 1] = own.w; Sn[4 * i + 2] = own.w; Sn[4 * i + 3] = own.w;
+            uint8_t* cp = rowp + (((half * 4 + i) ^ (r & 7)) << 4);
+            const uint4 v = *reinterpret_cast<const uint4*>(cp);
+            const float4 ca = cc4[2 * i], cb = cc4[2 * i + 1];
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+            const float2 cc[4] = {make_float2(ca.x, ca.y), make_float2(ca.z, ca.w), make_float2(cb.x, cb.y),
+                                  make_float2(cb.z, cb.w)};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 g = __fadd2_rn(make_float2(y16_lo(u[e]), y16_hi(u[e])), nb2);
+              const float2 tp = __ffma2_rn(g, is2, cc[e]);
+              const float2 pv = make_float2(ex2_approx(tp.x), ex2_approx(tp.y));
+              float2 hh = __ffma2_rn(pv, a2, a1);
+              hh = __ffma2_rn(pv, hh, mc2);
+              o[e] = pack_f16x2_sat(hh.x, hh.y);
+            }
+            *reinterpret_cast<uint4*>(cp) = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          const int jh = j0 + h * 16;
-          if (row_dead) {
+        } else {
+          // ---- checked path: range test per 16 elements, exact terms where the series does not hold ----
+          const bool row_dead = clause >= pp.N;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            uint32_t yh[8];
+            float tt[16], Sn[16], d[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) d[i] = 0.f;
-          } else {
-            yg_dlogit16(tt, Sn, c, jh + 16 <= pp.V, pp.V - jh, d);
+            for (int i = 0; i < 2; ++i) {
+              const uint4 v = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + h * 2 + i) ^ (r & 7)) << 4));
+              yh[4 * i] = v.x; yh[4 * i + 1] = v.y; yh[4 * i + 2] = v.z; yh[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 a4 = cc4[h * 4 + i];
+              const uint32_t u0 = yh[2 * i], u1 = yh[2 * i + 1];
+              const float2 g0 = __fadd2_rn(make_float2(y16_lo(u0), y16_hi(u0)), nb2);     // exact: integers below 2^24
+              const float2 g1 = __fadd2_rn(make_float2(y16_lo(u1), y16_hi(u1)), nb2);
+              const float2 t0 = __ffma2_rn(g0, is2, make_float2(a4.x + own.z, a4.y + own.z));
+              const float2 t1 = __ffma2_rn(g1, is2, make_float2(a4.z + own.z, a4.w + own.z));
+              tt[4 * i] = t0.x; tt[4 * i + 1] = t0.y; tt[4 * i + 2] = t1.x; tt[4 * i + 3] = t1.y;
+              Sn[4 * i] = own.w; Sn[4 * i + 1] = own.w; Sn[4 * i + 2] = own.w; Sn[4 * i + 3] = own.w;
+            }
+            const int jh = j0 + h * 16;
+            if (row_dead) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) d[i] = 0.f;
+            } else {
+              yg_dlogit16(tt, Sn, c, jh + 16 <= pp.V, pp.V - jh, d);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              *reinterpret_cast<uint4*>(rowp + (((half * 4 + h * 2 + i) ^ (r & 7)) << 4)) =
+                  make_uint4(pack_f16x2_sat(d[8 * i], d[8 * i + 1]), pack_f16x2_sat(d[8 * i + 2], d[8 * i + 3]),
+                             pack_f16x2_sat(d[8 * i + 4], d[8 * i + 5]), pack_f16x2_sat(d[8 * i + 6], d[8 * i + 7]));
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ph[h * 8 + i] = pack_f16x2_sat(d[2 * i], d[2 * i + 1]);
         }
-        // ---- dlogits back over the logits they came from; visible to the tensor core (async proxy) ----
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ch = (half * 4 + i) ^ (r & 7);
-          *reinterpret_cast<uint4*>(rowp + ch * 16) = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
-        }
+        // ---- the dlogits lie over the logits they came from; make them visible to the tensor core (async proxy) ----
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[ys]);
+        if (threadIdx.x == 0) CAREL_TRACE(3, tn);
+        if (threadIdx.x == 15 * 32) CAREL_TRACE(7, tn);
         if (++ys == kYgYStages) { ys = 0; yphase ^= 1; }
       }
       // ---- write-out of this item's accumulator(s) ----
@@ -384,7 +444,7 @@ template <bool TRANS>
 int launch_ygrad(const CUtensorMap& ty, const CUtensorMap& tb, const ChainSched& s, const YGradParams& pp,
                  cudaStream_t st, const char* tag) {
   auto kern = ygrad_kernel<TRANS>;
-  const int smem = yg_smem_bytes(s.k16);
+  const int smem = yg_smem_bytes(s.k16, TRANS);
   static int attr_smem = 0;
   if (smem > attr_smem) {
     CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -38,9 +38,11 @@ t0 = min(v for v in ev[0] if v > 0)
 if which in ("fwd", "mmdfwd"):
     names = ["tile_load", "mma_start", "mma_issued", "epi_start", "epi_done", "-", "-", "-"]
 else:
-  names = ["load_issue", "g1_issue", "g2_issue", "epi_acc1_ready", "epi_ld_done", "epi_p_arrive", "g1_issued", "g2_issued"]
+  names = (["y_slot_free", "b_loads_issued", "epi_y_ready", "epi_arrived", "mma_p_ready", "mma_b_ready", "mma_issued", "epi15_arrived"]
+           if which in ("dz", "dw") else
+           ["load_issue", "g1_issue", "g2_issue", "epi_acc1_ready", "epi_ld_done", "epi_p_arrive", "g1_issued", "g2_issued"])
 print("tile " + " ".join(f"{n:>14s}" for n in names))
-for i in list(range(0, 8)) + (list(range(8, 29)) if which in ('fwd', 'mmdfwd') else list(range(100, 112))):
+for i in list(range(0, 8)) + (list(range(8, 29)) if which in ('fwd', 'mmdfwd') else list(range(50, 70))):
     print(f"{i:4d} " + " ".join(f"{ev[s][i] - t0:14d}" for s in range(8)))
 for s in range(8):
     d_ = [ev[s][i + 1] - ev[s][i] for i in (range(4, 26) if which in ('fwd', 'mmdfwd') else range(20, 100))]
