@@ -29,7 +29,11 @@ struct MmdBwdParams {
   float a_scale[kMaxAlphas];  // -2 alpha log2 e
   float a_shift[kMaxAlphas];  // -alpha eps log2 e
   float a_pos[kMaxAlphas];    // alpha
-  float w_scale, inv_w_scale; // power-of-two scaling that puts W into fp16's range
+  // FP16 weights: W is scaled by the power of two that puts its LARGEST possible entry, wmax_coef * kmax with
+  // wmax_coef = max|c| max alpha and kmax = the forward pass's maximum off-diagonal kernel value, just below 2^10;
+  // hi + lo then resolve weights down to 2^-34 of the largest one, whatever the absolute scale of the kernel values
+  const unsigned* kmax_bits;  // device scalar written by the forward pass (EpiMMD), float bits
+  float wmax_coef;
   int atomic;                 // 0: each gradient row is produced by exactly one work item -> plain stores
   // fp32 mode (3-term split operands, pack3_rows_kernel): acc2 holds W.s1 in columns [0, kp) and W.s2 in
   // [kp, 2 kp), the row sum in column 2 kp; s_i itself is read in fp32 from S32.
@@ -37,14 +41,27 @@ struct MmdBwdParams {
   const float* S32;
 };
 
-struct PolMmdBwd {
+template <bool F16_>
+struct PolMmdBwdT {
   using Params = MmdBwdParams;
+  static constexpr bool kF16 = F16_;      // FP16 operands + FP16 (hi + lo) weights, scaled into range by w_scale
   static constexpr bool kHiLo = true;     // P = W as bf16 hi + lo: the 2^-9 rounding of a single bf16 would
                                           // otherwise dominate the gradient error of small samples
   const Params& p;
   bool fast;
-  float cf;
-  CAREL_DEVINL PolMmdBwd(const Params& p_, const ChainCtx&) : p(p_), fast(false), cf(0.f) {}
+  float cf, wscale, inv_wscale;
+  CAREL_DEVINL PolMmdBwdT(const Params& p_, const ChainCtx&) : p(p_), fast(false), cf(0.f), wscale(1.f), inv_wscale(1.f) {
+    if (kF16) {
+      const float wmax = p.wmax_coef * __uint_as_float(__ldg(p.kmax_bits));
+      if (wmax > 0.f) {
+        int e;
+        frexpf(wmax, &e);                       // wmax = m 2^e, m in [0.5, 1)
+        e = max(-100, min(e, 100));
+        wscale = ldexpf(1.f, 10 - e);
+        inv_wscale = ldexpf(1.f, e - 10);
+      }
+    }
+  }
   CAREL_DEVINL void begin_item(const ChainCtx&) {}
   CAREL_DEVINL void prefetch(const ChainCtx&, int) {}
   CAREL_DEVINL float ksum(float a) const {   // sum_alpha alpha * exp(-alpha (|d2| + eps))
@@ -65,7 +82,7 @@ struct PolMmdBwd {
     const int r0 = ctx.owner * 128, r1 = r0 + 127, j1 = j0 + R - 1;
     fast = r1 < p.M && j1 < p.M && ((r1 < p.n1) || (r0 >= p.n1)) && ((j1 < p.n1) || (j0 >= p.n1)) &&
            (j0 > r1 || j1 < r0);
-    cf = coef(r0, j0) * p.w_scale;
+    cf = coef(r0, j0) * wscale;
   }
   CAREL_DEVINL void weights16(const ChainCtx& ctx, int jc, const uint32_t (&r)[16], const uint32_t (&)[16],
                               float (&w)[16]) {
@@ -83,7 +100,7 @@ struct PolMmdBwd {
       // boundary / diagonal tiles: same arithmetic, branch-free per-element coefficient
       const int row = ctx.row;
       const bool row_ok = row < p.M, rx = row < p.n1;
-      const float c_same = (rx ? p.c00 : p.c01) * p.w_scale, c_other = (rx ? p.c01 : p.c11) * p.w_scale;
+      const float c_same = (rx ? p.c00 : p.c01) * wscale, c_other = (rx ? p.c01 : p.c11) * wscale;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int col = jc + i;
@@ -104,7 +121,7 @@ struct PolMmdBwd {
     const float rtot = __uint_as_float(rtot_bits);
     const int nfeat16 = p.split ? (p.kp >> 4) : ctx.n2_16;
     const int q0 = (nfeat16 * ctx.half) / kChainSplit, q1 = (nfeat16 * (ctx.half + 1)) / kChainSplit;
-    const float g4 = 4.f * __ldg(p.grad_out) * p.inv_w_scale;
+    const float g4 = 4.f * __ldg(p.grad_out) * inv_wscale;
     const bool row_ok = valid && ctx.row < p.M;
     const int rowc = min(ctx.row, p.M - 1);
     const __nv_bfloat16* srow = p.SA + size_t(rowc) * p.ldp;
@@ -126,7 +143,7 @@ struct PolMmdBwd {
         const uint32_t u[8] = {sv0.x, sv0.y, sv0.z, sv0.w, sv1.x, sv1.y, sv1.z, sv1.w};
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
-          const float2 s2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
+          const float2 s2 = kF16 ? unpack_f16x2(u[h]) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[h]));
           sv[2 * h] = s2.x;
           sv[2 * h + 1] = s2.y;
         }
@@ -162,5 +179,6 @@ struct PolMmdBwd {
   }
   CAREL_DEVINL void finish() {}
 };
+using PolMmdBwd = PolMmdBwdT<false>;
 
 }  // namespace carel

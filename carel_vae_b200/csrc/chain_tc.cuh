@@ -107,6 +107,7 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   constexpr int MAXST = Cfg::kMaxStages;
   constexpr int R = BN1 / kChainSplit;       // columns of the inner tile per epilogue thread
   constexpr bool HILO = Pol::kHiLo;
+  constexpr bool F16 = Pol::kF16;            // operands and the weight tile P in FP16 instead of BF16
   const int K16 = sched.k16;
   const int KB = Cfg::kb(K16);
   const int STAGES = sched.stages;
@@ -204,8 +205,8 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     int g2_buf = 0; uint32_t p_phases = 0;     // bit b = phase of p_full[b]
     uint32_t aphase = 0, acc2_phase = 0;
     int trace_g1 = 0, trace_g2 = 0; (void)trace_g1; (void)trace_g2;
-    constexpr uint32_t idesc1 = make_idesc_bf16(128, BN1, 0, 0);
-    const uint32_t idesc2 = make_idesc_bf16(128, 16 * sched.n2_16, 0, 1);
+    constexpr uint32_t idesc1 = F16 ? make_idesc_f16(128, BN1, 0, 0) : make_idesc_bf16(128, BN1, 0, 0);
+    const uint32_t idesc2 = F16 ? make_idesc_f16(128, 16 * sched.n2_16, 0, 1) : make_idesc_bf16(128, 16 * sched.n2_16, 0, 1);
     const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(sA), 16, 1024);
     const uint32_t b_base0 = smem_u32(sB);
     const uint32_t acc2_addr = tmem_base + Cfg::kAcc2Base;
@@ -327,11 +328,19 @@ chain_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const __nv_bfloat162 b = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
-            hi[i] = *reinterpret_cast<const uint32_t*>(&b);
-            if (HILO) {
-              const float2 f = __bfloat1622float2(b);
-              lo[i] = pack_bf16x2(w[2 * i] - f.x, w[2 * i + 1] - f.y);
+            if (F16) {
+              hi[i] = pack_f16x2_sat(w[2 * i], w[2 * i + 1]);
+              if (HILO) {
+                const float2 f = unpack_f16x2(hi[i]);
+                lo[i] = pack_f16x2(w[2 * i] - f.x, w[2 * i + 1] - f.y);
+              }
+            } else {
+              const __nv_bfloat162 b = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
+              hi[i] = *reinterpret_cast<const uint32_t*>(&b);
+              if (HILO) {
+                const float2 f = __bfloat1622float2(b);
+                lo[i] = pack_bf16x2(w[2 * i] - f.x, w[2 * i + 1] - f.y);
+              }
             }
           }
           tmem_st8(reg0 + c * 8, hi);

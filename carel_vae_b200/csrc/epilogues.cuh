@@ -135,6 +135,8 @@ struct EpiPairwise {
 // ---------------------------------------------------------------------------------------------
 struct EpiMMDParams {
   double* accum;       // [3]
+  unsigned* kmax_bits; // optional: running maximum (float bits) of the off-diagonal kernel values sum_alpha e_alpha;
+                       // the FP16 backward scales its weight tile by it (chain_policies.cuh)
   int M, n1, tri, n_alpha;
   float a_scale[kMaxAlphas];  // -2 alpha log2(e)
   float a_shift[kMaxAlphas];  // -alpha eps log2(e)
@@ -145,7 +147,8 @@ struct EpiMMD {
   using Params = EpiMMDParams;
   const Params& p;
   double acc0, acc1, acc2;
-  CAREL_DEVINL EpiMMD(const Params& p_, const TileCtx&) : p(p_), acc0(0.0), acc1(0.0), acc2(0.0) {}
+  float kmx;
+  CAREL_DEVINL EpiMMD(const Params& p_, const TileCtx&) : p(p_), acc0(0.0), acc1(0.0), acc2(0.0), kmx(0.f) {}
   CAREL_DEVINL void prefetch(const TileCtx&) {}
 
   CAREL_DEVINL float kmulti(float a) const {
@@ -179,17 +182,23 @@ struct EpiMMD {
         for_each_chunk32(taddr, HALF / 32, [&](int, const uint32_t (&r)[32]) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            s += ex2_approx(fmaf(fabsf(__uint_as_float(r[i])), sc, sh));
-            s1 += ex2_approx(fmaf(fabsf(__uint_as_float(r[i + 1])), sc, sh));
-            s2 += ex2_approx(fmaf(fabsf(__uint_as_float(r[i + 2])), sc, sh));
-            s3 += ex2_approx(fmaf(fabsf(__uint_as_float(r[i + 3])), sc, sh));
+            const float e0 = ex2_approx(fmaf(fabsf(__uint_as_float(r[i])), sc, sh));
+            const float e1 = ex2_approx(fmaf(fabsf(__uint_as_float(r[i + 1])), sc, sh));
+            const float e2 = ex2_approx(fmaf(fabsf(__uint_as_float(r[i + 2])), sc, sh));
+            const float e3 = ex2_approx(fmaf(fabsf(__uint_as_float(r[i + 3])), sc, sh));
+            s += e0; s1 += e1; s2 += e2; s3 += e3;
+            kmx = fmax3(fmax3(kmx, e0, e1), e2, e3);
           }
         });
         s += (s1 + s2) + s3;
       } else {
         for_each_chunk16(taddr, HALF / 16, [&](int, const uint32_t (&r)[16]) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) s += kmulti(fabsf(__uint_as_float(r[i])));
+          for (int i = 0; i < 16; ++i) {
+            const float k = kmulti(fabsf(__uint_as_float(r[i])));
+            s += k;
+            kmx = fmaxf(kmx, k);
+          }
         });
       }
       const int type = (r0 < p.n1) ? ((c0 < p.n1) ? 0 : 2) : ((c0 < p.n1) ? 2 : 1);
@@ -209,6 +218,7 @@ struct EpiMMD {
           const float k = single ? ex2_approx(fmaf(a, sc, sh)) : kmulti(a);
           const bool ok = row_ok && (col < p.M) && (p.tri ? (col > row) : (col != row));
           const bool cx = col < p.n1;
+          kmx = ok ? fmaxf(kmx, k) : kmx;
           s0 += (ok && rx && cx) ? k : 0.f;
           s1 += (ok && !rx && !cx) ? k : 0.f;
           s2 += (ok && (rx != cx)) ? k : 0.f;
@@ -225,6 +235,10 @@ struct EpiMMD {
       if (v0 != 0.0) atomicAdd(p.accum + 0, v0);
       if (v1 != 0.0) atomicAdd(p.accum + 1, v1);
       if (v2 != 0.0) atomicAdd(p.accum + 2, v2);
+    }
+    if (p.kmax_bits != nullptr) {
+      const float km = warp_max(kmx);        // kernel values are >= 0: their float bits order like unsigned integers
+      if ((threadIdx.x & 31) == 0 && km > 0.f) atomicMax(p.kmax_bits, __float_as_uint(km));
     }
   }
 };

@@ -159,6 +159,7 @@ struct HsicBwdParams {
 struct PolHsicBwd {
   using Params = HsicBwdParams;
   static constexpr bool kHiLo = true;
+  static constexpr bool kF16 = false;
   const Params& p;
   float ci;
   CAREL_DEVINL PolHsicBwd(const Params& p_, const ChainCtx&) : p(p_), ci(0.f) {}

@@ -32,6 +32,12 @@ static MmdWs carve_mmd(void* ws, int64_t M, int64_t dim, int precision) {
   return r;
 }
 
+// FP16 operands: bf16-mode, short-K samples evaluated over their FULL row range (the weight scale of the FP16
+// backward is the forward pass's maximum kernel value, which a row-block shard does not see completely).
+static inline bool mmd_uses_f16(int precision, int ldp, int t0, int t1, int m_tiles) {
+  return !precision && ldp <= 256 && t0 == 0 && t1 == m_tiles;
+}
+
 static __global__ void mmd_finalize_kernel(const double* __restrict__ acc, double a00, double a11,
                                            double a01, float* __restrict__ out) {
   if (threadIdx.x == 0 && blockIdx.x == 0)
@@ -72,9 +78,14 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_mmd_fwd: workspace too small");
   double* acc = partial_sums ? partial_sums : w.accum;
 
+  // short-K bf16-mode samples (the head's latent codes: an intermediate of bounded range) go to the tensor core as
+  // FP16 -- same MMA rate, 11 mantissa bits; the wide Gram sweep and the split (fp32-mode) operands stay BF16
+  const int m_tiles_all = int((M + 127) / 128);
+  const bool f16 = mmd_uses_f16(precision, ldp, int(row_tile_begin < 0 ? 0 : row_tile_begin),
+                                int((row_tile_end < 0 || row_tile_end > m_tiles_all) ? m_tiles_all : row_tile_end), m_tiles_all);
   if (!precision) {
     pack_rows_kernel<<<int((M + 7) / 8), 256, 0, st>>>(x, int(M), int(dim), int(ldx), w.SA, w.SB, ldp, 0, 1, nullptr,
-                                                      nullptr, y, int(n1), int(ldy));
+                                                      nullptr, y, int(n1), int(ldy), f16 ? 1 : 0);
     CAREL_LAUNCHED();
   } else {
     const Pack3Out oa{w.SA, 0, 0}, ob{w.SB, 1, 1};
@@ -84,6 +95,8 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
     CAREL_LAUNCHED();
   }
   CAREL_CHECK_CUDA(cudaMemsetAsync(acc, 0, 3 * sizeof(double), st));
+  unsigned* kmax_bits = reinterpret_cast<unsigned*>(w.accum + 3);
+  CAREL_CHECK_CUDA(cudaMemsetAsync(kmax_bits, 0, sizeof(double), st));
 
   CUtensorMap ta, tb;
   CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.SA, M, ldp, ldp, 128) == 0, "carel_mmd_fwd: tensor map failed");
@@ -103,7 +116,7 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
     s.num_items = (t1 - t0) * s.n_tiles;
   }
   EpiMMDParams ep;
-  ep.accum = acc; ep.M = int(M); ep.n1 = int(n1); ep.tri = tri; ep.n_alpha = n_alpha;
+  ep.accum = acc; ep.kmax_bits = kmax_bits; ep.M = int(M); ep.n1 = int(n1); ep.tri = tri; ep.n_alpha = n_alpha;
   for (int i = 0; i < kMaxAlphas; ++i) {
     const float a = (i < n_alpha) ? alphas_host[i] : 0.f;
     ep.a_scale[i] = -2.f * a * kLog2e;
@@ -112,7 +125,11 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
   if (ldp <= 256) {
     // short K (latent-sized samples): A-stationary schedule, only the column operand is streamed
     AsSched as = make_as_sched(M, M, ldp, sm_count(), tri, t0, t1);
-    if (int rc = launch_gemm_as<EpiMMD<256>>(ta, tb, as, ep, st, "mmd_gram_fwd")) return rc;
+    if (f16) {
+      if (int rc = launch_gemm_as<EpiMMD<256>, true>(ta, tb, as, ep, st, "mmd_gram_fwd")) return rc;
+    } else if (int rc = launch_gemm_as<EpiMMD<256>>(ta, tb, as, ep, st, "mmd_gram_fwd")) {
+      return rc;
+    }
   } else if ((t0 & 1) == 0 && ((t1 & 1) == 0 || t1 == s.m_tiles) && !(flags & CAREL_MMD_NO_PAIRS)) {
     // long K (the d = 768 Gram sweep): CTA pairs, one M = 256 UMMA across two SMs (gemm_2sm.cuh)
     PairSched ps = make_pair_sched(M, M, ldp, tri, t0, t1, sm_count());
@@ -124,7 +141,7 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
   return 0;
 }
 
-template <int BN1, int NB>
+template <int BN1, int NB, bool F16 = false>
 static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, int n2_16, int t0, int t1,
                           float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy, int64_t n1, int64_t n2,
                           int64_t dim, cudaStream_t st) {
@@ -142,7 +159,7 @@ static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, i
     CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_x, size_t(ldgx) * 4, 0, size_t(dim) * 4, size_t(n1), st));
     CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_y, size_t(ldgy) * 4, 0, size_t(dim) * 4, size_t(n2), st));
   }
-  return launch_chain<PolMmdBwd, 1, BN1, NB>(ta, tb, ta, tb, s, pp, st, "mmd_gram_bwd");
+  return launch_chain<PolMmdBwdT<F16>, 1, BN1, NB>(ta, tb, ta, tb, s, pp, st, "mmd_gram_bwd");
 }
 
 extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int64_t dim,
@@ -172,24 +189,21 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   pp.c11 = float(1.0 / (double(n2) * double(n2 - 1)));
   pp.c01 = float(-1.0 / (double(n1) * double(n2)));
   pp.n_alpha = n_alpha;
-  float asum = 0.f;
+  float amax = 0.f;
   for (int i = 0; i < kMaxAlphas; ++i) {
     const float a = (i < n_alpha) ? alphas_host[i] : 0.f;
     pp.a_scale[i] = -2.f * a * kLog2e;
     pp.a_shift[i] = -a * eps * kLog2e;
     pp.a_pos[i] = a;
-    asum += fabsf(a);
+    amax = fmaxf(amax, fabsf(a));
   }
-  // kind::f16 does not accept an FP16 A with a BF16 B (illegal instruction on sm_100a), so P stays
-  // bf16; the scale hook is kept at 1 (bf16 has fp32's exponent range).
-  (void)asum;
-  pp.w_scale = 1.f;
-  pp.inv_w_scale = 1.f;
-#ifdef CAREL_MMD_BWD_BN64
-  return mmd_bwd_launch<64, 4>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
-#else
+  // kind::f16 does not accept an FP16 A with a BF16 B (illegal instruction on sm_100a): the weight tile P has the
+  // operands' format.  BF16 has fp32's exponent range; FP16 weights are scaled in the kernel (PolMmdBwdT).
+  pp.kmax_bits = reinterpret_cast<const unsigned*>(w.accum + 3);
+  pp.wmax_coef = fmaxf(fmaxf(pp.c00, pp.c11), fabsf(pp.c01)) * amax;
+  if (mmd_uses_f16(precision, ldp, t0, t1, m_tiles))
+    return mmd_bwd_launch<128, 2, true>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
   return mmd_bwd_launch<128, 2>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
-#endif
 }
 
 #ifdef CAREL_CHAIN_TRACE

@@ -19,11 +19,35 @@ inline __host__ __device__ int aug_width(int K) { return (K + 6 + 15) / 16 * 16;
 //   norms (optional) receives |s|^2.
 //   aug == 2:  like aug == 1 with h = 0.
 //   hvec (optional, aug == 1): h = hvec[r] instead of -|s|^2/2 (decoder: bias / -logsumexp).
+//   f16 != 0: the same layout in FP16 (11 mantissa bits at the same MMA rate; values saturate at +-65504): used where
+//              the rows are an INTERMEDIATE of bounded range (the latent sample in the head's MMD) whose 8-bit bf16
+//              rounding is not shared with the reference and would dominate the gradient error of small batches.
+// 16-bit conversions of both formats behind one flag (bit patterns; round-to-nearest-even)
+struct Cvt16 {
+  int f16;
+  CAREL_DEVINL uint16_t to(float v) const {
+    if (f16) {
+      const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+      return *reinterpret_cast<const uint16_t*>(&h);
+    }
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    return *reinterpret_cast<const uint16_t*>(&b);
+  }
+  CAREL_DEVINL float from(uint16_t u) const {
+    if (f16) return __half2float(*reinterpret_cast<const __half*>(&u));
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+  }
+};
+
 static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows, int K, int ld,
-                                        __nv_bfloat16* __restrict__ A, __nv_bfloat16* __restrict__ B,
+                                        __nv_bfloat16* __restrict__ A_, __nv_bfloat16* __restrict__ B_,
                                         int ldp, int dst_row0, int aug, float* __restrict__ norms,
                                         const float* __restrict__ hvec = nullptr,
-                                        const float* __restrict__ src1 = nullptr, int rows0 = 0, int ld1 = 0) {
+                                        const float* __restrict__ src1 = nullptr, int rows0 = 0, int ld1 = 0,
+                                        int f16 = 0) {
+  uint16_t* A = reinterpret_cast<uint16_t*>(A_);
+  uint16_t* B = reinterpret_cast<uint16_t*>(B_);
+  const Cvt16 cv{f16};
   // optional second source: rows [rows0, rows) come from src1 (stacked samples cat(x, y) in ONE launch)
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -31,28 +55,27 @@ static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows,
        r += gridDim.x * warps_per_block) {
     const bool second = src1 != nullptr && r >= rows0;
     const float* s = second ? src1 + size_t(r - rows0) * ld1 : src + size_t(r) * ld;
-    __nv_bfloat16* a = (A != nullptr) ? A + size_t(dst_row0 + r) * ldp : nullptr;
-    __nv_bfloat16* b = (B != nullptr) ? B + size_t(dst_row0 + r) * ldp : nullptr;
+    uint16_t* a = (A != nullptr) ? A + size_t(dst_row0 + r) * ldp : nullptr;
+    uint16_t* b = (B != nullptr) ? B + size_t(dst_row0 + r) * ldp : nullptr;
     float nrm = 0.f;
     const bool vec = ((K & 3) == 0) && (((second ? ld1 : ld) & 3) == 0) && ((ldp & 3) == 0) &&
                      ((reinterpret_cast<uintptr_t>(second ? src1 : src) & 15) == 0);
     if (vec) {
       for (int k = lane * 4; k < K; k += 128) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(s + k));
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
-        const float2 flo = __bfloat1622float2(lo), fhi = __bfloat1622float2(hi);
-        nrm += flo.x * flo.x + flo.y * flo.y + fhi.x * fhi.x + fhi.y * fhi.y;
+        const uint16_t q0 = cv.to(v.x), q1 = cv.to(v.y), q2 = cv.to(v.z), q3 = cv.to(v.w);
+        const float f0 = cv.from(q0), f1 = cv.from(q1), f2 = cv.from(q2), f3 = cv.from(q3);
+        nrm += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
         uint2 o;
-        o.x = *reinterpret_cast<const uint32_t*>(&lo);
-        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        o.x = uint32_t(q0) | (uint32_t(q1) << 16);
+        o.y = uint32_t(q2) | (uint32_t(q3) << 16);
         if (a != nullptr) *reinterpret_cast<uint2*>(a + k) = o;
         if (b != nullptr) *reinterpret_cast<uint2*>(b + k) = o;
       }
     } else {
       for (int k = lane; k < K; k += 32) {
-        const __nv_bfloat16 v = __float2bfloat16_rn(__ldg(s + k));
-        const float f = __bfloat162float(v);
+        const uint16_t v = cv.to(__ldg(s + k));
+        const float f = cv.from(v);
         nrm += f * f;
         if (a != nullptr) a[k] = v;
         if (b != nullptr) b[k] = v;
@@ -62,13 +85,13 @@ static __global__ void pack_rows_kernel(const float* __restrict__ src, int rows,
     if (norms != nullptr && lane == 0) norms[dst_row0 + r] = nrm;
     // tail: augmentation columns and zero padding
     const float h = (aug == 2) ? 0.f : ((hvec != nullptr) ? __ldg(hvec + r) : -0.5f * nrm);
-    const __nv_bfloat16 h1 = __float2bfloat16_rn(h);
-    const float r1 = h - __bfloat162float(h1);
-    const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
-    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+    const uint16_t h1 = cv.to(h);
+    const float r1 = h - cv.from(h1);
+    const uint16_t h2 = cv.to(r1);
+    const uint16_t h3 = cv.to(r1 - cv.from(h2));
+    const uint16_t one = cv.to(1.f), zero = 0;
     for (int k = K + lane; k < ldp; k += 32) {
-      __nv_bfloat16 va = zero, vb = zero;
+      uint16_t va = zero, vb = zero;
       if (aug) {
         const int t = k - K;
         if (t == 0) { va = h1; vb = one; }

@@ -73,10 +73,11 @@ def test_forward_backward_matches_oracle(variant, N, L, V, D, dropout):
 
     for o, r in zip(outs, orefs):
         assert rel(o.detach(), r.detach()) < (1e-4 if dropout == 0.0 else 1e-3), (variant, "output")
-    # the fp32 oracle (dropout case) carries its own ~1e-3 noise on the Gram-loss gradient
-    # head level: the latent sample z is an INTERMEDIATE, so its bf16 rounding as a tensor-core operand of the
-    # MMD / decoder kernels is not shared with the oracle (op-level tests, where it is, are at 1e-5..3e-4)
-    gtol = 2e-3 if dropout == 0.0 else 4e-3
+    # north_star tolerance for the bf16 tier: 1e-3 relative.  The latent sample z is an INTERMEDIATE, so its rounding
+    # as a tensor-core operand is not shared with the oracle: the MMD and decoder kernels take it as FP16 (11 bits),
+    # measured 1e-5..2e-4 (tools/head_err.py).  (With dropout the ORACLE runs in fp32 — see above — and carries its
+    # own rounding noise on the Gram-loss gradient.)
+    gtol = 1e-3
     assert rel(grads[0], rgrads[0]) < gtol, (variant, "grad X", rel(grads[0], rgrads[0]))
     for (k, g), r in zip(zip(params.keys(), grads[1:]), rgrads[1:]):
         if r is None:
@@ -185,11 +186,11 @@ def test_full_size_mmd_head_step_matches_oracle():
                                               b["bow"].double(), 3)
     rgrads = torch.autograd.grad(ref, [X64] + list(p64.values()), allow_unused=True)
     assert rel(loss.detach(), ref.detach()) < 1e-4
-    assert rel(grads[0], rgrads[0]) < 2e-3, ("grad X", rel(grads[0], rgrads[0]))
+    assert rel(grads[0], rgrads[0]) < 1e-3, ("grad X", rel(grads[0], rgrads[0]))
     for (k, g), r in zip(zip(params.keys(), grads[1:]), rgrads[1:]):
         if r is None:
             continue
-        assert rel(g, r) < 2e-3, (k, rel(g, r))
+        assert rel(g, r) < 1e-3, (k, rel(g, r))
 
 
 def test_weighted_sum_is_bit_identical_to_the_scalar_chain():

@@ -471,4 +471,6 @@ def test_bow_full_size_vs_oracle():
     assert rel(Z.grad, Zd.grad) < 1e-3 and rel(W.grad, Wd.grad) < 1e-3 and rel(b.grad, bd.grad) < 1e-3
     # size-independent property: the loss is invariant under a shift of all logits of a row (softmax), so the
     # gradient w.r.t. the bias sums to zero over the vocabulary
-    assert abs(float(b.grad.double().sum())) < 1e-6 * float(b.grad.double().abs().sum())
+    # (db is the column sum of the fp16-rounded dlogit tiles the dW tensor-core product consumes: the zero sum holds
+    # to their rounding noise, 2^-12 / sqrt(#terms) of sum |db| ~ 1e-5, far inside the 1e-3 gradient tolerance)
+    assert abs(float(b.grad.double().sum())) < 1e-4 * float(b.grad.double().abs().sum())
