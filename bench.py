@@ -1,23 +1,36 @@
 #!/usr/bin/env python
-"""bench.py — the reference's headline workload on B200 (contract: see the task statement).
+"""bench.py — the reference's headline workloads on B200 (contract: see the task statement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload mmd|hsic|vi|gan|gram_sweep]
 
-Workload (BASELINE.json configs[1]): MMD-VAE head train step — latent projections + reparam + KL,
--MMD, classifier heads, BoW decoder + softmax-BCE over V = 30000 — on N = 8192 synthetic 768-d clause
-embeddings, latent 128, bf16 tensor-core operands / fp32 accumulation, Adam over model.get_params().
-One "step" = forward + backward + optimiser step on one such batch.  At --gpus N every rank runs its
-own 8192-clause batch (weak scaling); the decoder-weight gradient is all-reduced in place (ncclAvg) and the small
-gradients through one flat bucket.
+Default workload (BASELINE.json configs[1], the configuration the metric is quoted on): MMD-VAE head train step —
+latent projections + reparam + KL, -MMD, classifier heads, BoW decoder + softmax-BCE over V = 30000 — on N = 8192
+synthetic 768-d clause embeddings, latent 128, bf16-tier tensor-core operands / fp32 accumulation, Adam over
+model.get_params().  One "step" = forward + backward + optimiser step(s) on one such batch, with the optimiser
+choreography of the reference trainer (carel_vae_b200/train.py).  At --gpus N every rank runs its own 8192-clause
+batch (weak scaling) and the gradients are averaged over NCCL (carel_vae_b200.parallel.GradReducer).
 
-Printed JSON (rank 0, one line): value = aggregate 8192-clause steps/s with inputs resident in HBM;
-e2e = the same through the drop-in call with HOST buffers (pinned H2D of X, labels and the dense
-[N, V] fp32 BoW target the reference layout prescribes, D2H of the loss) inside the timed region;
-roofline = the MMD Gram kernel at N = 8192, d = 768 (the kernel BASELINE.json's metric names) against
-the measured bf16 peak; roofline_hbm = the step's one bandwidth-bound kernel (dense BoW target -> non-zero list,
-N*V*4 bytes read once) against the measured copy bandwidth; roofline_step = the whole step's algorithmic FLOPs against
-the sustained bf16 peak; cpu_baseline = the oracle port of the reference step on the host cores.
-`--impl reference` times that CPU implementation alone.
+Other workloads (the remaining BASELINE.json configs; one JSON line each, same keys):
+    hsic        configs[2]: HSIC-regularised head, N = 8192, latent 128
+    vi          configs[3]: VI variant (KL + CLUB), two optimisers / two backward passes per step; run it under torchrun
+    gan         the fourth trainer (three optimisers)
+    gram_sweep  configs[4]: MMD and HSIC Gram, value (d = 768) and value + gradient (d = 128), N = 4k..131k per
+                sample, Gram row blocks sharded over the ranks
+
+Printed JSON (rank 0, one line):
+    value         aggregate steps/s with inputs resident in HBM (CUDA-graph replay, device-timed, max over ranks)
+    e2e           the same through the drop-in call with HOST buffers: pinned H2D of X, labels and the dense [N, V] fp32
+                  BoW target the reference layout prescribes, D2H of the loss, inside the timed region
+    roofline      the DOMINANT kernel of the timed step (largest entry of kernels_us), algorithmic FLOPs per launch /
+                  its CUDA-event time, against the sustained bf16 peak (a kernel timed inside a long step)
+    roofline_step the whole step's algorithmic FLOPs against the sustained bf16 peak
+    roofline_hbm  the step's one bandwidth-bound kernel (dense BoW target -> non-zero list)
+    gram          the metric's second half: MMD Gram forward at N = 8192, d = 768 (TFLOP/s, full Gram and product schedule)
+    cpu_baseline  the oracle port of the reference step on the host cores (cfg2, and cfg1 = N 64 / latent 64 beside
+                  our GPU number for the same configuration); gpu_eager_baseline = the same plain-PyTorch port run
+                  eagerly in fp32 on this B200 (the honest competitor: the reference ships no Blackwell kernel)
+`--impl reference` times the CPU implementation alone (rank 0), same metric / unit / config.
 """
 from __future__ import annotations
 
@@ -36,10 +49,42 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_ROWS, D_EMB, LATENT, VOCAB, NNZ = 8192, 768, 128, 30000, 24
-STEP_FLOPS = 3 * (2 * N_ROWS * D_EMB * 4 * LATENT + 2 * (2 * N_ROWS) ** 2 * LATENT + 2 * N_ROWS * 2 * LATENT * VOCAB)
-GRAM_FLOPS = 2 * (2 * N_ROWS) ** 2 * D_EMB          # full Gram, no symmetry credit
 METRIC = "vae_head_train_steps_per_s"
 UNIT = "8192-clause steps/s"
+
+# algorithmic FLOPs: what roofline.achieved is computed from
+F_LATENT = 2 * N_ROWS * D_EMB * 4 * LATENT                    # 6.44e9
+F_MMD = 2 * (2 * N_ROWS) ** 2 * LATENT                        # 6.87e10 (full Gram, no symmetry credit)
+F_HSIC = 2 * 2 * N_ROWS ** 2 * LATENT                         # 3.44e10 (two Grams)
+F_DEC = 2 * N_ROWS * 2 * LATENT * VOCAB                       # 1.258e11
+GRAM_FLOPS = 2 * (2 * N_ROWS) ** 2 * D_EMB                    # 4.12e11
+STEP_FLOPS = {"mmd": 3 * (F_LATENT + F_MMD + F_DEC), "hsic": 3 * (F_LATENT + F_HSIC + F_DEC),
+              "vi": 3 * (F_LATENT + F_DEC), "gan": 3 * (F_LATENT + F_DEC)}
+# timing tags of the library (carel_vae_b200._lib.timing_report) -> (kernel, algorithmic FLOPs per launch)
+KERNEL_FLOPS = {
+    "bow_passF": ("gemm_as_kernel<EpiBowFused> (decoder forward: logits GEMM + online softmax sums + stored logits)", F_DEC),
+    "bow_dw": ("ygrad_kernel<true> (decoder dW = dlogit^T Z from the stored logits)", F_DEC),
+    "bow_dz": ("ygrad_kernel<false> (decoder dZ = dlogit W from the stored logits)", F_DEC),
+    "mmd_gram_fwd": ("gemm_as_kernel<EpiMMD> (MMD Gram forward, K = latent)", F_MMD),
+    "mmd_gram_bwd": ("chain_tc_kernel<PolMmdBwd> (MMD backward: Gram recompute + W S)", 2 * F_MMD),
+    "hsic_gram_fwd": ("gemm_tc_kernel<EpiHsic> (HSIC forward: two Grams per tile)", F_HSIC),
+    "hsic_gram_bwd": ("chain_tc_kernel<PolHsicBwd> (HSIC backward, per side)", 2 * F_HSIC),
+    "latent_proj_fwd": ("gemm_tc_kernel<EpiStore> (latent projections)", F_LATENT),
+    "latent_dw": ("gemm_tc_kernel<EpiStore> (latent dW, split-K)", F_LATENT),
+    "latent_dx": ("gemm_tc_kernel<EpiStore> (latent dX)", F_LATENT),
+}
+
+WORKLOADS = {
+    "mmd": "drl_classifier_ec_mmd_final_mul MMD-VAE head + BoW reconstruction, N=8192 clauses/GPU, d=768, latent=128, "
+           "vocab=30000, Adam(get_params)",
+    "hsic": "drl_classifier_ec_hsic HSIC-regularised head + BoW reconstruction, N=8192 clauses/GPU, d=768, latent=128, "
+            "vocab=30000, Adam(get_params)",
+    "vi": "drl_classifier_ec_vi_final VI head (KL + CLUB) + BoW reconstruction, N=8192 clauses/GPU, d=768, latent=128, "
+          "vocab=30000, two Adam optimisers, two backward passes per step",
+    "gan": "drl_classifier_ec_gan adversarial head + BoW reconstruction, N=8192 clauses/GPU, d=768, latent=128, "
+           "vocab=30000, RMSprop x2 + Adam",
+}
+L2_NOTE = "inputs larger than L2 (the dense BoW target, 983 MB per step, is re-read every step)"
 
 
 def peaks():
@@ -49,6 +94,18 @@ def peaks():
         return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], hbm_gbs=d["hbm_gbs"],
                     source="measured (MEASURED_PEAKS.json)")
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def kernel_traffic():
+    """DRAM bytes per launch of the step's kernels, written by tools/ncu_traffic.py from an `ncu --set full` capture
+    (dram__bytes_read.sum + dram__bytes_write.sum); None when no capture of the current kernels is committed."""
+    p = ROOT / "profiles" / "kernel_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:  # noqa: BLE001
+            return {}
+    return {}
 
 
 class ClockSampler:
@@ -90,147 +147,40 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# workload
+# synthetic inputs (SURVEY.md §8(d) canonical definition; host tensors)
 # ------------------------------------------------------------------------------------------------
-def synthetic_batch(device, seed=0):
-    """SURVEY.md §8(d) canonical inputs (host tensors)."""
+def synthetic_batch(device=None, seed=0, n_rows=N_ROWS, vocab=VOCAB, d_emb=D_EMB, ell=True):
     g = torch.Generator().manual_seed(seed)
-    X = torch.tanh(torch.randn(N_ROWS, D_EMB, generator=g))
-    emo = torch.randint(0, 6, (N_ROWS, 1), generator=g)
-    pair = (torch.rand(N_ROWS, 1, generator=g) < 0.5).float()
-    idx = torch.randint(0, VOCAB, (N_ROWS, NNZ), generator=g)
-    bow = torch.zeros(N_ROWS, VOCAB)
-    bow.scatter_add_(1, idx, torch.ones(N_ROWS, NNZ))
+    X = torch.tanh(torch.randn(n_rows, d_emb, generator=g))
+    emo = torch.randint(0, 6, (n_rows, 1), generator=g)
+    pair = (torch.rand(n_rows, 1, generator=g) < 0.5).float()
+    idx = torch.randint(0, vocab, (n_rows, NNZ), generator=g)
+    bow = torch.zeros(n_rows, vocab)
+    bow.scatter_add_(1, idx, torch.ones(n_rows, NNZ))
     bow = bow / bow.sum(1, keepdim=True).clamp_min(1.0)
-    # compact form of the same target (SURVEY §8f.1): per-row non-zero list, capacity 32
-    cap = 32
-    cols = torch.zeros(N_ROWS, cap, dtype=torch.int32)
-    vals = torch.zeros(N_ROWS, cap)
-    srt, _ = torch.sort(idx, dim=1)
-    first = torch.ones_like(srt, dtype=torch.bool)
-    first[:, 1:] = srt[:, 1:] != srt[:, :-1]
-    pos = torch.cumsum(first.int(), 1) - 1
-    nnz = first.sum(1).int()
-    rows = torch.arange(N_ROWS)[:, None].expand_as(srt)
-    cols[rows[first], pos[first]] = srt[first].int()
-    vals[rows[first], pos[first]] = bow[rows[first], srt[first]]
-    return dict(X=X, emo=emo, cau=pair.clone(), pair=pair, bow=bow, ell_cols=cols, ell_vals=vals, ell_nnz=nnz)
+    out = dict(X=X, emo=emo, cau=pair.clone(), pair=pair, bow=bow)
+    if ell:
+        # compact form of the same target: per-row non-zero list, capacity 32
+        cap = 32
+        cols = torch.zeros(n_rows, cap, dtype=torch.int32)
+        vals = torch.zeros(n_rows, cap)
+        srt, _ = torch.sort(idx, dim=1)
+        first = torch.ones_like(srt, dtype=torch.bool)
+        first[:, 1:] = srt[:, 1:] != srt[:, :-1]
+        pos = torch.cumsum(first.int(), 1) - 1
+        rows = torch.arange(n_rows)[:, None].expand_as(srt)
+        cols[rows[first], pos[first]] = srt[first].int()
+        vals[rows[first], pos[first]] = bow[rows[first], srt[first]]
+        out.update(ell_cols=cols, ell_vals=vals, ell_nnz=first.sum(1).int())
+    return out
 
 
-WORKLOAD = ("drl_classifier_ec_mmd_final_mul MMD-VAE head + BoW reconstruction, N=8192 clauses/GPU, d=768, latent=128, "
-            "vocab=30000, Adam(get_params)")
+def dist_env():
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def run_ours(args):
+def make_timers(dev, world, local):
     import torch.distributed as dist
-    import carel_vae_b200 as cv
-    from carel_vae_b200 import _lib, functional as F
-    from carel_vae_b200.parallel import FlatGradBucket
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    opt = cv.default_opt("mmd", ec_dim=LATENT, pair_bow_dim=VOCAB, bert_dim=D_EMB, dropout=0.5)
-    torch.manual_seed(1234)
-    model = cv.DrlClassifierMMD(opt, encoder=cv.IdentityEncoder()).to(dev).train()
-    host = synthetic_batch(dev, seed=rank)
-    pinned = {k: v.pin_memory() for k, v in host.items()}
-    static = {k: v.to(dev) for k, v in host.items()}            # device-resident inputs (value) / H2D targets (e2e)
-    params = model.get_params()
-    # N = 1: no bucket (autograd assigns fresh gradient tensors: no 31 MB zero-fill + accumulate per step).
-    # N > 1: the decoder weight gradient (99 % of the bytes) is all-reduced in place (ncclAvg: no zero-fill, no
-    # accumulate, no divide), the few small gradients go through one flat bucket: two NCCL calls between the fwd+bwd
-    # graph and the Adam graph.  (Launching the big one from a post-accumulate hook inside the capture, to hide it
-    # under the rest of the backward pass, dead-locked on this stack and is left for a later round.)
-    big = max(params, key=lambda p: p.numel())
-    bucket = FlatGradBucket([p for p in params if p is not big]) if world > 1 else None
-
-    def allreduce_grads():
-        dist.all_reduce(big.grad, op=dist.ReduceOp.AVG)
-        dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG)
-    # the four latent projections receive gradients but are not stepped (reference get_params, mmd:292-297)
-    optim = torch.optim.Adam(params, lr=1e-5, capturable=True, fused=True)
-    loss_buf = torch.zeros((), device=dev)
-    it_counter = [0]
-
-    def make_stepper(target):
-        """(eager step, graph-replaying step) for a BoW target given as static device tensor(s)."""
-        def compute():
-            if bucket is not None:
-                bucket.zero_()
-                big.grad = None
-            else:
-                for p in params:
-                    p.grad = None
-            for p in model.parameters():
-                if p.grad is not None and not any(p is q for q in params):
-                    p.grad = None
-            loss = model(static["X"], None, None, static["emo"], static["cau"], static["pair"], target, it_counter[0])
-            loss.backward()
-            loss_buf.copy_(loss.detach())
-
-        def update():
-            optim.step()
-
-        def step():
-            compute()
-            if bucket is not None:
-                allreduce_grads()
-            update()
-
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        # CUDA graphs of the step (streams + graphs instead of a tracing compiler).  At N > 1 the NCCL
-        # all-reduce stays OUTSIDE the graphs: graph(fwd+bwd) -> all_reduce(flat bucket) -> graph(Adam).
-        graphs = None
-        if not args.no_graph:
-            try:
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    step()
-                torch.cuda.current_stream().wait_stream(s)
-                torch.cuda.synchronize()
-                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                if world == 1:
-                    with torch.cuda.graph(g1):
-                        compute()
-                        update()
-                    graphs = (g1, None)
-                else:
-                    with torch.cuda.graph(g1):
-                        compute()
-                    with torch.cuda.graph(g2, pool=g1.pool()):
-                        update()
-                    graphs = (g1, g2)
-                torch.cuda.synchronize()
-            except Exception as e:  # noqa: BLE001
-                if rank == 0:
-                    print(f"[bench] CUDA-graph capture failed, running eagerly: {repr(e)[:300]}", file=sys.stderr)
-                graphs = None
-                torch.cuda.synchronize()
-
-        def run_step():
-            if graphs is None:
-                step()
-            elif graphs[1] is None:
-                graphs[0].replay()
-            else:
-                graphs[0].replay()
-                allreduce_grads()
-                graphs[1].replay()
-        return step, run_step, graphs is not None
-
-    torch.manual_seed(7 + rank)
-    step, run_step, use_graph = make_stepper(static["bow"])
-    ell_target = (static["ell_cols"], static["ell_vals"], static["ell_nnz"])
-    _, run_step_ell, _ = make_stepper(ell_target)
 
     def barrier():
         torch.cuda.synchronize()
@@ -250,114 +200,268 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
+    return barrier, timed
+
+
+# ------------------------------------------------------------------------------------------------
+# head workloads
+# ------------------------------------------------------------------------------------------------
+class HeadStep:
+    """The train step of one head variant as a list of SEGMENTS with gradient all-reduces between them (the optimiser
+    choreography of the reference trainers, carel_vae_b200/train.py); captured as CUDA graphs (one graph at N = 1,
+    one per segment with the NCCL calls between them at N > 1)."""
+
+    def __init__(self, variant, dev, world, target, static, opt_kw=None, use_graph=True):
+        import carel_vae_b200 as cv
+        from carel_vae_b200.parallel import GradReducer
+        self.variant, self.dev, self.world = variant, dev, world
+        opt = cv.default_opt(variant, ec_dim=LATENT, pair_bow_dim=VOCAB, bert_dim=D_EMB, dropout=0.5, **(opt_kw or {}))
+        torch.manual_seed(1234)
+        self.model = model = cv.VARIANTS[variant](opt, encoder=cv.IdentityEncoder()).to(dev).train()
+        groups = model.get_params()
+        groups = [list(groups)] if variant in ("mmd", "hsic") else [list(g) for g in groups]
+        self.groups = groups
+        lr = 1e-5
+        if variant == "gan":        # gan:906-908
+            self.optims = [torch.optim.RMSprop(groups[0], lr=lr, capturable=True), torch.optim.RMSprop(groups[1], lr=lr, capturable=True),
+                           torch.optim.Adam(groups[2], lr=lr, capturable=True, fused=True)]
+        else:                       # mmd:936, hsic:874, vi_final:878-879
+            self.optims = [torch.optim.Adam(g, lr=lr, capturable=True, fused=True) for g in groups]
+        self.reducers = [GradReducer(g) for g in groups] if world > 1 else None
+        self.loss_buf = torch.zeros((), device=dev)
+        self.static, self.target = static, target
+        self.all_params = list(model.parameters())
+        self.emo = static["emo"] if variant in ("mmd", "vi") else static["pair"]
+        self.state = {}
+        self.segments = self._build_segments()
+        # Warm up on the stream the graphs are captured on: autograd's AccumulateGrad nodes remember the stream they
+        # were created on, and a node created on the legacy default stream forces a cross-stream wait that invalidates
+        # a later capture whenever it has to ACCUMULATE into an existing gradient.
+        self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            for _ in range(3):
+                self.eager_step()
+        torch.cuda.current_stream().wait_stream(self.stream)
+        torch.cuda.synchronize()
+        self.graphs = None
+        if use_graph:
+            self._capture()
+
+    # ---- the step as segments; segment k is followed by reduce k (None = nothing to reduce) ----
+    def _forward(self):
+        s = self.static
+        return self.model(s["X"], None, None, self.emo, s["cau"], s["pair"], self.target, 0)
+
+    def _build_segments(self):
+        v, st = self.variant, self.state
+
+        def clear():
+            for p in self.all_params:
+                p.grad = None
+
+        if v in ("mmd", "hsic"):
+            def seg0():
+                clear()
+                loss = self._forward()
+                loss.backward()
+                self.loss_buf.copy_(loss.detach())
+
+            def seg1():
+                self.optims[0].step()
+            return [(seg0, 0), (seg1, None)]
+        if v == "vi":               # vi_final:756-781
+            def seg0():
+                clear()
+                st["z_e"], st["z_c"], st["aprx"], st["loss"] = self._forward()
+                st["aprx"].backward(retain_graph=True)
+
+            def seg1():
+                self.optims[0].step()
+                rj = self.model.get_ec_upper_loss(st["z_e"], st["z_c"])
+                loss = st["loss"] + 0.1 * rj                       # beta of epoch 2
+                # vae_and_cls_opt.zero_grad().  (The reference leaves the approximation net's stale gradients in place
+                # and accumulates into them; they are zeroed before their next use, so clearing them here is the same
+                # training step without an in-place accumulation inside the graph.)
+                clear()
+                loss.backward()
+                self.loss_buf.copy_(loss.detach())
+
+            def seg2():
+                self.optims[1].step()
+            return [(seg0, 0), (seg1, 1), (seg2, None)]
+
+        def seg0():                 # gan:784-802
+            clear()
+            d1, d2, loss = self._forward()
+            d1.backward(retain_graph=True)
+            d2.backward(retain_graph=True)
+            loss.backward()
+            self.loss_buf.copy_(loss.detach())
+
+        def seg1():
+            for o in self.optims:
+                o.step()
+        return [(seg0, "all"), (seg1, None)]
+
+    def _reduce(self, which):
+        if self.reducers is None or which is None:
+            return
+        for k, r in enumerate(self.reducers):
+            if which == "all" or which == k:
+                r.reduce()
+
+    def eager_step(self):
+        for fn, red in self.segments:
+            fn()
+            self._reduce(red)
+
+    def _capture(self):
+        try:
+            s = self.stream
+            graphs = []
+            if self.world == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    for fn, _ in self.segments:
+                        fn()
+                graphs.append((g, None))
+            else:
+                pool = None
+                for fn, red in self.segments:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool, stream=s):
+                        fn()
+                    pool = g.pool()
+                    graphs.append((g, red))
+                    with torch.cuda.stream(s):          # the collective between two segments, as in run()
+                        self._reduce(red)
+            torch.cuda.synchronize()
+            self.graphs = graphs
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] CUDA-graph capture failed, running eagerly: {repr(e)[:300]}", file=sys.stderr)
+            self.graphs = None
+            torch.cuda.synchronize()
+
+    def run(self):
+        if self.variant == "vi":
+            self.model.redraw_negative_index(N_ROWS)      # next CLUB permutation into the pinned slot the captured copy reads
+        if self.graphs is None:
+            self.eager_step()
+            return
+        for g, red in self.graphs:
+            g.replay()
+            self._reduce(red)
+
+
+def run_head(args):
+    import torch.distributed as dist
+    import carel_vae_b200 as cv
+    from carel_vae_b200 import _lib, functional as F
+
+    variant = args.workload
+    world, rank, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    barrier, timed = make_timers(dev, world, local)
+
+    host = synthetic_batch(seed=rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    static = {k: v.to(dev) for k, v in host.items()}            # device-resident inputs (value) / H2D targets (e2e)
+    torch.manual_seed(7 + rank)
+    dense = HeadStep(variant, dev, world, static["bow"], static, use_graph=not args.no_graph)
+    ell = HeadStep(variant, dev, world, (static["ell_cols"], static["ell_vals"], static["ell_nnz"]), static,
+                   use_graph=not args.no_graph)
 
     # ---- value: inputs resident in HBM ----
     for _ in range(max(args.warmup, 3)):
-        run_step()
+        dense.run()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _lib.launch_count()
-    total_ms = timed(run_step, args.steps)
-    launches_eager = None
+    total_ms = timed(dense.run, args.steps)
     ms_per_step = total_ms / args.steps
     # The timed region is a few tens of ms, shorter than nvidia-smi's sampling period: keep the SAME load running
     # (untimed, same step, same count on every rank) for ~0.4 s so that the clock / throttle samples are taken under it.
     for _ in range(min(2000, int(400.0 / max(ms_per_step, 0.05)))):
-        run_step()
+        dense.run()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     value = world * 1e3 / ms_per_step
 
+    # ---- DP consistency: the stepped parameters are bit-identical on every rank after the steps ----
+    dp_identical = None
+    if world > 1:
+        from carel_vae_b200.parallel import identical_across_ranks
+        dp_identical = bool(identical_across_ranks([p for g in dense.groups for p in g]))
+
     # ---- e2e: host buffers -> H2D -> step -> D2H loss ----
     loss_host = torch.zeros((), pin_memory=True)
+    dense_keys = ("X", "emo", "cau", "pair", "bow")
+    ell_keys = ("X", "emo", "cau", "pair", "ell_cols", "ell_vals", "ell_nnz")
 
     def e2e_step():
-        for k in ("X", "emo", "cau", "pair", "bow"):
+        for k in dense_keys:
             static[k].copy_(pinned[k], non_blocking=True)
-        run_step()
-        loss_host.copy_(loss_buf, non_blocking=True)
+        dense.run()
+        loss_host.copy_(dense.loss_buf, non_blocking=True)
+
+    def e2e_ell_step():
+        for k in ell_keys:
+            static[k].copy_(pinned[k], non_blocking=True)
+        ell.run()
+        loss_host.copy_(ell.loss_buf, non_blocking=True)
 
     for _ in range(2):
         e2e_step()
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms = timed(e2e_step, e2e_steps) / e2e_steps
-    dense_keys = ("X", "emo", "cau", "pair", "bow")
     h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in dense_keys)
-
-    # same, with the BoW target handed over as its non-zero list instead of dense rows
-    ell_keys = ("X", "emo", "cau", "pair", "ell_cols", "ell_vals", "ell_nnz")
-
-    def e2e_ell_step():
-        for k in ell_keys:
-            static[k].copy_(pinned[k], non_blocking=True)
-        run_step_ell()
-        loss_host.copy_(loss_buf, non_blocking=True)
-
     for _ in range(2):
         e2e_ell_step()
     e2e_ell_ms = timed(e2e_ell_step, args.steps) / args.steps
     h2d_ell = sum(pinned[k].numel() * pinned[k].element_size() for k in ell_keys)
-    ell_resident_ms = timed(run_step_ell, args.steps) / args.steps
+    ell_resident_ms = timed(ell.run, args.steps) / args.steps
 
-    # ---- launches per step + per-kernel breakdown (eager pass, events inside the library) ----
+    # ---- launches per step + per-kernel times: the same step run eagerly with CUDA events around every launch of the
+    #      library's tensor-core kernels, on the stream they are launched on (a graph replay cannot be instrumented) ----
     torch.cuda.synchronize()
     l0 = _lib.launch_count()
-    step()
+    dense.eager_step()
     torch.cuda.synchronize()
-    launches_eager = _lib.launch_count() - l0
-    kernels = {}
+    launches = _lib.launch_count() - l0
     _lib.timing_enable(True)                 # every rank runs the same (collective) steps
-    for _ in range(3):
-        step()
+    for _ in range(5):
+        dense.eager_step()
     rep = _lib.timing_report()
     _lib.timing_enable(False)
     kernels = {k: round(v[0] / v[1] * 1e3, 1) for k, v in rep.items()}       # us per launch
 
-    # ---- roofline: the MMD Gram kernel at N = 8192, d = 768 (BASELINE metric point) ----
-    roof, gram = None, None
+    out = None
     if rank == 0:
         pk = peaks()
-        g = torch.Generator().manual_seed(0)
-        xs = torch.tanh(torch.randn(N_ROWS, D_EMB, generator=g)).to(dev)
-        ys = torch.tanh(torch.randn(N_ROWS, D_EMB, generator=g)).to(dev)
-        xs, ys = xs / xs.norm(dim=1, keepdim=True), ys / ys.norm(dim=1, keepdim=True)
-        res = {}
-        for name, full in (("triangular", False), ("full_gram", True)):
-            for _ in range(5):
-                F.mmd(xs, ys, [0.1], full_gram=full)
-            _lib.timing_enable(True)
-            for _ in range(20):
-                F.mmd(xs, ys, [0.1], full_gram=full)
-            rep = _lib.timing_report()
-            _lib.timing_enable(False)
-            ms = rep["mmd_gram_fwd"][0] / rep["mmd_gram_fwd"][1]
-            res[name] = ms
-        # Primary roofline line: the launch that EXECUTES the algorithmic FLOPs (every tile of the Gram), so achieved / peak
-        # is a tensor-pipe utilisation <= 1.  The product's default schedule computes only the j > i tiles (the Gram is
-        # symmetric) and is reported next to it: same algorithmic FLOPs in about half the time.
-        full_tf = GRAM_FLOPS / (res["full_gram"] * 1e-3) / 1e12
-        tri_tf = GRAM_FLOPS / (res["triangular"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_2sm_kernel<EpiMMD> (MMD Gram forward on CTA pairs, N=8192, d=768, every tile executed)",
-                "achieved": round(full_tf, 1), "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-                "frac": round(full_tf / pk["bf16_burst"], 3),
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-                # (profiles/r01_final_ncu_summary.txt): 51.47 MB + 0.90 MB per launch; algorithmic 2 x 25.7 MB operands
-                "traffic": 52.37e6, "traffic_unit": "bytes/launch (ncu, profiles/r01_final_ncu_summary.txt)",
-                "peak_source": pk["source"],
-                "note": "algorithmic FLOPs = 2*(2N)^2*d = 4.12e11 (full Gram as the reference computes it, SURVEY §8d)",
-                "product_schedule": {"kernel": "same kernel, j>i tiles only (what MMDStatistic runs)",
-                                     "algorithmic_tflops": round(tri_tf, 1),
-                                     "algorithmic_frac": round(tri_tf / pk["bf16_burst"], 3),
-                                     "note": "half of the tiles are skipped by symmetry, so algorithmic FLOPs / time exceeds the peak; "
-                                             "executed-FLOP utilisation is about half of this figure"},
-                "us_per_launch": {k: round(v * 1e3, 1) for k, v in res.items()}}
-        gram = {"metric": "mmd_gram_tflops_n8192_d768", "value": round(tri_tf, 1), "unit": "TFLOP/s (algorithmic, product schedule)",
-                "executed_tflops_full_gram": round(full_tf, 1)}
-        step_tflops = STEP_FLOPS / (ms_per_step * 1e-3) / 1e12
+        traffic = kernel_traffic()
+        # ---- roofline: the dominant kernel of the timed step ----
+        known = {k: v for k, v in kernels.items() if k in KERNEL_FLOPS}
+        top = max(known, key=known.get)
+        desc, flops = KERNEL_FLOPS[top]
+        tfl = flops / (known[top] * 1e-6) / 1e12
+        roof = {"bound": "tensor", "kernel": desc, "tag": top, "achieved": round(tfl, 1), "peak": pk["bf16_sustained"],
+                "unit": "TFLOP/s", "frac": round(tfl / pk["bf16_sustained"], 3), "us_per_launch": known[top],
+                "algorithmic_flops_per_launch": flops, "traffic": traffic.get(top),
+                "traffic_unit": "bytes/launch: dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/kernel_traffic.json)",
+                "peak_source": pk["source"] + ", sustained (kernel timed inside the step)",
+                "share_of_step": round(known[top] / (ms_per_step * 1e3), 3),
+                "note": "largest entry of kernels_us; CUDA events around each launch of an eager replica of the timed step",
+                "others": {k: {"us": v, "tflops": round(KERNEL_FLOPS[k][1] / (v * 1e-6) / 1e12, 1),
+                               "frac": round(KERNEL_FLOPS[k][1] / (v * 1e-6) / 1e12 / pk["bf16_sustained"], 3)}
+                           for k, v in sorted(known.items(), key=lambda kv: -kv[1]) if k != top}}
+        step_tflops = STEP_FLOPS[variant] / (ms_per_step * 1e-3) / 1e12
         roof_step = {"bound": "tensor", "achieved": round(step_tflops, 1), "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": round(step_tflops / pk["bf16_sustained"], 3),
-                     "note": "whole step, algorithmic 6.03e11 FLOP / step time vs sustained bf16 peak"}
+                     "note": f"whole step, algorithmic {STEP_FLOPS[variant]:.3g} FLOP / step time vs sustained bf16 peak"}
         # ---- HBM roofline of the step's one bandwidth-bound kernel: dense BoW target -> ELL (N*V*4 bytes read once) ----
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
@@ -372,23 +476,21 @@ def run_ours(args):
         roof_hbm = {"bound": "hbm", "kernel": "bow_pack_ell_kernel (dense [N,V] fp32 BoW target -> ELL list, once per step)",
                     "achieved": round(pack_bytes / (pack_us * 1e-6) / 1e9, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": round(pack_bytes / (pack_us * 1e-6) / 1e9 / pk["hbm_gbs"], 3),
-                    # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/r01h_ncu_summary_hbm_and_forward.txt)
-                    "traffic": 988.1e6, "traffic_unit": "bytes/launch (ncu); algorithmic N*V*4 = 983.0e6",
+                    "traffic": traffic.get("bow_pack_ell"), "traffic_unit": "bytes/launch (ncu); algorithmic N*V*4 = 983.0e6",
                     "us_per_launch": round(pack_us, 1), "peak_source": pk["source"],
                     "note": "the target is larger than L2 (983 MB), 20 back-to-back launches timed with CUDA events"}
-
-    # ---- cpu baseline (rank 0, N = 1 only): the oracle port of the reference step on the host cores ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference(max_steps=2, budget_s=40.0)
-
-    if rank == 0:
+        gram = gram_point(dev, pk, traffic) if variant == "mmd" else None
+        cpu = gpu_eager = cfg1 = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_reference(variant, max_steps=2, budget_s=40.0)
+            gpu_eager = gpu_eager_reference(variant, dev)
+            if variant == "mmd":
+                cfg1 = config1_numbers(dev)
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": WORKLOAD,
-                          "global_batch": N_ROWS * world, "parallelism": f"dp{world}", "cuda_graph": use_graph,
-                          "l2": "inputs larger than L2 (dense BoW target 983 MB/step is re-read every step)"},
+               "config": {"workload": WORKLOADS[variant], "global_batch": N_ROWS * world, "parallelism": f"dp{world}", "l2": L2_NOTE},
+               "cuda_graph": dense.graphs is not None,
                "clocks": clocks,
                "e2e": {"value": round(world * 1e3 / e2e_ms, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3),
@@ -396,70 +498,284 @@ def run_ours(args):
                "e2e_ell": {"value": round(world * 1e3 / e2e_ell_ms, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_ell,
                            "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ell_ms, 3),
                            "resident_ms_per_step": round(ell_resident_ms, 4),
-                           "note": "BoW target passed as an ELL non-zero list (cols/vals [N,32], nnz [N]) instead of dense rows"},
-               "gpu_launches": int(launches_eager) * args.steps, "gpu_launches_per_step": int(launches_eager),
+                           "note": "BoW target passed as an ELL non-zero list (cols/vals [N,32], nnz [N]) instead of dense rows "
+                                   "(carel_vae_b200.data.ell_collate_fn produces it from the reference dataset)"},
+               "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
                "roofline": roof, "roofline_step": roof_step, "roofline_hbm": roof_hbm, "gram": gram, "kernels_us": kernels,
-               "cpu_baseline": cpu}
+               "dp_params_identical_across_ranks": dp_identical,
+               "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "config1": cfg1}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-# ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference head on the host cores
-# ------------------------------------------------------------------------------------------------
-def cpu_reference(max_steps: int, budget_s: float, warmup: int = 1):
-    from oracle import head_oracle as ho
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
-    opt = ho.default_opt("mmd", ec_dim=LATENT, pair_bow_dim=VOCAB, bert_dim=D_EMB, dropout=0.5)
-    params = {k: v.requires_grad_(True) for k, v in ho.init_state(opt, "mmd", seed=1234).items()}
-    stepped = [v for k, v in params.items() if not any(k.startswith(p) for p in
-               ("emotion_mu", "emotion_log_var", "cause_mu", "cause_log_var"))]
-    optim = torch.optim.Adam(stepped, lr=1e-5)
-    b = synthetic_batch("cpu", seed=0)
-    oracle = ho.HeadOracle(opt, "mmd")
+def gram_point(dev, pk, traffic):
+    """The metric's second half: MMD Gram forward at N = 8192, d = 768 against the measured bf16 burst peak."""
+    from carel_vae_b200 import _lib, functional as F
+    g = torch.Generator().manual_seed(0)
+    xs = torch.tanh(torch.randn(N_ROWS, D_EMB, generator=g)).to(dev)
+    ys = torch.tanh(torch.randn(N_ROWS, D_EMB, generator=g)).to(dev)
+    xs, ys = xs / xs.norm(dim=1, keepdim=True), ys / ys.norm(dim=1, keepdim=True)
+    res = {}
+    for name, full in (("triangular", False), ("full_gram", True)):
+        for _ in range(5):
+            F.mmd(xs, ys, [0.1], full_gram=full)
+        _lib.timing_enable(True)
+        for _ in range(20):
+            F.mmd(xs, ys, [0.1], full_gram=full)
+        rep = _lib.timing_report()
+        _lib.timing_enable(False)
+        res[name] = rep["mmd_gram_fwd"][0] / rep["mmd_gram_fwd"][1]
+    full_tf = GRAM_FLOPS / (res["full_gram"] * 1e-3) / 1e12
+    tri_tf = GRAM_FLOPS / (res["triangular"] * 1e-3) / 1e12
+    return {"metric": "mmd_gram_tflops_n8192_d768", "kernel": "gemm_2sm_kernel<EpiMMD> (CTA pairs, cta_group::2)",
+            "value": round(tri_tf, 1), "unit": "TFLOP/s (algorithmic 2(2N)^2 d = 4.12e11 FLOP; product schedule: j>i tiles only)",
+            "executed_tflops_full_gram": round(full_tf, 1), "frac_of_burst_peak_full_gram": round(full_tf / pk["bf16_burst"], 3),
+            "peak": pk["bf16_burst"], "peak_source": pk["source"] + ", burst (kernel timed alone)",
+            "traffic": traffic.get("mmd_gram_fwd_d768"),
+            "us_per_launch": {k: round(v * 1e3, 1) for k, v in res.items()},
+            "note": "the every-tile launch executes exactly the algorithmic FLOPs (frac <= 1); the product's j>i schedule does the "
+                    "same algorithmic work in about half the time"}
 
-    def step(it):
-        loss = oracle.forward(params, b["X"], b["emo"], b["cau"], b["pair"], b["bow"], it)
-        optim.zero_grad()
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / baselines: the oracle port of the reference head (plain PyTorch, fp32)
+# ------------------------------------------------------------------------------------------------
+def oracle_stepper(variant, device, n_rows=N_ROWS, latent=LATENT, vocab=VOCAB, seed=0):
+    """One training iteration of the reference trainer on the oracle restatement (oracle/head_oracle.py), same
+    optimiser choreography as carel_vae_b200/train.py."""
+    from oracle import head_oracle as ho
+    opt = ho.default_opt(variant, ec_dim=latent, pair_bow_dim=vocab, bert_dim=D_EMB, dropout=0.5)
+    params = {k: v.to(device).requires_grad_(True) for k, v in ho.init_state(opt, variant, seed=1234).items()}
+    lat = ("emotion_mu", "emotion_log_var", "cause_mu", "cause_log_var")
+    aprx = [v for k, v in params.items() if k.startswith(("ec_mu", "ec_log_var"))]
+    disc1 = [v for k, v in params.items() if k.startswith("ec_disc")]
+    disc2 = [v for k, v in params.items() if k.startswith("ce_disc")]
+    core = [v for k, v in params.items() if not k.startswith(lat + ("ec_mu", "ec_log_var", "ec_disc", "ce_disc"))]
+    b = synthetic_batch(seed=seed, n_rows=n_rows, vocab=vocab, ell=False)
+    b = {k: v.to(device) for k, v in b.items()}
+    emo = b["emo"] if variant in ("mmd", "vi") else b["pair"]
+    oracle = ho.HeadOracle(opt, variant)
+    lr = 1e-5
+    if variant in ("mmd", "hsic"):
+        optims = [torch.optim.Adam(core, lr=lr)]
+    elif variant == "vi":
+        optims = [torch.optim.Adam(aprx, lr=lr), torch.optim.Adam(core, lr=lr)]
+    else:
+        optims = [torch.optim.RMSprop(disc1, lr=lr), torch.optim.RMSprop(disc2, lr=lr), torch.optim.Adam(core, lr=lr)]
+
+    def clear():
         for v in params.values():
             v.grad = None
-        loss.backward()
-        optim.step()
-        return float(loss)
 
+    def step(it):
+        clear()
+        out = oracle.forward(params, b["X"], emo, b["cau"], b["pair"], b["bow"], it)
+        if variant in ("mmd", "hsic"):
+            out.backward()
+            optims[0].step()
+            return out.detach()
+        if variant == "vi":
+            z_e, z_c, aprx_loss, loss = out
+            aprx_loss.backward(retain_graph=True)
+            optims[0].step()
+            loss = loss + 0.1 * oracle.ec_upper_loss(params, z_e, z_c)
+            for v in core:
+                v.grad = None
+            loss.backward()
+            optims[1].step()
+            return loss.detach()
+        d1, d2, loss = out
+        d1.backward(retain_graph=True)
+        d2.backward(retain_graph=True)
+        loss.backward()
+        for o in optims:
+            o.step()
+        return loss.detach()
+    return step
+
+
+def cpu_reference(variant, max_steps: int, budget_s: float, warmup: int = 1, n_rows=N_ROWS, latent=LATENT, vocab=VOCAB):
+    """Mean wall-clock time of `max_steps` full train steps of the oracle port on the host cores (all threads)."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    step = oracle_stepper(variant, "cpu", n_rows, latent, vocab)
     torch.manual_seed(7)
     t_all = time.perf_counter()
     times = []
+    done_warm = 0
     for i in range(warmup + max_steps):
         t0 = time.perf_counter()
         step(i)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        else:
+            done_warm += 1
         if time.perf_counter() - t_all > budget_s and times:
             break
-    best = min(times)
-    return {"value": round(1.0 / best, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(times)} full 8192-clause train steps (best of) after {warmup} warm-up; fp32, Adam(get_params), "
-                      f"oracle/head_oracle.py restatement of drl_classifier_ec_mmd_final_mul.py",
-            "s_per_step": round(best, 3)}
+    mean = sum(times) / len(times)
+    return {"value": round(1.0 / mean, 4), "unit": f"{n_rows}-clause steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "steps_timed": len(times), "warmup_done": done_warm,
+            "sample": f"{len(times)} full {n_rows}-clause train steps (mean) after {done_warm} warm-up; fp32, latent {latent}, vocab {vocab}, "
+                      f"oracle/head_oracle.py restatement of the {variant} trainer's step",
+            "s_per_step": round(mean, 4)}
+
+
+def gpu_eager_reference(variant, dev):
+    """The same plain-PyTorch fp32 port run EAGERLY on this B200 (cuBLAS / ATen kernels, TF32 off like torch's default):
+    the honest competitor of BASELINE.md §5.6."""
+    try:
+        step = oracle_stepper(variant, dev)
+        torch.manual_seed(7)
+        for i in range(2):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k = 3 if variant == "hsic" else 5
+        e0.record()
+        for i in range(k):
+            step(2 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / k
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+        return {"value": round(1e3 / ms, 2), "unit": UNIT, "ms_per_step": round(ms, 2), "steps_timed": k, "dtype": "f32",
+                "peak_mem_gib": round(peak_gb, 1),
+                "note": "oracle/head_oracle.py (plain PyTorch restatement of the reference step) run eagerly on the same GPU, "
+                        "inputs resident, device-timed"}
+    except Exception as e:  # noqa: BLE001
+        torch.cuda.synchronize()
+        return {"unavailable": repr(e)[:200]}
+    finally:
+        torch.cuda.empty_cache()
+
+
+def config1_numbers(dev):
+    """BASELINE configs[0]: batch 64, latent 64 (vocab 30000) — the reference's own CPU-runnable case, beside our head
+    on the GPU at the same size (launch-latency bound: one CUDA-graph replay per step)."""
+    import carel_vae_b200 as cv
+    n, lat = 64, 64
+    cpu = cpu_reference("mmd", max_steps=10, budget_s=20.0, warmup=2, n_rows=n, latent=lat)
+    host = synthetic_batch(seed=0, n_rows=n, ell=False)
+    st = {k: v.to(dev) for k, v in host.items()}
+    opt = cv.default_opt("mmd", ec_dim=lat, pair_bow_dim=VOCAB, bert_dim=D_EMB, dropout=0.5)
+    torch.manual_seed(1234)
+    model = cv.DrlClassifierMMD(opt, encoder=cv.IdentityEncoder()).to(dev).train()
+    optim = torch.optim.Adam(model.get_params(), lr=1e-5, capturable=True, fused=True)
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        model(st["X"], None, None, st["emo"], st["cau"], st["pair"], st["bow"], 0).backward()
+        optim.step()
+    for _ in range(3):
+        step()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    for _ in range(5):
+        g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 50
+    return {"workload": "BASELINE configs[0]: MMD-VAE head, batch 64, latent 64, vocab 30000", "unit": "64-clause steps/s",
+            "ours_gpu": round(1e3 / ms, 1), "ours_ms_per_step": round(ms, 4), "cpu_baseline": cpu}
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    """The reference's own CPU implementation of the path (oracle port: the reference is a set of scripts that cannot
+    be installed), all host threads, K steps after W warm-up as asked (bounded to ~4 minutes), mean."""
+    world, rank, _ = dist_env()
     if rank != 0:
         return
-    cpu = cpu_reference(max_steps=max(1, min(args.steps, 8)), budget_s=150.0, warmup=min(max(args.warmup, 1), 2))
+    variant = args.workload if args.workload in WORKLOADS else "mmd"
+    warm = min(max(args.warmup, 1), 5)
+    if variant == "hsic":          # the reference's O(m^3) centring: minutes per step at m = 8192
+        warm = 0
+    cpu = cpu_reference(variant, max_steps=max(1, args.steps), budget_s=240.0, warmup=warm)
     out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / cpu["value"], 2),
+           "steps": cpu["steps_timed"], "warmup": cpu["warmup_done"], "ms_per_step": round(1e3 * cpu["s_per_step"], 2),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "global_batch": N_ROWS, "parallelism": "host cores (rank 0 only)",
-                      "cuda_graph": False, "l2": "n/a (CPU)"},
+           "config": {"workload": WORKLOADS[variant], "global_batch": N_ROWS * world, "parallelism": f"dp{world}", "l2": L2_NOTE},
+           "cuda_graph": False,
+           "note": f"host cores, rank 0 only; asked for {args.steps} steps / {args.warmup} warm-up, ran the counts reported here "
+                   "(bounded to ~4 minutes); mean over the timed steps, like the GPU arm",
            "cpu_baseline": cpu,
            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: large-N MMD / HSIC Gram sweep with row-block sharding
+# ------------------------------------------------------------------------------------------------
+def run_gram_sweep(args):
+    import torch.distributed as dist
+    from carel_vae_b200 import parallel as par
+
+    world, rank, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    barrier, timed = make_timers(dev, world, local)
+    sizes = [int(s) for s in args.sizes.split(",")] if args.sizes else [4096, 8192, 16384, 32768, 65536, 131072]
+    rows = []
+    for N in sizes:
+        for loss in ("mmd", "hsic"):
+            for d, grad in ((D_EMB, False), (LATENT, True)):
+                if loss == "hsic" and N > 65536 and not grad:
+                    continue          # two full N x N Grams at d = 768: > 1 minute per evaluation at 131072
+                g = torch.Generator(device="cpu").manual_seed(N + d)
+                x = torch.empty(N, d, device=dev)
+                y = torch.empty(N, d, device=dev)
+                for t in (x, y):      # unit-norm rows (SURVEY 8d): squared distances in [0, 4]; chunked to bound host memory
+                    for r0 in range(0, N, 16384):
+                        blk = torch.tanh(torch.randn(min(16384, N - r0), d, generator=g))
+                        t[r0:r0 + blk.shape[0]] = (blk / blk.norm(dim=1, keepdim=True)).to(dev)
+                if grad:
+                    x.requires_grad_(True)
+                    y.requires_grad_(True)
+
+                def fn():
+                    v = par.sharded_mmd(x, y, [0.1]) if loss == "mmd" else par.sharded_hsic(x, y, 2.0, 2.0)
+                    if grad:
+                        x.grad = y.grad = None
+                        v.backward()
+                    return v
+                for _ in range(2):
+                    v = fn()
+                reps = 5 if N <= 32768 else 2
+                ms = timed(fn, reps) / reps
+                gram_flops = 2.0 * (2 * N) ** 2 * d if loss == "mmd" else 2.0 * 2.0 * N ** 2 * d
+                flops = gram_flops * (3 if grad else 1)
+                rows.append({"loss": loss, "N": N, "d": d, "gradient": grad, "ms": round(ms, 3),
+                             "algorithmic_tflops": round(flops / (ms * 1e-3) / 1e12, 1), "value": float(v.detach())})
+                del x, y
+    if rank == 0:
+        pk = peaks()
+        best = max(rows, key=lambda r: r["algorithmic_tflops"])
+        print(json.dumps({"metric": "gram_sweep_algorithmic_tflops", "value": best["algorithmic_tflops"], "unit": "TFLOP/s",
+                          "n_gpus": world, "steps": 1, "warmup": 2, "ms_per_step": best["ms"], "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": "large-N MMD / HSIC Gram sweep, N = 4k..131k rows per sample, Gram row blocks sharded over "
+                                                 "the ranks (value at d = 768, value + gradient at d = 128), all-reduce of the partial sums",
+                                     "parallelism": f"row blocks x{world}"},
+                          "peak": pk["bf16_burst"], "peak_source": pk["source"],
+                          "note": "algorithmic FLOPs: full Gram(s), no symmetry credit; x3 with the gradient (recompute + W S); whole "
+                                  "evaluation incl. operand packing, all-reduce and finalize; device time, max over ranks",
+                          "sweep": rows}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -468,15 +784,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mmd", choices=["mmd", "hsic", "vi", "gan", "gram_sweep"])
+    ap.add_argument("--sizes", default="", help="gram_sweep: comma-separated N list")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / gpu_eager_baseline legs")
     args = ap.parse_args()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "gram_sweep":
+        run_gram_sweep(args)
     else:
-        run_ours(args)
+        run_head(args)
 
 
 if __name__ == "__main__":

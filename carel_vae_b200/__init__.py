@@ -9,9 +9,10 @@ CUDA kernels of libcarel_head.so, reached through the C ABI in include/carel_hea
 CPU / PyTorch fallback: without the built extension every op raises.
 """
 from ._lib import CarelError, get_precision, launch_count, lib, set_precision  # noqa: F401
-from . import functional  # noqa: F401
+from . import data, functional, parallel, train  # noqa: F401
 from .losses import (GaussianKernelMatrix, HSIC, MMDStatistic, pairwise_distances, pdist,  # noqa: F401
                      permutation_test_mat)
+from .data import ECPEDataset, ell_collate_fn  # noqa: F401
 from .head import (DrlClassifier, DrlClassifierGAN, DrlClassifierHSIC, DrlClassifierMMD, DrlClassifierVI,  # noqa: F401
                    IdentityEncoder, VARIANTS, default_opt)
 

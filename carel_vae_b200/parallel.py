@@ -62,23 +62,65 @@ def finalize_mmd(partial: torch.Tensor, n_1: int, n_2: int) -> torch.Tensor:
     return a00 * partial[0] + a11 * partial[1] + a01 * partial[2]
 
 
-def sharded_mmd(x: torch.Tensor, y: torch.Tensor, alphas: Sequence[float], group=None, eps: float = 1e-5,
-                partial_fn=None) -> torch.Tensor:
-    """MMD^2 of replicated samples with the Gram row blocks sharded over the ranks of `group`.
+class _ShardedMMDFn(torch.autograd.Function):
+    """Row-block-sharded MMD^2 as ONE autograd node: forward = block sums of this rank's row tiles (carel_mmd_fwd with a
+    row-tile range) -> all-reduce of 3 doubles -> carel_mmd_finalize; backward = carel_mmd_bwd over the same row tiles,
+    which writes the COMPLETE gradient rows of the rank's block (it sees every column) and zeros elsewhere."""
 
-    Every rank passes the SAME x, y (all-gather DP-sharded inputs first) and gets the same value.
-    `partial_fn(x, y, alphas, eps, t0, t1) -> float64[3]` computes the block sums of row tiles
-    [t0, t1); by default it launches the CUDA kernel (carel_mmd_fwd with a row-tile range)."""
+    @staticmethod
+    def forward(ctx, x, y, alphas, eps, t0, t1, group, all_rows):
+        from . import functional as F
+        F._require_cuda(x, y)
+        xf, yf = F._rowmajor_f32(x), F._rowmajor_f32(y)
+        n1, d = xf.shape
+        n2 = yf.shape[0]
+        L = F.lib()
+        ws = F._workspace(L.carel_mmd_workspace_bytes(n1, n2, d, 0), xf.device)
+        partial = torch.empty(3, dtype=torch.float64, device=xf.device)
+        out = torch.empty((), dtype=torch.float32, device=xf.device)
+        F.check(L.carel_mmd_fwd(F._p(xf), xf.stride(0), F._p(yf), yf.stride(0), n1, n2, d, F.float_array(alphas), len(alphas),
+                                float(eps), 0, t0, t1, F._p(partial), F._p(None), F._p(ws), ws.numel(), 0, F._stream()),
+                "carel_mmd_fwd")
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+        F.check(L.carel_mmd_finalize(F._p(partial), n1, n2, F._p(out), F._stream()), "carel_mmd_finalize")
+        ctx.ws, ctx.group, ctx.all_rows = ws, group, all_rows
+        ctx.meta = (n1, n2, d, tuple(float(a) for a in alphas), float(eps), t0, t1, x.dtype, y.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import functional as F
+        n1, n2, d, alphas, eps, t0, t1, dtx, dty = ctx.meta
+        ws = ctx.ws
+        g = g.reshape(()).float().contiguous()
+        gxy = torch.empty((n1 + n2, d), dtype=torch.float32, device=ws.device)      # one buffer: one collective
+        gx, gy = gxy[:n1], gxy[n1:]
+        F.check(F.lib().carel_mmd_bwd(F._p(g), n1, n2, d, F.float_array(alphas), len(alphas), eps, t0, t1, F._p(gx), d,
+                                      F._p(gy), d, F._p(ws), ws.numel(), 0, F._stream()), "carel_mmd_bwd")
+        if ctx.all_rows and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+            dist.all_reduce(gxy, op=dist.ReduceOp.SUM, group=ctx.group)             # rows of other ranks are zero here
+        return gx.to(dtx), gy.to(dty), None, None, None, None, None, None
+
+
+def sharded_mmd(x: torch.Tensor, y: torch.Tensor, alphas: Sequence[float], group=None, eps: float = 1e-5,
+                partial_fn=None, all_rows: bool = False) -> torch.Tensor:
+    """MMD^2 of replicated samples with the Gram row blocks sharded over the ranks of `group`; differentiable.
+
+    Every rank passes the SAME x, y (all-gather DP-sharded inputs first) and gets the same value.  In backward every
+    rank receives the complete gradient rows of ITS row block and zeros elsewhere (no collective); with
+    `all_rows=True` the blocks are summed over the ranks so that every rank holds the full gradient.
+    `partial_fn(x, y, alphas, eps, t0, t1) -> float64[3]` replaces the CUDA launch by a host function (CPU tests of
+    the sharding logic; not differentiable)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     ranges = balanced_tri_ranges(x.shape[0] + y.shape[0], world)
     t0, t1 = ranges[rank]
     if partial_fn is None:
-        from . import functional as F
-        partial = F._MMDFn.apply(x, y, tuple(alphas), eps, 0, (t0, t1 if t1 > t0 else t0), 0)
-    else:
-        partial = partial_fn(x, y, alphas, eps, t0, t1)
-    partial = partial.clone()
+        return _ShardedMMDFn.apply(x, y, tuple(alphas), eps, t0, t1 if t1 > t0 else t0, group, all_rows)
+    if x.requires_grad or y.requires_grad:
+        raise RuntimeError("sharded_mmd(partial_fn=...) is a forward-only test hook; drop partial_fn for gradients")
+    partial = partial_fn(x, y, alphas, eps, t0, t1).clone()
     if world > 1:
         dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
     return finalize_mmd(partial, x.shape[0], y.shape[0]).to(torch.float32)
@@ -120,3 +162,60 @@ class FlatGradBucket:
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(dist.get_world_size(group))
+
+
+class GradReducer:
+    """Data-parallel gradient averaging for one optimiser's parameter list (head DP): tensors of at
+    least `big_numel` elements (the decoder weight: 99 % of the bytes) are all-reduced IN PLACE with ncclAvg — no
+    staging copy, no divide —, all the small ones travel through one flat buffer (pack, one all-reduce, unpack: two
+    multi-tensor launches).  Works on whatever `.grad` tensors the backward pass left, so the reference loops'
+    `optimizer.zero_grad()` / `loss.backward()` stay as they are: call `reduce()` between backward and `step()`."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, big_numel: int = 1 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.big = [p for p in self.params if p.numel() >= big_numel]
+        self.small = [p for p in self.params if p.numel() < big_numel]
+        n = sum(p.numel() for p in self.small)
+        dev = self.params[0].device if self.params else "cpu"
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p in self.small:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def reduce(self) -> None:
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        avg = dist.ReduceOp.AVG if self.flat.is_cuda else dist.ReduceOp.SUM        # gloo (CPU tests) has no AVG
+        scale = None if self.flat.is_cuda else 1.0 / dist.get_world_size(self.group)
+        for p in self.big:
+            if p.grad is not None:
+                dist.all_reduce(p.grad, op=avg, group=self.group)
+                if scale is not None:
+                    p.grad.mul_(scale)
+        live = [(p, v) for p, v in zip(self.small, self.views) if p.grad is not None]
+        if not live:
+            return
+        if len(live) != len(self.small):
+            self.flat.zero_()
+        torch._foreach_copy_([v for _, v in live], [p.grad for p, _ in live])
+        dist.all_reduce(self.flat, op=avg, group=self.group)
+        if scale is not None:
+            self.flat.mul_(scale)
+        torch._foreach_copy_([p.grad for p, _ in live], [v for _, v in live])
+
+
+def identical_across_ranks(tensors: Iterable[torch.Tensor], group=None) -> bool:
+    """True if every rank holds bit-identical tensors (data-parallel replicas must, after any number of steps): the
+    int32 views are all-reduced with MIN and MAX and compared."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return True
+    ok = True
+    for t in tensors:
+        bits = t.detach().contiguous().view(torch.int32).reshape(-1)
+        lo, hi = bits.clone(), bits.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        ok = ok and bool(torch.equal(lo, hi))
+    return ok

@@ -61,3 +61,38 @@ def test_bow_tokenize_matches_the_live_reference_function():
     for _ in range(300):
         s = "".join(rng.choice(alphabet, size=rng.integers(0, 60)))
         assert bow_tokenize(s) == ns["bow_tokenize"](s), repr(s)
+
+
+def test_drop_in_dataset_dense_rows_and_ell_collate():
+    """carel_vae_b200.data.ECPEDataset (reference :86-146): same item dict (keys, dtypes, dense fp32 [V] bow_reps equal
+    to the reference loop); with dense_bow=False + ell_collate_fn the batch carries the same targets as an ELL triple."""
+    import pandas as pd
+    from torch.utils.data import DataLoader
+    from carel_vae_b200.data import ECPEDataset, ell_collate_fn
+
+    rng = np.random.default_rng(1)
+    vocab = [f"w{i}" for i in range(300)]
+    pairs = [" ".join(f"w{int(j)}" for j in rng.integers(0, 400, size=rng.integers(0, 30))) for _ in range(37)]
+    df = pd.DataFrame({"pair": pairs, "label": rng.integers(0, 2, 37), "emotion": rng.integers(0, 6, 37)})
+    emb = torch.randn(37, 16)
+    ds = ECPEDataset(df, tokenizer=None, bow_features=vocab, embeddings=emb)
+    item = ds[5]
+    assert set(item) == {"input_ids", "labels", "emo_labels", "cau_labels", "bow_reps"}
+    assert item["labels"].dtype == torch.float32 and item["emo_labels"].dtype == torch.int64
+    assert item["bow_reps"].dtype == torch.float32 and item["bow_reps"].shape == (300,)
+    for i in range(37):
+        assert np.array_equal(ds[i]["bow_reps"].numpy(), _reference_rows(vocab, bow_tokenize(pairs[i])))
+    dense_batches = list(DataLoader(ds, batch_size=16))
+    ds2 = ECPEDataset(df, tokenizer=None, bow_features=vocab, embeddings=emb, dense_bow=False)
+    ell_batches = list(DataLoader(ds2, batch_size=16, collate_fn=ell_collate_fn(cap=32)))
+    assert len(dense_batches) == len(ell_batches) == 3
+    for bd, be in zip(dense_batches, ell_batches):
+        cols, vals, nnz = be["bow_reps"]
+        assert cols.dtype == torch.int32 and vals.dtype == torch.float32 and nnz.dtype == torch.int32
+        rebuilt = torch.zeros_like(bd["bow_reps"])
+        for b in range(cols.shape[0]):
+            n = int(nnz[b])
+            rebuilt[b, cols[b, :n].long()] = vals[b, :n]
+        assert torch.equal(rebuilt, bd["bow_reps"])
+        for k in ("input_ids", "labels", "emo_labels", "cau_labels"):
+            assert torch.equal(bd[k], be[k])

@@ -93,3 +93,46 @@ def test_sharded_mmd_and_flat_bucket_world2():
         assert is_view
     assert torch.allclose(res[0][4], (res[0][3] + res[1][3]) / 2)
     assert torch.equal(res[0][4], res[1][4])
+
+
+def _worker_reducer(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(3)                                   # same parameters on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 2))
+    red = par.GradReducer(net.parameters(), big_numel=100)   # the [16, 8] weight goes in place, the rest through the flat buffer
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    same0 = par.identical_across_ranks(net.parameters())
+    x = torch.ones(4, 8) * (rank + 1)
+    opt.zero_grad()
+    net(x).sum().backward()
+    local = [p.grad.clone() for p in net.parameters()]
+    red.reduce()
+    opt.step()
+    same1 = par.identical_across_ranks(net.parameters())
+    differ = par.identical_across_ranks([torch.full((3,), float(rank))])
+    # plain lists: a tensor in the queue is shared by file descriptor and this process may exit before the parent maps it
+    q.put((rank, [t.tolist() for t in local], [p.grad.tolist() for p in net.parameters()], len(red.big), len(red.small),
+           same0, same1, differ))
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_world2():
+    """GradReducer (data-parallel head training): averaged gradients through both paths, replicas stay
+    bit-identical after the optimiser step, and identical_across_ranks notices a difference."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_reducer, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, g0, nb, ns, s00, s01, d0), (_, l1, g1, _, _, s10, s11, d1) = res
+    assert nb == 1 and ns == 3
+    for a, b, ga, gb in zip(l0, l1, g0, g1):
+        a, b, ga, gb = (torch.tensor(t) for t in (a, b, ga, gb))
+        assert torch.allclose(ga, (a + b) / 2) and torch.equal(ga, gb)
+    assert s00 and s01 and s10 and s11 and not d0 and not d1

@@ -26,4 +26,4 @@ for i in range(steps):
     loss.backward()
     optim.step()
 torch.cuda.synchronize()
-print("ok", float(loss))
+print("ok", float(loss.detach()))
