@@ -63,6 +63,30 @@ _SIGNATURES = {
     "carel_hsic_finalize": (C.c_int, [i64, i64, i64, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "carel_hsic_bwd": (C.c_int, [c_ptr, i64, i64, i64, C.c_float, C.c_float, i64, i64, c_ptr, i64, c_ptr, i64, c_ptr,
                                  C.c_size_t, c_ptr]),
+    # ---- fp32 precision tier ----
+    "carel_f32_gemm": (C.c_int, [c_ptr, i64, C.c_int, c_ptr, i64, C.c_int, i64, i64, i64, c_ptr, i64, c_ptr, C.c_float,
+                                 C.c_int, C.c_int, c_ptr]),
+    "carel_latent_f32_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
+    "carel_latent_f32_fwd": (C.c_int, [c_ptr, i64, i64, i64, i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_ptr,
+                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "carel_latent_f32_bwd": (C.c_int, [c_ptr, i64, c_ptr, c_ptr, i64, C.POINTER(C.c_void_p), c_ptr, c_ptr, c_ptr, i64, i64,
+                                       i64, c_ptr, i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_ptr, C.c_size_t,
+                                       c_ptr]),
+    "carel_mmd_f32_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
+    "carel_mmd_f32_fwd": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.POINTER(C.c_float), C.c_int, C.c_float, i64,
+                                    i64, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "carel_mmd_f32_bwd": (C.c_int, [c_ptr, c_ptr, i64, c_ptr, i64, i64, i64, i64, C.POINTER(C.c_float), C.c_int, C.c_float,
+                                    i64, i64, c_ptr, i64, c_ptr, i64, c_ptr, C.c_size_t, c_ptr]),
+    "carel_hsic_f32_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
+    "carel_hsic_f32_fwd": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.c_float, C.c_float, c_ptr, c_ptr, C.c_size_t,
+                                     c_ptr]),
+    "carel_hsic_f32_bwd": (C.c_int, [c_ptr, c_ptr, i64, c_ptr, i64, i64, i64, i64, C.c_float, C.c_float, c_ptr, i64, c_ptr,
+                                     i64, c_ptr, C.c_size_t, c_ptr]),
+    "carel_bow_f32_workspace_bytes": (C.c_size_t, [i64, i64, i64, C.c_int]),
+    "carel_bow_f32_fwd": (C.c_int, [c_ptr, i64, c_ptr, c_ptr, c_ptr, i64, c_ptr, c_ptr, c_ptr, i64, i64, i64, i64, C.c_float,
+                                    c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "carel_bow_f32_bwd": (C.c_int, [c_ptr, c_ptr, i64, c_ptr, c_ptr, i64, i64, i64, i64, C.c_float, c_ptr, i64, c_ptr, c_ptr,
+                                    c_ptr, C.c_size_t, c_ptr]),
     "carel_pairwise_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "carel_pairwise": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.c_int, C.POINTER(C.c_float),
                                  C.c_int, C.c_float, c_ptr, i64, c_ptr, C.c_size_t, c_ptr]),
@@ -132,10 +156,13 @@ def timing_report() -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
-# precision mode of the ops: "bf16" (tensor-core operands rounded to bf16; default) or "fp32"
-# (operands split into two bf16 terms, ~1e-5 accurate, 3x the tensor work)
+# precision tier of the ops (north_star: 1e-3 relative in bf16, 1e-5 in fp32):
+#   "bf16"   (default, the product path) 16-bit tensor-core operands, fp32 accumulation
+#   "fp32"   fp32 FFMA arithmetic on the CUDA cores over materialised intermediates (csrc/sgemm.cuh): every op of the head
+#   "bf16x3" MMD only: operands split into two bf16 terms, three products in one K-concatenated tensor-core GEMM
+#            (~1e-5 accurate at 3x the tensor work; fused backward for dim <= 112)
 # ------------------------------------------------------------------------------------------------
-_PRECISION = {"bf16": 0, "fp32": 1}
+_PRECISION = {"bf16": 0, "bf16x3": 1, "fp32": 2}
 _default_precision = "bf16"
 
 

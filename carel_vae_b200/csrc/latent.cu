@@ -15,6 +15,7 @@
 #include "epilogues.cuh"
 #include "gemm_launch.cuh"
 #include "pack.cuh"
+#include "sgemm.cuh"
 
 namespace carel {
 
@@ -356,6 +357,86 @@ extern "C" int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* 
                                                     grad_w4[2], grad_w4[3], grad_b4[0], grad_b4[1],
                                                     grad_b4[2], grad_b4[3]);
     CAREL_LAUNCHED();
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 precision tier (sgemm.cuh): the same layer with fp32 GEMMs on the CUDA cores
+// ---------------------------------------------------------------------------------------------
+namespace carel {
+
+// fp32 d(pre) [N, 4L] (same formulas as reparam_kl_bwd_kernel, no bf16 split)
+static __global__ void reparam_kl_bwd_f32_kernel(const float* __restrict__ pre, const float* __restrict__ eps_e,
+                                                 const float* __restrict__ eps_c, const float* __restrict__ gz, int ldgz,
+                                                 const float* __restrict__ gkl, int N, int L, float* __restrict__ dpre) {
+  const float invN = 1.f / float(N);
+  const float g0 = gkl ? __ldg(gkl) : 0.f, g1 = gkl ? __ldg(gkl + 1) : 0.f;
+  const long long total = 1LL * N * 2 * L;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c = int(t % L);
+    const int sp = int((t / L) % 2);
+    const int row = int(t / (2LL * L));
+    const size_t o = size_t(row) * 4 * L + sp * 2 * L + c;
+    const float mu = pre[o], lv = pre[o + L];
+    const float eps = __ldg((sp ? eps_c : eps_e) + c);
+    const float dz = gz ? gz[size_t(row) * ldgz + sp * L + c] : 0.f;
+    const float g = sp ? g1 : g0;
+    const float e = expf(lv);
+    dpre[o] = dz + g * mu * invN;
+    dpre[o + L] = dz * eps * e - 0.5f * g * (1.f - e) * invN;
+  }
+}
+
+}  // namespace carel
+
+extern "C" size_t carel_latent_f32_workspace_bytes(int64_t N, int64_t D, int64_t L) {
+  (void)D;
+  return align_up(size_t(N) * 4 * L * sizeof(float), 256) + 256;
+}
+
+extern "C" int carel_latent_f32_fwd(const float* x, int64_t ldx, int64_t N, int64_t D, int64_t L, const float* const* w4,
+                                    const float* const* b4, const float* eps_e, const float* eps_c, float* pre, float* z,
+                                    float* kl, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(N > 0 && D > 0 && L > 0, "carel_latent_f32_fwd: empty problem");
+  CAREL_REQUIRE(ws != nullptr && ws_bytes >= carel_latent_f32_workspace_bytes(N, D, L), "carel_latent_f32_fwd: workspace too small");
+  double* klacc = reinterpret_cast<double*>(static_cast<uint8_t*>(ws) + align_up(size_t(N) * 4 * L * sizeof(float), 256));
+  for (int i = 0; i < 4; ++i)       // pre[:, iL:(i+1)L] = X W_i^T + b_i   (nn.Linear, mmd:312-336)
+    if (int rc = launch_sgemm(false, false, x, ldx, w4[i], D, pre + i * L, 4 * L, N, L, D, 1.f, b4[i], 0, 1, st)) return rc;
+  CAREL_CHECK_CUDA(cudaMemsetAsync(klacc, 0, 2 * sizeof(double), st));
+  const long long work = N * 2 * ((L + 3) / 4);
+  const int blocks = int(std::min<long long>((work + 255) / 256, 148LL * 16));
+  reparam_kl_fwd_kernel<<<blocks, 256, 0, st>>>(pre, int(4 * L), eps_e, eps_c, z, int(2 * L), int(N), int(L), klacc);
+  CAREL_LAUNCHED();
+  kl_finalize_kernel<<<1, 32, 0, st>>>(klacc, int(N), kl);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
+extern "C" int carel_latent_f32_bwd(const float* grad_z, int64_t ldgz, const float* grad_kl, const float* x, int64_t ldx,
+                                    const float* const* w4, const float* pre, const float* eps_e, const float* eps_c,
+                                    int64_t N, int64_t D, int64_t L, float* grad_x, int64_t ldgx, float* const* grad_w4,
+                                    float* const* grad_b4, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(ws != nullptr && ws_bytes >= carel_latent_f32_workspace_bytes(N, D, L), "carel_latent_f32_bwd: workspace too small");
+  float* dpre = static_cast<float*>(ws);
+  const long long work = N * 2 * L;
+  reparam_kl_bwd_f32_kernel<<<int(std::min<long long>((work + 255) / 256, 148LL * 16)), 256, 0, st>>>(
+      pre, eps_e, eps_c, grad_z, int(ldgz), grad_kl, int(N), int(L), dpre);
+  CAREL_LAUNCHED();
+  for (int i = 0; i < 4; ++i) {
+    const float* dp = dpre + i * L;                       // [N, L] block of d(pre), pitch 4L
+    if (grad_x != nullptr)                                // dX (+)= dpre_i W_i
+      if (int rc = launch_sgemm(false, true, dp, 4 * L, w4[i], D, grad_x, ldgx, N, D, L, 1.f, nullptr, i ? 1 : 0, 1, st)) return rc;
+    if (grad_w4[i] != nullptr) {                          // dW_i = dpre_i^T X   (reduction over the N rows: split-K)
+      CAREL_CHECK_CUDA(cudaMemsetAsync(grad_w4[i], 0, size_t(L) * D * sizeof(float), st));
+      if (int rc = launch_sgemm(true, true, dp, 4 * L, x, ldx, grad_w4[i], D, L, D, N, 1.f, nullptr, 2, 0, st)) return rc;
+    }
+    if (grad_b4[i] != nullptr) {
+      CAREL_CHECK_CUDA(cudaMemsetAsync(grad_b4[i], 0, size_t(L) * sizeof(float), st));
+      if (int rc = launch_f32_colsum(dp, 4 * L, N, L, 1.f, grad_b4[i], st)) return rc;
+    }
   }
   return 0;
 }

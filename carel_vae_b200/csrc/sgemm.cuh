@@ -1,0 +1,184 @@
+// sgemm.cuh — the GEMM of the fp32 precision tier: plain IEEE fp32 FFMA arithmetic on the CUDA cores.
+//
+// north_star asks for two tiers: "1e-3 relative in bf16 and 1e-5 in fp32".  The bf16 tier is the product path
+// (tcgen05 kernels).  The fp32 tier exists to be CHECKED against the reference at 1e-5, so it computes what the
+// reference's fp32 ATen path computes — fp32 products, fp32 accumulation — and materialises the same intermediates
+// (logits [N, V], Gram blocks) instead of fusing them away; its speed is that of a CUDA-core SGEMM (tens of TFLOP/s),
+// a deliberate trade: one simple register-tiled kernel with every layout switch instead of a second set of tensor-core
+// kernels on split operands.
+//
+//   C[M, N] (op)= alpha * opA(A) * opB(B) (+ bias[N])
+//   TA = false: A is [M, K] row-major (lda);   TA = true: A is [K, M] row-major (the product uses A^T)
+//   TB = false: B is [N, K] row-major (ldb): C = A B^T (nn.Linear);   TB = true: B is [K, N] row-major: C = A B
+//   mode 0: store, 1: C += (same stream, no concurrency on C), 2: atomicAdd (split-K over gridDim.z, C pre-zeroed)
+// 128 x 128 x 16 tiles, 256 threads, 8 x 8 outputs per thread as 2 x 2 blocks of 4 x 4 (float4 shared-memory reads),
+// register prefetch of the next k-block, any shape / pitch (scalar, coalesced global loads with bounds checks).
+#pragma once
+#include <algorithm>
+
+#include "api_common.cuh"
+
+namespace carel {
+
+constexpr int kSgBM = 128, kSgBN = 128, kSgBK = 16, kSgPad = 4;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ C,
+             int64_t ldc, int M, int N, int K, int k_chunk, float alpha, const float* __restrict__ bias, int mode) {
+  __shared__ __align__(16) float As[2][kSgBK][kSgBM + kSgPad];
+  __shared__ __align__(16) float Bs[2][kSgBK][kSgBN + kSgPad];
+  const int t = threadIdx.x;
+  const int m0 = blockIdx.y * kSgBM, n0 = blockIdx.x * kSgBN;
+  const int k_begin = blockIdx.z * k_chunk, k_end = min(K, k_begin + k_chunk);
+  if (k_begin >= k_end) return;
+  float ra[8], rb[8];
+  // global -> registers: 8 elements of each operand tile per thread, consecutive threads along the contiguous dim
+  auto load = [&](int kb) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m, k;
+      if (TA) { m = t & 127; k = (t >> 7) + 2 * i; } else { k = t & 15; m = (t >> 4) + 16 * i; }
+      const int gm = m0 + m, gk = kb + k;
+      ra[i] = (gm < M && gk < k_end) ? (TA ? __ldg(A + int64_t(gk) * lda + gm) : __ldg(A + int64_t(gm) * lda + gk)) : 0.f;
+      int n, kk;
+      if (TB) { n = t & 127; kk = (t >> 7) + 2 * i; } else { kk = t & 15; n = (t >> 4) + 16 * i; }
+      const int gn = n0 + n, gk2 = kb + kk;
+      rb[i] = (gn < N && gk2 < k_end) ? (TB ? __ldg(B + int64_t(gk2) * ldb + gn) : __ldg(B + int64_t(gn) * ldb + gk2)) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int m, k;
+      if (TA) { m = t & 127; k = (t >> 7) + 2 * i; } else { k = t & 15; m = (t >> 4) + 16 * i; }
+      As[buf][k][m] = ra[i];
+      int n, kk;
+      if (TB) { n = t & 127; kk = (t >> 7) + 2 * i; } else { kk = t & 15; n = (t >> 4) + 16 * i; }
+      Bs[buf][kk][n] = rb[i];
+    }
+  };
+  const int tx = t & 15, ty = t >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  load(k_begin);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int kb = k_begin; kb < k_end; kb += kSgBK) {
+    const bool more = kb + kSgBK < k_end;
+    if (more) load(kb + kSgBK);
+#pragma unroll
+    for (int kk = 0; kk < kSgBK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  const bool add_bias = bias != nullptr && blockIdx.z == 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= N) continue;
+      float v = alpha * acc[i][j];
+      if (add_bias) v += __ldg(bias + gn);
+      float* c = C + int64_t(gm) * ldc + gn;
+      if (mode == 0) *c = v;
+      else if (mode == 1) *c += v;
+      else atomicAdd(c, v);
+    }
+  }
+}
+
+// ksplit <= 0: chosen so that the grid fills the GPU when M x N alone gives too few tiles (mode must then be 2
+// with C zeroed by the caller, or ksplit forced to 1).
+inline int launch_sgemm(bool ta, bool tb, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                        int64_t M, int64_t N, int64_t K, float alpha, const float* bias, int mode, int ksplit,
+                        cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  CAREL_REQUIRE(M < (int64_t(1) << 31) && N < (int64_t(1) << 31) && K < (int64_t(1) << 31), "sgemm: dimension too large");
+  const int gx = int((N + kSgBN - 1) / kSgBN), gy = int((M + kSgBM - 1) / kSgBM);
+  CAREL_REQUIRE(gy <= 65535, "sgemm: too many row tiles");
+  if (ksplit <= 0) {
+    ksplit = 1;
+    if (mode == 2) {
+      const int tiles = gx * gy, want = 2 * sm_count();
+      ksplit = std::max(1, std::min<int>(want / std::max(tiles, 1), int((K + 4 * kSgBK - 1) / (4 * kSgBK))));
+    }
+  }
+  CAREL_REQUIRE(ksplit == 1 || mode == 2, "sgemm: split-K needs the atomic mode");
+  int k_chunk = int((K + ksplit - 1) / ksplit);
+  k_chunk = (k_chunk + kSgBK - 1) / kSgBK * kSgBK;
+  const dim3 grid(gx, gy, ksplit);
+  if (ta && tb) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, int(M), int(N), int(K), k_chunk, alpha, bias, mode);
+  else if (ta) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, int(M), int(N), int(K), k_chunk, alpha, bias, mode);
+  else if (tb) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, int(M), int(N), int(K), k_chunk, alpha, bias, mode);
+  else sgemm_kernel<false, false><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, int(M), int(N), int(K), k_chunk, alpha, bias, mode);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
+}  // namespace carel
+
+// ---------------------------------------------------------------------------------------------
+// small fp32-tier helpers shared by the ops
+// ---------------------------------------------------------------------------------------------
+namespace carel {
+
+// n[r] = sum_k x[r, k]^2 (fp32, one warp per row, the reference's (x ** 2).sum(1))
+static __global__ void f32_rownorm_kernel(const float* __restrict__ x, int64_t ld, int rows, int K, float* __restrict__ n) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const float* s = x + int64_t(r) * ld;
+    float a = 0.f;
+    for (int k = lane; k < K; k += 32) { const float v = __ldg(s + k); a = fmaf(v, v, a); }
+    a = warp_sum(a);
+    if (lane == 0) n[r] = a;
+  }
+}
+
+// out[c] += scale * sum_r a[r, c]: blocks of 32 columns x 256 rows, coalesced rows, one atomic per column and block
+static __global__ void __launch_bounds__(256)
+f32_colsum_kernel(const float* __restrict__ a, int64_t ld, int rows, int cols, float scale, float* __restrict__ out) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = blockIdx.y * 256 + w; r < min(rows, (blockIdx.y + 1) * 256); r += 8) s += a[int64_t(r) * ld + c];
+  sh[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    atomicAdd(out + c, t * scale);
+  }
+}
+inline int launch_f32_colsum(const float* a, int64_t ld, int64_t rows, int64_t cols, float scale, float* out, cudaStream_t st) {
+  const dim3 grid(unsigned((cols + 31) / 32), unsigned((rows + 255) / 256));
+  CAREL_REQUIRE(grid.y <= 65535, "colsum: too many rows");
+  f32_colsum_kernel<<<grid, 256, 0, st>>>(a, ld, int(rows), int(cols), scale, out);
+  CAREL_LAUNCHED();
+  return 0;
+}
+
+}  // namespace carel

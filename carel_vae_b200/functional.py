@@ -49,6 +49,40 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # MMD
 # --------------------------------------------------------------------------------------------
+def _mmd_wide(d: int, prec: int) -> bool:
+    """Feature widths the fused tensor-core backward cannot hold (bf16: d + 6 columns > 256) take their gradient from
+    the materialising fp32 kernels (carel_mmd_f32_bwd): MMDStatistic is differentiable at any width."""
+    return prec == 0 and d > 250
+
+
+def _mmd_forward(xf, ldx, yf, ldy, n1, n2, d, alphas, eps, flags, t0, t1, partial, out, prec):
+    """Launch the forward of the chosen tier; returns the workspace the matching backward needs."""
+    L = lib()
+    al = float_array(alphas)
+    if prec == 2:
+        ws = _workspace(L.carel_mmd_f32_workspace_bytes(n1, n2, d), out.device if out is not None else partial.device)
+        check(L.carel_mmd_f32_fwd(xf, ldx, yf, ldy, n1, n2, d, al, len(alphas), float(eps), t0, t1, _p(partial),
+                                  _p(None if partial is not None else out), _p(ws), ws.numel(), _stream()), "carel_mmd_f32_fwd")
+        return ws
+    ws = _workspace(L.carel_mmd_workspace_bytes(n1, n2, d, prec), out.device if out is not None else partial.device)
+    check(L.carel_mmd_fwd(xf, ldx, yf, ldy, n1, n2, d, al, len(alphas), float(eps), int(flags), t0, t1, _p(partial),
+                          _p(None if partial is not None else out), _p(ws), ws.numel(), prec, _stream()), "carel_mmd_fwd")
+    return ws
+
+
+def _mmd_backward(g, xf, ldx, yf, ldy, n1, n2, d, alphas, eps, t0, t1, gx, ldgx, gy, ldgy, ws, prec, dev):
+    L = lib()
+    al = float_array(alphas)
+    if prec == 2 or _mmd_wide(d, prec):
+        if prec != 2:
+            ws = _workspace(L.carel_mmd_f32_workspace_bytes(n1, n2, d), dev)
+        check(L.carel_mmd_f32_bwd(_p(g), xf, ldx, yf, ldy, n1, n2, d, al, len(alphas), eps, t0, t1, gx, ldgx, gy, ldgy,
+                                  _p(ws), ws.numel(), _stream()), "carel_mmd_f32_bwd")
+    else:
+        check(L.carel_mmd_bwd(_p(g), n1, n2, d, al, len(alphas), eps, t0, t1, gx, ldgx, gy, ldgy, _p(ws), ws.numel(), prec,
+                              _stream()), "carel_mmd_bwd")
+
+
 class _MMDFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, alphas, eps, flags, tile_range, prec=0):
@@ -58,19 +92,14 @@ class _MMDFn(torch.autograd.Function):
         n2, d2 = yf.shape
         if d != d2:
             raise ValueError("sample_1 and sample_2 must have the same feature width")
-        L = lib()
-        ws = _workspace(L.carel_mmd_workspace_bytes(n1, n2, d, prec), xf.device)
         out = torch.empty((), dtype=torch.float32, device=xf.device)
-        al = float_array(alphas)
         t0, t1 = tile_range
         partial = None
         if t0 != 0 or t1 != -1:
             partial = torch.empty(3, dtype=torch.float64, device=xf.device)
-        check(L.carel_mmd_fwd(_p(xf), xf.stride(0), _p(yf), yf.stride(0), n1, n2, d, al, len(alphas),
-                              float(eps), int(flags), t0, t1, _p(partial),
-                              _p(None if partial is not None else out), _p(ws), ws.numel(), prec, _stream()),
-              "carel_mmd_fwd")
-        ctx.ws = ws
+        ctx.ws = _mmd_forward(_p(xf), xf.stride(0), _p(yf), yf.stride(0), n1, n2, d, alphas, eps, flags, t0, t1, partial, out,
+                              prec)
+        ctx.keep = (xf, yf) if (prec == 2 or _mmd_wide(d, prec)) else None      # the fp32 kernels re-read the samples
         ctx.meta = (n1, n2, d, tuple(float(a) for a in alphas), float(eps), t0, t1, x.dtype, y.dtype, prec)
         if partial is not None:
             ctx.mark_non_differentiable(partial)
@@ -84,9 +113,9 @@ class _MMDFn(torch.autograd.Function):
         g = g.reshape(()).float().contiguous()
         gx = torch.empty((n1, d), dtype=torch.float32, device=ws.device)
         gy = torch.empty((n2, d), dtype=torch.float32, device=ws.device)
-        al = float_array(alphas)
-        check(lib().carel_mmd_bwd(_p(g), n1, n2, d, al, len(alphas), eps, t0, t1, _p(gx), d, _p(gy), d,
-                                  _p(ws), ws.numel(), prec, _stream()), "carel_mmd_bwd")
+        xf, yf = ctx.keep if ctx.keep is not None else (None, None)
+        _mmd_backward(g, _p(xf), 0 if xf is None else xf.stride(0), _p(yf), 0 if yf is None else yf.stride(0), n1, n2, d,
+                      alphas, eps, t0, t1, _p(gx), d, _p(gy), d, ws, prec, ws.device)
         return gx.to(dtx), gy.to(dty), None, None, None, None, None
 
 
@@ -102,14 +131,10 @@ class _MMDHalvesFn(torch.autograd.Function):
         N = zf.shape[0]
         if zf.shape[1] != 2 * L:
             raise ValueError("z must be [N, 2L]")
-        lb = lib()
-        ws = _workspace(lb.carel_mmd_workspace_bytes(N, N, L, prec), zf.device)
         out = torch.empty((), dtype=torch.float32, device=zf.device)
-        al = float_array(alphas)
         x, y = zf[:, :L], zf[:, L:]
-        check(lb.carel_mmd_fwd(_p(x), zf.stride(0), _p(y), zf.stride(0), N, N, L, al, len(alphas), float(eps), 0, 0, -1,
-                               _p(None), _p(out), _p(ws), ws.numel(), prec, _stream()), "carel_mmd_fwd")
-        ctx.ws = ws
+        ctx.ws = _mmd_forward(_p(x), zf.stride(0), _p(y), zf.stride(0), N, N, L, alphas, eps, 0, 0, -1, None, out, prec)
+        ctx.keep = zf if (prec == 2 or _mmd_wide(L, prec)) else None
         ctx.meta = (N, L, tuple(float(a) for a in alphas), float(eps), z.dtype, prec)
         return out
 
@@ -119,8 +144,13 @@ class _MMDHalvesFn(torch.autograd.Function):
         ws = ctx.ws
         g = g.reshape(()).float().contiguous()
         gz = torch.empty((N, 2 * L), dtype=torch.float32, device=ws.device)
-        check(lib().carel_mmd_bwd(_p(g), N, N, L, float_array(alphas), len(alphas), eps, 0, -1, _p(gz[:, :L]), 2 * L,
-                                  _p(gz[:, L:]), 2 * L, _p(ws), ws.numel(), prec, _stream()), "carel_mmd_bwd")
+        zf = ctx.keep
+        xp = yp = C.c_void_p(0)
+        ldz = 0
+        if zf is not None:
+            xp, yp, ldz = _p(zf[:, :L]), _p(zf[:, L:]), zf.stride(0)
+        _mmd_backward(g, xp, ldz, yp, ldz, N, N, L, alphas, eps, 0, -1, _p(gz[:, :L]), 2 * L, _p(gz[:, L:]), 2 * L, ws, prec,
+                      ws.device)
         return gz.to(dtz), None, None, None, None
 
 
@@ -180,7 +210,7 @@ def _ptr_array(tensors):
 
 class _LatentFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, eps_e, eps_c, *wb):
+    def forward(ctx, x, eps_e, eps_c, prec, *wb):
         # wb = (W_emu, b_emu, W_elv, b_elv, W_cmu, b_cmu, W_clv, b_clv)
         _require_cuda(x, eps_e, eps_c, *wb)
         xf = _rowmajor_f32(x)
@@ -190,13 +220,16 @@ class _LatentFn(torch.autograd.Function):
         L = ws_[0].shape[0]
         ee, ec = eps_e.detach().float().contiguous(), eps_c.detach().float().contiguous()
         lb = lib()
-        ws = _workspace(lb.carel_latent_workspace_bytes(N, D, L), xf.device)
+        f32 = prec == 2
+        ws = _workspace((lb.carel_latent_f32_workspace_bytes if f32 else lb.carel_latent_workspace_bytes)(N, D, L), xf.device)
         pre = torch.empty((N, 4 * L), dtype=torch.float32, device=xf.device)
         z = torch.empty((N, 2 * L), dtype=torch.float32, device=xf.device)
         kl = torch.empty(2, dtype=torch.float32, device=xf.device)
-        check(lb.carel_latent_fwd(_p(xf), xf.stride(0), N, D, L, _ptr_array(ws_), _ptr_array(bs_), _p(ee), _p(ec),
-                                  _p(pre), _p(z), _p(kl), _p(ws), ws.numel(), _stream()), "carel_latent_fwd")
+        check((lb.carel_latent_f32_fwd if f32 else lb.carel_latent_fwd)(
+            _p(xf), xf.stride(0), N, D, L, _ptr_array(ws_), _ptr_array(bs_), _p(ee), _p(ec), _p(pre), _p(z), _p(kl), _p(ws),
+            ws.numel(), _stream()), "carel_latent_fwd")
         ctx.ws, ctx.pre, ctx.eps = ws, pre, (ee, ec)
+        ctx.f32_keep = (xf, ws_) if f32 else None       # the fp32 kernels read x and the weights again in backward
         ctx.dims = (N, D, L)
         ctx.x_dtype = x.dtype
         ctx.wb_meta = [(t.dtype, tuple(t.shape)) for t in wb]
@@ -215,22 +248,29 @@ class _LatentFn(torch.autograd.Function):
         gx = torch.empty((N, D), dtype=torch.float32, device=dev) if need[0] else None
         gws, gbs = [], []
         for i in range(4):
-            gws.append(torch.empty((L, D), dtype=torch.float32, device=dev) if need[3 + 2 * i] else None)
-            gbs.append(torch.empty((L,), dtype=torch.float32, device=dev) if need[4 + 2 * i] else None)
-        check(lib().carel_latent_bwd(_p(gz), 0 if gz is None else gz.stride(0), _p(gkl), _p(pre), _p(ee), _p(ec),
-                                     N, D, L, _p(gx), D, _ptr_array(gws), _ptr_array(gbs), _p(ws), ws.numel(),
-                                     _stream()), "carel_latent_bwd")
-        out = [None if gx is None else gx.to(ctx.x_dtype), None, None]
+            gws.append(torch.empty((L, D), dtype=torch.float32, device=dev) if need[4 + 2 * i] else None)
+            gbs.append(torch.empty((L,), dtype=torch.float32, device=dev) if need[5 + 2 * i] else None)
+        if ctx.f32_keep is not None:
+            xf, ws_ = ctx.f32_keep
+            check(lib().carel_latent_f32_bwd(_p(gz), 0 if gz is None else gz.stride(0), _p(gkl), _p(xf), xf.stride(0),
+                                             _ptr_array(ws_), _p(pre), _p(ee), _p(ec), N, D, L, _p(gx), D, _ptr_array(gws),
+                                             _ptr_array(gbs), _p(ws), ws.numel(), _stream()), "carel_latent_f32_bwd")
+        else:
+            check(lib().carel_latent_bwd(_p(gz), 0 if gz is None else gz.stride(0), _p(gkl), _p(pre), _p(ee), _p(ec),
+                                         N, D, L, _p(gx), D, _ptr_array(gws), _ptr_array(gbs), _p(ws), ws.numel(),
+                                         _stream()), "carel_latent_bwd")
+        out = [None if gx is None else gx.to(ctx.x_dtype), None, None, None]
         for i in range(4):
             out.append(gws[i])
             out.append(gbs[i])
         return tuple(out)
 
 
-def latent(x, eps_e, eps_c, w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_clv):
+def latent(x, eps_e, eps_c, w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_clv, precision: str | None = None):
     """Fused latent layer.  Returns (z [N, 2L] = [z_e | z_c], kl [2] = (kl_e, kl_c), pre [N, 4L] =
     [mu_e | lv_e | mu_c | lv_c] (detached))."""
-    return _LatentFn.apply(x, eps_e, eps_c, w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_clv)
+    return _LatentFn.apply(x, eps_e, eps_c, _lib.precision_code(precision), w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu,
+                           w_clv, b_clv)
 
 
 # --------------------------------------------------------------------------------------------
@@ -404,7 +444,7 @@ DEFAULT_ELL_CAP = 64
 
 class _BowFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, dec_w, dec_b, bow_dense, ell, label_smoothing, ell_cap):
+    def forward(ctx, z, dec_w, dec_b, bow_dense, ell, label_smoothing, ell_cap, prec=0):
         _require_cuda(z, dec_w, dec_b)
         zf = _rowmajor_f32(z)
         wf = dec_w.detach().float().contiguous()
@@ -422,11 +462,19 @@ class _BowFn(torch.autograd.Function):
             cols, vals, nnz = cols.int().contiguous(), vals.float().contiguous(), nnz.int().contiguous()
             ell_cap = cols.shape[1]
         lb = lib()
-        ws = _workspace(lb.carel_bow_workspace_bytes(N, K, V, ell_cap), zf.device)
         loss = torch.empty((), dtype=torch.float32, device=zf.device)
-        check(lb.carel_bow_fwd(_p(zf), zf.stride(0), _p(wf), _p(bf_), _p(bd), 0 if bd is None else bd.stride(0),
-                               _p(cols), _p(vals), _p(nnz), N, K, V, ell_cap, float(label_smoothing), _p(loss),
-                               _p(ws), ws.numel(), _stream()), "carel_bow_fwd")
+        if prec == 2:        # fp32 tier: materialised logits, fp32 GEMMs on the CUDA cores
+            ws = _workspace(lb.carel_bow_f32_workspace_bytes(N, K, V, 1 if bd is None else 0), zf.device)
+            check(lb.carel_bow_f32_fwd(_p(zf), zf.stride(0), _p(wf), _p(bf_), _p(bd), 0 if bd is None else bd.stride(0),
+                                       _p(cols), _p(vals), _p(nnz), N, K, V, ell_cap, float(label_smoothing), _p(loss),
+                                       _p(ws), ws.numel(), _stream()), "carel_bow_f32_fwd")
+            ctx.f32_keep = (zf, wf)
+        else:
+            ws = _workspace(lb.carel_bow_workspace_bytes(N, K, V, ell_cap), zf.device)
+            check(lb.carel_bow_fwd(_p(zf), zf.stride(0), _p(wf), _p(bf_), _p(bd), 0 if bd is None else bd.stride(0),
+                                   _p(cols), _p(vals), _p(nnz), N, K, V, ell_cap, float(label_smoothing), _p(loss),
+                                   _p(ws), ws.numel(), _stream()), "carel_bow_fwd")
+            ctx.f32_keep = None
         ctx.ws, ctx.bd = ws, bd
         ctx.meta = (N, K, V, int(ell_cap), float(label_smoothing), z.dtype, dec_w.dtype, dec_b.dtype)
         return loss
@@ -441,10 +489,15 @@ class _BowFn(torch.autograd.Function):
         gz = torch.empty((N, K), dtype=torch.float32, device=dev)
         gw = torch.empty((V, K), dtype=torch.float32, device=dev) if need[1] else None
         gb = torch.empty((V,), dtype=torch.float32, device=dev) if need[2] else None
-        check(lib().carel_bow_bwd(_p(g), _p(bd), 0 if bd is None else bd.stride(0), N, K, V, cap, ls, _p(gz), K,
-                                  _p(gw), _p(gb), _p(ws), ws.numel(), _stream()), "carel_bow_bwd")
+        if ctx.f32_keep is not None:
+            zf, wf = ctx.f32_keep
+            check(lib().carel_bow_f32_bwd(_p(g), _p(zf), zf.stride(0), _p(wf), _p(bd), 0 if bd is None else bd.stride(0), N, K,
+                                          V, ls, _p(gz), K, _p(gw), _p(gb), _p(ws), ws.numel(), _stream()), "carel_bow_f32_bwd")
+        else:
+            check(lib().carel_bow_bwd(_p(g), _p(bd), 0 if bd is None else bd.stride(0), N, K, V, cap, ls, _p(gz), K,
+                                      _p(gw), _p(gb), _p(ws), ws.numel(), _stream()), "carel_bow_bwd")
         return (gz.to(dtz) if need[0] else None, None if gw is None else gw.to(dtw),
-                None if gb is None else gb.to(dtb), None, None, None, None)
+                None if gb is None else gb.to(dtb), None, None, None, None, None)
 
 
 def bow_pack_ell(content_bow: torch.Tensor, ell_cap: int = DEFAULT_ELL_CAP):
@@ -462,11 +515,11 @@ def bow_pack_ell(content_bow: torch.Tensor, ell_cap: int = DEFAULT_ELL_CAP):
 
 
 def bow_reconstruction_loss(z, dec_w, dec_b, content_bow=None, label_smoothing: float = 0.1, ell=None,
-                            ell_cap: int = DEFAULT_ELL_CAP):
+                            ell_cap: int = DEFAULT_ELL_CAP, precision: str | None = None):
     """BCELoss(softmax(z dec_w^T + dec_b), content_bow (1 - ls) + ls / V) without materialising [N, V]
     (reference :253-254 + get_reconstruct_loss :381-387).  `content_bow` is the reference's dense
     [N, V] target; `ell=(cols[N,C] int32, vals[N,C] fp32, nnz[N] int32)` is the compact alternative."""
-    return _BowFn.apply(z, dec_w, dec_b, content_bow, ell, label_smoothing, ell_cap)
+    return _BowFn.apply(z, dec_w, dec_b, content_bow, ell, label_smoothing, ell_cap, _lib.precision_code(precision))
 
 
 # --------------------------------------------------------------------------------------------
@@ -474,7 +527,7 @@ def bow_reconstruction_loss(z, dec_w, dec_b, content_bow=None, label_smoothing: 
 # --------------------------------------------------------------------------------------------
 class _HSICFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, y, s_x, s_y, tile_range, reduce_fn):
+    def forward(ctx, x, y, s_x, s_y, tile_range, reduce_fn, prec=0):
         _require_cuda(x, y)
         xf, yf = _rowmajor_f32(x), _rowmajor_f32(y)
         m, dx = xf.shape
@@ -482,6 +535,17 @@ class _HSICFn(torch.autograd.Function):
         if m != m2:
             raise ValueError("HSIC needs paired samples (same number of rows)")
         lb = lib()
+        ctx.f32_keep = None
+        if prec == 2:        # fp32 tier: both kernel matrices materialised (no row-block sharding in this tier)
+            if reduce_fn is not None or tuple(tile_range) != (0, -1):
+                raise ValueError("the fp32 tier of HSIC evaluates the whole Gram on one GPU")
+            ws = _workspace(lb.carel_hsic_f32_workspace_bytes(m, dx, dy), xf.device)
+            out = torch.empty((), dtype=torch.float32, device=xf.device)
+            check(lb.carel_hsic_f32_fwd(_p(xf), xf.stride(0), _p(yf), yf.stride(0), m, dx, dy, float(s_x), float(s_y), _p(out),
+                                        _p(ws), ws.numel(), _stream()), "carel_hsic_f32_fwd")
+            ctx.ws, ctx.f32_keep = ws, (xf, yf)
+            ctx.meta = (m, dx, dy, float(s_x), float(s_y), 0, -1, x.dtype, y.dtype)
+            return out
         ws = _workspace(lb.carel_hsic_workspace_bytes(m, dx, dy), xf.device)
         out = torch.empty((), dtype=torch.float32, device=xf.device)
         t0, t1 = tile_range
@@ -506,15 +570,20 @@ class _HSICFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         gx = torch.empty((m, dx), dtype=torch.float32, device=ws.device) if need[0] else None
         gy = torch.empty((m, dy), dtype=torch.float32, device=ws.device) if need[1] else None
-        check(lib().carel_hsic_bwd(_p(g), m, dx, dy, s_x, s_y, t0, t1, _p(gx), dx, _p(gy), dy, _p(ws), ws.numel(),
-                                   _stream()), "carel_hsic_bwd")
-        return (None if gx is None else gx.to(dtx), None if gy is None else gy.to(dty), None, None, None, None)
+        if ctx.f32_keep is not None:
+            xf, yf = ctx.f32_keep
+            check(lib().carel_hsic_f32_bwd(_p(g), _p(xf), xf.stride(0), _p(yf), yf.stride(0), m, dx, dy, s_x, s_y, _p(gx), dx,
+                                           _p(gy), dy, _p(ws), ws.numel(), _stream()), "carel_hsic_f32_bwd")
+        else:
+            check(lib().carel_hsic_bwd(_p(g), m, dx, dy, s_x, s_y, t0, t1, _p(gx), dx, _p(gy), dy, _p(ws), ws.numel(),
+                                       _stream()), "carel_hsic_bwd")
+        return (None if gx is None else gx.to(dtx), None if gy is None else gy.to(dty), None, None, None, None, None)
 
 
 def hsic(x: torch.Tensor, y: torch.Tensor, s_x: float = 1.0, s_y: float = 1.0, tile_range=(0, -1),
-         reduce_fn=None) -> torch.Tensor:
+         reduce_fn=None, precision: str | None = None) -> torch.Tensor:
     """HSIC(x, y) of the reference (hsic.py:540-547) as a 0-dim fp32 tensor, differentiable.
     `tile_range` / `reduce_fn` implement the multi-GPU row-block sharding (see parallel.sharded_hsic):
     the rank computes Gram row tiles [t0, t1) only, `reduce_fn(t)` sums a float64 tensor over the ranks in
     place; the gradient rows of the rank's block are complete (other rows are zero)."""
-    return _HSICFn.apply(x, y, s_x, s_y, tuple(tile_range), reduce_fn)
+    return _HSICFn.apply(x, y, s_x, s_y, tuple(tile_range), reduce_fn, _lib.precision_code(precision))

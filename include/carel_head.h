@@ -214,6 +214,56 @@ int carel_club_bwd(const float* grad_out, const float* mu_hat, const float* lv_h
                    const int64_t* perm, int64_t N, int64_t L, float* grad_mu, float* grad_lv, float* grad_e,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * fp32 precision tier (north_star: "1e-5 in fp32"): the same operators with fp32 FFMA arithmetic on the CUDA cores
+ * (csrc/sgemm.cuh) on materialised intermediates, as the reference's fp32 ATen path computes them.  Selected by
+ * carel_vae_b200.set_precision("fp32") / precision="fp32"; the bf16 tier above is the product path.
+ * carel_mmd_f32_bwd is also the gradient of the bf16 tier for feature widths its fused backward cannot hold
+ * (dim > 250, e.g. the d = 768 Gram): MMDStatistic is differentiable at any width, like the reference's
+ * (drl_classifier_ec_mmd_final_mul.py:547-596).
+ * ------------------------------------------------------------------------------------------ */
+/* C[M,N] (op)= alpha opA(A) opB(B) (+ bias[N]); ta: A is [K,M]; tb: B is [K,N] (else [N,K], nn.Linear);
+ * mode 0 store, 1 add, 2 atomic add (split-K, ksplit <= 0: automatic). */
+int carel_f32_gemm(const float* a, int64_t lda, int ta, const float* b, int64_t ldb, int tb, int64_t M, int64_t N,
+                   int64_t K, float* c, int64_t ldc, const float* bias, float alpha, int mode, int ksplit, void* stream);
+/* latent layer (same contract as carel_latent_fwd / carel_latent_bwd; the backward takes x and the weights again
+ * instead of packed copies in the workspace) */
+size_t carel_latent_f32_workspace_bytes(int64_t N, int64_t D, int64_t L);
+int carel_latent_f32_fwd(const float* x, int64_t ldx, int64_t N, int64_t D, int64_t L, const float* const* w4,
+                         const float* const* b4, const float* eps_e, const float* eps_c, float* pre, float* z, float* kl,
+                         void* ws, size_t ws_bytes, void* stream);
+int carel_latent_f32_bwd(const float* grad_z, int64_t ldgz, const float* grad_kl, const float* x, int64_t ldx,
+                         const float* const* w4, const float* pre, const float* eps_e, const float* eps_c, int64_t N,
+                         int64_t D, int64_t L, float* grad_x, int64_t ldgx, float* const* grad_w4, float* const* grad_b4,
+                         void* ws, size_t ws_bytes, void* stream);
+/* MMD on materialised row blocks (<= 256 MB each) of the Gram, any feature width; row-tile ranges as in carel_mmd_fwd */
+size_t carel_mmd_f32_workspace_bytes(int64_t n1, int64_t n2, int64_t dim);
+int carel_mmd_f32_fwd(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t n1, int64_t n2, int64_t dim,
+                      const float* alphas_host, int n_alpha, float eps, int64_t row_tile_begin, int64_t row_tile_end,
+                      double* partial_sums, float* out_mmd, void* ws, size_t ws_bytes, void* stream);
+int carel_mmd_f32_bwd(const float* grad_out, const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t n1,
+                      int64_t n2, int64_t dim, const float* alphas_host, int n_alpha, float eps, int64_t row_tile_begin,
+                      int64_t row_tile_end, float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy, void* ws,
+                      size_t ws_bytes, void* stream);
+/* HSIC (drl_classifier_ec_hsic.py:529-547) with both m x m kernel matrices materialised (m <= 46340); the backward
+ * must follow the forward on the same workspace */
+size_t carel_hsic_f32_workspace_bytes(int64_t m, int64_t dx, int64_t dy);
+int carel_hsic_f32_fwd(const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t m, int64_t dx, int64_t dy,
+                       float s_x, float s_y, float* out, void* ws, size_t ws_bytes, void* stream);
+int carel_hsic_f32_bwd(const float* grad_out, const float* x, int64_t ldx, const float* y, int64_t ldy, int64_t m,
+                       int64_t dx, int64_t dy, float s_x, float s_y, float* grad_x, int64_t ldgx, float* grad_y,
+                       int64_t ldgy, void* ws, size_t ws_bytes, void* stream);
+/* BoW decoder + loss with the logits [N, V] materialised (any K); the backward must follow the forward on the same
+ * workspace.  need_dense_target = 1 when only an ELL triple is given (it is expanded into the workspace). */
+size_t carel_bow_f32_workspace_bytes(int64_t N, int64_t K, int64_t V, int need_dense_target);
+int carel_bow_f32_fwd(const float* z, int64_t ldz, const float* dec_w, const float* dec_b, const float* bow_dense,
+                      int64_t ld_bow, const int32_t* ell_cols, const float* ell_vals, const int32_t* ell_nnz, int64_t N,
+                      int64_t K, int64_t V, int64_t ell_cap, float label_smoothing, float* loss_out, void* ws,
+                      size_t ws_bytes, void* stream);
+int carel_bow_f32_bwd(const float* grad_out, const float* z, int64_t ldz, const float* dec_w, const float* bow_dense,
+                      int64_t ld_bow, int64_t N, int64_t K, int64_t V, float label_smoothing, float* grad_z, int64_t ldgz,
+                      float* grad_w, float* grad_b, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
