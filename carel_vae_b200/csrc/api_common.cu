@@ -1,5 +1,6 @@
 // api_common.cu — error string, version, launch counter, debug GEMM and dense pairwise entry points.
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,13 +19,15 @@ std::atomic<long long>& launch_counter() {
   static std::atomic<long long> c{0};
   return c;
 }
+// SM count of the CURRENT device (cached per device index: a process may drive several GPUs).
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -34,22 +37,31 @@ struct TimingEntry {
   const char* tag;
   cudaEvent_t e0, e1;
 };
-bool g_timing = false;
+// The timing log is a profiling aid for eager passes; launches may come from the caller's thread and from autograd's
+// backward thread, so the log is guarded and each thread closes the entry IT opened.
+std::atomic<bool> g_timing{false};
+std::mutex g_timing_mu;
 std::vector<TimingEntry> g_entries;
+thread_local long long t_open_entry = -1;
 }  // namespace
-bool timing_enabled() { return g_timing; }
+bool timing_enabled() { return g_timing.load(); }
 void timing_begin(const char* tag, cudaStream_t st) {
-  if (!g_timing) return;
+  if (!g_timing.load()) return;
   TimingEntry e;
   e.tag = tag;
   cudaEventCreate(&e.e0);
   cudaEventCreate(&e.e1);
   cudaEventRecord(e.e0, st);
+  std::lock_guard<std::mutex> lk(g_timing_mu);
   g_entries.push_back(e);
+  t_open_entry = (long long)g_entries.size() - 1;
 }
 void timing_end(cudaStream_t st) {
-  if (!g_timing || g_entries.empty()) return;
-  cudaEventRecord(g_entries.back().e1, st);
+  if (!g_timing.load()) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (t_open_entry < 0 || t_open_entry >= (long long)g_entries.size()) return;
+  cudaEventRecord(g_entries[size_t(t_open_entry)].e1, st);
+  t_open_entry = -1;
 }
 
 }  // namespace carel
@@ -57,8 +69,9 @@ void timing_end(cudaStream_t st) {
 using namespace carel;
 
 extern "C" void carel_timing_enable(int on) {
-  g_timing = on != 0;
-  if (!g_timing) {
+  g_timing.store(on != 0);
+  if (!on) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
     for (auto& e : g_entries) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
     g_entries.clear();
   }
@@ -66,6 +79,7 @@ extern "C" void carel_timing_enable(int on) {
 // Writes "tag total_ms count\n" lines (one per kernel tag, in first-launch order) and clears the log.
 extern "C" int carel_timing_report(char* buf, size_t n) {
   cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_timing_mu);
   std::vector<const char*> order;
   std::map<std::string, std::pair<double, int>> agg;
   for (auto& e : g_entries) {

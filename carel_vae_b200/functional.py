@@ -463,6 +463,8 @@ class _BowFn(torch.autograd.Function):
             ell_cap = cols.shape[1]
         lb = lib()
         loss = torch.empty((), dtype=torch.float32, device=zf.device)
+        if K > 256:
+            prec = 2         # the tensor-core decoder holds 2 ec_dim <= 256 input columns; wider ones take the fp32 kernels
         if prec == 2:        # fp32 tier: materialised logits, fp32 GEMMs on the CUDA cores
             ws = _workspace(lb.carel_bow_f32_workspace_bytes(N, K, V, 1 if bd is None else 0), zf.device)
             check(lb.carel_bow_f32_fwd(_p(zf), zf.stride(0), _p(wf), _p(bf_), _p(bd), 0 if bd is None else bd.stride(0),

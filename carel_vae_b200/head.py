@@ -112,7 +112,7 @@ class _DrlClassifierBase(nn.Module):
         masks = []
 
         def draw_masks():
-            if side is None or not self._fused_heads_ok():
+            if side is None:
                 return
             n = emb.shape[0]
             side.wait_stream(main)
@@ -225,11 +225,19 @@ class _DrlClassifierBase(nn.Module):
     _guard_inf = False     # reference mmd:510-511 only
 
     def _fused_heads_ok(self):
+        """The head kernels cover every configuration the reference trainers use (ec_dim <= 128, one cause / pair
+        logit, <= 8 emotion classes).  Anything else raises: there is no eager PyTorch fallback on the forward path
+        (the per-head get_*_mul_loss methods stay available to outside callers under the reference's names)."""
         o = self.opt
-        return (getattr(o, "fused_heads", True) and o.ec_dim <= 128 and self.cause_classifier.out_features == 1 and
-                self.pair_classifier.out_features == 1 and
-                (self.emotion_classifier.out_features == 1 if self._emo_mode == 1
-                 else self.emotion_classifier.out_features <= 8))
+        ok = (o.ec_dim <= 128 and self.cause_classifier.out_features == 1 and self.pair_classifier.out_features == 1 and
+              (self.emotion_classifier.out_features == 1 if self._emo_mode == 1
+               else self.emotion_classifier.out_features <= 8))
+        if not ok:
+            raise NotImplementedError(
+                "carel_vae_b200 classifier-head kernels need ec_dim <= 128, one cause / pair logit and at most 8 emotion "
+                f"classes (got ec_dim={o.ec_dim}, emotion classes={self.emotion_classifier.out_features}, cause "
+                f"logits={self.cause_classifier.out_features}, pair logits={self.pair_classifier.out_features})")
+        return True
 
     def _mask(self, n, k, device):
         """Scaled dropout mask with the RNG consumption of `self.dropout(x)` on a contiguous [n, k] tensor (the
@@ -248,15 +256,11 @@ class _DrlClassifierBase(nn.Module):
         return (o.ec_mul_loss_weight, o.ec_mul_loss_weight, o.pair_mul_loss_weight)
 
     def _heads(self, z, emotion_labels, cause_labels, pair_labels, masks=None):
-        """w_e emo_mul_loss + w_c cau_mul_loss + w_p pair_mul_loss: fused kernels when the shapes fit, the reference's
-        per-head methods otherwise.  `masks` = pre-drawn (m_e, m_c, m_p) if the caller had to interleave other
+        """w_e emo_mul_loss + w_c cau_mul_loss + w_p pair_mul_loss through carel_heads_fwd/bwd.  `masks` = pre-drawn (m_e, m_c, m_p) if the caller had to interleave other
         dropout draws (GAN); otherwise they are drawn here in the reference order emotion, cause, pair."""
         w = self._head_weights()
         L = self.opt.ec_dim
-        if not self._fused_heads_ok():
-            return (w[0] * self.get_emotion_mul_loss(z[:, :L], emotion_labels) +
-                    w[1] * self.get_cause_mul_loss(z[:, L:], cause_labels) +
-                    w[2] * self.get_pair_mul_loss(z, pair_labels))
+        self._fused_heads_ok()
         if masks is None:
             n = z.shape[0]
             masks = (self._mask(n, L, z.device), self._mask(n, L, z.device), self._mask(n, 2 * L, z.device))
@@ -373,9 +377,7 @@ class DrlClassifierVI(_DrlClassifierBase):
 
     def get_ec_aprx_loss(self, e_embedding, c_embedding):
         ec_mu, ec_log_var = self.get_ec_emb(c_embedding.detach())
-        if e_embedding.is_cuda:
-            return F.club_aprx_loss(ec_mu, ec_log_var, e_embedding)
-        return -((-(ec_mu - e_embedding) ** 2 / ec_log_var.exp() - ec_log_var).sum(dim=1).mean(dim=0))
+        return F.club_aprx_loss(ec_mu, ec_log_var, e_embedding)          # raises on non-CUDA tensors: no CPU path
 
     # ---- CLUB negative sampling ---------------------------------------------------------------
     def _negative_slots(self, n):
@@ -412,13 +414,9 @@ class DrlClassifierVI(_DrlClassifierBase):
 
     def get_ec_upper_loss(self, e_embedding, c_embedding):
         ec_mu, ec_log_var = self.get_ec_emb(c_embedding)
-        if e_embedding.is_cuda:
-            random_index = self._negative_index(e_embedding.shape[0], e_embedding.device)
-            return F.club_upper_bound(ec_mu, ec_log_var, e_embedding, random_index)
-        random_index = torch.randperm(e_embedding.shape[0]).long()          # CPU generator, as the reference
-        positive = -(ec_mu - e_embedding) ** 2 / ec_log_var.exp()
-        negative = -(ec_mu - e_embedding[random_index]) ** 2 / ec_log_var.exp()
-        return (positive.sum(dim=-1) - negative.sum(dim=-1)).mean() / 2.0
+        F._require_cuda(e_embedding)                                      # no CPU path
+        random_index = self._negative_index(e_embedding.shape[0], e_embedding.device)   # CPU generator, as the reference
+        return F.club_upper_bound(ec_mu, ec_log_var, e_embedding, random_index)
 
     def forward(self, input_ids, att_masks, token_type_ids, emotion_labels, cause_labels, pair_labels, content_bow,
                 iteration):
@@ -465,25 +463,18 @@ class DrlClassifierGAN(_DrlClassifierBase):
         z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
         z_e, z_c = z[:, :L], z[:, L:]
         # dropout draws in the reference's order: ec_disc, emotion head, ce_disc, cause head, pair head
-        n, fused = z.shape[0], self._fused_heads_ok()
+        n = z.shape[0]
+        self._fused_heads_ok()
         ec_disc_preds = self.get_ec_disc_preds(z_c)
         ec_disc_loss = self.get_ec_disc_loss(ec_disc_preds, emotion_labels)
         ec_entropy_loss = self.get_entropy_loss(ec_disc_preds)
-        if fused:
-            m_e = self._mask(n, L, z.device)
-        else:
-            emo_mul_loss = self.get_emotion_mul_loss(z_e, emotion_labels)
+        m_e = self._mask(n, L, z.device)
         ce_disc_preds = self.get_ce_disc_preds(z_e)
         ce_disc_loss = self.get_ec_disc_loss(ce_disc_preds, cause_labels)
         ce_entropy_loss = self.get_entropy_loss(ce_disc_preds)
-        if fused:
-            m_c = self._mask(n, L, z.device)
-            m_p = self._mask(n, 2 * L, z.device)
-            heads = self._heads(z, emotion_labels, cause_labels, pair_labels, masks=(m_e, m_c, m_p))
-        else:
-            cau_mul_loss = self.get_cause_mul_loss(z_c, cause_labels)
-            pair_mul_loss = self.get_pair_mul_loss(z, pair_labels)
-            heads = o.ec_mul_loss_weight * (emo_mul_loss + cau_mul_loss) + o.pair_mul_loss_weight * pair_mul_loss
+        m_c = self._mask(n, L, z.device)
+        m_p = self._mask(n, 2 * L, z.device)
+        heads = self._heads(z, emotion_labels, cause_labels, pair_labels, masks=(m_e, m_c, m_p))
         reconstruction_loss = self._reconstruction(z, content_bow)
         loss = self._assemble([(ec_entropy_loss + ce_entropy_loss, float(o.ecce_adv_loss_weight)), (heads, 1.0)],
                               kl, iteration, reconstruction_loss)

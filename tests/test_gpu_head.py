@@ -88,8 +88,10 @@ def test_forward_backward_matches_oracle(variant, N, L, V, D, dropout):
 
 @pytest.mark.parametrize("variant", ["mmd", "hsic", "vi", "gan"])
 def test_golden_reference_head(golden_dir, variant):
-    """The reference's own outputs (fp32, parameters not bf16-representable): bf16 operand rounding is
-    the whole error budget here."""
+    """bf16 tier against the reference's own outputs (fp32; inputs and parameters NOT bf16-representable, so the 2^-9
+    rounding of the 768-wide projection operands is the whole error budget here: ~3e-3 on the latent codes).  The
+    same golden vectors are met at 1e-5, gradients and dropout cases included, by the fp32 tier:
+    tests/test_gpu_fp32.py::test_golden_reference_head_fp32."""
     for c in [c for c in torch.load(golden_dir / "head.pt") if c["variant"] == variant]:
         opt = cv.default_opt(variant, ec_dim=c["L"], pair_bow_dim=c["V"], bert_dim=c["D"], dropout=c["dropout"])
         model = cv.VARIANTS[variant](opt, encoder=cv.IdentityEncoder())
@@ -168,29 +170,36 @@ def test_train_steps_reduce_loss():
     assert not any(p is q for p in model.get_params() for q in model.emotion_mu.parameters())  # ... but are not stepped
 
 
-def test_full_size_mmd_head_step_matches_oracle():
-    """BASELINE configs[1] at its real size (N = 8192 clauses, d = 768, latent 128, vocab 30000, dropout off):
-    loss and gradients of one forward/backward against the fp64 oracle."""
-    variant, N, L, V, D = "mmd", 8192, 128, 30000, 768
+@pytest.mark.parametrize("variant", ["mmd", "hsic", "vi", "gan"])
+def test_full_size_head_step_matches_oracle(variant):
+    """BASELINE configs[1] (MMD), [2] (HSIC), [3] (VI) and the GAN trainer at their real size (N = 8192 clauses, d = 768,
+    latent 128, vocab 30000, dropout off): every output and every gradient of one forward/backward against the fp64
+    oracle, bf16 tier, north_star tolerance 1e-3."""
+    N, L, V, D = 8192, 128, 30000, 768
     opt, model, b = _setup(variant, N, L, V, D, 0.0, seed=5)
     model.train()
     X = b["X"].clone().requires_grad_(True)
+    emo = b["emo"] if variant in ("mmd", "vi") else b["emo"].float()
     torch.manual_seed(99)
-    loss = model(X, None, None, b["emo"], b["cau"], b["pair"], b["bow"], 3)
+    outs, total = _total(variant, model(X, None, None, emo, b["cau"], b["pair"], b["bow"], 3))
     params = dict(model.named_parameters())
-    grads = torch.autograd.grad(loss, [X] + list(params.values()), allow_unused=True)
+    grads = torch.autograd.grad(total, [X] + list(params.values()), allow_unused=True)
     p64 = {k: v.detach().double().requires_grad_(True) for k, v in params.items()}
     X64 = b["X"].double().requires_grad_(True)
     torch.manual_seed(99)
-    ref = ho.HeadOracle(opt, variant).forward(p64, X64, b["emo"], b["cau"].double(), b["pair"].double(),
-                                              b["bow"].double(), 3)
-    rgrads = torch.autograd.grad(ref, [X64] + list(p64.values()), allow_unused=True)
-    assert rel(loss.detach(), ref.detach()) < 1e-4
+    emo64 = emo if emo.dtype == torch.int64 else emo.double()
+    orefs, rtotal = _total(variant, ho.HeadOracle(opt, variant).forward(p64, X64, emo64, b["cau"].double(), b["pair"].double(),
+                                                                        b["bow"].double(), 3))
+    rgrads = torch.autograd.grad(rtotal, [X64] + list(p64.values()), allow_unused=True)
+    for o, r in zip(outs, orefs):
+        assert rel(o.detach(), r.detach()) < 1e-4, (variant, "output", rel(o.detach(), r.detach()))
     assert rel(grads[0], rgrads[0]) < 1e-3, ("grad X", rel(grads[0], rgrads[0]))
     for (k, g), r in zip(zip(params.keys(), grads[1:]), rgrads[1:]):
         if r is None:
             continue
-        assert rel(g, r) < 1e-3, (k, rel(g, r))
+        assert rel(g, r) < 1e-3, (variant, k, rel(g, r))
+    del p64, X64, orefs, rtotal, rgrads
+    torch.cuda.empty_cache()
 
 
 def test_weighted_sum_is_bit_identical_to_the_scalar_chain():
