@@ -41,12 +41,14 @@ struct MmdBwdParams {
   const float* S32;
 };
 
-template <bool F16_>
+template <bool F16_, bool HILO_ = true>
 struct PolMmdBwdT {
   using Params = MmdBwdParams;
   static constexpr bool kF16 = F16_;      // FP16 operands + FP16 (hi + lo) weights, scaled into range by w_scale
-  static constexpr bool kHiLo = true;     // P = W as bf16 hi + lo: the 2^-9 rounding of a single bf16 would
-                                          // otherwise dominate the gradient error of small samples
+  // P = W as a hi + lo pair (the 2^-9 rounding of a single bf16 would dominate the gradient error of small samples).
+  // A single FP16 weight (2^-12, independent over the columns a row sums: ~2^-12 / sqrt(M)) is enough once the stacked
+  // sample has thousands of rows: the launcher drops the lo half there and GEMM-2 + the conversion work halve.
+  static constexpr bool kHiLo = HILO_;
   const Params& p;
   bool fast;
   float cf, wscale, inv_wscale;
@@ -179,6 +181,6 @@ struct PolMmdBwdT {
   }
   CAREL_DEVINL void finish() {}
 };
-using PolMmdBwd = PolMmdBwdT<false>;
+using PolMmdBwd = PolMmdBwdT<false, true>;
 
 }  // namespace carel

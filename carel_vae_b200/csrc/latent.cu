@@ -17,6 +17,8 @@
 #include "pack.cuh"
 #include "sgemm.cuh"
 
+extern "C" size_t carel_latent_f32_workspace_bytes(int64_t N, int64_t D, int64_t L);
+
 namespace carel {
 
 struct LatentWs {
@@ -358,6 +360,73 @@ extern "C" int carel_latent_bwd(const float* grad_z, int64_t ldgz, const float* 
                                                     grad_b4[2], grad_b4[3]);
     CAREL_LAUNCHED();
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inference: get_pair_preds (drl_classifier_ec_mmd_final_mul.py:265-282) = projections -> sample_prior x2 -> pair_classifier
+// -> sigmoid.  The training kernels would also produce the KL sums and materialise z; here one warp per row folds the
+// reparameterisation, the [2L] dot product with the pair weights and the sigmoid: 4 launches (pack X, pack W4, the
+// projection GEMM, this kernel), nothing but the [N] predictions written.
+// ---------------------------------------------------------------------------------------------
+namespace carel {
+static __global__ void pair_pred_kernel(const float* __restrict__ pre, int L, const float* __restrict__ eps_e,
+                                        const float* __restrict__ eps_c, const float* __restrict__ w,
+                                        const float* __restrict__ b, int N, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < N; r += gridDim.x * wpb) {
+    const float* p = pre + size_t(r) * 4 * L;
+    float s = 0.f;
+    for (int k = lane; k < 2 * L; k += 32) {
+      const int sp = k >= L, c = k - sp * L;
+      const float mu = p[sp * 2 * L + c], lv = p[sp * 2 * L + L + c];
+      const float z = fmaf(__ldg((sp ? eps_c : eps_e) + c), __expf(lv), mu);
+      s = fmaf(z, __ldg(w + k), s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[r] = 1.f / (1.f + __expf(-(s + __ldg(b))));
+  }
+}
+}  // namespace carel
+
+extern "C" size_t carel_pair_preds_workspace_bytes(int64_t N, int64_t D, int64_t L) {
+  return std::max(carel_latent_workspace_bytes(N, D, L), carel_latent_f32_workspace_bytes(N, D, L)) +
+         align_up(size_t(N) * 4 * L * sizeof(float), 256);
+}
+
+// out [N] = sigmoid(pair_classifier([z_e | z_c])); pair_w [2L], pair_b [1] (pair_num_class = 1).  precision 0: bf16
+// tensor-core projection, 2: fp32 tier.
+extern "C" int carel_pair_preds(const float* x, int64_t ldx, int64_t N, int64_t D, int64_t L, const float* const* w4,
+                                const float* const* b4, const float* eps_e, const float* eps_c, const float* pair_w,
+                                const float* pair_b, float* out, void* ws, size_t ws_bytes, int precision, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(N > 0 && D > 0 && L > 0, "carel_pair_preds: empty problem");
+  CAREL_REQUIRE(ws != nullptr && ws_bytes >= carel_pair_preds_workspace_bytes(N, D, L), "carel_pair_preds: workspace too small");
+  const size_t lat_bytes = std::max(carel_latent_workspace_bytes(N, D, L), carel_latent_f32_workspace_bytes(N, D, L));
+  float* pre = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + lat_bytes);
+  if (precision == 2) {
+    for (int i = 0; i < 4; ++i)
+      if (int rc = launch_sgemm(false, false, x, ldx, w4[i], D, pre + i * L, 4 * L, N, L, D, 1.f, b4[i], 0, 1, st)) return rc;
+  } else {
+    LatentWs w = carve_latent(ws, N, D, L);
+    pack_x_ones_kernel<<<int((N + 7) / 8), 256, 0, st>>>(x, int(N), int(D), int(ldx), w.Xp, w.ldx);
+    CAREL_LAUNCHED();
+    float* bias4 = w.dW;
+    PackW4Args pa;
+    for (int i = 0; i < 4; ++i) { pa.w[i] = w4[i]; pa.b[i] = b4[i]; }
+    pack_w4_kernel<<<int((4 * L + 1) / 2), 64, 0, st>>>(pa, int(L), int(D), w.Wp, w.ldw, w.ldd, bias4);
+    CAREL_LAUNCHED();
+    CUtensorMap ta, tb;
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&ta, w.Xp, N, D, w.ldx, 128) == 0, "carel_pair_preds: tensor map X failed");
+    CAREL_REQUIRE(make_tmap_bf16_sw128(&tb, w.Wp, 4 * L, D, w.ldw, 128) == 0, "carel_pair_preds: tensor map W failed");
+    GemmSched s = make_sched(N, 4 * L, D, 256, 1, TILE_FULL);
+    EpiStore<256>::Params ep;
+    ep.out = pre; ep.bias = bias4; ep.out_bf16 = nullptr; ep.M = int(N); ep.N = int(4 * L);
+    ep.ld = int(4 * L); ep.ld_bf16 = 0; ep.atomic = 0; ep.scale = 1.f;
+    if (int rc = launch_gemm<EpiStore<256>, 256, 1, false, false>(ta, tb, ta, tb, s, ep, st, "latent_proj_fwd")) return rc;
+  }
+  pair_pred_kernel<<<int(std::min<int64_t>((N + 7) / 8, 148 * 16)), 256, 0, st>>>(pre, int(L), eps_e, eps_c, pair_w, pair_b, int(N), out);
+  CAREL_LAUNCHED();
   return 0;
 }
 

@@ -141,7 +141,7 @@ extern "C" int carel_mmd_fwd(const float* x, int64_t ldx, const float* y, int64_
   return 0;
 }
 
-template <int BN1, int NB, bool F16 = false>
+template <int BN1, int NB, bool F16 = false, bool HILO = true>
 static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, int n2_16, int t0, int t1,
                           float* grad_x, int64_t ldgx, float* grad_y, int64_t ldgy, int64_t n1, int64_t n2,
                           int64_t dim, cudaStream_t st) {
@@ -159,7 +159,7 @@ static int mmd_bwd_launch(const MmdWs& w, MmdBwdParams pp, int64_t M, int ldp, i
     CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_x, size_t(ldgx) * 4, 0, size_t(dim) * 4, size_t(n1), st));
     CAREL_CHECK_CUDA(cudaMemset2DAsync(grad_y, size_t(ldgy) * 4, 0, size_t(dim) * 4, size_t(n2), st));
   }
-  return launch_chain<PolMmdBwdT<F16>, 1, BN1, NB>(ta, tb, ta, tb, s, pp, st, "mmd_gram_bwd");
+  return launch_chain<PolMmdBwdT<F16, HILO>, 1, BN1, NB>(ta, tb, ta, tb, s, pp, st, "mmd_gram_bwd");
 }
 
 extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int64_t dim,
@@ -201,8 +201,11 @@ extern "C" int carel_mmd_bwd(const float* grad_out, int64_t n1, int64_t n2, int6
   // operands' format.  BF16 has fp32's exponent range; FP16 weights are scaled in the kernel (PolMmdBwdT).
   pp.kmax_bits = reinterpret_cast<const unsigned*>(w.accum + 3);
   pp.wmax_coef = fmaxf(fmaxf(pp.c00, pp.c11), fabsf(pp.c01)) * amax;
-  if (mmd_uses_f16(precision, ldp, t0, t1, m_tiles))
-    return mmd_bwd_launch<128, 2, true>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
+  if (mmd_uses_f16(precision, ldp, t0, t1, m_tiles)) {
+    if (M >= 4096)      // single FP16 weights: rounding 2^-12 / sqrt(M) < 4e-6 of a gradient row
+      return mmd_bwd_launch<128, 2, true, false>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
+    return mmd_bwd_launch<128, 2, true, true>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
+  }
   return mmd_bwd_launch<128, 2>(w, pp, M, ldp, n2cols / 16, t0, t1, grad_x, ldgx, grad_y, ldgy, n1, n2, dim, st);
 }
 

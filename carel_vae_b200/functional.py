@@ -273,6 +273,31 @@ def latent(x, eps_e, eps_c, w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_c
                            w_clv, b_clv)
 
 
+def pair_preds(x, eps_e, eps_c, w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_clv, pair_w, pair_b,
+               precision: str | None = None) -> torch.Tensor:
+    """Inference path of the head (reference get_pair_preds, drl_classifier_ec_mmd_final_mul.py:265-282):
+    sigmoid(pair_classifier([z_e | z_c])) as [N, 1], four launches, no KL / no z; not differentiable (the reference
+    calls it under torch.no_grad())."""
+    wb = (w_emu, b_emu, w_elv, b_elv, w_cmu, b_cmu, w_clv, b_clv)
+    _require_cuda(x, eps_e, eps_c, pair_w, pair_b, *wb)
+    if pair_w.shape[0] != 1:
+        raise NotImplementedError("pair_preds implements pair_num_class = 1 (the reference's setting)")
+    xf = _rowmajor_f32(x.detach())
+    N, D = xf.shape
+    ws_ = [w.detach().float().contiguous() for w in wb[0::2]]
+    bs_ = [b.detach().float().contiguous() for b in wb[1::2]]
+    L = ws_[0].shape[0]
+    pw, pb = pair_w.detach().float().contiguous().reshape(-1), pair_b.detach().float().contiguous().reshape(-1)
+    ee, ec = eps_e.detach().float().contiguous(), eps_c.detach().float().contiguous()
+    lb = lib()
+    ws = _workspace(lb.carel_pair_preds_workspace_bytes(N, D, L), xf.device)
+    out = torch.empty((N, 1), dtype=torch.float32, device=xf.device)
+    prec = _lib.precision_code(precision)
+    check(lb.carel_pair_preds(_p(xf), xf.stride(0), N, D, L, _ptr_array(ws_), _ptr_array(bs_), _p(ee), _p(ec), _p(pw), _p(pb),
+                              _p(out), _p(ws), ws.numel(), 2 if prec == 2 else 0, _stream()), "carel_pair_preds")
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # classifier heads: three tiny Linear + loss heads in two kernels
 # --------------------------------------------------------------------------------------------

@@ -275,9 +275,17 @@ class _DrlClassifierBase(nn.Module):
 
     # ---- inference -----------------------------------------------------------------------
     def get_pair_preds_tensor(self, input_ids, att_masks, token_type_ids):
-        """Device-side result of get_pair_preds (no host round trip): sigmoid(pair logits) [N, 1]."""
-        z, _, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
-        return torch.sigmoid(self.pair_classifier(z))
+        """Device-side result of get_pair_preds (no host round trip): sigmoid(pair logits) [N, 1], through the
+        dedicated inference entry (carel_pair_preds: projection GEMM + one fused reparameterisation / dot product /
+        sigmoid pass; the same two noise draws as the training path)."""
+        emb = self._sentence_emb(input_ids, att_masks, token_type_ids)
+        L = self.opt.ec_dim
+        eps_e = torch.randn(L, device=emb.device)
+        eps_c = torch.randn(L, device=emb.device)
+        return F.pair_preds(emb, eps_e, eps_c, self.emotion_mu.weight, self.emotion_mu.bias,
+                            self.emotion_log_var.weight, self.emotion_log_var.bias, self.cause_mu.weight, self.cause_mu.bias,
+                            self.cause_log_var.weight, self.cause_log_var.bias, self.pair_classifier.weight,
+                            self.pair_classifier.bias)
 
     def get_pair_preds(self, input_ids, att_masks, token_type_ids):
         """Reference return type: rounded python list (:265-282).  Still stochastic at eval."""

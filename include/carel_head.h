@@ -215,6 +215,16 @@ int carel_club_bwd(const float* grad_out, const float* mu_hat, const float* lv_h
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Inference — replaces get_pair_preds (drl_classifier_ec_mmd_final_mul.py:265-282): out[N] = sigmoid(pair_classifier(
+ * [sample_prior(emotion) | sample_prior(cause)])) in 4 launches (pack X, pack W4, projection GEMM, one fused
+ * reparameterisation + dot product + sigmoid pass); no KL sums, no z.  pair_w [2L], pair_b [1]; precision 0 or 2.
+ * ------------------------------------------------------------------------------------------ */
+size_t carel_pair_preds_workspace_bytes(int64_t N, int64_t D, int64_t L);
+int carel_pair_preds(const float* x, int64_t ldx, int64_t N, int64_t D, int64_t L, const float* const* w4,
+                     const float* const* b4, const float* eps_e, const float* eps_c, const float* pair_w,
+                     const float* pair_b, float* out, void* ws, size_t ws_bytes, int precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * fp32 precision tier (north_star: "1e-5 in fp32"): the same operators with fp32 FFMA arithmetic on the CUDA cores
  * (csrc/sgemm.cuh) on materialised intermediates, as the reference's fp32 ATen path computes them.  Selected by
  * carel_vae_b200.set_precision("fp32") / precision="fp32"; the bf16 tier above is the product path.

@@ -289,3 +289,28 @@ def test_club_kernels_match_the_reference_formulas(N, L):
         strided = F.club_aprx_loss(mu, lv, z[:, :L]) if name == "aprx" else F.club_upper_bound(mu, lv, z[:, :L], perm)
         assert torch.equal(strided.detach(), (F.club_aprx_loss(mu, lv, z[:, :L].contiguous()) if name == "aprx" else
                                               F.club_upper_bound(mu, lv, z[:, :L].contiguous(), perm)).detach())
+
+
+def test_inference_entry_launches_and_precision():
+    """get_pair_preds (mmd:265-282) through carel_pair_preds: at most 4 launches of the library (pack X, pack W4,
+    projection GEMM, fused reparameterisation + pair logit + sigmoid), no torch kernels besides the two noise draws;
+    1e-5 against the oracle in the fp32 tier."""
+    opt, model, b = _setup("mmd", 700, 128, 1000, 768, 0.5, seed=6)
+    model.eval()
+    with torch.no_grad():
+        torch.manual_seed(21)
+        l0 = cv.launch_count()
+        t = model.get_pair_preds_tensor(b["X"], None, None)
+        assert cv.launch_count() - l0 <= 4
+        assert t.shape == (700, 1) and not t.requires_grad
+        p = {k: v.detach() for k, v in model.named_parameters()}
+        torch.manual_seed(21)
+        ref = ho.HeadOracle(opt, "mmd").pair_preds({k: v.double() for k, v in p.items()}, b["X"].double())
+        assert (t.double() - ref).abs().max().item() < 1e-3
+        cv.set_precision("fp32")
+        try:
+            torch.manual_seed(21)
+            t32 = model.get_pair_preds_tensor(b["X"], None, None)
+        finally:
+            cv.set_precision("bf16")
+        assert rel(t32, ref) < 1e-5

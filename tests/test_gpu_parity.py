@@ -112,7 +112,11 @@ def test_mmd_full_size_properties():
     gx, gy = torch.autograd.grad(out, (x, y))
     ref, rgx, rgy = ho.mmd_blocked(x.detach().double(), y.detach().double(), [0.1], block=2048)
     assert relv(out, ref) < 1e-4
-    assert rel(gx, rgx) < 1e-4 and rel(gy, rgy) < 1e-4
+    # north_star tolerance of the bf16 tier: 1e-3.  At M >= 4096 rows the backward carries its weight tile as ONE fp16
+    # value per element (2^-12); in this regime (d2 ~ 340, K ~ e^-34) a gradient row is dominated by a handful of
+    # nearest neighbours, so the rounding does not average out: measured 1.4e-4 (1e-5 with the hi + lo pair used
+    # below 4096 rows, where accuracy is free).
+    assert rel(gx, rgx) < 3e-4 and rel(gy, rgy) < 3e-4
     assert relv(F.mmd(x, y, [0.1], full_gram=True), out) < 1e-5          # triangular schedule == full Gram
     assert relv(F.mmd(y, x, [0.1]), out) < 1e-5                           # MMD(x, y) == MMD(y, x)
     same = F.mmd(x.detach(), x.detach(), [0.1])
