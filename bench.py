@@ -304,12 +304,18 @@ class HeadStep:
                 o.step()
         return [(seg0, "all"), (seg1, None)]
 
-    def _reduce(self, which):
+    def _reduce(self, which, snaps=None):
         if self.reducers is None or which is None:
             return
         for k, r in enumerate(self.reducers):
             if which == "all" or which == k:
-                r.reduce()
+                r.reduce(None if snaps is None else snaps[k])
+
+    def _snapshot(self, which):
+        """The gradient tensors a reduction point must all-reduce on every replay (see GradReducer.snapshot)."""
+        if self.reducers is None or which is None:
+            return None
+        return {k: r.snapshot() for k, r in enumerate(self.reducers) if which == "all" or which == k}
 
     def eager_step(self):
         for fn, red in self.segments:
@@ -325,7 +331,7 @@ class HeadStep:
                 with torch.cuda.graph(g, stream=s):
                     for fn, _ in self.segments:
                         fn()
-                graphs.append((g, None))
+                graphs.append((g, None, None))
             else:
                 pool = None
                 for fn, red in self.segments:
@@ -333,9 +339,10 @@ class HeadStep:
                     with torch.cuda.graph(g, pool=pool, stream=s):
                         fn()
                     pool = g.pool()
-                    graphs.append((g, red))
+                    snaps = self._snapshot(red)
+                    graphs.append((g, red, snaps))
                     with torch.cuda.stream(s):          # the collective between two segments, as in run()
-                        self._reduce(red)
+                        self._reduce(red, snaps)
             torch.cuda.synchronize()
             self.graphs = graphs
         except Exception as e:  # noqa: BLE001
@@ -349,9 +356,9 @@ class HeadStep:
         if self.graphs is None:
             self.eager_step()
             return
-        for g, red in self.graphs:
+        for g, red, snaps in self.graphs:
             g.replay()
-            self._reduce(red)
+            self._reduce(red, snaps)
 
 
 def run_head(args):

@@ -234,7 +234,16 @@ static __global__ void bow_pack_f16_kernel(const float* __restrict__ src, int ro
       }
     }
   }
-  if (wsum == nullptr && lane == 0 && wmax2 > 0.f) atomicMax(rmax_bits, __float_as_uint(sqrtf(wmax2) * 1.0001f));
+  if (wsum == nullptr) {      // one atomic per BLOCK (30000 per-warp atomics on one address serialise to ~30 us)
+    __shared__ float sh_max[32];
+    if (lane == 0) sh_max[threadIdx.x >> 5] = wmax2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int i = 0; i < wpb; ++i) m = fmaxf(m, sh_max[i]);
+      if (m > 0.f) atomicMax(rmax_bits, __float_as_uint(sqrtf(m) * 1.0001f));
+    }
+  }
 }
 
 // Column sums of the packed decoder operand WH [V, ldk] (fp16 -> fp32: sum_j z_i.w_j = ZH_i . wsum), wsum[ldk] =
@@ -994,7 +1003,7 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.lossacc, 0, 2 * sizeof(double), st));
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.counters, 0, 4 * sizeof(int), st));
   unsigned* rmax_bits = reinterpret_cast<unsigned*>(w.wsum + w.ldk + 1);
-  bow_pack_f16_kernel<<<int(std::min<int64_t>((V + 7) / 8, sms * 32)), 256, 0, st>>>(dec_w, int(V), int(K), K, w.WH, w.ldk,
+  bow_pack_f16_kernel<<<int(std::min<int64_t>((V + 7) / 8, sms * 8)), 256, 0, st>>>(dec_w, int(V), int(K), K, w.WH, w.ldk,
                                                                                    nullptr, 0.f, nullptr, nullptr, nullptr, rmax_bits);
   CAREL_LAUNCHED();
   {

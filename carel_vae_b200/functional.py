@@ -368,6 +368,55 @@ def classifier_heads(z, masks, emotion_classifier, cause_classifier, pair_classi
 
 
 # --------------------------------------------------------------------------------------------
+# GAN discriminators: both adversaries, their BCE losses and the entropy terms in one kernel
+# --------------------------------------------------------------------------------------------
+class _DiscFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, m_ec, m_ce, w_ec, b_ec, w_ce, b_ce, y_emo, y_cau, cfg):
+        ls, n_class, eps = cfg
+        _require_cuda(z, w_ec, w_ce)
+        if w_ec.shape[0] != 1 or w_ce.shape[0] != 1:
+            raise NotImplementedError("the discriminator kernels implement ec_num_class = 1 (the reference's setting)")
+        zf = _rowmajor_f32(z.detach())
+        N, twoL = zf.shape
+        L = twoL // 2
+        masks = [None if m is None else m.detach().float().contiguous() for m in (m_ec, m_ce)]
+        params = [t.detach().float().contiguous() for t in (w_ec, b_ec, w_ce, b_ce)]
+        ye, yc = y_emo.reshape(-1).float().contiguous(), y_cau.reshape(-1).float().contiguous()
+        lb = lib()
+        ws = _workspace(lb.carel_disc_workspace_bytes(N), zf.device)
+        out = torch.empty(3, dtype=torch.float32, device=zf.device)
+        check(lb.carel_disc_fwd(_p(zf), zf.stride(0), N, L, _ptr_array(masks), _ptr_array(params), _p(ye), _p(yc), float(ls),
+                                float(n_class), float(eps), _p(out), _p(ws), ws.numel(), _stream()), "carel_disc_fwd")
+        ctx.keep = (zf, masks, params, ye, yc, ws)
+        ctx.meta = (N, L, float(ls), float(n_class), float(eps), [t.dtype for t in (w_ec, b_ec, w_ce, b_ce)],
+                    [tuple(t.shape) for t in (w_ec, b_ec, w_ce, b_ce)])
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_ec, g_ce, g_ent):
+        zf, masks, params, ye, yc, ws = ctx.keep
+        N, L, ls, n_class, eps, dts, shapes = ctx.meta
+        gs = [None if g is None else g.reshape(()).float().contiguous() for g in (g_ec, g_ce, g_ent)]
+        flat = torch.empty(2 * L + 2, dtype=torch.float32, device=zf.device)
+        grads = [flat[:L], flat[L:L + 1], flat[L + 1:2 * L + 1], flat[2 * L + 1:]]
+        check(lib().carel_disc_bwd(_ptr_array(gs), _p(zf), zf.stride(0), N, L, _ptr_array(masks), _ptr_array(params), _p(ye),
+                                   _p(yc), ls, n_class, eps, _ptr_array(grads), _p(ws), ws.numel(), _stream()), "carel_disc_bwd")
+        need = ctx.needs_input_grad
+        outs = [g.reshape(shape).to(dt) if need[3 + i] else None for i, (g, shape, dt) in enumerate(zip(grads, shapes, dts))]
+        return (None, None, None, *outs, None, None, None)
+
+
+def gan_discriminators(z, m_ec, m_ce, ec_disc, ce_disc, emotion_labels, cause_labels, label_smoothing: float,
+                       n_class: float, eps: float):
+    """The adversarial branch of the GAN trainer (drl_classifier_ec_gan.py:222-233, :430-477) on the DETACHED latents:
+    returns (ec_disc_loss, ce_disc_loss, ec_entropy + ce_entropy), differentiable w.r.t. the two discriminators'
+    parameters only (z carries no gradient here, as in the reference).  m_ec / m_ce: scaled dropout masks [N, L] or None."""
+    return _DiscFn.apply(z, m_ec, m_ce, ec_disc.weight, ec_disc.bias, ce_disc.weight, ce_disc.bias, emotion_labels,
+                         cause_labels, (label_smoothing, n_class, eps))
+
+
+# --------------------------------------------------------------------------------------------
 # loss assembly: one launch for the weighted sum of the loss terms
 # --------------------------------------------------------------------------------------------
 class _WeightedSumFn(torch.autograd.Function):

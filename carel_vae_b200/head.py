@@ -444,7 +444,8 @@ class DrlClassifierVI(_DrlClassifierBase):
 
 
 class DrlClassifierGAN(_DrlClassifierBase):
-    """drl_classifier_ec_gan.py: adversarial discriminators on the detached latents + entropy terms."""
+    """drl_classifier_ec_gan.py: adversarial discriminators on the detached latents + entropy terms (forward() runs them
+    through carel_disc_fwd/bwd; the get_*_disc_* methods keep the reference's PyTorch form for outside callers)."""
     variant = "gan"
 
     def _build_variant_modules(self, opt):
@@ -470,22 +471,20 @@ class DrlClassifierGAN(_DrlClassifierBase):
         o, L = self.opt, self.opt.ec_dim
         z, kl, _ = self._latents(self._sentence_emb(input_ids, att_masks, token_type_ids))
         z_e, z_c = z[:, :L], z[:, L:]
-        # dropout draws in the reference's order: ec_disc, emotion head, ce_disc, cause head, pair head
         n = z.shape[0]
         self._fused_heads_ok()
-        ec_disc_preds = self.get_ec_disc_preds(z_c)
-        ec_disc_loss = self.get_ec_disc_loss(ec_disc_preds, emotion_labels)
-        ec_entropy_loss = self.get_entropy_loss(ec_disc_preds)
+        # dropout draws in the reference's order: ec_disc, emotion head, ce_disc, cause head, pair head
+        m_ec = self._mask(n, L, z.device)
         m_e = self._mask(n, L, z.device)
-        ce_disc_preds = self.get_ce_disc_preds(z_e)
-        ce_disc_loss = self.get_ec_disc_loss(ce_disc_preds, cause_labels)
-        ce_entropy_loss = self.get_entropy_loss(ce_disc_preds)
+        m_ce = self._mask(n, L, z.device)
         m_c = self._mask(n, L, z.device)
         m_p = self._mask(n, 2 * L, z.device)
+        # both discriminators, their BCE losses and the entropy terms: one kernel (carel_disc_fwd)
+        ec_disc_loss, ce_disc_loss, entropy = F.gan_discriminators(z, m_ec, m_ce, self.ec_disc, self.ce_disc, emotion_labels,
+                                                                   cause_labels, o.label_smoothing, o.ec_num_class, o.epsilon)
         heads = self._heads(z, emotion_labels, cause_labels, pair_labels, masks=(m_e, m_c, m_p))
         reconstruction_loss = self._reconstruction(z, content_bow)
-        loss = self._assemble([(ec_entropy_loss + ce_entropy_loss, float(o.ecce_adv_loss_weight)), (heads, 1.0)],
-                              kl, iteration, reconstruction_loss)
+        loss = self._assemble([(entropy, float(o.ecce_adv_loss_weight)), (heads, 1.0)], kl, iteration, reconstruction_loss)
         return ec_disc_loss, ce_disc_loss, loss
 
     def get_params(self):

@@ -184,26 +184,37 @@ class GradReducer:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
-    def reduce(self) -> None:
+    def snapshot(self):
+        """The gradient tensors as they are NOW (one per parameter, None where there is none).  CUDA-graph users: a
+        replay writes into the tensors that existed at capture time, while `param.grad` keeps pointing at whatever
+        the LAST captured segment assigned — take a snapshot right after capturing the segment whose gradients are
+        to be reduced and hand it to `reduce()` on every replay."""
+        return [p.grad for p in self.params]
+
+    def reduce(self, grads=None) -> None:
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
+        if grads is None:
+            grads = self.snapshot()
+        gmap = {id(p): g for p, g in zip(self.params, grads)}
         avg = dist.ReduceOp.AVG if self.flat.is_cuda else dist.ReduceOp.SUM        # gloo (CPU tests) has no AVG
         scale = None if self.flat.is_cuda else 1.0 / dist.get_world_size(self.group)
         for p in self.big:
-            if p.grad is not None:
-                dist.all_reduce(p.grad, op=avg, group=self.group)
+            g = gmap[id(p)]
+            if g is not None:
+                dist.all_reduce(g, op=avg, group=self.group)
                 if scale is not None:
-                    p.grad.mul_(scale)
-        live = [(p, v) for p, v in zip(self.small, self.views) if p.grad is not None]
+                    g.mul_(scale)
+        live = [(gmap[id(p)], v) for p, v in zip(self.small, self.views) if gmap[id(p)] is not None]
         if not live:
             return
         if len(live) != len(self.small):
             self.flat.zero_()
-        torch._foreach_copy_([v for _, v in live], [p.grad for p, _ in live])
+        torch._foreach_copy_([v for _, v in live], [g for g, _ in live])
         dist.all_reduce(self.flat, op=avg, group=self.group)
         if scale is not None:
             self.flat.mul_(scale)
-        torch._foreach_copy_([p.grad for p, _ in live], [v for _, v in live])
+        torch._foreach_copy_([g for g, _ in live], [v for _, v in live])
 
 
 def identical_across_ranks(tensors: Iterable[torch.Tensor], group=None) -> bool:

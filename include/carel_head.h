@@ -215,6 +215,22 @@ int carel_club_bwd(const float* grad_out, const float* mu_hat, const float* lv_h
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * GAN discriminators — replace get_ec_disc_preds / get_ce_disc_preds / get_ec_disc_loss / get_entropy_loss
+ * (drl_classifier_ec_gan.py:430-477; call sites in forward :222-233), ec_num_class = 1:
+ *   p_ec = sigmoid(ec_disc(dropout(z_c.detach()))), p_ce = sigmoid(ce_disc(dropout(z_e.detach())))
+ *   out[3] = { BCELoss(p_ec, smooth(y_emo)), BCELoss(p_ce, smooth(y_cau)), mean p_ec log(p_ec + eps) + mean p_ce log(p_ce + eps) }
+ * masks[2] = {m_ec, m_ce}: scaled dropout masks [N, L] or NULL; params[4] = {ec_disc.weight [L], ec_disc.bias [1],
+ * ce_disc.weight [L], ce_disc.bias [1]}.  Backward: g[3] device scalars (NULL = 0) -> grads[4] of the four parameters.
+ * ------------------------------------------------------------------------------------------ */
+size_t carel_disc_workspace_bytes(int64_t N);
+int carel_disc_fwd(const float* z, int64_t ldz, int64_t N, int64_t L, const float* const* masks, const float* const* params,
+                   const float* y_emo, const float* y_cau, float label_smoothing, float n_class, float eps, float* out,
+                   void* ws, size_t ws_bytes, void* stream);
+int carel_disc_bwd(const float* const* g, const float* z, int64_t ldz, int64_t N, int64_t L, const float* const* masks,
+                   const float* const* params, const float* y_emo, const float* y_cau, float label_smoothing, float n_class,
+                   float eps, float* const* grads, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Inference — replaces get_pair_preds (drl_classifier_ec_mmd_final_mul.py:265-282): out[N] = sigmoid(pair_classifier(
  * [sample_prior(emotion) | sample_prior(cause)])) in 4 launches (pack X, pack W4, projection GEMM, one fused
  * reparameterisation + dot product + sigmoid pass); no KL sums, no z.  pair_w [2L], pair_b [1]; precision 0 or 2.

@@ -314,3 +314,40 @@ def test_inference_entry_launches_and_precision():
         finally:
             cv.set_precision("bf16")
         assert rel(t32, ref) < 1e-5
+
+
+@pytest.mark.parametrize("N,L,drop", [(1, 24, False), (300, 128, True), (8192, 128, True)])
+def test_gan_discriminator_kernels_match_the_reference_formulas(N, L, drop):
+    """carel_disc_fwd/bwd against the reference's PyTorch expressions in fp64 (gan:430-477, forward :222-233): the three
+    scalars and the parameter gradients for each of the trainer's three backward passes (gan:790-798), 1e-5."""
+    import torch.nn as nn
+    import torch.nn.functional as TF
+    from carel_vae_b200 import functional as F
+    torch.manual_seed(N + L)
+    z = torch.randn(N, 2 * L, device=DEV, requires_grad=True)
+    ec, ce = nn.Linear(L, 1).to(DEV), nn.Linear(L, 1).to(DEV)
+    y_e = torch.ones(N, 1, device=DEV)
+    y_c = (torch.rand(N, 1, device=DEV) < 0.5).float()
+    m1 = TF.dropout(torch.ones(N, L, device=DEV), 0.5, True) if drop else None
+    m2 = TF.dropout(torch.ones(N, L, device=DEV), 0.5, True) if drop else None
+    outs = F.gan_discriminators(z, m1, m2, ec, ce, y_e, y_c, 0.1, 1, 1e-8)
+    params = [ec.weight, ec.bias, ce.weight, ce.bias]
+    p64 = [p.detach().double().requires_grad_(True) for p in params]
+    zd = z.detach().double()
+    xc = zd[:, L:] * (m1.double() if drop else 1.0)
+    xe = zd[:, :L] * (m2.double() if drop else 1.0)
+    p_ec = torch.sigmoid(xc @ p64[0].T + p64[1])
+    p_ce = torch.sigmoid(xe @ p64[2].T + p64[3])
+    refs = (TF.binary_cross_entropy(p_ec, y_e.double() * 0.9 + 0.1), TF.binary_cross_entropy(p_ce, y_c.double() * 0.9 + 0.1),
+            (p_ec * torch.log(p_ec + 1e-8)).sum(1).mean() + (p_ce * torch.log(p_ce + 1e-8)).sum(1).mean())
+    for o, r in zip(outs, refs):
+        assert abs(float(o.detach()) - float(r)) <= 1e-5 * abs(float(r))
+    for k in range(3):
+        g = torch.autograd.grad(outs[k], params, retain_graph=True, allow_unused=True)
+        rg = torch.autograd.grad(refs[k], p64, retain_graph=True, allow_unused=True)
+        for a, b in zip(g, rg):
+            if b is None:
+                assert a is None or float(a.abs().max()) == 0.0
+            else:
+                assert (a.double() - b).norm().item() <= 1e-5 * b.norm().item() + 1e-12
+    assert z.grad is None          # the latents are detached in this branch, as in the reference
