@@ -63,6 +63,10 @@ _SIGNATURES = {
     "carel_hsic_finalize": (C.c_int, [i64, i64, i64, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "carel_hsic_bwd": (C.c_int, [c_ptr, i64, i64, i64, C.c_float, C.c_float, i64, i64, c_ptr, i64, c_ptr, i64, c_ptr,
                                  C.c_size_t, c_ptr]),
+    "carel_club_mlp_workspace_bytes": (C.c_size_t, [i64, i64]),
+    "carel_club_mlp_fwd": (C.c_int, [c_ptr, i64, i64, i64, C.POINTER(C.c_void_p), c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "carel_club_mlp_bwd": (C.c_int, [c_ptr, c_ptr, c_ptr, i64, c_ptr, i64, i64, C.POINTER(C.c_void_p), c_ptr, i64,
+                                     C.POINTER(C.c_void_p), c_ptr, C.c_size_t, c_ptr]),
     "carel_disc_workspace_bytes": (C.c_size_t, [i64]),
     "carel_disc_fwd": (C.c_int, [c_ptr, i64, i64, i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_ptr, c_ptr, C.c_float,
                                  C.c_float, C.c_float, c_ptr, c_ptr, C.c_size_t, c_ptr]),

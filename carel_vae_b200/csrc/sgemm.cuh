@@ -23,14 +23,12 @@ namespace carel {
 constexpr int kSgBM = 128, kSgBN = 128, kSgBK = 16, kSgPad = 4;
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256)
-sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ C,
-             int64_t ldc, int M, int N, int K, int k_chunk, float alpha, const float* __restrict__ bias, int mode) {
+__device__ __forceinline__ void sgemm_tile(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+                                           float* __restrict__ C, int64_t ldc, int M, int N, int m0, int n0, int k_begin,
+                                           int k_end, float alpha, const float* __restrict__ bias, int mode) {
   __shared__ __align__(16) float As[2][kSgBK][kSgBM + kSgPad];
   __shared__ __align__(16) float Bs[2][kSgBK][kSgBN + kSgPad];
   const int t = threadIdx.x;
-  const int m0 = blockIdx.y * kSgBM, n0 = blockIdx.x * kSgBN;
-  const int k_begin = blockIdx.z * k_chunk, k_end = min(K, k_begin + k_chunk);
   if (k_begin >= k_end) return;
   float ra[8], rb[8];
   // global -> registers: 8 elements of each operand tile per thread, consecutive threads along the contiguous dim
@@ -90,7 +88,7 @@ sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__
       buf ^= 1;
     }
   }
-  const bool add_bias = bias != nullptr && blockIdx.z == 0;
+  const bool add_bias = bias != nullptr;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -107,6 +105,41 @@ sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__
       else atomicAdd(c, v);
     }
   }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ C,
+             int64_t ldc, int M, int N, int K, int k_chunk, float alpha, const float* __restrict__ bias, int mode) {
+  const int k_begin = blockIdx.z * k_chunk;
+  sgemm_tile<TA, TB>(A, lda, B, ldb, C, ldc, M, N, blockIdx.y * kSgBM, blockIdx.x * kSgBN, k_begin, min(K, k_begin + k_chunk), alpha,
+                     blockIdx.z == 0 ? bias : nullptr, mode);
+}
+
+// Up to four independent products C_b (+)= A_b^T B_b of at most 128 x 128 outputs each (reductions over K rows, e.g. the
+// weight gradients of small layers) in ONE launch: blockIdx.y = product, blockIdx.x = K split (atomic accumulation).
+struct SgemmBatch4 {
+  const float* A[4]; int64_t lda[4];      // [K, M] row-major
+  const float* B[4]; int64_t ldb[4];      // [K, N] row-major
+  float* C[4];                            // [M, N] (ldc), pre-zeroed; NULL = skip
+};
+static __global__ void __launch_bounds__(256)
+sgemm_batch4_tt_kernel(const SgemmBatch4 b, int64_t ldc, int M, int N, int K, int k_chunk) {
+  const int p = blockIdx.y;
+  if (b.C[p] == nullptr || b.A[p] == nullptr) return;
+  const int k_begin = blockIdx.x * k_chunk;
+  sgemm_tile<true, true>(b.A[p], b.lda[p], b.B[p], b.ldb[p], b.C[p], ldc, M, N, 0, 0, k_begin, min(K, k_begin + k_chunk), 1.f,
+                         nullptr, 2);
+}
+inline int launch_sgemm_batch4_tt(const SgemmBatch4& b, int64_t ldc, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+  CAREL_REQUIRE(M <= kSgBM && N <= kSgBN, "sgemm_batch4: outputs of at most 128 x 128");
+  int splits = std::max(1, sm_count() / 4);
+  int k_chunk = int((K + splits - 1) / splits);
+  k_chunk = std::max(kSgBK, (k_chunk + kSgBK - 1) / kSgBK * kSgBK);
+  splits = int((K + k_chunk - 1) / k_chunk);
+  sgemm_batch4_tt_kernel<<<dim3(splits, 4), 256, 0, st>>>(b, ldc, int(M), int(N), int(K), k_chunk);
+  CAREL_LAUNCHED();
+  return 0;
 }
 
 // ksplit <= 0: chosen so that the grid fills the GPU when M x N alone gives too few tiles (mode must then be 2

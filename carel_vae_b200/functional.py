@@ -500,6 +500,51 @@ class _ClubFn(torch.autograd.Function):
         return tuple(None if t is None else t.to(dt) for t, dt in zip(gs, ctx.dts)) + (None,)
 
 
+class _ClubMlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c, *w8):
+        _require_cuda(c, *w8)
+        cf = _rowmajor_f32(c)
+        N, L = cf.shape
+        ws8 = [t.detach().float().contiguous() for t in w8]
+        lb = lib()
+        ws = _workspace(lb.carel_club_mlp_workspace_bytes(N, L), cf.device)
+        mu = torch.empty((N, L), dtype=torch.float32, device=cf.device)
+        lv = torch.empty((N, L), dtype=torch.float32, device=cf.device)
+        check(lb.carel_club_mlp_fwd(_p(cf), cf.stride(0), N, L, _ptr_array(ws8), _p(mu), _p(lv), _p(ws), ws.numel(), _stream()),
+              "carel_club_mlp_fwd")
+        ctx.keep = (cf, ws8, ws, lv)
+        ctx.meta = (N, L, c.dtype, [t.dtype for t in w8], [tuple(t.shape) for t in w8])
+        return mu, lv
+
+    @staticmethod
+    def backward(ctx, dmu, dlv):
+        cf, ws8, ws, lv = ctx.keep
+        N, L, cdt, wdts, wshapes = ctx.meta
+        dmu = None if dmu is None else dmu.float().contiguous()
+        dlv = None if dlv is None else dlv.float().contiguous()
+        need = ctx.needs_input_grad
+        dc = torch.empty((N, L), dtype=torch.float32, device=cf.device) if need[0] else None
+        # the eight parameter gradients are carved out of ONE zeroed buffer (the kernels accumulate into them)
+        sizes = [int(torch.Size(shape).numel()) if need[1 + i] else 0 for i, shape in enumerate(wshapes)]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=cf.device)
+        g8, off = [], 0
+        for n, shape in zip(sizes, wshapes):
+            g8.append(flat[off:off + n].view(shape) if n else None)
+            off += n
+        check(lib().carel_club_mlp_bwd(_p(dmu), _p(dlv), _p(cf), cf.stride(0), _p(lv), N, L, _ptr_array(ws8), _p(dc), L,
+                                       _ptr_array(g8), _p(ws), ws.numel(), _stream()), "carel_club_mlp_bwd")
+        return (None if dc is None else dc.to(cdt), *[None if g is None else g.to(dt) for g, dt in zip(g8, wdts)])
+
+
+def club_mlp(c_embedding, ec_mu, ec_log_var):
+    """(mu_hat, lv_hat) = (ec_mu(c), ec_log_var(c)) of the VI trainer's approximation network (reference get_ec_emb,
+    drl_classifier_ec_vi_final.py:342-347; ec_mu = Sequential(Linear, ReLU, Linear), ec_log_var = Sequential(Linear, ReLU,
+    Linear, Tanh), :155-162): both MLPs in one kernel forward and one backward."""
+    return _ClubMlpFn.apply(c_embedding, ec_mu[0].weight, ec_mu[0].bias, ec_mu[2].weight, ec_mu[2].bias,
+                            ec_log_var[0].weight, ec_log_var[0].bias, ec_log_var[2].weight, ec_log_var[2].bias)
+
+
 def club_aprx_loss(mu_hat, lv_hat, e_embedding) -> torch.Tensor:
     """-mean_i sum_d [-(mu - e)^2 / exp(lv) - lv]  (get_ec_aprx_loss, drl_classifier_ec_vi_final.py:421-426, after the MLPs)."""
     return _ClubFn.apply(mu_hat, lv_hat, e_embedding, None)

@@ -381,7 +381,13 @@ class DrlClassifierVI(_DrlClassifierBase):
         return TF.cross_entropy(preds, emotion_labels.flatten())
 
     def get_ec_emb(self, cause_emb):
-        return self.ec_mu(cause_emb), self.ec_log_var(cause_emb)
+        """(ec_mu(c), ec_log_var(c)) — vi_final:342-347 — through the fused MLP kernels (carel_club_mlp_fwd/bwd) when the
+        latent width fits them (ec_dim <= 128, multiple of 4: every configuration of the reference trainers); the two
+        nn.Sequential modules stay the owners of the parameters (state_dict keys unchanged)."""
+        L = self.opt.ec_dim
+        if L <= 128 and L % 4 == 0:
+            return F.club_mlp(cause_emb, self.ec_mu, self.ec_log_var)
+        raise NotImplementedError(f"the CLUB approximation-network kernels need ec_dim <= 128 and a multiple of 4 (got {L})")
 
     def get_ec_aprx_loss(self, e_embedding, c_embedding):
         ec_mu, ec_log_var = self.get_ec_emb(c_embedding.detach())

@@ -215,6 +215,21 @@ int carel_club_bwd(const float* grad_out, const float* mu_hat, const float* lv_h
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * CLUB approximation network q(e | c) of the VI trainer — replaces get_ec_emb (drl_classifier_ec_vi_final.py:342-347) over
+ * ec_mu = Linear-ReLU-Linear and ec_log_var = Linear-ReLU-Linear-Tanh (:155-162): both MLPs and both layers in one
+ * kernel per direction (ec_dim <= 128, multiple of 4).
+ *   w8[8] = {ec_mu.0.weight, ec_mu.0.bias, ec_mu.2.weight, ec_mu.2.bias, ec_log_var.0.weight, .0.bias, .2.weight, .2.bias}
+ *   mu, lv [N, L] contiguous.  Backward: dmu / dlv (may be NULL), dc (NULL for a detached input), g8[8] (each may be NULL;
+ *   accumulated: the caller passes them zeroed).
+ * ------------------------------------------------------------------------------------------ */
+size_t carel_club_mlp_workspace_bytes(int64_t N, int64_t L);
+int carel_club_mlp_fwd(const float* c, int64_t ldc, int64_t N, int64_t L, const float* const* w8, float* mu, float* lv,
+                       void* ws, size_t ws_bytes, void* stream);
+int carel_club_mlp_bwd(const float* dmu, const float* dlv, const float* c, int64_t ldc, const float* lv, int64_t N, int64_t L,
+                       const float* const* w8, float* dc, int64_t lddc, float* const* g8, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * GAN discriminators — replace get_ec_disc_preds / get_ce_disc_preds / get_ec_disc_loss / get_entropy_loss
  * (drl_classifier_ec_gan.py:430-477; call sites in forward :222-233), ec_num_class = 1:
  *   p_ec = sigmoid(ec_disc(dropout(z_c.detach()))), p_ce = sigmoid(ce_disc(dropout(z_e.detach())))

@@ -351,3 +351,39 @@ def test_gan_discriminator_kernels_match_the_reference_formulas(N, L, drop):
             else:
                 assert (a.double() - b).norm().item() <= 1e-5 * b.norm().item() + 1e-12
     assert z.grad is None          # the latents are detached in this branch, as in the reference
+
+
+@pytest.mark.parametrize("N,L", [(1, 24), (77, 64), (300, 128), (8192, 128)])
+def test_club_mlp_kernels_match_torch(N, L):
+    """carel_club_mlp_fwd/bwd against the nn.Sequential modules they replace (vi_final:155-162, :342-347) in fp64:
+    outputs and the gradients of the input and of all eight parameters, 1e-5."""
+    import copy
+    import torch.nn as nn
+    from carel_vae_b200 import functional as F
+    torch.manual_seed(N + L)
+    ec_mu = nn.Sequential(nn.Linear(L, L), nn.ReLU(), nn.Linear(L, L)).to(DEV)
+    ec_lv = nn.Sequential(nn.Linear(L, L), nn.ReLU(), nn.Linear(L, L), nn.Tanh()).to(DEV)
+    z = torch.randn(N, 2 * L, device=DEV)
+    # ReLU's derivative is discontinuous: a hidden unit whose pre-activation lies within fp32 rounding of zero gets the
+    # other side's mask in fp64 and moves the gradients by O(1e-3) (it is a different, equally valid subgradient).
+    # Rows with such a unit (|pre| < 1e-4, a few per thousand) are left out of the comparison batch.
+    with torch.no_grad():
+        c64 = z[:, L:].double()
+        pre = torch.cat((c64 @ ec_mu[0].weight.double().T + ec_mu[0].bias.double(),
+                         c64 @ ec_lv[0].weight.double().T + ec_lv[0].bias.double()), 1)
+        keep = pre.abs().min(dim=1).values > 1e-4
+        if N > 1:
+            z = z[keep].contiguous()
+    z.requires_grad_(True)
+    mu, lv = F.club_mlp(z[:, L:], ec_mu, ec_lv)            # strided column view, like z_c
+    gm, gl = torch.randn_like(mu), torch.randn_like(lv)
+    params = list(ec_mu.parameters()) + list(ec_lv.parameters())
+    grads = torch.autograd.grad((mu * gm).sum() + (lv * gl).sum(), [z] + params)
+    mu64, lv64 = copy.deepcopy(ec_mu).double(), copy.deepcopy(ec_lv).double()
+    zd = z.detach().double().requires_grad_(True)
+    rmu, rlv = mu64(zd[:, L:]), lv64(zd[:, L:])
+    rgrads = torch.autograd.grad((rmu * gm.double()).sum() + (rlv * gl.double()).sum(),
+                                 [zd] + list(mu64.parameters()) + list(lv64.parameters()))
+    assert rel(mu, rmu) < 1e-5 and rel(lv, rlv) < 1e-5
+    for g, r in zip(grads, rgrads):
+        assert rel(g, r) < 1e-5
