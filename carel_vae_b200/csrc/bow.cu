@@ -349,6 +349,12 @@ struct EpiBowFused {
       const int sw = (lane >> 1) & 3;
       const float2 ea2 = make_float2(enc.x, enc.x), eb2 = make_float2(enc.y, enc.y);
       for_each_chunk16(ctx.taddr + ctx.half * HALF, HALF / 16, [&](int c, const uint32_t (&r)[16]) {
+        // b_j log2(e) of this chunk's 16 words: issued before the store block below (whose fences the compiler does
+        // not move loads across), so the global-load latency is covered by it (ncu: 15 % of the stall samples sat
+        // on the first use when the loads followed the fence)
+        float4 bc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bc[i] = __ldg(cc4 + c * 4 + i);
         // ---- stored logits: low 16 bits of fl(acc a_i + bmagic_i) -> swizzled stage -> TMA store per 32 columns ----
         {
           if ((c & 1) == 0) {                   // the previous store of this warp has read the stage
@@ -381,7 +387,7 @@ struct EpiBowFused {
         float y[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 b4 = __ldg(cc4 + c * 4 + i);
+          const float4 b4 = bc[i];
           const float2 y0 = __ffma2_rn(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), l2e,
                                        make_float2(b4.x, b4.y));
           const float2 y1 = __ffma2_rn(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), l2e,
@@ -1103,12 +1109,16 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   yp.rowc = w.rowc; yp.bl2e = w.bl2e; yp.grad_out = grad_out;
   yp.N = int(N); yp.V = int(V); yp.K = int(K); yp.Npad = w.Npad;
   yp.c = label_smoothing / float(V); yp.inv_nv = inv_nv;
+  yp.probe = 0;
+  if (const char* e = getenv("CAREL_YG_PROBE")) yp.probe = atoi(e);      // timing probes (ygrad.cuh), never set in product runs
   CUtensorMap ty, tb;
   if (need_w) {      // owner = 128 words, step = 128 clauses: dW += dlogit^T Z, db
     CAREL_REQUIRE(make_tmap_f16_sw128(&ty, w.Y, N, V, w.ldy, 128) == 0, "carel_bow_bwd: tensor map Y failed");
     CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.ZH, N, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z failed");
-    ChainSched cs = make_chain_sched(0, int((V + 127) / 128), int((N + 127) / 128), k16, yg_b_stages(k16, true), 0);
-    yp.out = gw; yp.gb = gb; yp.ldo = K;
+    int ys, bs;
+    yg_stages(k16, true, &ys, &bs);
+    ChainSched cs = make_chain_sched(0, int((V + 127) / 128), int((N + 127) / 128), k16, bs, 0);
+    yp.out = gw; yp.gb = gb; yp.ldo = K; yp.y_stages = ys;
     if (int rc = launch_ygrad<true>(ty, tb, cs, yp, st, "bow_dw")) return rc;
   }
 #ifdef CAREL_CHAIN_TRACE
@@ -1117,8 +1127,10 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   {                  // owner = 256 clauses, step = 64 words: dZ += dlogit W_d
     CAREL_REQUIRE(make_tmap_f16_sw128(&ty, w.Y, N, V, w.ldy, 256) == 0, "carel_bow_bwd: tensor map Y failed");
     CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.WH, V, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
-    ChainSched cs = make_chain_sched(0, int((N + 255) / 256), int((V + 63) / 64), k16, yg_b_stages(k16, false), 0);
-    yp.out = grad_z; yp.gb = nullptr; yp.ldo = ldgz;
+    int ys, bs;
+    yg_stages(k16, false, &ys, &bs);
+    ChainSched cs = make_chain_sched(0, int((N + 255) / 256), int((V + 63) / 64), k16, bs, 0);
+    yp.out = grad_z; yp.gb = nullptr; yp.ldo = ldgz; yp.y_stages = ys;
     if (int rc = launch_ygrad<false>(ty, tb, cs, yp, st, "bow_dz")) return rc;
   }
   return 0;

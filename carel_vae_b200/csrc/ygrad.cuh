@@ -36,7 +36,7 @@
 namespace carel {
 
 constexpr float kYgScale = 1024.f;
-constexpr int kYgYStages = 3, kYgMaxBStages = 4;
+constexpr int kYgMaxYStages = 5, kYgMaxBStages = 4;   // ring depths are chosen per launch (yg_stages)
 constexpr int kYgYBytes = 32768;                // one Y piece: [256 clauses x 64 words] or 2 x [128 clauses x 64 words]
 constexpr int kYgOnesBytes = 1024;              // [8 rows x 128 B] of fp16 1.0: B operand of the db MMA (N = 16: the
                                                 // second 8-row group aliases the first, SBO = 0)
@@ -55,17 +55,33 @@ struct YGradParams {
   int64_t ldo;
   int N, V, K;           // K = feature columns written out (<= 16 * k16)
   float c, inv_nv;
+  int y_stages;          // Y ring depth (the B ring depth travels in ChainSched::stages)
+  int probe;             // timing probes only (results are garbage): 1 = no B loads, 2 = no Y loads (tools/yg_sweep.sh)
 };
 
 // one B piece: 64 reduction rows x ldk features = ldk / 64 boxes of [64 rows x 128 B]
 static __host__ __device__ inline int yg_b_bytes(int k16) { return ((k16 + 3) / 4) * 8192; }
-static __host__ inline int yg_b_stages(int k16, bool trans) {
-  const int budget = 227 * 1024 - kYgYStages * (kYgYBytes + yg_c_bytes(trans)) - kYgOnesBytes - 256;
-  const int st = budget / yg_b_bytes(k16);
-  return st > kYgMaxBStages ? kYgMaxBStages : st;
+// Ring depths (Y, B) from the 227 KB budget.  The Y pieces come from HBM (measured ~3100 clk from issue to landing
+// under load), the B pieces from L2: the Y ring gets the depth first.  CAREL_YG_STAGES="y,b" overrides (experiments).
+static __host__ inline void yg_stages(int k16, bool trans, int* ys, int* bs) {
+  const int fixed = kYgOnesBytes + 256;
+  // measured at N = 8192, V = 30000, K = 256 (tools/yg_sweep.sh): dZ (Y, B) = (3,4) 158.6, (4,3) 149.0, (5,2) 159.4 us;
+  // dW consumes two B pieces per step and needs four of them in flight: (3,4) 182.0, (3,3) 205.2, (4,2) 215.8 us
+  int y = trans ? 3 : 4, b = trans ? 4 : 3;
+  if (const char* e = getenv(trans ? "CAREL_YG_STAGES_DW" : "CAREL_YG_STAGES_DZ")) {
+    int ey = 0, eb = 0;
+    if (sscanf(e, "%d,%d", &ey, &eb) == 2 && ey >= 2 && ey <= kYgMaxYStages && eb >= 2 && eb <= kYgMaxBStages) { y = ey; b = eb; }
+  }
+  while (y > 2 && fixed + y * (kYgYBytes + yg_c_bytes(trans)) + 2 * yg_b_bytes(k16) > 227 * 1024) --y;
+  const int left = 227 * 1024 - fixed - y * (kYgYBytes + yg_c_bytes(trans));
+  int bmax = left / yg_b_bytes(k16);
+  if (bmax > kYgMaxBStages) bmax = kYgMaxBStages;
+  if (b > bmax) b = bmax;
+  *ys = y;
+  *bs = b;
 }
-static __host__ inline int yg_smem_bytes(int k16, bool trans) {
-  return kYgYStages * (kYgYBytes + yg_c_bytes(trans)) + yg_b_stages(k16, trans) * yg_b_bytes(k16) + kYgOnesBytes + 256;
+static __host__ inline int yg_smem_bytes(int k16, bool trans, int ys, int bs) {
+  return ys * (kYgYBytes + yg_c_bytes(trans)) + bs * yg_b_bytes(k16) + kYgOnesBytes + 256;
 }
 
 // exact per-element terms (chunks that leave the series' range)
@@ -112,7 +128,9 @@ static CAREL_DEVINL void yg_dlogit16(const float (&t)[16], const float (&Sn)[16]
   }
 }
 
-template <bool TRANS>
+// EP: epilogue timing probes, instantiated only under -DCAREL_YG_PROBES (results are garbage): 1 = no MUFU,
+// 2 = no shared-memory store of the dlogits, 4 = no shared-memory load of the logits, 8 = no arithmetic at all
+template <bool TRANS, int EP = 0>
 __global__ void __launch_bounds__(kChainThreads, 1)
 ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ ChainSched sched, const __grid_constant__ YGradParams pp) {
@@ -121,18 +139,19 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
   const int KB = (K16 + 3) / 4;
   const int b_bytes = yg_b_bytes(K16);
   const int BST = sched.stages;                   // B ring depth
+  const int YST = pp.y_stages;                    // Y ring depth
   constexpr int kCB = yg_c_bytes(TRANS);
   // the base of dynamic shared memory is 1024-byte aligned (no static shared memory in this kernel); checked below
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sY = smem;
-  uint8_t* sB = smem + kYgYStages * kYgYBytes;
+  uint8_t* sB = smem + YST * kYgYBytes;
   uint8_t* sOnes = sB + BST * b_bytes;
   uint8_t* sC = sOnes + kYgOnesBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + kYgYStages * kCB);
-  uint64_t* y_full = bars;                        // [3]  TMA bytes (Y piece + its constants)
-  uint64_t* y_empty = y_full + kYgYStages;        // [3]  tcgen05.commit (the MMAs that read the piece are done)
-  uint64_t* p_full = y_empty + kYgYStages;        // [3]  16 epilogue warps (dlogits written in place)
-  uint64_t* b_full = p_full + kYgYStages;         // [4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + YST * kCB);
+  uint64_t* y_full = bars;                        // [5]  TMA bytes (Y piece + its constants)
+  uint64_t* y_empty = y_full + kYgMaxYStages;     // [5]  tcgen05.commit (the MMAs that read the piece are done)
+  uint64_t* p_full = y_empty + kYgMaxYStages;     // [5]  16 epilogue warps (dlogits written in place)
+  uint64_t* b_full = p_full + kYgMaxYStages;      // [4]
   uint64_t* b_empty = b_full + kYgMaxBStages;     // [4]  tcgen05.commit
   uint64_t* acc_full = b_empty + kYgMaxBStages;   // [1]
   uint64_t* acc_empty = acc_full + 1;             // [1]  16 epilogue warps
@@ -148,7 +167,7 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     }
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < kYgYStages; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); mbar_init(&p_full[i], kEpi); }
+    for (int i = 0; i < kYgMaxYStages; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); mbar_init(&p_full[i], kEpi); }
     for (int i = 0; i < kYgMaxBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, kEpi);
@@ -173,9 +192,13 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     uint32_t yphase = 0, bphase = 0;
     auto load_b = [&](int row0) {
       mbar_wait(&b_empty[bs], bphase ^ 1);
-      mbar_expect_tx(&b_full[bs], b_bytes);
+      if (pp.probe & 1) {
+        mbar_arrive(&b_full[bs]);
+      } else {
+        mbar_expect_tx(&b_full[bs], b_bytes);
 #pragma unroll 1
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + bs * b_bytes + kb * 8192, &tmB, &b_full[bs], kb * 64, row0);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + bs * b_bytes + kb * 8192, &tmB, &b_full[bs], kb * 64, row0);
+      }
       if (++bs == BST) { bs = 0; bphase ^= 1; }
     };
     int tn = 0;
@@ -184,9 +207,11 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
       for (int t = it.t0; t < it.t1; ++t, ++tn) {
         mbar_wait(&y_empty[ys], yphase ^ 1);
         CAREL_TRACE(0, tn);
-        mbar_expect_tx(&y_full[ys], kYgYBytes + kCB);
+        mbar_expect_tx(&y_full[ys], ((pp.probe & 2) ? 0 : kYgYBytes) + kCB);
         uint8_t* cst = sC + ys * kCB;
-        if (TRANS) {          // two boxes [128 clauses x 64 words]; rowc planes of the clauses; b of the owner's words
+        if (pp.probe & 2) {
+          bulk_load_1d(cst, pp.bl2e + (TRANS ? it.owner * 128 : t * 64), kCB, &y_full[ys]);
+        } else if (TRANS) {          // two boxes [128 clauses x 64 words]; rowc planes of the clauses; b of the owner's words
           tma_load_2d(sY + ys * kYgYBytes, &tmY, &y_full[ys], it.owner * 128, t * 128);
           tma_load_2d(sY + ys * kYgYBytes + 16384, &tmY, &y_full[ys], it.owner * 128 + 64, t * 128);
           bulk_load_1d(cst, pp.bl2e + it.owner * 128, 512, &y_full[ys]);
@@ -194,7 +219,7 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           tma_load_2d(sY + ys * kYgYBytes, &tmY, &y_full[ys], t * 64, it.owner * 256);
           bulk_load_1d(cst, pp.bl2e + t * 64, 256, &y_full[ys]);
         }
-        if (++ys == kYgYStages) { ys = 0; yphase ^= 1; }
+        if (++ys == YST) { ys = 0; yphase ^= 1; }
         if (TRANS) {
           load_b(t * 128);
           load_b(t * 128 + 64);
@@ -261,7 +286,7 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         }
         umma_commit(&y_empty[ys]);
         CAREL_TRACE(6, tn);
-        if (++ys == kYgYStages) { ys = 0; yphase ^= 1; }
+        if (++ys == YST) { ys = 0; yphase ^= 1; }
       }
       umma_commit(acc_full);
     }
@@ -315,25 +340,47 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
           //      operand rows or unwritten output rows; their values only have to be finite) ----
           // (certified rows have every p < 2^-8; the p'^3 term is dropped, see bow_combine_kernel)
           const float2 a1 = make_float2(pol.x, pol.x), a2 = make_float2(pol.y, pol.y);
+          // The dlogits overwrite the logits they came from, so the compiler must keep every shared-memory load
+          // behind the stores written before it: all four 16-byte pieces of the row segment are loaded up front
+          // (and the word constants one block ahead) instead of one load -> ... -> store chain per block, whose
+          // load latency was exposed four times per step (ncu: 25 % of the kernel's stall samples).
+          uint4 vy[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if constexpr (EP & 4) vy[i] = make_uint4(0x12345678u + i, 0x23456789u, 0x3456789au, 0x456789abu + r);
+            else vy[i] = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + i) ^ (r & 7)) << 4));
+          }
+          float4 ca = cc4[0], cb = cc4[1];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint8_t* cp = rowp + (((half * 4 + i) ^ (r & 7)) << 4);
-            const uint4 v = *reinterpret_cast<const uint4*>(cp);
-            const float4 ca = cc4[2 * i], cb = cc4[2 * i + 1];
+            const uint4 v = vy[i];
+            float4 ca_n = ca, cb_n = cb;
+            if (i < 3) { ca_n = cc4[2 * i + 2]; cb_n = cc4[2 * i + 3]; }
             const uint32_t u[4] = {v.x, v.y, v.z, v.w};
             const float2 cc[4] = {make_float2(ca.x, ca.y), make_float2(ca.z, ca.w), make_float2(cb.x, cb.y),
                                   make_float2(cb.z, cb.w)};
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 g = __fadd2_rn(make_float2(y16_lo(u[e]), y16_hi(u[e])), nb2);
-              const float2 tp = __ffma2_rn(g, is2, cc[e]);
-              const float2 pv = make_float2(ex2_approx(tp.x), ex2_approx(tp.y));
-              float2 hh = __ffma2_rn(pv, a2, a1);
-              hh = __ffma2_rn(pv, hh, mc2);
-              o[e] = pack_f16x2_sat(hh.x, hh.y);
+              if constexpr (EP & 8) {
+                o[e] = u[e] ^ __float_as_uint(cc[e].x);
+              } else {
+                const float2 g = __fadd2_rn(make_float2(y16_lo(u[e]), y16_hi(u[e])), nb2);
+                const float2 tp = __ffma2_rn(g, is2, cc[e]);
+                const float2 pv = (EP & 1) ? tp : make_float2(ex2_approx(tp.x), ex2_approx(tp.y));
+                float2 hh = __ffma2_rn(pv, a2, a1);
+                hh = __ffma2_rn(pv, hh, mc2);
+                o[e] = pack_f16x2_sat(hh.x, hh.y);
+              }
             }
-            *reinterpret_cast<uint4*>(cp) = make_uint4(o[0], o[1], o[2], o[3]);
+            if constexpr (EP & 2) {
+              if ((o[0] ^ o[1] ^ o[2] ^ o[3]) == 0x9e3779b9u) *reinterpret_cast<uint4*>(cp) = make_uint4(o[0], o[1], o[2], o[3]);
+            } else {
+              *reinterpret_cast<uint4*>(cp) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            ca = ca_n;
+            cb = cb_n;
           }
         } else {
           // ---- checked path: range test per 16 elements, exact terms where the series does not hold ----
@@ -378,7 +425,7 @@ ygrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(&p_full[ys]);
         if (threadIdx.x == 0) CAREL_TRACE(3, tn);
         if (threadIdx.x == 15 * 32) CAREL_TRACE(7, tn);
-        if (++ys == kYgYStages) { ys = 0; yphase ^= 1; }
+        if (++ys == YST) { ys = 0; yphase ^= 1; }
       }
       // ---- write-out of this item's accumulator(s) ----
       mbar_wait(acc_full, acc_phase);
@@ -444,7 +491,18 @@ template <bool TRANS>
 int launch_ygrad(const CUtensorMap& ty, const CUtensorMap& tb, const ChainSched& s, const YGradParams& pp,
                  cudaStream_t st, const char* tag) {
   auto kern = ygrad_kernel<TRANS>;
-  const int smem = yg_smem_bytes(s.k16, TRANS);
+#ifdef CAREL_YG_PROBES
+  switch (pp.probe >> 2) {
+    case 1: kern = ygrad_kernel<TRANS, 1>; break;
+    case 2: kern = ygrad_kernel<TRANS, 2>; break;
+    case 4: kern = ygrad_kernel<TRANS, 4>; break;
+    case 8: kern = ygrad_kernel<TRANS, 8>; break;
+    case 14: kern = ygrad_kernel<TRANS, 14>; break;
+    default: break;
+  }
+  CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#endif
+  const int smem = yg_smem_bytes(s.k16, TRANS, pp.y_stages, s.stages);
   static int attr_smem = 0;
   if (smem > attr_smem) {
     CAREL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
