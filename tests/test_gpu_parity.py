@@ -252,6 +252,30 @@ def test_bow_sparse_equals_dense_target():
     assert relv(sparse, dense) < 1e-6
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_bow_ell_only_overflow_is_reported_not_read(precision):
+    """An ELL triple WITHOUT the dense target whose nnz exceeds the list capacity (bow_pack_ell documents that it may)
+    cannot be evaluated: the loss comes back NaN and the gradients finite or NaN — never a read through the missing
+    dense pointer (round-1 advisor finding: illegal address in bow_sparse_kernel) — and the context stays usable."""
+    torch.manual_seed(9)
+    N, K, V, cap = 96, 64, 900, 8
+    Z = torch.randn(N, K, device=DEV, requires_grad=True)
+    W = (torch.randn(V, K, device=DEV) / 8).requires_grad_(True)
+    b = torch.zeros(V, device=DEV, requires_grad=True)
+    bow = ho.synthetic_batch(N, V, D=8, nnz=40, seed=1, device=DEV)["bow"]
+    cols, vals, nnz = F.bow_pack_ell(bow, cap)
+    assert int(nnz.max()) > cap
+    loss = F.bow_reconstruction_loss(Z, W, b, None, 0.1, ell=(cols, vals, nnz), precision=precision)
+    loss.backward()
+    torch.cuda.synchronize()                       # a fault would surface here as a sticky CUDA error
+    assert torch.isnan(loss)
+    # the same call with a list that fits is fine afterwards
+    cols, vals, nnz = F.bow_pack_ell(bow, 64)
+    ok = F.bow_reconstruction_loss(Z, W, b, None, 0.1, ell=(cols, vals, nnz), precision=precision)
+    ref = ho.bow_reconstruction(Z.detach().double(), W.detach().double(), b.detach().double(), bow.double(), 0.1)
+    assert relv(ok, ref) < 1e-3
+
+
 @pytest.mark.parametrize("N,V,nnz,cap", [(1, 7, 3, 4), (37, 1001, 5, 8), (300, 30000, 24, 64), (64, 2050, 40, 8)])
 def test_bow_pack_ell_matches_nonzero(N, V, nnz, cap):
     """carel_bow_pack_ell (bit-exact index / byte work): every non-zero of a row exactly once (order within a 128-column
