@@ -211,9 +211,9 @@ class HeadStep:
     choreography of the reference trainers, carel_vae_b200/train.py); captured as CUDA graphs (one graph at N = 1,
     one per segment with the NCCL calls between them at N > 1)."""
 
-    def __init__(self, variant, dev, world, target, static, opt_kw=None, use_graph=True):
+    def __init__(self, variant, dev, world, target, static, opt_kw=None, use_graph=True, overlap_sms=0):
         import carel_vae_b200 as cv
-        from carel_vae_b200.parallel import GradReducer
+        from carel_vae_b200.parallel import GradReducer, OverlappedGradReducer
         self.variant, self.dev, self.world = variant, dev, world
         opt = cv.default_opt(variant, ec_dim=LATENT, pair_bow_dim=VOCAB, bert_dim=D_EMB, dropout=0.5, **(opt_kw or {}))
         torch.manual_seed(1234)
@@ -227,7 +227,14 @@ class HeadStep:
                            torch.optim.Adam(groups[2], lr=lr, capturable=True, fused=True)]
         else:                       # mmd:936, hsic:874, vi_final:878-879
             self.optims = [torch.optim.Adam(g, lr=lr, capturable=True, fused=True) for g in groups]
-        self.reducers = [GradReducer(g) for g in groups] if world > 1 else None
+        # overlap_sms > 0: the big all-reduce runs under the rest of the backward pass on that many reserved SMs and
+        # the whole step (collectives included) is ONE graph; 0: plain reducers between per-segment graphs
+        self.overlap_sms = overlap_sms if world > 1 else 0
+        if world > 1:
+            self.reducers = [OverlappedGradReducer(g, reserved_sms=overlap_sms) if self.overlap_sms > 0 else GradReducer(g)
+                             for g in groups]
+        else:
+            self.reducers = None
         self.loss_buf = torch.zeros((), device=dev)
         self.static, self.target = static, target
         self.all_params = list(model.parameters())
@@ -322,15 +329,39 @@ class HeadStep:
             fn()
             self._reduce(red)
 
+    def check_overlap(self):
+        """Overlapped reduction against the plain one on the SAME local gradients (same seed, no optimiser step in
+        between): max relative difference over the optimiser's parameters, or None where it does not apply."""
+        import torch.distributed as dist
+        if self.overlap_sms <= 0 or self.variant not in ("mmd", "hsic"):
+            return None
+        seg0 = self.segments[0][0]
+        out = []
+        for enabled in (False, True):
+            for r in self.reducers:
+                r.enabled = enabled
+            torch.manual_seed(99 + dist.get_rank())
+            seg0()
+            self._reduce(0)
+            torch.cuda.synchronize()
+            out.append([p.grad.detach().clone() for p in self.groups[0]])
+        for r in self.reducers:
+            r.enabled = True
+        worst = 0.0
+        for a, b in zip(*out):
+            worst = max(worst, float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)))
+        return worst
+
     def _capture(self):
         try:
             s = self.stream
             graphs = []
-            if self.world == 1:
+            if self.world == 1 or self.overlap_sms > 0:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=s):
-                    for fn, _ in self.segments:
+                    for fn, red in self.segments:
                         fn()
+                        self._reduce(red)           # no-op at world == 1; captured NCCL nodes otherwise
                 graphs.append((g, None, None))
             else:
                 pool = None
@@ -348,6 +379,8 @@ class HeadStep:
         except Exception as e:  # noqa: BLE001
             print(f"[bench] CUDA-graph capture failed, running eagerly: {repr(e)[:300]}", file=sys.stderr)
             self.graphs = None
+            from carel_vae_b200 import _lib
+            _lib.set_reserved_sms(0)
             torch.cuda.synchronize()
 
     def run(self):
@@ -370,7 +403,11 @@ def run_head(args):
     world, rank, local = dist_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # measured (profiles/r02_dp_overlap_*): 2 GPUs 16 -> 1.289 ms, 24 -> 1.322; 8 GPUs 8 -> 1.524, 16 -> 1.352, 24 -> 1.332, 32 -> 1.357
+    overlap_sms = (args.dp_reserved_sms if args.dp_reserved_sms >= 0 else (16 if world <= 2 else 24)) if world > 1 else 0
     if world > 1:
+        if overlap_sms > 0:      # the overlapped all-reduce runs on the SMs the persistent kernels leave free
+            os.environ.setdefault("NCCL_MAX_CTAS", str(overlap_sms))
         dist.init_process_group("nccl", device_id=dev)
     barrier, timed = make_timers(dev, world, local)
 
@@ -378,10 +415,15 @@ def run_head(args):
     pinned = {k: v.pin_memory() for k, v in host.items()}
     static = {k: v.to(dev) for k, v in host.items()}            # device-resident inputs (value) / H2D targets (e2e)
     torch.manual_seed(7 + rank)
-    dense = HeadStep(variant, dev, world, static["bow"], static, use_graph=not args.no_graph)
+    dense = HeadStep(variant, dev, world, static["bow"], static, use_graph=not args.no_graph, overlap_sms=overlap_sms)
     ell = HeadStep(variant, dev, world, (static["ell_cols"], static["ell_vals"], static["ell_nnz"]), static,
-                   use_graph=not args.no_graph)
+                   use_graph=not args.no_graph, overlap_sms=overlap_sms)
 
+    overlap_check = None
+    if world > 1:
+        with torch.cuda.stream(dense.stream):
+            overlap_check = dense.check_overlap()
+        torch.cuda.synchronize()
     # ---- value: inputs resident in HBM ----
     for _ in range(max(args.warmup, 3)):
         dense.run()
@@ -498,6 +540,9 @@ def run_head(args):
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                "config": {"workload": WORKLOADS[variant], "global_batch": N_ROWS * world, "parallelism": f"dp{world}", "l2": L2_NOTE},
                "cuda_graph": dense.graphs is not None,
+               "dp_overlap": ({"reserved_sms": dense.overlap_sms, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"),
+                               "single_graph": dense.graphs is not None and len(dense.graphs) == 1,
+                               "max_rel_diff_vs_plain_allreduce": overlap_check} if world > 1 else None),
                "clocks": clocks,
                "e2e": {"value": round(world * 1e3 / e2e_ms, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3),
@@ -511,9 +556,21 @@ def run_head(args):
                "roofline": roof, "roofline_step": roof_step, "roofline_hbm": roof_hbm, "gram": gram, "kernels_us": kernels,
                "dp_params_identical_across_ranks": dp_identical,
                "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "config1": cfg1}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        # Graphs that hold captured NCCL nodes go first; if the process group still does not come down (its watchdog
+        # can wait for ever on work objects created during capture) the rank leaves without it — the line is printed.
+        dense.graphs = ell.graphs = None
+        del dense, ell
+        torch.cuda.synchronize()
+        bail = threading.Timer(15.0, lambda: os._exit(0))
+        bail.daemon = True
+        bail.start()
         dist.destroy_process_group()
+        bail.cancel()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)              # nothing left to do; skips interpreter teardown with NCCL state around
 
 
 def gram_point(dev, pk, traffic):
@@ -794,6 +851,9 @@ def main():
     ap.add_argument("--workload", default="mmd", choices=["mmd", "hsic", "vi", "gan", "gram_sweep"])
     ap.add_argument("--sizes", default="", help="gram_sweep: comma-separated N list")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--dp-reserved-sms", type=int, default=int(os.environ.get("CAREL_DP_RESERVED_SMS", "-1")),
+                    help="N > 1: SMs left to the NCCL all-reduce of the decoder gradient while it runs under the rest of "
+                         "the backward pass (parallel.OverlappedGradReducer); 0 = plain all-reduce between two graphs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / gpu_eager_baseline legs")
     args = ap.parse_args()
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -23,6 +23,8 @@ _SIGNATURES = {
     "carel_last_error": (C.c_char_p, []),
     "carel_launch_count": (i64, []),
     "carel_timing_enable": (None, [C.c_int]),
+    "carel_set_reserved_sms": (None, [C.c_int]),
+    "carel_get_reserved_sms": (C.c_int, []),
     "carel_timing_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "carel_gemm_bf16": (C.c_int, [c_ptr, i64, C.c_int, c_ptr, i64, C.c_int, i64, i64, i64, c_ptr, i64,
                                   c_ptr, C.c_int, c_ptr]),
@@ -56,6 +58,8 @@ _SIGNATURES = {
                                 C.c_float, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "carel_bow_bwd": (C.c_int, [c_ptr, c_ptr, i64, i64, i64, i64, i64, C.c_float, c_ptr, i64, c_ptr, c_ptr,
                                 c_ptr, C.c_size_t, c_ptr]),
+    "carel_bow_bwd_parts": (C.c_int, [c_ptr, c_ptr, i64, i64, i64, i64, i64, C.c_float, c_ptr, i64, c_ptr, c_ptr,
+                                      c_ptr, C.c_size_t, C.c_int, c_ptr]),
     "carel_hsic_workspace_bytes": (C.c_size_t, [i64, i64, i64]),
     "carel_hsic_fwd": (C.c_int, [c_ptr, i64, c_ptr, i64, i64, i64, i64, C.c_float, C.c_float, i64, i64, c_ptr, c_ptr,
                                  C.c_size_t, c_ptr]),
@@ -151,6 +155,15 @@ def float_array(values):
 
 def launch_count() -> int:
     return int(lib().carel_launch_count())
+
+
+def set_reserved_sms(n: int) -> None:
+    """Leave `n` SMs free in every kernel launched from now on (0 = use all): see carel_set_reserved_sms."""
+    lib().carel_set_reserved_sms(int(n))
+
+
+def reserved_sms() -> int:
+    return int(lib().carel_get_reserved_sms())
 
 
 def timing_enable(on: bool) -> None:

@@ -19,7 +19,9 @@ std::atomic<long long>& launch_counter() {
   static std::atomic<long long> c{0};
   return c;
 }
-// SM count of the CURRENT device (cached per device index: a process may drive several GPUs).
+// SMs the persistent kernels leave free (carel_set_reserved_sms): a concurrent NCCL collective gets them.
+std::atomic<int> g_reserved_sms{0};
+// SM count of the CURRENT device (cached per device index: a process may drive several GPUs), minus the reservation.
 int sm_count() {
   static std::atomic<int> cache[64];
   int dev = 0;
@@ -29,7 +31,8 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cache[dev].store(n, std::memory_order_relaxed);
   }
-  return n;
+  const int r = g_reserved_sms.load(std::memory_order_relaxed);
+  return (r > 0 && n - r >= 8) ? n - r : n;
 }
 
 namespace {
@@ -67,6 +70,9 @@ void timing_end(cudaStream_t st) {
 }  // namespace carel
 
 using namespace carel;
+
+extern "C" void carel_set_reserved_sms(int n) { g_reserved_sms.store(n < 0 ? 0 : n, std::memory_order_relaxed); }
+extern "C" int carel_get_reserved_sms(void) { return g_reserved_sms.load(std::memory_order_relaxed); }
 
 extern "C" void carel_timing_enable(int on) {
   g_timing.store(on != 0);

@@ -1073,11 +1073,26 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   return 0;
 }
 
+// parts: 1 = everything that completes grad_w / grad_b (the O(nnz) gathers of both gradients, the overflow rows and the
+// dense dW kernel), 2 = the dense dZ kernel, 3 = both.  A data-parallel caller runs part 1, starts the all-reduce of
+// grad_w on another stream and runs part 2 underneath it (parallel.OverlappedGradReducer).
+extern "C" int carel_bow_bwd_parts(const float* grad_out, const float* bow_dense, int64_t ld_bow, int64_t N,
+                                   int64_t K, int64_t V, int64_t ell_cap, float label_smoothing,
+                                   float* grad_z, int64_t ldgz, float* grad_w, float* grad_b, void* ws,
+                                   size_t ws_bytes, int parts, void* stream);
 extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int64_t ld_bow, int64_t N,
                              int64_t K, int64_t V, int64_t ell_cap, float label_smoothing,
                              float* grad_z, int64_t ldgz, float* grad_w, float* grad_b, void* ws,
                              size_t ws_bytes, void* stream) {
+  return carel_bow_bwd_parts(grad_out, bow_dense, ld_bow, N, K, V, ell_cap, label_smoothing, grad_z, ldgz, grad_w, grad_b,
+                             ws, ws_bytes, 3, stream);
+}
+extern "C" int carel_bow_bwd_parts(const float* grad_out, const float* bow_dense, int64_t ld_bow, int64_t N,
+                                   int64_t K, int64_t V, int64_t ell_cap, float label_smoothing,
+                                   float* grad_z, int64_t ldgz, float* grad_w, float* grad_b, void* ws,
+                                   size_t ws_bytes, int parts, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CAREL_REQUIRE(parts >= 1 && parts <= 3, "carel_bow_bwd_parts: parts must be 1, 2 or 3");
   BowWs w = carve_bow(ws, N, K, V, ell_cap);
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_bow_bwd: workspace too small");
   CAREL_REQUIRE(grad_z != nullptr, "carel_bow_bwd: grad_z is required");
@@ -1089,6 +1104,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   float* gw = grad_w != nullptr ? grad_w : w.dWacc;
   float* gb = grad_b != nullptr ? grad_b : w.dbacc;
   const float inv_nv = float(1.0 / (double(N) * double(V)));
+  if (parts & 1) {
   bow_sparse_dz_kernel<<<int(std::min<int64_t>((N + 7) / 8, sms * 16)), 256, 0, st>>>(
       w.WH, w.ldk, int(K), w.ell_cols, w.ell_nnz, w.ell_ev, int(N), int(ell_cap), truncate, grad_out, inv_nv, grad_z, ldgz);
   CAREL_LAUNCHED();
@@ -1103,6 +1119,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
         int(ell_cap), 1.f - label_smoothing, grad_out, inv_nv, grad_z, ldgz, gw, gb);
     CAREL_LAUNCHED();
   }
+  }
   // ---- dense part: two single-GEMM kernels over the stored logits (ygrad.cuh) ----
   const int k16 = w.ldk / 16;
   YGradParams yp;
@@ -1112,7 +1129,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
   yp.probe = 0;
   if (const char* e = getenv("CAREL_YG_PROBE")) yp.probe = atoi(e);      // timing probes (ygrad.cuh), never set in product runs
   CUtensorMap ty, tb;
-  if (need_w) {      // owner = 128 words, step = 128 clauses: dW += dlogit^T Z, db
+  if (need_w && (parts & 1)) {      // owner = 128 words, step = 128 clauses: dW += dlogit^T Z, db
     CAREL_REQUIRE(make_tmap_f16_sw128(&ty, w.Y, N, V, w.ldy, 128) == 0, "carel_bow_bwd: tensor map Y failed");
     CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.ZH, N, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map Z failed");
     int ys, bs;
@@ -1124,7 +1141,7 @@ extern "C" int carel_bow_bwd(const float* grad_out, const float* bow_dense, int6
 #ifdef CAREL_CHAIN_TRACE
   if (getenv("CAREL_TRACE_SKIP_DZ") != nullptr) return 0;      // debug: keep the dW kernel's timeline
 #endif
-  {                  // owner = 256 clauses, step = 64 words: dZ += dlogit W_d
+  if (parts & 2) {   // owner = 256 clauses, step = 64 words: dZ += dlogit W_d
     CAREL_REQUIRE(make_tmap_f16_sw128(&ty, w.Y, N, V, w.ldy, 256) == 0, "carel_bow_bwd: tensor map Y failed");
     CAREL_REQUIRE(make_tmap_f16_sw128(&tb, w.WH, V, w.ldk, w.ldk, 64) == 0, "carel_bow_bwd: tensor map W failed");
     int ys, bs;

@@ -560,6 +560,12 @@ def club_upper_bound(mu_hat, lv_hat, e_embedding, perm) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 DEFAULT_ELL_CAP = 64
 
+#: Callables `hook(dec_w, grad_w) -> bool` run INSIDE the decoder's backward, after the kernels that complete the weight
+#: gradient have been launched and before the latent-gradient kernel is: a data-parallel reducer starts the all-reduce
+#: of grad_w there, underneath everything that follows (parallel.OverlappedGradReducer registers itself here).  A hook
+#: that returns True has taken ownership of grad_w (it has made it `dec_w.grad` itself); autograd then gets None.
+decoder_grad_hooks: list = []
+
 
 class _BowFn(torch.autograd.Function):
     @staticmethod
@@ -597,6 +603,7 @@ class _BowFn(torch.autograd.Function):
                                    _p(ws), ws.numel(), _stream()), "carel_bow_fwd")
             ctx.f32_keep = None
         ctx.ws, ctx.bd = ws, bd
+        ctx.dec_w = dec_w
         ctx.meta = (N, K, V, int(ell_cap), float(label_smoothing), z.dtype, dec_w.dtype, dec_b.dtype)
         return loss
 
@@ -614,6 +621,17 @@ class _BowFn(torch.autograd.Function):
             zf, wf = ctx.f32_keep
             check(lib().carel_bow_f32_bwd(_p(g), _p(zf), zf.stride(0), _p(wf), _p(bd), 0 if bd is None else bd.stride(0), N, K,
                                           V, ls, _p(gz), K, _p(gw), _p(gb), _p(ws), ws.numel(), _stream()), "carel_bow_f32_bwd")
+        elif decoder_grad_hooks and gw is not None and dtw == torch.float32:
+            # weight gradient first, hooks (the DP all-reduce forks here), then the latent gradient underneath it
+            args = (_p(g), _p(bd), 0 if bd is None else bd.stride(0), N, K, V, cap, ls, _p(gz), K, _p(gw), _p(gb), _p(ws),
+                    ws.numel())
+            check(lib().carel_bow_bwd_parts(*args, 1, _stream()), "carel_bow_bwd_parts")
+            taken = False
+            for hook in list(decoder_grad_hooks):
+                taken = bool(hook(ctx.dec_w, gw)) or taken
+            check(lib().carel_bow_bwd_parts(*args, 2, _stream()), "carel_bow_bwd_parts")
+            if taken:
+                gw = None
         else:
             check(lib().carel_bow_bwd(_p(g), _p(bd), 0 if bd is None else bd.stride(0), N, K, V, cap, ls, _p(gz), K,
                                       _p(gw), _p(gb), _p(ws), ws.numel(), _stream()), "carel_bow_bwd")

@@ -217,6 +217,106 @@ class GradReducer:
         torch._foreach_copy_([g for g, _ in live], [v for _, v in live])
 
 
+class OverlappedGradReducer(GradReducer):
+    """GradReducer that hides the big all-reduces under the rest of the backward pass (hard part 5).
+
+    The decoder weight gradient (31 MB at V = 30000, L = 128: 99 % of the DP bytes) is complete as soon as the decoder's
+    backward has run — the MMD / HSIC backward, the heads and the whole latent backward (~250 us at N = 8192) still
+    follow.  The reducer forks a communication stream as early as the gradient exists and issues the in-place ncclAvg
+    all-reduce on it: for the decoder weight that is INSIDE the decoder's backward, between the kernels that complete
+    the weight gradient and the latent-gradient kernel (`functional.decoder_grad_hooks`, ~400 us of cover); any other
+    big parameter is caught by a post-accumulate-grad hook.  `reduce()` joins and sends the small gradients through
+    the flat bucket as before.  Two things make the overlap real:
+      * the library's persistent kernels own every SM (one 225 KB CTA each), so a collective launched beside them would
+        only queue behind them: between the hook and the join `carel_set_reserved_sms(reserved_sms)` makes every kernel
+        of the library size its grid for that many fewer SMs, and NCCL (capped to as many CTAs: NCCL_MAX_CTAS) runs on
+        the ones left free;
+      * fork and join are plain stream dependencies, so the whole step — collective included — can be captured in ONE
+        CUDA graph (call `reduce()` inside the captured region).
+    The trainer-facing protocol is unchanged: `reducer.reduce()` between `loss.backward()` and `optimizer.step()`."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, big_numel: int = 1 << 20, reserved_sms: int = 16):
+        super().__init__(params, group, big_numel)
+        self.reserved_sms = int(reserved_sms)
+        self.enabled = True
+        self._comm = None
+        self._done = {}          # id(param) -> the gradient tensor that was all-reduced from the hook in this pass
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_big_grad) for p in self.big]
+        self._big_ids = {id(p): p for p in self.big}
+        from . import functional as F
+        F.decoder_grad_hooks.append(self._on_decoder_grad)
+
+    def _active(self) -> bool:
+        return self.enabled and self.flat.is_cuda and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _start(self, p: torch.nn.Parameter, g: torch.Tensor) -> None:
+        from . import _lib
+        main = torch.cuda.current_stream(g.device)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=g.device)
+        self._comm.wait_stream(main)                 # fork: the gradient is complete on `main` here
+        with torch.cuda.stream(self._comm):
+            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+        self._done[id(p)] = g
+        if self.reserved_sms > 0:
+            _lib.set_reserved_sms(self.reserved_sms)  # everything launched until reduce() leaves these SMs to NCCL
+
+    def _on_decoder_grad(self, dec_w, grad_w: torch.Tensor) -> bool:
+        """Called by the decoder's backward with the freshly written weight gradient.  When the parameter has no
+        gradient yet (`zero_grad(set_to_none=True)`, torch's default) the tensor BECOMES `.grad` here — what autograd's
+        AccumulateGrad would do a moment later, except that autograd declines to adopt a tensor somebody else (the
+        collective's work object) also references and would clone it underneath the running all-reduce — and its
+        all-reduce starts; returns True so that the backward hands autograd None for it.  Otherwise (accumulation into
+        an existing gradient) nothing happens here and the post-accumulate hook takes over."""
+        p = self._big_ids.get(id(dec_w))
+        if p is None or not self._active() or p.grad is not None or not grad_w.is_contiguous() or id(p) in self._done:
+            return False
+        if grad_w.dtype != p.dtype or grad_w.shape != p.shape:
+            return False
+        p.grad = grad_w
+        self._start(p, grad_w)
+        return True
+
+    def _on_big_grad(self, p: torch.nn.Parameter) -> None:
+        if not self._active() or p.grad is None or not p.grad.is_cuda or id(p) in self._done:
+            return
+        self._start(p, p.grad)
+
+    def reduce(self, grads=None) -> None:
+        if not self._active():
+            return super().reduce(grads)
+        from . import _lib
+        if self.reserved_sms > 0:
+            _lib.set_reserved_sms(0)
+        if grads is None:
+            grads = self.snapshot()
+        gmap = {id(p): g for p, g in zip(self.params, grads)}
+        if self._done:
+            torch.cuda.current_stream().wait_stream(self._comm)      # join
+        for p in self.big:
+            g = gmap[id(p)]
+            d = self._done.get(id(p))
+            if g is not None and (d is None or d.data_ptr() != g.data_ptr()):     # not seen by a hook (or replaced since)
+                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+        self._done.clear()
+        live = [(gmap[id(p)], v) for p, v in zip(self.small, self.views) if gmap[id(p)] is not None]
+        if not live:
+            return
+        if len(live) != len(self.small):
+            self.flat.zero_()
+        torch._foreach_copy_([v for _, v in live], [g for g, _ in live])
+        dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        torch._foreach_copy_([g for g, _ in live], [v for _, v in live])
+
+    def close(self) -> None:
+        from . import functional as F
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        if self._on_decoder_grad in F.decoder_grad_hooks:
+            F.decoder_grad_hooks.remove(self._on_decoder_grad)
+
+
 def identical_across_ranks(tensors: Iterable[torch.Tensor], group=None) -> bool:
     """True if every rank holds bit-identical tensors (data-parallel replicas must, after any number of steps): the
     int32 views are all-reduced with MIN and MAX and compared."""

@@ -40,6 +40,13 @@ int64_t carel_launch_count(void);
  * tensor-core kernel launch is bracketed by CUDA events on its stream; carel_timing_report writes
  * "tag total_ms count" lines into buf (device-synchronising) and clears the log. */
 void carel_timing_enable(int on);
+/* Data-parallel overlap (no reference counterpart: the reference has no multi-GPU path): while n > 0
+ * every kernel launched by this library sizes its grid for (SM count - n) SMs, so that a collective running on
+ * another stream (the NCCL all-reduce of the decoder gradient under the rest of the backward pass) finds free SMs
+ * instead of queueing behind the one-CTA-per-SM persistent kernels.  Process-wide, read at launch time (a captured
+ * CUDA graph keeps the grid it was captured with). */
+void carel_set_reserved_sms(int n);
+int carel_get_reserved_sms(void);
 int carel_timing_report(char* buf, size_t n);
 
 /* ------------------------------------------------------------------------------------------
@@ -136,6 +143,12 @@ int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, const float* 
 int carel_bow_bwd(const float* grad_out, const float* bow_dense, int64_t ld_bow, int64_t N, int64_t K,
                   int64_t V, int64_t ell_cap, float label_smoothing, float* grad_z, int64_t ldgz,
                   float* grad_w, float* grad_b, void* ws, size_t ws_bytes, void* stream);
+/* carel_bow_bwd in two parts (data-parallel overlap; the reference has no multi-GPU path): parts = 1 runs everything
+ * that completes grad_w / grad_b (and initialises grad_z), parts = 2 the dense grad_z kernel, 3 = both = carel_bow_bwd.
+ * Call 1 then 2 with the same arguments; between them grad_w may be handed to a collective on another stream. */
+int carel_bow_bwd_parts(const float* grad_out, const float* bow_dense, int64_t ld_bow, int64_t N, int64_t K,
+                  int64_t V, int64_t ell_cap, float label_smoothing, float* grad_z, int64_t ldgz,
+                  float* grad_w, float* grad_b, void* ws, size_t ws_bytes, int parts, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HSIC — replaces HSIC / GaussianKernelMatrix / pairwise_distances (drl_classifier_ec_hsic.py:529-547):
