@@ -4,6 +4,7 @@ the kernel's contract (block sums of a row-tile range) so no GPU is needed."""
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -95,12 +96,13 @@ def test_sharded_mmd_and_flat_bucket_world2():
     assert torch.equal(res[0][4], res[1][4])
 
 
-def _worker_reducer(rank, world, port, q):
+def _worker_reducer(rank, world, port, q, overlapped=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(3)                                   # same parameters on every rank
     net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 2))
-    red = par.GradReducer(net.parameters(), big_numel=100)   # the [16, 8] weight goes in place, the rest through the flat buffer
+    # the [16, 8] weight goes in place, the rest through the flat buffer
+    red = (par.OverlappedGradReducer if overlapped else par.GradReducer)(net.parameters(), big_numel=100)
     opt = torch.optim.SGD(net.parameters(), lr=0.1)
     same0 = par.identical_across_ranks(net.parameters())
     x = torch.ones(4, 8) * (rank + 1)
@@ -117,13 +119,16 @@ def _worker_reducer(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_grad_reducer_world2():
+@pytest.mark.parametrize("overlapped", [False, True])
+def test_grad_reducer_world2(overlapped):
     """GradReducer (data-parallel head training): averaged gradients through both paths, replicas stay
-    bit-identical after the optimiser step, and identical_across_ranks notices a difference."""
+    bit-identical after the optimiser step, and identical_across_ranks notices a difference.  OverlappedGradReducer
+    keeps the same protocol; on CPU tensors (gloo) its hooks stay inert and reduce() is the plain reduction — the
+    overlapped NCCL path is checked on GPUs inside bench.py (dp_overlap.max_rel_diff_vs_plain_allreduce)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_reducer, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker_reducer, args=(r, 2, port, q, overlapped)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
