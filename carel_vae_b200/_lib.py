@@ -54,6 +54,7 @@ _SIGNATURES = {
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_ptr, C.c_size_t, c_ptr]),
     "carel_bow_workspace_bytes": (C.c_size_t, [i64, i64, i64, i64]),
     "carel_bow_pack_ell": (C.c_int, [c_ptr, i64, i64, i64, i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "carel_bow_pack_ell_host": (C.c_int, [c_ptr, i64, i64, i64, i64, c_ptr, c_ptr, c_ptr, C.c_int]),
     "carel_bow_fwd": (C.c_int, [c_ptr, i64, c_ptr, c_ptr, c_ptr, i64, c_ptr, c_ptr, c_ptr, i64, i64, i64, i64,
                                 C.c_float, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "carel_bow_bwd": (C.c_int, [c_ptr, c_ptr, i64, i64, i64, i64, i64, C.c_float, c_ptr, i64, c_ptr, c_ptr,

@@ -106,3 +106,105 @@ def ell_collate_fn(cap: int = 64):
         out["bow_reps"] = (cols, vals, nnz)
         return out
     return collate
+
+
+def pack_ell_host(content_bow: torch.Tensor, cap: int = 64, out=None, threads: int = 0):
+    """Dense fp32 [B, V] BoW rows in HOST memory -> the ELL triple (cols int32 [B, cap], vals fp32 [B, cap], nnz int32 [B])
+    in host memory, by the library's multi-threaded scan (carel_bow_pack_ell_host): the same output as
+    `functional.bow_pack_ell` bit for bit.  `out` = a previously returned triple to reuse (pinned buffers stay pinned)."""
+    import ctypes as C
+    from ._lib import check, lib
+    if content_bow.is_cuda or content_bow.dtype != torch.float32 or content_bow.dim() != 2:
+        raise ValueError("pack_ell_host expects a 2-D fp32 CPU tensor (use functional.bow_pack_ell on the GPU)")
+    if content_bow.stride(1) != 1:
+        content_bow = content_bow.contiguous()
+    B, V = content_bow.shape
+    if out is None:
+        out = (torch.zeros((B, cap), dtype=torch.int32), torch.zeros((B, cap), dtype=torch.float32),
+               torch.zeros((B,), dtype=torch.int32))
+    cols, vals, nnz = out
+    if tuple(cols.shape) != (B, cap) or tuple(vals.shape) != (B, cap) or tuple(nnz.shape) != (B,):
+        raise ValueError("pack_ell_host: `out` does not match the batch")
+    check(lib().carel_bow_pack_ell_host(C.c_void_p(content_bow.data_ptr()), content_bow.stride(0), B, V, cap,
+                                        C.c_void_p(cols.data_ptr()), C.c_void_p(vals.data_ptr()),
+                                        C.c_void_p(nnz.data_ptr()), int(threads)), "carel_bow_pack_ell_host")
+    return out
+
+
+class HostBowStager:
+    """Moves a HOST-resident dense BoW target [B, V] (the reference's layout, mmd:100-119 / :830) to the GPU as the ELL
+    triple `DrlClassifier.forward(content_bow=...)` accepts, using the host cores and the PCIe link TOGETHER: the first
+    `host_rows` rows are scanned by the host threads (pack_ell_host; 27 MB of list instead of 983 MB of rows per 8192
+    clauses) while the copy engine ships the remaining rows dense and the GPU scans those (functional.bow_pack_ell).
+    `calibrate()` times both routes once and splits the rows so that they finish together.  Everything is issued on the
+    current stream without a host sync; the returned tensors are the stager's own device buffers, valid until the
+    next `stage()`.  One stager per (batch size, vocabulary, device)."""
+
+    def __init__(self, batch: int, vocab: int, device, cap: int = 64, host_fraction: float = 0.5, threads: int = 0,
+                 out=None):
+        self.B, self.V, self.cap, self.device, self.threads = batch, vocab, cap, torch.device(device), threads
+        self.host_rows = max(0, min(batch, int(round(batch * host_fraction))))
+        self._host = (torch.zeros((batch, cap), dtype=torch.int32).pin_memory(),
+                      torch.zeros((batch, cap), dtype=torch.float32).pin_memory(),
+                      torch.zeros((batch,), dtype=torch.int32).pin_memory())
+        if out is not None:          # caller-owned device buffers (e.g. the static inputs of a captured CUDA graph)
+            self.cols, self.vals, self.nnz = out
+        else:
+            self.cols = torch.zeros((batch, cap), dtype=torch.int32, device=self.device)
+            self.vals = torch.zeros((batch, cap), dtype=torch.float32, device=self.device)
+            self.nnz = torch.zeros((batch,), dtype=torch.int32, device=self.device)
+        self._dense = torch.empty((batch, vocab), dtype=torch.float32, device=self.device)   # landing zone of the dense part
+        self._done = None
+
+    def bytes_per_stage(self) -> int:
+        h = self.host_rows
+        return h * (self.cap * 8 + 4) + (self.B - h) * self.V * 4
+
+    def stage(self, content_bow: torch.Tensor):
+        from . import functional as F
+        if content_bow.is_cuda or tuple(content_bow.shape) != (self.B, self.V):
+            raise ValueError(f"HostBowStager.stage expects a CPU tensor of shape ({self.B}, {self.V})")
+        h = self.host_rows
+        if self._done is not None:
+            self._done.synchronize()        # the previous stage's copies have read the pinned list buffers
+        # (1) dense rows [h, B): async copy + GPU scan — enqueued first, so the DMA runs while the host scans
+        if h < self.B:
+            self._dense[h:].copy_(content_bow[h:], non_blocking=True)
+            c, v, n = F.bow_pack_ell(self._dense[h:], self.cap)
+            self.cols[h:].copy_(c, non_blocking=True)
+            self.vals[h:].copy_(v, non_blocking=True)
+            self.nnz[h:].copy_(n, non_blocking=True)
+        # (2) rows [0, h): host scan into pinned buffers, then the (small) list copy
+        if h > 0:
+            hc, hv, hn = (t[:h] for t in self._host)
+            pack_ell_host(content_bow[:h], self.cap, out=(hc, hv, hn), threads=self.threads)
+            self.cols[:h].copy_(hc, non_blocking=True)
+            self.vals[:h].copy_(hv, non_blocking=True)
+            self.nnz[:h].copy_(hn, non_blocking=True)
+        self._done = torch.cuda.Event()
+        self._done.record()
+        return self.cols, self.vals, self.nnz
+
+    def calibrate(self, content_bow: torch.Tensor, rounds: int = 2) -> float:
+        """Times the host scan and the dense copy + GPU scan (each on the full batch, alone) and sets `host_rows` to the
+        split at which both finish together; returns the host fraction."""
+        import time
+        from . import functional as F
+        t_host = 1e30
+        for _ in range(rounds):
+            t0 = time.perf_counter()
+            pack_ell_host(content_bow, self.cap, out=self._host, threads=self.threads)
+            t_host = min(t_host, time.perf_counter() - t0)
+        t_dev = 1e30
+        for _ in range(rounds):
+            torch.cuda.synchronize(self.device)
+            t0 = time.perf_counter()
+            self._dense.copy_(content_bow, non_blocking=True)
+            F.bow_pack_ell(self._dense, self.cap)
+            torch.cuda.synchronize(self.device)
+            t_dev = min(t_dev, time.perf_counter() - t0)
+        frac = t_dev / (t_dev + t_host)
+        self.host_rows = max(0, min(self.B, int(round(self.B * frac / 8)) * 8))
+        self.calibration = {"host_scan_ms": round(1e3 * t_host, 3), "copy_plus_gpu_scan_ms": round(1e3 * t_dev, 3),
+                            "host_fraction": round(self.host_rows / self.B, 3)}
+        return self.host_rows / self.B

@@ -96,3 +96,30 @@ def test_drop_in_dataset_dense_rows_and_ell_collate():
         assert torch.equal(rebuilt, bd["bow_reps"])
         for k in ("input_ids", "labels", "emo_labels", "cau_labels"):
             assert torch.equal(bd[k], be[k])
+
+
+def test_host_ell_packer_matches_a_plain_scan():
+    """carel_bow_pack_ell_host (data.pack_ell_host): ascending columns, v != 0 (so -0.0 is skipped), nnz counts every
+    non-zero while only the first `cap` are stored, ragged widths / unaligned rows, any thread count.  Pure host code:
+    runs without a GPU.  (The GPU scan carel_bow_pack_ell is held to the same outputs in tests/test_gpu_parity.py.)"""
+    import numpy as np
+    import torch
+    from carel_vae_b200 import _lib
+    from carel_vae_b200.data import pack_ell_host
+    if not _lib.LIB_PATH.exists():
+        pytest.skip("libcarel_head.so not built")
+    rng = np.random.default_rng(0)
+    for (B, V, per_row, cap, threads) in [(1, 7, 3, 4, 1), (37, 1001, 5, 8, 3), (64, 2050, 40, 8, 0), (300, 30000, 24, 64, 4)]:
+        dense = np.zeros((B, V + 3), dtype=np.float32)[:, 1:V + 1]          # row pitch != V, rows not 8-byte aligned
+        for r in range(B):
+            idx = rng.choice(V, size=min(per_row, V), replace=False)
+            dense[r, idx] = rng.random(len(idx)).astype(np.float32) + 0.01
+        dense[0, 0] = -0.0
+        t = torch.from_numpy(dense)
+        cols, vals, nnz = pack_ell_host(t, cap, threads=threads)
+        for r in range(B):
+            nz = np.flatnonzero(dense[r] != 0)
+            assert int(nnz[r]) == len(nz)
+            k = min(len(nz), cap)
+            assert np.array_equal(cols[r, :k].numpy(), nz[:k].astype(np.int32))
+            assert np.array_equal(vals[r, :k].numpy(), dense[r, nz[:k]])
