@@ -4,8 +4,9 @@
 // (ECPEDataset._get_bow_representations, drl_classifier_ec_mmd_final_mul.py:100-119) and copies them to the GPU every
 // step (:830): 983 MB per 8192-clause batch, 19 ms over PCIe Gen5 — 16x the whole train step.  A row holds ~24
 // non-zeros, so a host that scans its own rows and ships the list instead moves 27 MB.  This is the same scan as
-// carel_bow_pack_ell (bow.cu), bit for bit: ascending columns, `v != 0.f` (so -0.0 is skipped), the first `cap`
-// non-zeros of a row are stored and nnz[r] counts all of them.  Rows are split over `n_threads` std::threads; the
+// carel_bow_pack_ell (bow.cu): `v != 0.f` (so -0.0 is skipped), the first `cap` non-zeros of a row are stored and
+// nnz[r] counts all of them; the list is in ascending column order here (the GPU scan interleaves the four columns of a
+// lane inside a 128-column group: the same set of (column, value) pairs, which is all the consumers rely on).  Rows are split over `n_threads` std::threads; the
 // common all-zero stretch is skipped on the raw bits, 128 bytes at a time with AVX2 (runtime check), else 32.
 #include <immintrin.h>
 

@@ -110,8 +110,8 @@ def ell_collate_fn(cap: int = 64):
 
 def pack_ell_host(content_bow: torch.Tensor, cap: int = 64, out=None, threads: int = 0):
     """Dense fp32 [B, V] BoW rows in HOST memory -> the ELL triple (cols int32 [B, cap], vals fp32 [B, cap], nnz int32 [B])
-    in host memory, by the library's multi-threaded scan (carel_bow_pack_ell_host): the same output as
-    `functional.bow_pack_ell` bit for bit.  `out` = a previously returned triple to reuse (pinned buffers stay pinned)."""
+    in host memory, by the library's multi-threaded scan (carel_bow_pack_ell_host): the same non-zeros as
+    `functional.bow_pack_ell`, in ascending column order.  `out` = a previously returned triple to reuse (pinned buffers stay pinned)."""
     import ctypes as C
     from ._lib import check, lib
     if content_bow.is_cuda or content_bow.dtype != torch.float32 or content_bow.dim() != 2:

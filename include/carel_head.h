@@ -137,7 +137,8 @@ int carel_bow_pack_ell(const float* bow_dense, int64_t ld_bow, int64_t N, int64_
                        int32_t* ell_cols, float* ell_vals, int32_t* ell_nnz, void* stream);
 /* The same scan on the HOST (plain C++, std::thread; no CUDA call): for callers whose dense rows live in host memory,
  * as the reference's DataLoader yields them (:100-119) before the `.to(device)` of :830.  Same output as
- * carel_bow_pack_ell bit for bit (ascending columns, v != 0.f, nnz counts every non-zero, the first ell_cap are stored).
+ * carel_bow_pack_ell as a SET per row (v != 0.f, nnz counts every non-zero, the first ell_cap are stored); the host list
+ * is in ascending column order, the GPU scan interleaves the four columns of a lane inside a 128-column group.
  * n_threads <= 0: one per hardware thread.  The list (27 MB at N = 8192, cap = 32) replaces a 983 MB host-to-device copy. */
 int carel_bow_pack_ell_host(const float* bow_dense, int64_t ld_bow, int64_t N, int64_t V, int64_t ell_cap,
                             int32_t* ell_cols, float* ell_vals, int32_t* ell_nnz, int n_threads);

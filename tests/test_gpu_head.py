@@ -387,3 +387,60 @@ def test_club_mlp_kernels_match_torch(N, L):
     assert rel(mu, rmu) < 1e-5 and rel(lv, rlv) < 1e-5
     for g, r in zip(grads, rgrads):
         assert rel(g, r) < 1e-5
+
+
+@pytest.mark.parametrize("variant", ["mmd", "hsic"])
+def test_reserved_sms_do_not_change_the_result(variant):
+    """carel_set_reserved_sms (the data-parallel overlap leaves SMs to NCCL): every kernel sizes its grid for fewer SMs
+    and still computes the same step — values to 1e-6, gradients to 1e-5 of the full-grid run (different split-K /
+    stream-K cuts change the fp32 summation order, nothing else) — at a size where every persistent kernel has work
+    for all CTAs."""
+    from carel_vae_b200 import _lib
+    opt, model, b = _setup(variant, 2048, 128, 9000, 768, 0.0, seed=5)
+    model.train()
+    emo = b["emo"] if variant == "mmd" else b["emo"].float()
+    res = []
+    try:
+        for reserved in (0, 24, 100):
+            _lib.set_reserved_sms(reserved)
+            assert _lib.reserved_sms() == reserved
+            X = b["X"].clone().requires_grad_(True)
+            torch.manual_seed(3)
+            loss = model(X, None, None, emo, b["cau"], b["pair"], b["bow"], 3)
+            params = list(model.parameters())
+            grads = torch.autograd.grad(loss, [X] + params, allow_unused=True)
+            res.append((loss.detach(), grads))
+    finally:
+        _lib.set_reserved_sms(0)
+    (l0, g0) = res[0]
+    for (l, g) in res[1:]:
+        assert rel(l, l0) < 1e-6
+        for a, r in zip(g, g0):
+            if r is None:
+                assert a is None
+                continue
+            assert rel(a, r) < 1e-5
+
+
+def test_host_bow_stager_equals_the_gpu_scan():
+    """data.HostBowStager: host rows scanned on the host, the rest copied dense and scanned on the GPU — the staged ELL
+    triple holds exactly the non-zeros of the batch for any split (the host list is in ascending column order, the GPU
+    scan interleaves the four columns of a lane inside a 128-column group: same set, same values)."""
+    from carel_vae_b200.data import HostBowStager
+    from carel_vae_b200 import functional as F
+    N, V, cap = 300, 5000, 32
+    bow = ho.synthetic_batch(N, V, D=8, nnz=24, seed=2, device="cpu")["bow"].pin_memory()
+    ref = F.bow_pack_ell(bow.to(DEV), cap)
+    for frac in (0.0, 0.37, 1.0):
+        st = HostBowStager(N, V, DEV, cap=cap, host_fraction=frac, threads=3)
+        for _ in range(2):                                  # second call reuses the pinned buffers
+            cols, vals, nnz = st.stage(bow)
+        torch.cuda.synchronize()
+        assert torch.equal(nnz, ref[2])
+        k = torch.arange(cap, device=DEV)[None, :] < nnz[:, None]
+        back = torch.zeros(N, V, device=DEV)
+        rows = torch.arange(N, device=DEV)[:, None].expand(N, cap)
+        back[rows[k], cols[k].long()] = vals[k]
+        assert torch.equal(back, bow.to(DEV))
+    st.calibrate(bow)
+    assert 0 <= st.host_rows <= N and st.bytes_per_stage() > 0
