@@ -136,54 +136,144 @@ class HostBowStager:
     triple `DrlClassifier.forward(content_bow=...)` accepts, using the host cores and the PCIe link TOGETHER: the first
     `host_rows` rows are scanned by the host threads (pack_ell_host; 27 MB of list instead of 983 MB of rows per 8192
     clauses) while the copy engine ships the remaining rows dense and the GPU scans those (functional.bow_pack_ell).
-    `calibrate()` times both routes once and splits the rows so that they finish together.  Everything is issued on the
-    current stream without a host sync; the returned tensors are the stager's own device buffers, valid until the
-    next `stage()`.  One stager per (batch size, vocabulary, device)."""
+    `calibrate()` times both routes once and splits the rows so that they finish together; `adapt=True` keeps moving
+    the split towards the point where the two routes measured in the previous stages take the same time.
+
+    `pipelined=False`: everything is issued on the current stream; the returned tensors are the stager's own device
+    buffers (or `out`), valid until the next `stage()`.
+
+    `pipelined=True`: the copies and the GPU scan run on the stager's own stream into one of TWO buffer sets, so batch
+    k + 1 is staged (host scan and PCIe copy) while the current stream still trains on batch k; the current stream only
+    waits for the set to be complete and, when `out` is given (e.g. the static inputs of a captured CUDA graph), copies
+    it there device-to-device.  Without `out` the returned set stays valid until the next-but-one `stage()`, and
+    whatever reads it must be enqueued on the current stream before the next `stage()` call.  `stage(bow, copies=...)`
+    takes the batch's other host tensors along the same way (`(device_dst, host_src)` pairs).
+
+    No call synchronises the host with the GPU except on the buffer set used two stages (pipelined) / one stage ago.
+    One stager per (batch size, vocabulary, device)."""
 
     def __init__(self, batch: int, vocab: int, device, cap: int = 64, host_fraction: float = 0.5, threads: int = 0,
-                 out=None):
+                 out=None, pipelined: bool = False, adapt: bool = False):
         self.B, self.V, self.cap, self.device, self.threads = batch, vocab, cap, torch.device(device), threads
         self.host_rows = max(0, min(batch, int(round(batch * host_fraction))))
-        self._host = (torch.zeros((batch, cap), dtype=torch.int32).pin_memory(),
-                      torch.zeros((batch, cap), dtype=torch.float32).pin_memory(),
-                      torch.zeros((batch,), dtype=torch.int32).pin_memory())
-        if out is not None:          # caller-owned device buffers (e.g. the static inputs of a captured CUDA graph)
-            self.cols, self.vals, self.nnz = out
+        self.pipelined, self.adapt = bool(pipelined), bool(adapt)
+        nset = 2 if self.pipelined else 1
+
+        def dev_set():
+            return (torch.zeros((batch, cap), dtype=torch.int32, device=self.device),
+                    torch.zeros((batch, cap), dtype=torch.float32, device=self.device),
+                    torch.zeros((batch,), dtype=torch.int32, device=self.device))
+        self._hosts = [(torch.zeros((batch, cap), dtype=torch.int32).pin_memory(),
+                        torch.zeros((batch, cap), dtype=torch.float32).pin_memory(),
+                        torch.zeros((batch,), dtype=torch.int32).pin_memory()) for _ in range(nset)]
+        self._host = self._hosts[0]
+        self._out = tuple(out) if out is not None else None   # caller-owned device buffers
+        if self.pipelined:
+            self._sets = [dev_set() for _ in range(nset)]
         else:
-            self.cols = torch.zeros((batch, cap), dtype=torch.int32, device=self.device)
-            self.vals = torch.zeros((batch, cap), dtype=torch.float32, device=self.device)
-            self.nnz = torch.zeros((batch,), dtype=torch.int32, device=self.device)
+            self._sets = [self._out if self._out is not None else dev_set()]
+        self.cols, self.vals, self.nnz = self._out if self._out is not None else self._sets[0]
         self._dense = torch.empty((batch, vocab), dtype=torch.float32, device=self.device)   # landing zone of the dense part
-        self._done = None
+        self._side = torch.cuda.Stream(self.device) if self.pipelined else None
+        self._ready = [None] * nset       # copy-stream event: set i is complete (its pinned lists have been read)
+        self._consumed = [None] * nset    # current-stream event: everything that read set i has been enqueued before it
+        self._meas = [None] * nset        # (host rows, host scan ms, start event, end event) of the stage that filled set i
+        self._staging = [dict() for _ in range(nset)]
+        self._k = 0
+        self._last = None
+        self.calibration = None
 
     def bytes_per_stage(self) -> int:
         h = self.host_rows
         return h * (self.cap * 8 + 4) + (self.B - h) * self.V * 4
 
-    def stage(self, content_bow: torch.Tensor):
+    def _rebalance(self, i: int) -> None:
+        """Moves `host_rows` half-way to the split at which the two routes, at the rates measured when set i was
+        filled, finish together (fixed point: host scan time == copy + GPU scan time)."""
+        m, self._meas[i] = self._meas[i], None
+        if m is None or not self.adapt:
+            return
+        h, t_host, e0, e1 = m
+        t_dev = e0.elapsed_time(e1)
+        if not (0 < h < self.B) or t_host <= 0.0 or t_dev <= 0.0:
+            return
+        r_host, r_dev = h / t_host, (self.B - h) / t_dev
+        target = self.B * r_host / (r_host + r_dev)
+        new = self.host_rows + 0.5 * (target - self.host_rows)
+        self.host_rows = max(8, min(self.B - 8, int(round(new / 8)) * 8)) if self.B >= 24 else self.host_rows
+
+    def stage(self, content_bow: torch.Tensor, copies=()):
+        import time
         from . import functional as F
         if content_bow.is_cuda or tuple(content_bow.shape) != (self.B, self.V):
             raise ValueError(f"HostBowStager.stage expects a CPU tensor of shape ({self.B}, {self.V})")
+        main = torch.cuda.current_stream(self.device)
+        i = (self._k & 1) if self.pipelined else 0
+        self._k += 1
+        if self.pipelined and self._last is not None and self._out is None:
+            ev = torch.cuda.Event()           # the caller has enqueued its reads of the previous set by now
+            ev.record(main)
+            self._consumed[self._last] = ev
+        if self._ready[i] is not None:
+            self._ready[i].synchronize()      # the copies that read pinned set i (one / two stages ago) have finished
+            self._rebalance(i)
         h = self.host_rows
-        if self._done is not None:
-            self._done.synchronize()        # the previous stage's copies have read the pinned list buffers
-        # (1) dense rows [h, B): async copy + GPU scan — enqueued first, so the DMA runs while the host scans
-        if h < self.B:
-            self._dense[h:].copy_(content_bow[h:], non_blocking=True)
-            c, v, n = F.bow_pack_ell(self._dense[h:], self.cap)
-            self.cols[h:].copy_(c, non_blocking=True)
-            self.vals[h:].copy_(v, non_blocking=True)
-            self.nnz[h:].copy_(n, non_blocking=True)
+        side = self._side if self.pipelined else main
+        cols, vals, nnz = self._sets[i]
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        staged = []
+        with torch.cuda.stream(side):
+            if self.pipelined and self._consumed[i] is not None:
+                side.wait_event(self._consumed[i])          # set i is free to be overwritten
+            e0.record(side)
+            for j, (dst, src) in enumerate(copies):
+                if self.pipelined:
+                    stg = self._staging[i].get(j)
+                    if stg is None or stg.shape != dst.shape or stg.dtype != dst.dtype:
+                        stg = self._staging[i][j] = torch.empty_like(dst)
+                    stg.copy_(src, non_blocking=True)
+                    staged.append((dst, stg))
+                else:
+                    dst.copy_(src, non_blocking=True)
+            # (1) dense rows [h, B): async copy + GPU scan — enqueued first, so the DMA runs while the host scans
+            if h < self.B:
+                self._dense[h:].copy_(content_bow[h:], non_blocking=True)
+                c, v, n = F.bow_pack_ell(self._dense[h:], self.cap)
+                cols[h:].copy_(c, non_blocking=True)
+                vals[h:].copy_(v, non_blocking=True)
+                nnz[h:].copy_(n, non_blocking=True)
+            e1.record(side)
         # (2) rows [0, h): host scan into pinned buffers, then the (small) list copy
+        t_host = 0.0
         if h > 0:
-            hc, hv, hn = (t[:h] for t in self._host)
+            hc, hv, hn = (t[:h] for t in self._hosts[i])
+            t0 = time.perf_counter()
             pack_ell_host(content_bow[:h], self.cap, out=(hc, hv, hn), threads=self.threads)
-            self.cols[:h].copy_(hc, non_blocking=True)
-            self.vals[:h].copy_(hv, non_blocking=True)
-            self.nnz[:h].copy_(hn, non_blocking=True)
-        self._done = torch.cuda.Event()
-        self._done.record()
-        return self.cols, self.vals, self.nnz
+            t_host = 1e3 * (time.perf_counter() - t0)
+            with torch.cuda.stream(side):
+                cols[:h].copy_(hc, non_blocking=True)
+                vals[:h].copy_(hv, non_blocking=True)
+                nnz[:h].copy_(hn, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(side)
+        self._ready[i] = ready
+        self._meas[i] = (h, t_host, e0, e1)
+        self._last = i
+        if not self.pipelined:
+            return self._sets[0]
+        main.wait_event(ready)
+        for dst, stg in staged:
+            dst.copy_(stg, non_blocking=True)
+        if self._out is None:
+            self.cols, self.vals, self.nnz = cols, vals, nnz
+            return cols, vals, nnz
+        for dst, src in zip(self._out, (cols, vals, nnz)):
+            dst.copy_(src, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._consumed[i] = ev
+        return self._out
 
     def calibrate(self, content_bow: torch.Tensor, rounds: int = 2) -> float:
         """Times the host scan and the dense copy + GPU scan (each on the full batch, alone) and sets `host_rows` to the
@@ -193,7 +283,7 @@ class HostBowStager:
         t_host = 1e30
         for _ in range(rounds):
             t0 = time.perf_counter()
-            pack_ell_host(content_bow, self.cap, out=self._host, threads=self.threads)
+            pack_ell_host(content_bow, self.cap, out=self._hosts[0], threads=self.threads)
             t_host = min(t_host, time.perf_counter() - t0)
         t_dev = 1e30
         for _ in range(rounds):

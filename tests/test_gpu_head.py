@@ -444,3 +444,36 @@ def test_host_bow_stager_equals_the_gpu_scan():
         assert torch.equal(back, bow.to(DEV))
     st.calibrate(bow)
     assert 0 <= st.host_rows <= N and st.bytes_per_stage() > 0
+
+
+@pytest.mark.parametrize("with_out", [False, True])
+def test_host_bow_stager_pipelined_keeps_batches_apart(with_out):
+    """HostBowStager(pipelined=True): staging runs on the stager's own stream into two buffer sets while the current
+    stream consumes the previous batch.  Six DIFFERENT batches in a row, each consumed by a (deliberately slow) kernel
+    queue on the current stream: every staged triple and every side copy must be its own batch's, for a caller-owned
+    `out` (graph inputs) and for the stager's own sets, with the split adapting on the way."""
+    from carel_vae_b200.data import HostBowStager
+    from carel_vae_b200 import functional as F
+    N, V, cap = 264, 4000, 32
+    batches = [ho.synthetic_batch(N, V, D=8, nnz=20, seed=10 + s, device="cpu")["bow"].pin_memory() for s in range(6)]
+    extras = [torch.full((N, 8), float(s)).pin_memory() for s in range(6)]
+    out = tuple(torch.zeros_like(t) for t in F.bow_pack_ell(batches[0].to(DEV), cap)) if with_out else None
+    x_dev = torch.zeros(N, 8, device=DEV)
+    st = HostBowStager(N, V, DEV, cap=cap, host_fraction=0.4, threads=2, out=out, pipelined=True, adapt=True)
+    busy = torch.randn(2048, 2048, device=DEV)
+    got = []
+    for s, (bow, ex) in enumerate(zip(batches, extras)):
+        cols, vals, nnz = st.stage(bow, copies=[(x_dev, ex)])
+        for _ in range(4):                                   # keeps the current stream busy past the next stage() call
+            busy = (busy @ busy).clamp_(-1, 1)
+        k = torch.arange(cap, device=DEV)[None, :] < nnz[:, None]
+        back = torch.zeros(N, V, device=DEV)
+        rows = torch.arange(N, device=DEV)[:, None].expand(N, cap)
+        back[rows[k], cols[k].long()] = vals[k]
+        got.append((back, nnz.clone(), x_dev.clone()))
+    torch.cuda.synchronize()
+    for s, (back, nnz, x) in enumerate(got):
+        assert torch.equal(back, batches[s].to(DEV)), f"batch {s}"
+        assert torch.equal(nnz.cpu(), (batches[s] != 0).sum(1).int()), f"batch {s}"
+        assert torch.equal(x.cpu(), extras[s]), f"batch {s}"
+    assert 8 <= st.host_rows <= N - 8 and st.host_rows % 8 == 0
