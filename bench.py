@@ -561,7 +561,7 @@ def run_head(args):
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                "config": {"workload": WORKLOADS[variant], "global_batch": N_ROWS * world, "parallelism": f"dp{world}", "l2": L2_NOTE},
-               "cuda_graph": dense.graphs is not None,
+               "cuda_graph": dense.graphs is not None, "side_branches": _lib.side_branches(),
                "dp_overlap": ({"reserved_sms": dense.overlap_sms, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"),
                                "single_graph": dense.graphs is not None and len(dense.graphs) == 1,
                                "max_rel_diff_vs_plain_allreduce": overlap_check} if world > 1 else None),

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "carel_timing_enable": (None, [C.c_int]),
     "carel_set_reserved_sms": (None, [C.c_int]),
     "carel_get_reserved_sms": (C.c_int, []),
+    "carel_set_side_branches": (None, [C.c_int]),
+    "carel_get_side_branches": (C.c_int, []),
     "carel_timing_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "carel_gemm_bf16": (C.c_int, [c_ptr, i64, C.c_int, c_ptr, i64, C.c_int, i64, i64, i64, c_ptr, i64,
                                   c_ptr, C.c_int, c_ptr]),
@@ -165,6 +167,15 @@ def set_reserved_sms(n: int) -> None:
 
 def reserved_sms() -> int:
     return int(lib().carel_get_reserved_sms())
+
+
+def set_side_branches(on: bool) -> None:
+    """carel_bow_fwd's sparse-target branch on the library's second stream (see carel_set_side_branches)."""
+    lib().carel_set_side_branches(1 if on else 0)
+
+
+def side_branches() -> bool:
+    return bool(lib().carel_get_side_branches())
 
 
 def timing_enable(on: bool) -> None:

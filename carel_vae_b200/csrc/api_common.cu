@@ -1,4 +1,6 @@
 // api_common.cu — error string, version, launch counter, debug GEMM and dense pairwise entry points.
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <string>
@@ -8,6 +10,10 @@
 #include "epilogues.cuh"
 #include "gemm_launch.cuh"
 #include "pack.cuh"
+
+#ifndef CAREL_SIDE_BRANCHES_DEFAULT
+#define CAREL_SIDE_BRANCHES_DEFAULT 0      // flipped to 1 once a GPU run has shown parity and a shorter step with it
+#endif
 
 namespace carel {
 
@@ -33,6 +39,31 @@ int sm_count() {
   }
   const int r = g_reserved_sms.load(std::memory_order_relaxed);
   return (r > 0 && n - r >= 8) ? n - r : n;
+}
+
+// Side branches (api_common.cuh): one stream + three events per device, created on first use.
+std::atomic<int> g_side_branches{[] {
+  const char* e = getenv("CAREL_SIDE_BRANCHES");
+  return e != nullptr ? (atoi(e) != 0 ? 1 : 0) : CAREL_SIDE_BRANCHES_DEFAULT;
+}()};
+SideBranch* side_branch() {
+  if (g_side_branches.load(std::memory_order_relaxed) == 0) return nullptr;
+  static std::mutex mu;
+  static SideBranch table[64];
+  static int state[64] = {0};          // 0 not tried, 1 ready, -1 failed
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (state[dev] == 0) {
+    SideBranch& b = table[dev];
+    const bool ok = cudaStreamCreateWithFlags(&b.s, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.ev_join[0], cudaEventDisableTiming) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&b.ev_join[1], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) (void)cudaGetLastError();
+    state[dev] = ok ? 1 : -1;
+  }
+  return state[dev] == 1 ? &table[dev] : nullptr;
 }
 
 namespace {
@@ -73,6 +104,9 @@ using namespace carel;
 
 extern "C" void carel_set_reserved_sms(int n) { g_reserved_sms.store(n < 0 ? 0 : n, std::memory_order_relaxed); }
 extern "C" int carel_get_reserved_sms(void) { return g_reserved_sms.load(std::memory_order_relaxed); }
+
+extern "C" void carel_set_side_branches(int on) { g_side_branches.store(on != 0 ? 1 : 0, std::memory_order_relaxed); }
+extern "C" int carel_get_side_branches(void) { return g_side_branches.load(std::memory_order_relaxed); }
 
 extern "C" void carel_timing_enable(int on) {
   g_timing.store(on != 0);

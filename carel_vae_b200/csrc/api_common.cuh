@@ -51,6 +51,26 @@ void timing_end(cudaStream_t st);
     CAREL_CHECK_CUDA(cudaGetLastError());              \
   } while (0)
 
+// A library-owned second stream per device for work that is independent of the caller's stream inside ONE entry point
+// (carel_bow_fwd: the sparse-target branch).  fork(): the side stream waits for everything enqueued on `st` so far;
+// join(k): `st` waits for everything enqueued on the side stream so far (k = which of the join events to use: a later
+// fork / join of the same call must not re-record an event an earlier wait still refers to under graph capture).
+// Event record / wait pairs are capturable: under CUDA-graph capture the side work becomes a parallel branch.
+// nullptr when disabled (carel_set_side_branches / CAREL_SIDE_BRANCHES) or when stream / event creation failed.
+struct SideBranch {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaError_t fork(cudaStream_t st) {
+    cudaError_t e = cudaEventRecord(ev_fork, st);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(s, ev_fork, 0);
+  }
+  cudaError_t join(cudaStream_t st, int k) {
+    cudaError_t e = cudaEventRecord(ev_join[k], s);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(st, ev_join[k], 0);
+  }
+};
+SideBranch* side_branch();
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int64_t round_up64(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 

@@ -1004,6 +1004,40 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   CAREL_REQUIRE(ws != nullptr && ws_bytes >= w.bytes, "carel_bow_fwd: workspace too small");
   const int cap = int(ell_cap), sms = sm_count();
   const int truncate = bow_dense == nullptr ? 1 : 0;
+  // ---- sparse target, on the side branch when there is one (api_common.cuh): the dense -> ELL scan (or the copy of the
+  //      caller's list) and the CSC view of the list for the backward gathers depend on the target only, so they run
+  //      beside the operand packing and whatever the dense pass leaves free; the list is joined in front of the sparse
+  //      corrections, the CSC view at the end of this call ----
+  SideBranch* sb = timing_enabled() ? nullptr : side_branch();      // per-kernel timing passes measure kernels alone
+  cudaStream_t ss = sb != nullptr ? sb->s : st;
+  if (sb != nullptr) CAREL_CHECK_CUDA(sb->fork(st));
+  if (ell_cols_in != nullptr) {
+    CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_cols, ell_cols_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, ss));
+    CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_vals, ell_vals_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, ss));
+    CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_nnz, ell_nnz_in, size_t(N) * 4, cudaMemcpyDeviceToDevice, ss));
+  } else {
+    bow_pack_ell_kernel<8, 256, 1><<<int(std::min<int64_t>((N + 7) / 8, sms * 32)), 256, 0, ss>>>(bow_dense, ld_bow, int(N), int(V), cap, w.ell_cols, w.ell_vals, w.ell_nnz);
+    CAREL_LAUNCHED();
+  }
+  auto csc_view = [&]() -> int {      // CSC view of the non-zero list for the backward gather (cheap: N*cap entries)
+    CAREL_CHECK_CUDA(cudaMemsetAsync(w.fillpos, 0, (size_t(V) + 1) * 4, ss));
+    csc_count_kernel<<<sms * 2, 256, 0, ss>>>(w.ell_cols, w.ell_nnz, int(N), cap, truncate, w.fillpos);
+    CAREL_LAUNCHED();
+    {
+      static const cudaError_t attr = cudaFuncSetAttribute(csc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           kScanSmemBytes);
+      CAREL_CHECK_CUDA(attr);
+    }
+    csc_scan_kernel<<<1, 1024, kScanSmemBytes, ss>>>(w.fillpos, int(V), w.colptr, w.fillpos);
+    CAREL_LAUNCHED();
+    csc_fill_kernel<<<sms * 2, 256, 0, ss>>>(w.ell_cols, w.ell_nnz, int(N), cap, truncate, w.fillpos, w.csc_row, w.csc_slot);
+    CAREL_LAUNCHED();
+    return 0;
+  };
+  if (sb != nullptr) {
+    CAREL_CHECK_CUDA(cudaEventRecord(sb->ev_join[0], ss));       // the list is complete here
+    if (int rc = csc_view()) return rc;
+  }
   // ---- operands: W_d -> fp16, its column sums / bias constants, then Z -> fp16 with the row references ----
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.wsum, 0, (size_t(w.ldk) + 4) * 4, st));
   CAREL_CHECK_CUDA(cudaMemsetAsync(w.lossacc, 0, 2 * sizeof(double), st));
@@ -1021,15 +1055,6 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   bow_pack_f16_kernel<<<int((N + 7) / 8), 256, 0, st>>>(z, int(N), int(K), ldz, w.ZH, w.ldk, w.wsum, 1.f / float(V), w.rm,
                                                       w.rowenc, w.rowc, rmax_bits);
   CAREL_LAUNCHED();
-  // ---- sparse target ----
-  if (ell_cols_in != nullptr) {
-    CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_cols, ell_cols_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, st));
-    CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_vals, ell_vals_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, st));
-    CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_nnz, ell_nnz_in, size_t(N) * 4, cudaMemcpyDeviceToDevice, st));
-  } else {
-    bow_pack_ell_kernel<8, 256, 1><<<int(std::min<int64_t>((N + 7) / 8, sms * 32)), 256, 0, st>>>(bow_dense, ld_bow, int(N), int(V), cap, w.ell_cols, w.ell_vals, w.ell_nnz);
-    CAREL_LAUNCHED();
-  }
   // ---- pass F: the one dense pass (online max, power sums, stored logits) + per-row combine ----
   CUtensorMap ta, tb;
   CAREL_REQUIRE(make_tmap_f16_sw128(&ta, w.ZH, N, w.ldk, w.ldk, 128) == 0, "carel_bow_fwd: tensor map Z failed");
@@ -1050,26 +1075,19 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   bow_exact_rows_kernel<<<sms * 4, 256, 0, st>>>(w.Y, w.ldy, int(V), label_smoothing / float(V), w.bl2e,
                                                 w.flag_list, w.counters, w.rowc, w.lossacc);
   CAREL_LAUNCHED();
-  // ---- sparse corrections ----
+  // ---- sparse corrections (need the list) ----
+  if (sb != nullptr) CAREL_CHECK_CUDA(cudaStreamWaitEvent(st, sb->ev_join[0], 0));
   bow_sparse_fwd_kernel<<<int(std::min<int64_t>((N + 7) / 8, sms * 16)), 256, 0, st>>>(
       w.Y, w.ldy, w.bl2e, w.rowc, w.ell_cols, w.ell_vals, w.ell_nnz, w.ell_ev, bow_dense, ld_bow, int(N), int(V), cap,
       1.f - label_smoothing, label_smoothing / float(V), w.Npad, w.lossacc, w.counters);
   CAREL_LAUNCHED();
   bow_loss_finalize_kernel<<<1, 32, 0, st>>>(w.lossacc, w.counters, 1.0 / (double(N) * double(V)), loss_out);
   CAREL_LAUNCHED();
-  // CSC view of the non-zero list for the backward gather (cheap: N*cap entries)
-  CAREL_CHECK_CUDA(cudaMemsetAsync(w.fillpos, 0, (size_t(V) + 1) * 4, st));
-  csc_count_kernel<<<sms * 2, 256, 0, st>>>(w.ell_cols, w.ell_nnz, int(N), cap, truncate, w.fillpos);
-  CAREL_LAUNCHED();
-  {
-    static const cudaError_t attr = cudaFuncSetAttribute(csc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         kScanSmemBytes);
-    CAREL_CHECK_CUDA(attr);
+  if (sb != nullptr) {
+    CAREL_CHECK_CUDA(sb->join(st, 1));      // the CSC view (and with it everything on the side stream) is complete
+  } else if (int rc = csc_view()) {
+    return rc;
   }
-  csc_scan_kernel<<<1, 1024, kScanSmemBytes, st>>>(w.fillpos, int(V), w.colptr, w.fillpos);
-  CAREL_LAUNCHED();
-  csc_fill_kernel<<<sms * 2, 256, 0, st>>>(w.ell_cols, w.ell_nnz, int(N), cap, truncate, w.fillpos, w.csc_row, w.csc_slot);
-  CAREL_LAUNCHED();
   return 0;
 }
 

@@ -47,6 +47,14 @@ void carel_timing_enable(int on);
  * CUDA graph keeps the grid it was captured with). */
 void carel_set_reserved_sms(int n);
 int carel_get_reserved_sms(void);
+/* Side branches (no reference counterpart): with on != 0, carel_bow_fwd enqueues the part of its work that depends on
+ * the BoW target only (dense -> ELL scan or the copy of a caller's ELL triple, then the CSC view the backward gathers
+ * through) on a library-owned second stream per device, forked from and joined back into the caller's stream with
+ * event record / wait pairs, so that it runs beside the operand packing and the tail of the dense pass; under
+ * CUDA-graph capture it becomes a parallel branch of the graph.  Results are identical (the same kernels on the same
+ * data).  Process-wide; the initial value comes from the environment variable CAREL_SIDE_BRANCHES when it is set. */
+void carel_set_side_branches(int on);
+int carel_get_side_branches(void);
 int carel_timing_report(char* buf, size_t n);
 
 /* ------------------------------------------------------------------------------------------
