@@ -168,10 +168,7 @@ def mmd(sample_1: torch.Tensor, sample_2: torch.Tensor, alphas: Sequence[float],
     return _MMDFn.apply(sample_1, sample_2, tuple(alphas), eps, flags, (0, -1), _lib.precision_code(precision))
 
 
-def pairwise(a: torch.Tensor, b: torch.Tensor, mode: int, alphas: Sequence[float] = (), eps: float = 1e-5):
-    """Dense [n1, n2] matrix: mode 0 kernel sum, 1 pdist, 2 squared distances, 3 exp(-d2 * alphas[0])."""
-    _require_cuda(a, b)
-    af, bf = _rowmajor_f32(a), _rowmajor_f32(b)
+def _pairwise_raw(af: torch.Tensor, bf: torch.Tensor, mode: int, alphas, eps: float) -> torch.Tensor:
     n1, d = af.shape
     n2 = bf.shape[0]
     L = lib()
@@ -181,6 +178,65 @@ def pairwise(a: torch.Tensor, b: torch.Tensor, mode: int, alphas: Sequence[float
     check(L.carel_pairwise(_p(af), af.stride(0), _p(bf), bf.stride(0), n1, n2, d, mode, al, len(alphas),
                            float(eps), _p(out), n2, _p(ws), ws.numel(), _stream()), "carel_pairwise")
     return out
+
+
+def _f32_gemm(a, ta: bool, b, tb: bool, M: int, N: int, K: int, alpha: float = 1.0) -> torch.Tensor:
+    """C[M, N] = alpha opA(A) opB(B) through carel_f32_gemm (ta: A is [K, M]; tb: B is [K, N], else [N, K])."""
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    check(lib().carel_f32_gemm(_p(a), a.stride(0), int(ta), _p(b), b.stride(0), int(tb), M, N, K, _p(c), N, None,
+                               float(alpha), 0, 1, _stream()), "carel_f32_gemm")
+    return c
+
+
+class _PairwiseFn(torch.autograd.Function):
+    """Dense pairwise matrices as differentiable ops (the reference's pdist / pairwise_distances /
+    GaussianKernelMatrix are plain autograd code, mmd:580-596, hsic:529-537).  With M_ij = f(d2_ij),
+    d2_ij = |a_i|^2 + |b_j|^2 - 2 a_i.b_j and W = G * f'(d2):  grad_a = 2 (rowsum(W) a - W b),
+    grad_b = 2 (colsum(W) b - W^T a); the two products run on the library's fp32 GEMM."""
+
+    @staticmethod
+    def forward(ctx, a, b, mode, alphas, eps):
+        af, bf = _rowmajor_f32(a), _rowmajor_f32(b)
+        out = _pairwise_raw(af, bf, mode, alphas, eps)
+        ctx.save_for_backward(af, bf, out)
+        ctx.meta = (mode, tuple(float(x) for x in alphas), float(eps), a.dtype, b.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        af, bf, out = ctx.saved_tensors
+        mode, alphas, eps, dta, dtb = ctx.meta
+        g = g.float().contiguous()
+        if mode == 2:                      # d2 itself
+            w = g
+        elif mode == 3:                    # exp(-alpha d2)
+            w = g * out * (-alphas[0])
+        elif mode == 1:                    # sqrt(eps + |d2|): the sign of d2 is torch's abs() rule, 0 at 0
+            d2 = _pairwise_raw(af, bf, 2, (), eps)
+            w = g * torch.sign(d2) / (2.0 * out)
+        else:
+            raise NotImplementedError("the kernel-sum matrix (MMDStatistic(..., ret_matrix=True)) is returned detached")
+        n1, d = af.shape
+        n2 = bf.shape[0]
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = 2.0 * (w.sum(1, keepdim=True) * af - _f32_gemm(w, False, bf, True, n1, d, n2))
+            ga = ga.to(dta)
+        if ctx.needs_input_grad[1]:
+            gb = 2.0 * (w.sum(0)[:, None] * bf - _f32_gemm(w, True, af, True, n2, d, n1))
+            gb = gb.to(dtb)
+        return ga, gb, None, None, None
+
+
+def pairwise(a: torch.Tensor, b: torch.Tensor, mode: int, alphas: Sequence[float] = (), eps: float = 1e-5):
+    """Dense [n1, n2] matrix: mode 0 kernel sum, 1 pdist, 2 squared distances, 3 exp(-d2 * alphas[0]).
+    Differentiable w.r.t. both inputs for modes 1-3 (`a is b` — pairwise_distances(x) — receives both halves)."""
+    _require_cuda(a, b)
+    if torch.is_grad_enabled() and (a.requires_grad or b.requires_grad):
+        if mode == 0:
+            raise NotImplementedError("pairwise mode 0 (kernel-sum matrix) is not differentiable; detach the inputs")
+        return _PairwiseFn.apply(a, b, int(mode), tuple(alphas), float(eps))
+    return _pairwise_raw(_rowmajor_f32(a), _rowmajor_f32(b), int(mode), alphas, eps)
 
 
 def gemm_bf16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, bias=None,

@@ -502,3 +502,35 @@ def test_bow_full_size_vs_oracle():
     # (db is the column sum of the fp16-rounded dlogit tiles the dW tensor-core product consumes: the zero sum holds
     # to their rounding noise, 2^-12 / sqrt(#terms) of sum |db| ~ 1e-5, far inside the 1e-3 gradient tolerance)
     assert abs(float(b.grad.double().sum())) < 1e-4 * float(b.grad.double().abs().sum())
+
+
+@pytest.mark.parametrize("n1,n2,d", [(130, 257, 64), (512, 300, 100)])
+def test_dense_pairwise_helpers_are_differentiable(n1, n2, d):
+    """pdist / pairwise_distances / GaussianKernelMatrix are plain autograd code in the reference (mmd:580-596,
+    hsic:529-537), so a loss built from them has gradients; here the backward is W = G f'(d2) followed by two fp32
+    GEMMs of the library.  Against the fp64 oracle on the same bf16-rounded inputs; the forward matrix carries the
+    bf16-tier's operand rounding, hence 2e-2 on the gradients (measured far below)."""
+    torch.manual_seed(n1 + d)
+    x = bf(torch.randn(n1, d, device=DEV)).requires_grad_(True)
+    y = bf(0.5 * torch.randn(n2, d, device=DEV) + 0.3).requires_grad_(True)
+    x64, y64 = x.detach().double().requires_grad_(True), y.detach().double().requires_grad_(True)
+    # pdist(x, y): both gradients
+    g = torch.randn(n1, n2, device=DEV)
+    out = cv.pdist(x, y)
+    ref = ho.pdist(x64, y64)
+    assert rel(out, ref) < 5e-3
+    gx, gy = torch.autograd.grad((out * g).sum(), [x, y])
+    rx, ry = torch.autograd.grad((ref * g.double()).sum(), [x64, y64])
+    assert rel(gx, rx) < 2e-2 and rel(gy, ry) < 2e-2
+    # pairwise_distances(x) and GaussianKernelMatrix(x, sigma): one tensor on both sides
+    g2 = torch.randn(n1, n1, device=DEV)
+    for fn, rfn in ((cv.pairwise_distances, ho.pairwise_distances),
+                    (lambda t: cv.GaussianKernelMatrix(t, 100.0), lambda t: ho.gaussian_kernel_matrix(t, 100.0))):
+        out, ref = fn(x), rfn(x64)
+        (gx,) = torch.autograd.grad((out * g2).sum(), [x])
+        (rx,) = torch.autograd.grad((ref * g2.double()).sum(), [x64])
+        assert rel(out, ref) < 1e-2 and rel(gx, rx) < 2e-2
+    # no graph when nothing asks for one
+    assert not cv.pdist(x.detach(), y.detach()).requires_grad
+    with torch.no_grad():
+        assert not cv.pairwise_distances(x).requires_grad
