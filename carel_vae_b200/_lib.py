@@ -169,13 +169,14 @@ def reserved_sms() -> int:
     return int(lib().carel_get_reserved_sms())
 
 
-def set_side_branches(on: bool) -> None:
-    """carel_bow_fwd's sparse-target branch on the library's second stream (see carel_set_side_branches)."""
-    lib().carel_set_side_branches(1 if on else 0)
+def set_side_branches(mask) -> None:
+    """Bit mask (True = 3): 1 carel_bow_fwd's sparse-target branch, 2 the two O(nnz) gathers of carel_bow_bwd side by side,
+    each on the library's second stream (see carel_set_side_branches)."""
+    lib().carel_set_side_branches(3 if mask is True else int(mask))
 
 
-def side_branches() -> bool:
-    return bool(lib().carel_get_side_branches())
+def side_branches() -> int:
+    return int(lib().carel_get_side_branches())
 
 
 def timing_enable(on: bool) -> None:

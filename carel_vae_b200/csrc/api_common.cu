@@ -44,8 +44,9 @@ int sm_count() {
 // Side branches (api_common.cuh): one stream + three events per device, created on first use.
 std::atomic<int> g_side_branches{[] {
   const char* e = getenv("CAREL_SIDE_BRANCHES");
-  return e != nullptr ? (atoi(e) != 0 ? 1 : 0) : CAREL_SIDE_BRANCHES_DEFAULT;
+  return e != nullptr ? (atoi(e) & 3) : CAREL_SIDE_BRANCHES_DEFAULT;
 }()};
+int side_branch_mask() { return g_side_branches.load(std::memory_order_relaxed); }
 SideBranch* side_branch() {
   if (g_side_branches.load(std::memory_order_relaxed) == 0) return nullptr;
   static std::mutex mu;
@@ -105,7 +106,7 @@ using namespace carel;
 extern "C" void carel_set_reserved_sms(int n) { g_reserved_sms.store(n < 0 ? 0 : n, std::memory_order_relaxed); }
 extern "C" int carel_get_reserved_sms(void) { return g_reserved_sms.load(std::memory_order_relaxed); }
 
-extern "C" void carel_set_side_branches(int on) { g_side_branches.store(on != 0 ? 1 : 0, std::memory_order_relaxed); }
+extern "C" void carel_set_side_branches(int mask) { g_side_branches.store(mask < 0 ? 0 : (mask & 3), std::memory_order_relaxed); }
 extern "C" int carel_get_side_branches(void) { return g_side_branches.load(std::memory_order_relaxed); }
 
 extern "C" void carel_timing_enable(int on) {

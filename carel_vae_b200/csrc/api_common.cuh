@@ -70,6 +70,7 @@ struct SideBranch {
   }
 };
 SideBranch* side_branch();
+int side_branch_mask();      // bit 0: carel_bow_fwd's sparse-target branch, bit 1: the two O(nnz) gathers of carel_bow_bwd
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int64_t round_up64(int64_t v, int64_t a) { return (v + a - 1) / a * a; }

@@ -1008,7 +1008,7 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   //      caller's list) and the CSC view of the list for the backward gathers depend on the target only, so they run
   //      beside the operand packing and whatever the dense pass leaves free; the list is joined in front of the sparse
   //      corrections, the CSC view at the end of this call ----
-  SideBranch* sb = timing_enabled() ? nullptr : side_branch();      // per-kernel timing passes measure kernels alone
+  SideBranch* sb = (!timing_enabled() && (side_branch_mask() & 1)) ? side_branch() : nullptr;   // timing passes measure kernels alone
   cudaStream_t ss = sb != nullptr ? sb->s : st;
   if (sb != nullptr) CAREL_CHECK_CUDA(sb->fork(st));
   if (ell_cols_in != nullptr) {
@@ -1123,7 +1123,11 @@ extern "C" int carel_bow_bwd_parts(const float* grad_out, const float* bow_dense
   float* gb = grad_b != nullptr ? grad_b : w.dbacc;
   const float inv_nv = float(1.0 / (double(N) * double(V)));
   if (parts & 1) {
-  bow_sparse_dz_kernel<<<int(std::min<int64_t>((N + 7) / 8, sms * 16)), 256, 0, st>>>(
+  // the two O(nnz) gathers write disjoint outputs (grad_z | grad_w, grad_b): side by side when side branches are on (bit 1)
+  SideBranch* sb = (need_w && !timing_enabled() && (side_branch_mask() & 2)) ? side_branch() : nullptr;
+  cudaStream_t ss = sb != nullptr ? sb->s : st;
+  if (sb != nullptr) CAREL_CHECK_CUDA(sb->fork(st));
+  bow_sparse_dz_kernel<<<int(std::min<int64_t>((N + 7) / 8, sms * 16)), 256, 0, ss>>>(
       w.WH, w.ldk, int(K), w.ell_cols, w.ell_nnz, w.ell_ev, int(N), int(ell_cap), truncate, grad_out, inv_nv, grad_z, ldgz);
   CAREL_LAUNCHED();
   if (need_w) {
@@ -1131,6 +1135,7 @@ extern "C" int carel_bow_bwd_parts(const float* grad_out, const float* bow_dense
                                                   int(V), grad_out, inv_nv, gw, gb);
     CAREL_LAUNCHED();
   }
+  if (sb != nullptr) CAREL_CHECK_CUDA(sb->join(st, 0));
   if (bow_dense != nullptr) {
     bow_overflow_bwd_kernel<<<int(std::min<int64_t>((N + 7) / 8, sms * 16)), 256, 0, st>>>(
         w.Y, w.ldy, w.bl2e, w.rowc, w.ZH, w.WH, w.ldk, int(K), w.ell_nnz, bow_dense, ld_bow, int(N), int(V),

@@ -47,13 +47,15 @@ void carel_timing_enable(int on);
  * CUDA graph keeps the grid it was captured with). */
 void carel_set_reserved_sms(int n);
 int carel_get_reserved_sms(void);
-/* Side branches (no reference counterpart): with on != 0, carel_bow_fwd enqueues the part of its work that depends on
- * the BoW target only (dense -> ELL scan or the copy of a caller's ELL triple, then the CSC view the backward gathers
- * through) on a library-owned second stream per device, forked from and joined back into the caller's stream with
- * event record / wait pairs, so that it runs beside the operand packing and the tail of the dense pass; under
- * CUDA-graph capture it becomes a parallel branch of the graph.  Results are identical (the same kernels on the same
- * data).  Process-wide; the initial value comes from the environment variable CAREL_SIDE_BRANCHES when it is set. */
-void carel_set_side_branches(int on);
+/* Side branches (no reference counterpart): work inside ONE entry point that does not depend on the rest of it is
+ * enqueued on a library-owned second stream per device, forked from and joined back into the caller's stream with
+ * event record / wait pairs; under CUDA-graph capture it becomes a parallel branch of the graph.  Bit mask:
+ *   1: carel_bow_fwd — what depends on the BoW target only (dense -> ELL scan or the copy of a caller's ELL triple,
+ *      then the CSC view the backward gathers through) beside the operand packing and the tail of the dense pass;
+ *   2: carel_bow_bwd — the two O(nnz) gathers (grad_z | grad_w, grad_b: disjoint outputs) side by side.
+ * Results are identical (the same kernels on the same data).  Process-wide; the initial value is the environment
+ * variable CAREL_SIDE_BRANCHES when it is set. */
+void carel_set_side_branches(int mask);
 int carel_get_side_branches(void);
 int carel_timing_report(char* buf, size_t n);
 
