@@ -19,6 +19,33 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _run_world2(target, extra=()):
+    """Two spawned gloo ranks; one retry on a fresh port (the free port can be taken between probing and rendezvous, and
+    a loaded machine can miss the queue deadline)."""
+    ctx = mp.get_context("spawn")
+    last = None
+    for _attempt in range(2):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, 2, port, q) + tuple(extra)) for r in range(2)]
+        for p in procs:
+            p.start()
+        try:
+            res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+            for p in procs:
+                p.join(timeout=60)
+            if all(p.exitcode == 0 for p in procs):
+                return res
+            last = RuntimeError(f"exit codes {[p.exitcode for p in procs]}")
+        except Exception as e:  # noqa: BLE001  (queue.Empty: a rank died or hung)
+            last = e
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+            p.join(timeout=10)
+    raise AssertionError(f"world-2 gloo run failed twice: {last!r}")
+
+
 def _partial_cpu(x, y, alphas, eps, t0, t1):
     """Contract of carel_mmd_fwd(row_tile_begin=t0, row_tile_end=t1) in its triangular mode: block sums over
     pairs (i, j) with i in the row tiles and j > i, each weighted 2."""
@@ -79,16 +106,7 @@ def test_row_tile_partition_covers_everything():
 
 
 def test_sharded_mmd_and_flat_bucket_world2():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _run_world2(_worker)
     for rank, val, ref, local, reduced, is_view in res:
         assert abs(val - ref) <= 1e-6 * abs(ref)
         assert is_view
@@ -125,16 +143,7 @@ def test_grad_reducer_world2(overlapped):
     bit-identical after the optimiser step, and identical_across_ranks notices a difference.  OverlappedGradReducer
     keeps the same protocol; on CPU tensors (gloo) its hooks stay inert and reduce() is the plain reduction — the
     overlapped NCCL path is checked on GPUs inside bench.py (dp_overlap.max_rel_diff_vs_plain_allreduce)."""
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker_reducer, args=(r, 2, port, q, overlapped)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _run_world2(_worker_reducer, (overlapped,))
     (_, l0, g0, nb, ns, s00, s01, d0), (_, l1, g1, _, _, s10, s11, d1) = res
     assert nb == 1 and ns == 3
     for a, b, ga, gb in zip(l0, l1, g0, g1):
