@@ -6,15 +6,19 @@
 // non-zeros, so a host that scans its own rows and ships the list instead moves 27 MB.  This is the same scan as
 // carel_bow_pack_ell (bow.cu): `v != 0.f` (so -0.0 is skipped), the first `cap` non-zeros of a row are stored and
 // nnz[r] counts all of them; the list is in ascending column order here (the GPU scan interleaves the four columns of a
-// lane inside a 128-column group: the same set of (column, value) pairs, which is all the consumers rely on).  Rows are split over `n_threads` std::threads; the
-// common all-zero stretch is skipped on the raw bits, 128 bytes at a time with AVX2 (runtime check), else 32.
+// lane inside a 128-column group: the same set of (column, value) pairs, which is all the consumers rely on).  Rows are handed out in chunks to a persistent pool of
+// `n_threads` - 1 workers plus the calling thread (below); the common all-zero stretch is skipped on the raw bits, 128 bytes at a time with AVX2 (runtime check), else 32.
 #include <immintrin.h>
 
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <thread>
-#include <vector>
 
 #include "api_common.cuh"
 
@@ -71,6 +75,88 @@ static void pack_rows_host(const float* dense, int64_t ld, int64_t r0, int64_t r
   }
 }
 
+// ---- persistent worker pool ----------------------------------------------------------------------------------------
+// A stage of 8192 rows is a few milliseconds of scanning; creating and joining 16 std::threads per call costs 0.3-0.6 ms
+// of that.  The workers are created once (detached, parked on a condition variable), the calling thread works too, and
+// rows are handed out in chunks from an atomic counter, so a thread that is descheduled for a while does not hold the
+// others up.  One job at a time (callers serialise on `call_mu`); a forked child starts a fresh pool (threads do not
+// survive fork).
+struct ScanJob {
+  const float* dense; int64_t ld, N, V, cap; int32_t* cols; float* vals; int32_t* nnz; bool avx2;
+  int64_t chunk;
+};
+
+class ScanPool {
+ public:
+  static ScanPool& get() {
+    static std::mutex mu;
+    static ScanPool* pool = nullptr;
+    static pid_t owner = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (pool == nullptr || owner != getpid()) {      // first use, or a forked child: the parent's workers are not here
+      pool = new ScanPool();                          // leaked on purpose: detached workers may outlive static destruction
+      owner = getpid();
+    }
+    return *pool;
+  }
+
+  void run(const ScanJob& j, int n_threads) {
+    std::lock_guard<std::mutex> call(call_mu_);
+    const int helpers = std::max(0, n_threads - 1);
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      while (int(n_workers_) < helpers) {
+        std::thread(&ScanPool::worker, this, n_workers_).detach();
+        ++n_workers_;
+      }
+      job_ = j;
+      next_.store(0, std::memory_order_relaxed);
+      wanted_ = helpers;           // workers with index < wanted_ take part in this job
+      pending_ = helpers;
+      ++generation_;
+    }
+    cv_work_.notify_all();
+    work(j);
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+  }
+
+ private:
+  void work(const ScanJob& j) {
+    for (;;) {
+      const int64_t r0 = next_.fetch_add(j.chunk, std::memory_order_relaxed);
+      if (r0 >= j.N) break;
+      pack_rows_host(j.dense, j.ld, r0, std::min(j.N, r0 + j.chunk), j.V, j.cap, j.cols, j.vals, j.nnz, j.avx2);
+    }
+  }
+  void worker(size_t index) {
+    uint64_t seen = 0;
+    for (;;) {
+      ScanJob j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        if (int(index) >= wanted_) continue;        // not part of this job
+        j = job_;
+      }
+      work(j);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        --pending_;
+      }
+      cv_done_.notify_one();
+    }
+  }
+  std::mutex call_mu_, mu_;
+  std::condition_variable cv_work_, cv_done_;
+  ScanJob job_{};
+  std::atomic<int64_t> next_{0};
+  size_t n_workers_ = 0;
+  int wanted_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+};
+
 }  // namespace carel
 
 extern "C" int carel_bow_pack_ell_host(const float* bow_dense, int64_t ld_bow, int64_t N, int64_t V, int64_t ell_cap,
@@ -79,18 +165,15 @@ extern "C" int carel_bow_pack_ell_host(const float* bow_dense, int64_t ld_bow, i
   CAREL_REQUIRE(bow_dense && ell_cols && ell_vals && ell_nnz, "carel_bow_pack_ell_host: null pointer");
   CAREL_REQUIRE(N >= 0 && V > 0 && ell_cap > 0 && ld_bow >= V, "carel_bow_pack_ell_host: bad shape");
   int nt = n_threads > 0 ? n_threads : int(std::thread::hardware_concurrency());
-  nt = int(std::max<int64_t>(1, std::min<int64_t>(nt, (N + 15) / 16)));
+  nt = int(std::max<int64_t>(1, std::min<int64_t>(std::min(nt, 256), (N + 15) / 16)));
   const bool avx2 = __builtin_cpu_supports("avx2");
   if (nt == 1) {
     pack_rows_host(bow_dense, ld_bow, 0, N, V, ell_cap, ell_cols, ell_vals, ell_nnz, avx2);
     return 0;
   }
-  std::vector<std::thread> pool;
-  pool.reserve(size_t(nt));
-  for (int t = 0; t < nt; ++t) {
-    const int64_t r0 = N * t / nt, r1 = N * (t + 1) / nt;
-    pool.emplace_back(pack_rows_host, bow_dense, ld_bow, r0, r1, V, ell_cap, ell_cols, ell_vals, ell_nnz, avx2);
-  }
-  for (auto& th : pool) th.join();
+  ScanJob j{bow_dense, ld_bow, N, V, ell_cap, ell_cols, ell_vals, ell_nnz, avx2, 0};
+  // ~8 chunks per thread: fine enough to even out a descheduled thread, coarse enough that the counter is not contended
+  j.chunk = std::max<int64_t>(4, (N + int64_t(nt) * 8 - 1) / (int64_t(nt) * 8));
+  ScanPool::get().run(j, nt);
   return 0;
 }

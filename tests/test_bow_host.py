@@ -123,3 +123,53 @@ def test_host_ell_packer_matches_a_plain_scan():
             k = min(len(nz), cap)
             assert np.array_equal(cols[r, :k].numpy(), nz[:k].astype(np.int32))
             assert np.array_equal(vals[r, :k].numpy(), dense[r, nz[:k]])
+
+
+def _pack_check(seed, B, V, cap, threads):
+    import numpy as np
+    import torch
+    from carel_vae_b200.data import pack_ell_host
+    rng = np.random.default_rng(seed)
+    dense = np.zeros((B, V), dtype=np.float32)
+    for r in range(B):
+        idx = rng.choice(V, size=int(rng.integers(0, min(V, cap) + 1)), replace=False)
+        dense[r, idx] = rng.random(len(idx)).astype(np.float32) + 0.01
+    cols, vals, nnz = pack_ell_host(torch.from_numpy(dense), cap, threads=threads)
+    back = np.zeros_like(dense)
+    for r in range(B):
+        n = int(nnz[r])
+        back[r, cols[r, :n].numpy()] = vals[r, :n].numpy()
+    return bool(np.array_equal(back, dense) and np.array_equal(nnz.numpy(), (dense != 0).sum(1).astype(np.int32)))
+
+
+def _pack_in_child(q):
+    q.put(_pack_check(5, 200, 3000, 16, 4))
+
+
+def test_host_ell_packer_worker_pool():
+    """The scan's persistent worker pool: many calls in a row with changing thread counts and batch shapes (the pool
+    grows, workers beyond the requested count sit a job out, chunks come from a shared counter), calls from two Python
+    threads at once (they serialise inside the library) and a call in a forked child after the parent has used the
+    pool (threads do not survive fork: the child builds its own)."""
+    import multiprocessing as mp
+    import threading
+    from carel_vae_b200 import _lib
+    if not _lib.LIB_PATH.exists():
+        pytest.skip("libcarel_head.so not built")
+    for i, (B, V, cap, threads) in enumerate([(64, 500, 8, 2), (513, 4000, 32, 8), (40, 100, 4, 16), (1000, 2000, 16, 3),
+                                              (16, 64, 4, 8), (257, 9000, 64, 5)] * 3):
+        assert _pack_check(i, B, V, cap, threads), (B, V, cap, threads)
+    ok = []
+    ts = [threading.Thread(target=lambda s=s: ok.append(_pack_check(100 + s, 300, 5000, 32, 4))) for s in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert ok == [True] * 4
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    p = ctx.Process(target=_pack_in_child, args=(q,))
+    p.start()
+    assert q.get(timeout=60) is True
+    p.join(timeout=30)
+    assert p.exitcode == 0
