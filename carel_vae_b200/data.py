@@ -177,7 +177,7 @@ class HostBowStager:
         self._side = torch.cuda.Stream(self.device) if self.pipelined else None
         self._ready = [None] * nset       # copy-stream event: set i is complete (its pinned lists have been read)
         self._consumed = [None] * nset    # current-stream event: everything that read set i has been enqueued before it
-        self._meas = [None] * nset        # (host rows, host scan ms, start event, end event) of the stage that filled set i
+        self._meas = [None] * nset        # (host rows, host scan ms, timing events) of the stage that filled set i
         self._staging = [dict() for _ in range(nset)]
         self._k = 0
         self._last = None
@@ -193,8 +193,8 @@ class HostBowStager:
         m, self._meas[i] = self._meas[i], None
         if m is None or not self.adapt:
             return
-        h, t_host, e0, e1 = m
-        t_dev = e0.elapsed_time(e1)
+        h, t_host, e0, e1, e2, e3 = m
+        t_dev = e0.elapsed_time(e1) + (e2.elapsed_time(e3) if e2 is not None else 0.0)   # dense route + list copy
         if not (0 < h < self.B) or t_host <= 0.0 or t_dev <= 0.0:
             return
         r_host, r_dev = h / t_host, (self.B - h) / t_dev
@@ -246,19 +246,24 @@ class HostBowStager:
             e1.record(side)
         # (2) rows [0, h): host scan into pinned buffers, then the (small) list copy
         t_host = 0.0
+        e2 = e3 = None
         if h > 0:
             hc, hv, hn = (t[:h] for t in self._hosts[i])
             t0 = time.perf_counter()
             pack_ell_host(content_bow[:h], self.cap, out=(hc, hv, hn), threads=self.threads)
             t_host = 1e3 * (time.perf_counter() - t0)
+            e2 = torch.cuda.Event(enable_timing=True)
+            e3 = torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(side):
+                e2.record(side)
                 cols[:h].copy_(hc, non_blocking=True)
                 vals[:h].copy_(hv, non_blocking=True)
                 nnz[:h].copy_(hn, non_blocking=True)
+                e3.record(side)
         ready = torch.cuda.Event()
         ready.record(side)
         self._ready[i] = ready
-        self._meas[i] = (h, t_host, e0, e1)
+        self._meas[i] = (h, t_host, e0, e1, e2, e3)
         self._last = i
         if not self.pipelined:
             return self._sets[0]
