@@ -12,7 +12,7 @@
 #include "pack.cuh"
 
 #ifndef CAREL_SIDE_BRANCHES_DEFAULT
-#define CAREL_SIDE_BRANCHES_DEFAULT 0      // flipped to 1 once a GPU run has shown parity and a shorter step with it
+#define CAREL_SIDE_BRANCHES_DEFAULT 3      // measured on B200 (profiles/r02_side_branches_ab.txt): 815 -> 851 steps/s, suite green either way
 #endif
 
 namespace carel {
