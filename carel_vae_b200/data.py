@@ -187,20 +187,27 @@ class HostBowStager:
         h = self.host_rows
         return h * (self.cap * 8 + 4) + (self.B - h) * self.V * 4
 
+    @staticmethod
+    def balanced_rows(batch: int, current: int, measured_rows: int, t_host: float, t_dev: float) -> int:
+        """New `host_rows`: half-way from `current` to the split at which the two routes finish together, given that
+        the host scanned `measured_rows` rows in `t_host` ms while the copy engine + GPU took `t_dev` ms for the other
+        `batch - measured_rows`.  Rates are taken as proportional to the rows, so the fixed point of repeated calls is
+        t_host == t_dev whatever constant costs either side carries.  Multiples of 8, at least 8 rows on each side;
+        unusable measurements (a route without rows, a zero time) leave the split alone."""
+        if batch < 24 or not (0 < measured_rows < batch) or t_host <= 0.0 or t_dev <= 0.0:
+            return current
+        r_host, r_dev = measured_rows / t_host, (batch - measured_rows) / t_dev
+        target = batch * r_host / (r_host + r_dev)
+        new = current + 0.5 * (target - current)
+        return max(8, min(batch - 8, int(round(new / 8)) * 8))
+
     def _rebalance(self, i: int) -> None:
-        """Moves `host_rows` half-way to the split at which the two routes, at the rates measured when set i was
-        filled, finish together (fixed point: host scan time == copy + GPU scan time)."""
         m, self._meas[i] = self._meas[i], None
         if m is None or not self.adapt:
             return
         h, t_host, e0, e1, e2, e3 = m
         t_dev = e0.elapsed_time(e1) + (e2.elapsed_time(e3) if e2 is not None else 0.0)   # dense route + list copy
-        if not (0 < h < self.B) or t_host <= 0.0 or t_dev <= 0.0:
-            return
-        r_host, r_dev = h / t_host, (self.B - h) / t_dev
-        target = self.B * r_host / (r_host + r_dev)
-        new = self.host_rows + 0.5 * (target - self.host_rows)
-        self.host_rows = max(8, min(self.B - 8, int(round(new / 8)) * 8)) if self.B >= 24 else self.host_rows
+        self.host_rows = self.balanced_rows(self.B, self.host_rows, h, t_host, t_dev)
 
     def stage(self, content_bow: torch.Tensor, copies=()):
         import time

@@ -173,3 +173,30 @@ def test_host_ell_packer_worker_pool():
     assert q.get(timeout=60) is True
     p.join(timeout=30)
     assert p.exitcode == 0
+
+
+def test_host_stager_split_converges_to_equal_times():
+    """HostBowStager.balanced_rows (the adaptive host / copy-engine split, pure arithmetic): iterating it against a
+    model with constant costs on both sides reaches the split where both routes take the same time; degenerate
+    measurements leave the split alone; the result stays a multiple of 8 with rows on both sides."""
+    from carel_vae_b200.data import HostBowStager as S
+    B = 8192
+    host = lambda h: 0.3 + h * (5.2 / B)              # ms: pool wake-up + scan
+    dev = lambda h: 0.9 + (B - h) * (19.5 / B)        # ms: X copy + list copy + dense rows over PCIe + GPU scan
+    h = 4096
+    for _ in range(40):
+        h = S.balanced_rows(B, h, h, host(h), dev(h))
+        assert h % 8 == 0 and 8 <= h <= B - 8
+    assert abs(host(h) - dev(h)) < 0.02 * host(h)
+    exact = (0.9 - 0.3 + 19.5) / (5.2 + 19.5) * B
+    assert abs(h - exact) <= 16
+    # a much slower copy route pushes everything but the minimum to the host, and back
+    h2 = 4096
+    for _ in range(60):
+        h2 = S.balanced_rows(B, h2, h2, 1e-3 * h2, 10.0 * (B - h2))
+    assert h2 == B - 8
+    for _ in range(60):
+        h2 = S.balanced_rows(B, h2, h2, 10.0 * h2, 1e-3 * (B - h2))
+    assert h2 == 8
+    assert S.balanced_rows(B, 4096, 0, 1.0, 1.0) == 4096 and S.balanced_rows(B, 4096, B, 1.0, 1.0) == 4096
+    assert S.balanced_rows(B, 4096, 100, 0.0, 1.0) == 4096 and S.balanced_rows(16, 8, 8, 1.0, 1.0) == 8
