@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "../../include/carel_head.h"
 #include "common.cuh"
@@ -58,6 +59,7 @@ void timing_end(cudaStream_t st);
 // Event record / wait pairs are capturable: under CUDA-graph capture the side work becomes a parallel branch.
 // nullptr when disabled (carel_set_side_branches / CAREL_SIDE_BRANCHES) or when stream / event creation failed.
 struct SideBranch {
+  std::mutex mu;      // held by an entry point from its fork to its last join: the events are per device, not per caller
   cudaStream_t s = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cudaError_t fork(cudaStream_t st) {

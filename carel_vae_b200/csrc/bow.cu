@@ -1010,6 +1010,8 @@ extern "C" int carel_bow_fwd(const float* z, int64_t ldz, const float* dec_w, co
   //      corrections, the CSC view at the end of this call ----
   SideBranch* sb = (!timing_enabled() && (side_branch_mask() & 1)) ? side_branch() : nullptr;   // timing passes measure kernels alone
   cudaStream_t ss = sb != nullptr ? sb->s : st;
+  std::unique_lock<std::mutex> sb_lock;      // two host threads driving the same device take turns on the branch
+  if (sb != nullptr) sb_lock = std::unique_lock<std::mutex>(sb->mu);
   if (sb != nullptr) CAREL_CHECK_CUDA(sb->fork(st));
   if (ell_cols_in != nullptr) {
     CAREL_CHECK_CUDA(cudaMemcpyAsync(w.ell_cols, ell_cols_in, size_t(N) * cap * 4, cudaMemcpyDeviceToDevice, ss));
@@ -1126,6 +1128,8 @@ extern "C" int carel_bow_bwd_parts(const float* grad_out, const float* bow_dense
   // the two O(nnz) gathers write disjoint outputs (grad_z | grad_w, grad_b): side by side when side branches are on (bit 1)
   SideBranch* sb = (need_w && !timing_enabled() && (side_branch_mask() & 2)) ? side_branch() : nullptr;
   cudaStream_t ss = sb != nullptr ? sb->s : st;
+  std::unique_lock<std::mutex> sb_lock;
+  if (sb != nullptr) sb_lock = std::unique_lock<std::mutex>(sb->mu);
   if (sb != nullptr) CAREL_CHECK_CUDA(sb->fork(st));
   bow_sparse_dz_kernel<<<int(std::min<int64_t>((N + 7) / 8, sms * 16)), 256, 0, ss>>>(
       w.WH, w.ldk, int(K), w.ell_cols, w.ell_nnz, w.ell_ev, int(N), int(ell_cap), truncate, grad_out, inv_nv, grad_z, ldgz);
@@ -1135,7 +1139,10 @@ extern "C" int carel_bow_bwd_parts(const float* grad_out, const float* bow_dense
                                                   int(V), grad_out, inv_nv, gw, gb);
     CAREL_LAUNCHED();
   }
-  if (sb != nullptr) CAREL_CHECK_CUDA(sb->join(st, 0));
+  if (sb != nullptr) {
+    CAREL_CHECK_CUDA(sb->join(st, 0));
+    sb_lock.unlock();
+  }
   if (bow_dense != nullptr) {
     bow_overflow_bwd_kernel<<<int(std::min<int64_t>((N + 7) / 8, sms * 16)), 256, 0, st>>>(
         w.Y, w.ldy, w.bl2e, w.rowc, w.ZH, w.WH, w.ldk, int(K), w.ell_nnz, bow_dense, ld_bow, int(N), int(V),
